@@ -1,0 +1,107 @@
+/*
+ * oracle/oracle.h -- CPU restatement of the reference RRTMG LW + SW + McICA column path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (geosradiation_gridcomp_b200/) may
+ * include, link or call this.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs use it, as the checker and the timed CPU baseline.
+ *
+ * PARITY UNPINNED: the reference tree ships no golden vectors, known-answer tests or
+ * fixtures for this path and no Fortran compiler exists in the build
+ * container, so this restatement cannot be checked against reference output.  It is a
+ * routine-by-routine restatement of the Fortran, with `real` promoted to 8 bytes (the
+ * north_star fp64 contract), same loop nests, same expression order, compiled with
+ * -ffp-contract=off.  Its pins are property tests (tests/test_oracle_*.py).
+ *
+ * Array layouts are those of the reference driver interfaces (column index fastest):
+ *   x(ncol,nlay) -> x[icol + ncol*ilay].
+ */
+#ifndef RRTMG_ORACLE_H
+#define RRTMG_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { NBNDLW = 16, NGPTLW = 140, NBNDSW = 14, NGPTSW = 112 };
+
+/* Optional taps on intermediates for parity tests; any pointer may be NULL. */
+typedef struct {
+    int *jp, *jt, *jt1;                /* (ncol,nlay)  1-based reference indices          */
+    int *indfor, *indself, *indminor;  /* (ncol,nlay)  (indself/indminor: LW lower only)  */
+    int *laytrop;                      /* (ncol)                                          */
+    double *fac00, *fac01, *fac10, *fac11; /* (ncol,nlay)                                 */
+    unsigned char *cldymc;             /* [icol][ig][ilay] binary McICA cloud mask        */
+    double *ciwpmc, *clwpmc;           /* [icol][ig][ilay]                                */
+    double *taug, *pfracs;             /* LW: [icol][ig][ilay]; SW: taug, taur            */
+    double *taucmc;                    /* [icol][ig][ilay] (LW: absorption od; SW: delta-scaled) */
+    double *pwvcm;                     /* (ncol) LW only                                  */
+    double *ssi;                       /* SW: [icol][ig] solar source per g-point          */
+} OracleTaps;
+
+int oracle_init(const char *blob_path);
+void oracle_finalize(void);
+/* ih: 0 homogeneous, 1 beta, 2 gamma (SH/cloud_condensate_inhomogeneity.F90:45-73);
+ * corr = {adl_am1, adl_am2, adl_am30, adl_am4, rdl_am1, rdl_am2, rdl_am30, rdl_am4}
+ * (SH/cloud_subcol_gen.F90:108-129); NULL keeps the Oreopoulos 2012 defaults. */
+int oracle_set_mcica(int ih, const double *corr);
+int oracle_num_threads(void);
+
+/* LW/src/rrtmg_lw_rad.F90:15-344.  Returns 0 or a negative code mirroring an error stop. */
+int oracle_rrtmg_lw(
+    int ncol, int nlay, int psize, int dudTs,
+    const double *play, const double *plev, const double *tlay, const double *tlev,
+    const double *tsfc, const double *emis,
+    const double *h2ovmr, const double *o3vmr, const double *co2vmr, const double *ch4vmr,
+    const double *n2ovmr, const double *o2vmr, const double *cfc11vmr, const double *cfc12vmr,
+    const double *cfc22vmr, const double *ccl4vmr,
+    const double *cldf, const double *ciwp, const double *clwp, const double *rei,
+    const double *rel, int iceflglw, int liqflglw,
+    const double *tauaer, const double *zm, const double *alat, int dyofyr,
+    int cloudLM, int cloudMH, int *clearCounts,
+    double *uflx, double *dflx, double *uflxc, double *dflxc,
+    double *duflx_dTs, double *duflxc_dTs,
+    const int *band_output, double *olrb, double *dolrb_dTs,
+    OracleTaps *taps);
+
+/* SW/src/rrtmg_sw_rad.F90:68-1801 (non-SOLAR_RADVAL build).  bndscl/indsolvar/solcycfrac may
+ * be NULL (absent optional arguments). drband/dfband only touched when do_drfband. */
+int oracle_rrtmg_sw(
+    int rpart, int ncol, int nlay,
+    double scon, double adjes, const double *coszen, int isolvar,
+    const double *play, const double *plev, const double *tlay,
+    const double *h2ovmr, const double *o3vmr, const double *co2vmr, const double *ch4vmr,
+    const double *o2vmr, int iceflgsw, int liqflgsw,
+    const double *cld, const double *ciwp, const double *clwp, const double *rei,
+    const double *rel, int dyofyr, const double *zm, const double *alat,
+    int iaer, const double *tauaer, const double *ssaaer, const double *asmaer,
+    const double *asdir, const double *asdif, const double *aldir, const double *aldif,
+    int cloudLM, int cloudMH, int normFlx,
+    int *clearCounts, double *swuflx, double *swdflx, double *swuflxc, double *swdflxc,
+    double *nirr, double *nirf, double *parr, double *parf, double *uvrr, double *uvrf,
+    double *fswband,
+    double *cotdtp, double *cotdhp, double *cotdmp, double *cotdlp,
+    double *cotntp, double *cotnhp, double *cotnmp, double *cotnlp,
+    int do_drfband, double *drband, double *dfband,
+    const double *bndscl, const double *indsolvar, const double *solcycfrac,
+    OracleTaps *taps);
+
+/* stand-alone McICA generator + clear counts for unit tests
+ * (SH/cloud_subcol_gen.F90:132-487, 611-769); arrays in the (nlay,dncol) partition layout. */
+int oracle_generate_stochastic_clouds(
+    int dncol, int ncol, int nsubcol, int nlay,
+    const double *zmid, const double *alat, int doy,
+    const double *play, const double *cldfrac, const double *ciwp, const double *clwp,
+    double cwp_tiny, unsigned char *cldy_stoch, double *ciwp_stoch, double *clwp_stoch,
+    const int *seed_order);
+int oracle_clearCounts_threeBand(int dncol, int ncol, int nsubcol, int nlay, int cloudLM,
+                                 int cloudMH, const unsigned char *cldy_stoch, int *clearCnts);
+void oracle_rng_kiss(int *s1, int *s2, int *s3, int *s4, double *ran);
+
+/* reduced (post-cmbgb) tables and lookup tables, for tests of the init restatement */
+const double *oracle_lw_table(const char *name, int band, int *n);
+const double *oracle_sw_table(const char *name, int band, int *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
