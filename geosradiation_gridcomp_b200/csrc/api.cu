@@ -1,0 +1,496 @@
+// C ABI of the library (include/rrtmgx.h): lifecycle, table upload, column chunking, the
+// host<->device staging pipeline for host-pointer callers, and the input traps of the
+// reference drivers (LW/src/rrtmg_lw_rad.F90:209-318, SW/src/rrtmg_sw_rad.F90:365-383).
+//
+// There is no CPU fallback: every entry point fails with RRTMGX_ENODEVICE / RRTMGX_ENOTINIT
+// when no CUDA device is usable.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+namespace rrtmgx {
+
+long long g_launches = 0;
+
+namespace {
+
+constexpr int NSIDE = 4;
+
+struct Path {   // per-path (LW or SW) execution resources
+    cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
+    cudaStream_t side[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[1 + NSIDE] = {};
+    cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_free[2] = {};
+    Slab slab;            // kernel scratch
+    Slab stage[2];        // host-pointer mode: device copies of one chunk's boundary arrays
+    KissJump *d_jumps = nullptr;
+    int jumps_nlay = -1, jumps_inhomo = -1;
+    int *d_err = nullptr;      // [0] trap code, [1] first negative-input position
+    int last_status = 0;
+    bool pending = false;
+    RrtmgxTaps taps;
+    bool has_taps = false;
+};
+
+struct Ctx {
+    bool ready = false;
+    int device = 0;
+    HostTables ht;
+    double *d_arena = nullptr;
+    McicaConfig mc;
+    Path lw, sw;
+    size_t chunk_cols = 0;   // 0: automatic
+    std::mutex mu;
+};
+
+Ctx g;
+
+const int kErrInit[2] = {0, 1 << 30};
+
+bool ok(cudaError_t e) { return e == cudaSuccess; }
+
+int grow(Slab &s, size_t bytes) {
+    if (s.cap >= bytes) return 0;
+    if (s.base) cudaFree(s.base);
+    s.base = nullptr;
+    s.cap = 0;
+    if (!ok(cudaMalloc((void **)&s.base, bytes))) { cudaGetLastError(); return RRTMGX_ECUDA; }
+    s.cap = bytes;
+    return 0;
+}
+
+int path_init(Path &p) {
+    if (!ok(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking))) return RRTMGX_ECUDA;
+    if (!ok(cudaStreamCreateWithFlags(&p.h2d, cudaStreamNonBlocking))) return RRTMGX_ECUDA;
+    if (!ok(cudaStreamCreateWithFlags(&p.d2h, cudaStreamNonBlocking))) return RRTMGX_ECUDA;
+    for (auto &s : p.side)
+        if (!ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking))) return RRTMGX_ECUDA;
+    for (auto &e : p.ev)
+        if (!ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming))) return RRTMGX_ECUDA;
+    for (int i = 0; i < 2; ++i) {
+        if (!ok(cudaEventCreateWithFlags(&p.ev_in[i], cudaEventDisableTiming))) return RRTMGX_ECUDA;
+        if (!ok(cudaEventCreateWithFlags(&p.ev_done[i], cudaEventDisableTiming))) return RRTMGX_ECUDA;
+        if (!ok(cudaEventCreateWithFlags(&p.ev_free[i], cudaEventDisableTiming))) return RRTMGX_ECUDA;
+    }
+    if (!ok(cudaMalloc((void **)&p.d_err, 2 * sizeof(int)))) return RRTMGX_ECUDA;
+    return 0;
+}
+
+void path_free(Path &p) {
+    if (p.stream) cudaStreamDestroy(p.stream);
+    if (p.h2d) cudaStreamDestroy(p.h2d);
+    if (p.d2h) cudaStreamDestroy(p.d2h);
+    for (auto &s : p.side) if (s) cudaStreamDestroy(s);
+    for (auto &e : p.ev) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (p.ev_in[i]) cudaEventDestroy(p.ev_in[i]);
+        if (p.ev_done[i]) cudaEventDestroy(p.ev_done[i]);
+        if (p.ev_free[i]) cudaEventDestroy(p.ev_free[i]);
+    }
+    if (p.slab.base) cudaFree(p.slab.base);
+    for (auto &s : p.stage) if (s.base) cudaFree(s.base);
+    if (p.d_jumps) cudaFree(p.d_jumps);
+    if (p.d_err) cudaFree(p.d_err);
+    p = Path();
+}
+
+std::string default_blob() {
+    if (const char *e = std::getenv("RRTMGX_TABLES")) return e;
+    Dl_info info;
+    if (dladdr((void *)&default_blob, &info) && info.dli_fname) {
+        std::string so(info.dli_fname);
+        size_t k = so.find_last_of('/');
+        std::string dir = k == std::string::npos ? "." : so.substr(0, k);
+        return dir + "/data/rrtmg_tables.bin";
+    }
+    return "rrtmg_tables.bin";
+}
+
+int ensure_jumps(Path &p, int nsub, int nlay) {
+    const int inhomo = g.mc.ih > 0;
+    if (p.d_jumps && p.jumps_nlay == nlay && p.jumps_inhomo == inhomo) return 0;
+    std::vector<KissJump> h(2 * (size_t)nsub);
+    kiss_jump_table(nsub, nlay, inhomo, h.data());
+    if (!p.d_jumps && !ok(cudaMalloc((void **)&p.d_jumps, sizeof(KissJump) * 2 * 140))) return RRTMGX_ECUDA;
+    // stream-ordered behind any work still reading the old table
+    cudaStreamSynchronize(p.stream);
+    if (!ok(cudaMemcpy(p.d_jumps, h.data(), sizeof(KissJump) * h.size(), cudaMemcpyHostToDevice))) return RRTMGX_ECUDA;
+    p.jumps_nlay = nlay;
+    p.jumps_inhomo = inhomo;
+    return 0;
+}
+
+__global__ void check_negative_kernel(const double *__restrict__ x, size_t n, int pos, int *negpos) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i < n; i += stride) bad |= x[i] < 0.;
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicMin(negpos, pos);
+}
+
+size_t pick_chunk(int ncol, int nlay, size_t per_col_bytes) {
+    if (g.chunk_cols) return std::min<size_t>(g.chunk_cols, (size_t)ncol);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    // scratch budget: a quarter of what is free, at most 12 GiB
+    size_t budget = std::min<size_t>(free_b / 4, (size_t)12 << 30);
+    size_t nc = std::max<size_t>(1024, budget / std::max<size_t>(per_col_bytes, 1));
+    nc = std::min<size_t>(nc, 65536);
+    nc &= ~(size_t)127;
+    (void)nlay;
+    return std::min<size_t>(nc, (size_t)ncol);
+}
+
+int status_from(Path &p) {
+    int h[2];
+    if (!ok(cudaMemcpyAsync(h, p.d_err, sizeof h, cudaMemcpyDeviceToHost, p.stream))) return RRTMGX_ECUDA;
+    if (!ok(cudaStreamSynchronize(p.stream))) { cudaGetLastError(); return RRTMGX_ECUDA; }
+    p.pending = false;
+    if (h[1] < (1 << 30)) return RRTMGX_ENEGATIVE - 1 - h[1];   // -(101 + position)
+    return h[0];
+}
+
+// One boundary array as seen by the chunk pipeline: `rows` rows of ncol elements (column
+// fastest), or band-fastest (16,ncol) outputs when `colmajor_inner` is set.
+struct Arr {
+    const void *host;   // caller pointer (host or device)
+    void **slot;        // where the per-chunk device pointer goes in the chunk args
+    size_t rows, elem;
+    bool inner;         // (k,ncol) layout: the chunk is contiguous
+    bool in, out;
+};
+
+// Host-pointer mode: run `fn(chunk_args, nc)` over chunks with H2D / compute / D2H overlapped
+// on three streams and two staging sets.
+template <class Args, class Fn>
+int run_staged(Path &p, const Args &a, Args &ca, std::vector<Arr> &arrs, int ncol, size_t chunk, Fn fn) {
+    size_t stage_bytes = 0;
+    for (auto &r : arrs) stage_bytes += ((r.rows * chunk * r.elem) + 255) & ~(size_t)255;
+    for (int s = 0; s < 2; ++s)
+        if (int rc = grow(p.stage[s], stage_bytes + 4096)) return rc;
+    int k = 0;
+    for (size_t col0 = 0; col0 < (size_t)ncol; col0 += chunk, ++k) {
+        const int s = k & 1;
+        const size_t nc = std::min(chunk, (size_t)ncol - col0);
+        Slab &st = p.stage[s];
+        st.used = 0;
+        std::vector<void *> dev(arrs.size());
+        if (k >= 2) cudaStreamWaitEvent(p.h2d, p.ev_free[s], 0);
+        for (size_t i = 0; i < arrs.size(); ++i) {
+            Arr &r = arrs[i];
+            dev[i] = r.host ? (void *)st.take<char>(r.rows * nc * r.elem) : nullptr;
+            if (!r.host || !r.in) continue;
+            if (r.inner)
+                cudaMemcpyAsync(dev[i], (const char *)r.host + col0 * r.rows * r.elem, r.rows * nc * r.elem,
+                                cudaMemcpyHostToDevice, p.h2d);
+            else
+                cudaMemcpy2DAsync(dev[i], nc * r.elem, (const char *)r.host + col0 * r.elem, (size_t)ncol * r.elem,
+                                  nc * r.elem, r.rows, cudaMemcpyHostToDevice, p.h2d);
+        }
+        cudaEventRecord(p.ev_in[s], p.h2d);
+        cudaStreamWaitEvent(p.stream, p.ev_in[s], 0);
+        ca = a;
+        ca.ncol = (int)nc;
+        for (size_t i = 0; i < arrs.size(); ++i) *arrs[i].slot = dev[i];
+        if (int rc = fn(ca, (int)nc)) return rc;
+        cudaEventRecord(p.ev_done[s], p.stream);
+        cudaStreamWaitEvent(p.d2h, p.ev_done[s], 0);
+        for (size_t i = 0; i < arrs.size(); ++i) {
+            Arr &r = arrs[i];
+            if (!r.host || !r.out) continue;
+            if (r.inner)
+                cudaMemcpyAsync((char *)r.host + col0 * r.rows * r.elem, dev[i], r.rows * nc * r.elem,
+                                cudaMemcpyDeviceToHost, p.d2h);
+            else
+                cudaMemcpy2DAsync((char *)r.host + col0 * r.elem, (size_t)ncol * r.elem, dev[i], nc * r.elem,
+                                  nc * r.elem, r.rows, cudaMemcpyDeviceToHost, p.d2h);
+        }
+        cudaEventRecord(p.ev_free[s], p.d2h);
+    }
+    if (!ok(cudaStreamSynchronize(p.d2h))) { cudaGetLastError(); return RRTMGX_ECUDA; }
+    return 0;
+}
+
+const double *dev_table(const char *name) {
+    TableRef r = g.ht.find(name);
+    return r.ok() ? g.d_arena + r.off : nullptr;
+}
+
+// RAD:798-819: heating rate of layer l from the net flux divergence across it
+__global__ void heating_rate_kernel(int ncol, int nlay, const double *__restrict__ fnet,
+                                    const double *__restrict__ plev, double *__restrict__ hr, double gcp) {
+    const size_t n = (size_t)ncol * nlay;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // fnet = up - down at levels (ncol,nlay+1), level 0 at the surface; plev in hPa
+    hr[i] = (fnet[i] - fnet[i + ncol]) * gcp / ((plev[i] - plev[i + ncol]) * 100.) * 86400.;
+}
+
+}  // namespace
+
+void launch_check_negative(const double *x, size_t n, int pos, int *d_negpos, cudaStream_t s) {
+    if (!x || !n) return;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    RRTMGX_LAUNCH(check_negative_kernel, blocks, 256, 0, s, x, n, pos, d_negpos);
+}
+
+}  // namespace rrtmgx
+
+using namespace rrtmgx;
+
+extern "C" {
+
+int rrtmgx_init(const RrtmgxConfig *cfg) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    int ndev = 0;
+    if (!ok(cudaGetDeviceCount(&ndev)) || ndev == 0) { cudaGetLastError(); return RRTMGX_ENODEVICE; }
+    if (cfg && cfg->device >= 0) {
+        if (!ok(cudaSetDevice(cfg->device))) { cudaGetLastError(); return RRTMGX_ENODEVICE; }
+    }
+    if (g.ready) {   // idempotent: GEOS calls the _ini routines on every refresh
+        if (cfg && cfg->inhomogeneity >= 0 && cfg->inhomogeneity <= 2) {
+            g.mc.ih = cfg->inhomogeneity;
+            if (cfg->corr) std::memcpy(g.mc.corr, cfg->corr, sizeof g.mc.corr);
+        }
+        return 0;
+    }
+    if (!ok(cudaGetDevice(&g.device))) return RRTMGX_ENODEVICE;
+    const std::string blob = (cfg && cfg->table_blob) ? cfg->table_blob : default_blob();
+    if (int rc = g.ht.load(blob)) return rc;
+    const size_t bytes = g.ht.arena.size() * sizeof(double);
+    if (!ok(cudaMalloc((void **)&g.d_arena, bytes))) { cudaGetLastError(); return RRTMGX_ENODEVICE; }
+    if (!ok(cudaMemcpy(g.d_arena, g.ht.arena.data(), bytes, cudaMemcpyHostToDevice))) return RRTMGX_ECUDA;
+    if (int rc = lw_upload_tables(g.ht, g.d_arena)) return rc;
+    if (int rc = sw_upload_tables(g.ht, g.d_arena)) return rc;
+    if (int rc = path_init(g.lw)) return rc;
+    if (int rc = path_init(g.sw)) return rc;
+    g.mc = McicaConfig();
+    if (cfg) {
+        if (cfg->inhomogeneity < 0 || cfg->inhomogeneity > 2) return RRTMGX_EINHOMO;
+        g.mc.ih = cfg->inhomogeneity;
+        if (cfg->corr) std::memcpy(g.mc.corr, cfg->corr, sizeof g.mc.corr);
+    }
+    if (const char *e = std::getenv("RRTMGX_CHUNK")) g.chunk_cols = (size_t)std::atoll(e);
+    g.ready = true;
+    return 0;
+}
+
+int rrtmgx_set_mcica(int ih, const double corr[8]) {
+    if (!g.ready) return RRTMGX_ENOTINIT;
+    if (ih < 0 || ih > 2) return RRTMGX_EINHOMO;
+    g.mc = McicaConfig();
+    g.mc.ih = ih;
+    if (corr) std::memcpy(g.mc.corr, corr, sizeof g.mc.corr);
+    return 0;
+}
+
+int rrtmgx_finalize(void) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return 0;
+    cudaDeviceSynchronize();
+    path_free(g.lw);
+    path_free(g.sw);
+    if (g.d_arena) cudaFree(g.d_arena);
+    g.d_arena = nullptr;
+    g.ready = false;
+    return 0;
+}
+
+const char *rrtmgx_strerror(int status) {
+    switch (status) {
+        case RRTMGX_OK: return "success";
+        case RRTMGX_ENODEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+        case RRTMGX_ENOTINIT: return "rrtmgx_init has not been called";
+        case RRTMGX_EBLOB: return "table blob missing or malformed";
+        case RRTMGX_EARG: return "bad scalar argument";
+        case RRTMGX_ECUDA: return "CUDA runtime failure";
+        case RRTMGX_EINHOMO: return "set_inhomogeneity: unknown inhomogeneity type";
+        case RRTMGX_ESEEDORDER: return "generate_stochastic_clouds: bad seed_order";
+        case RRTMGX_ESUPERLAYER: return "clearCounts_threeBand: invalid pressure super-layers!";
+        case RRTMGX_EPRESSURE: return "RRTMG LW pressure misordering";
+        case RRTMGX_EICEFLAG: return "cldprmc: invalid iceflag";
+        case RRTMGX_ERADIUS_ICE: return "cldprmc: ice radius extrapolation forbidden";
+        case RRTMGX_ELIQFLAG: return "cldprmc: invalid liqflag";
+        case RRTMGX_ERADIUS_LIQ: return "cldprmc: liquid radius extrapolation forbidden";
+        case RRTMGX_ESOLVAR: return "rrtmg_sw: invalid isolvar or missing optional argument";
+        default: break;
+    }
+    if (status <= RRTMGX_ENEGATIVE) return "negative values in an input array";
+    return "unknown status";
+}
+
+long long rrtmgx_launch_count(void) { return g_launches; }
+
+void rrtmgx_set_taps(const RrtmgxTaps *lw_taps, const RrtmgxTaps *sw_taps) {
+    g.lw.has_taps = lw_taps != nullptr;
+    if (lw_taps) g.lw.taps = *lw_taps;
+    g.sw.has_taps = sw_taps != nullptr;
+    if (sw_taps) g.sw.taps = *sw_taps;
+}
+
+const double *rrtmgx_table(const char *kind, const char *name, int band, int *n) {
+    if (n) *n = 0;
+    if (!g.ready) return nullptr;
+    char key[96];
+    const bool lw = std::strcmp(kind, "lw") == 0;
+    if (band > 0)
+        std::snprintf(key, sizeof key, lw ? "lw.%02d.%s" : "sw.%02d.%s", band, name);
+    else
+        std::snprintf(key, sizeof key, "%s.%s", kind, name);
+    TableRef r = g.ht.find(key);
+    if (!r.ok()) return nullptr;
+    if (n) *n = (int)r.n;
+    return g.ht.ptr(r);
+}
+
+int rrtmgx_lw_status(void) {
+    if (!g.ready) return RRTMGX_ENOTINIT;
+    if (!g.lw.pending) return g.lw.last_status;
+    g.lw.last_status = status_from(g.lw);
+    return g.lw.last_status;
+}
+
+int rrtmgx_sw_status(void) {
+    if (!g.ready) return RRTMGX_ENOTINIT;
+    if (!g.sw.pending) return g.sw.last_status;
+    g.sw.last_status = status_from(g.sw);
+    return g.sw.last_status;
+}
+
+int rrtmgx_lw_run(const RrtmgxLwArgs *a) {
+    if (!g.ready) return RRTMGX_ENOTINIT;
+    if (!a || a->ncol <= 0 || a->nlay <= 0 || a->nlay > 1000) return RRTMGX_EARG;
+    if (a->cloudLM == a->cloudMH) return RRTMGX_ESUPERLAYER;   // cloud_subcol_gen.F90:762-766
+    if (a->iceflglw < 0 || a->iceflglw > 4) return RRTMGX_EICEFLAG;
+    if (a->liqflglw != 1) return RRTMGX_ELIQFLAG;
+    Path &p = g.lw;
+    const bool devptr = a->flags & RRTMGX_DEVICE_PTRS;
+    if ((a->flags & RRTMGX_NO_SYNC) && !devptr) return RRTMGX_EARG;
+    const int ncol = a->ncol, nlay = a->nlay;
+    if (int rc = ensure_jumps(p, 140, nlay)) return rc;
+    static const int seed_order[4] = {1, 2, 3, 4};   // LW/src/rrtmg_lw_rad.F90:541-546
+    const McicaParams mp = mcica_params(g.mc, dev_table("mcica.xcw_beta"), dev_table("mcica.xcw_gamma"), a->dyofyr,
+                                        seed_order);
+    const RrtmgxTaps *taps = p.has_taps ? &p.taps : nullptr;
+    const bool dbg = taps && (taps->taug || taps->pfracs);
+    const size_t per_col = lw_scratch_bytes(1024, nlay, dbg) / 1024;
+    size_t chunk = pick_chunk(ncol, nlay, per_col + (devptr ? 0 : 2 * (size_t)(37 * nlay + 60) * 8));
+    if (int rc = grow(p.slab, lw_scratch_bytes((int)chunk, nlay, dbg))) return rc;
+    cudaStream_t stream = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
+    if (!ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, stream))) return RRTMGX_ECUDA;
+
+    auto run_chunks_device = [&](const RrtmgxLwArgs &da) -> int {
+        const int n = da.ncol;
+        if (!(da.flags & RRTMGX_SKIP_CHECKS)) {
+            const size_t n2 = (size_t)n * nlay, n2p = (size_t)n * (nlay + 1);
+            struct { const double *x; size_t cnt; } chk[] = {
+                {da.play, n2}, {da.plev, n2p}, {da.tlay, n2}, {da.tlev, n2p}, {da.tsfc, (size_t)n},
+                {da.h2ovmr, n2}, {da.o3vmr, n2}, {da.co2vmr, n2}, {da.ch4vmr, n2}, {da.n2ovmr, n2},
+                {da.o2vmr, n2}, {da.cfc11vmr, n2}, {da.cfc12vmr, n2}, {da.cfc22vmr, n2}, {da.ccl4vmr, n2},
+                {da.emis, (size_t)n * 16}, {da.cldf, n2}, {da.ciwp, n2}, {da.clwp, n2}, {da.rei, n2},
+                {da.rel, n2}, {da.tauaer, n2 * 16}};
+            for (int i = 0; i < (int)(sizeof chk / sizeof chk[0]); ++i)
+                launch_check_negative(chk[i].x, chk[i].cnt, i, p.d_err + 1, stream);
+        }
+        for (size_t col0 = 0; col0 < (size_t)n; col0 += chunk) {
+            const int nc = (int)std::min(chunk, (size_t)n - col0);
+            if (int rc = lw_run_chunk(&da, (int)col0, nc, mp, p.d_jumps, p.slab, p.d_err, stream, p.side, NSIDE, p.ev,
+                                      taps, p.d_err + 1))
+                return rc;
+        }
+        return 0;
+    };
+
+    if (devptr) {
+        if (int rc = run_chunks_device(*a)) return rc;
+        p.pending = true;
+        if (a->flags & RRTMGX_NO_SYNC) return 0;
+        p.last_status = status_from(p);
+        return p.last_status;
+    }
+
+    // host pointers: stage chunk by chunk
+    RrtmgxLwArgs ca = *a;
+    std::vector<Arr> arrs;
+    const size_t L = nlay, L1 = nlay + 1;
+    auto in = [&](const double *const &field, const double **slot, size_t rows) {
+        arrs.push_back({field, (void **)slot, rows, 8, false, true, false});
+    };
+    auto out = [&](double *const &field, double **slot, size_t rows, bool inner = false) {
+        arrs.push_back({field, (void **)slot, rows, 8, inner, false, true});
+    };
+    in(a->play, &ca.play, L); in(a->plev, &ca.plev, L1); in(a->tlay, &ca.tlay, L); in(a->tlev, &ca.tlev, L1);
+    in(a->tsfc, &ca.tsfc, 1); in(a->emis, &ca.emis, 16);
+    in(a->h2ovmr, &ca.h2ovmr, L); in(a->o3vmr, &ca.o3vmr, L); in(a->co2vmr, &ca.co2vmr, L);
+    in(a->ch4vmr, &ca.ch4vmr, L); in(a->n2ovmr, &ca.n2ovmr, L); in(a->o2vmr, &ca.o2vmr, L);
+    in(a->cfc11vmr, &ca.cfc11vmr, L); in(a->cfc12vmr, &ca.cfc12vmr, L); in(a->cfc22vmr, &ca.cfc22vmr, L);
+    in(a->ccl4vmr, &ca.ccl4vmr, L); in(a->cldf, &ca.cldf, L); in(a->ciwp, &ca.ciwp, L); in(a->clwp, &ca.clwp, L);
+    in(a->rei, &ca.rei, L); in(a->rel, &ca.rel, L); in(a->tauaer, &ca.tauaer, L * 16);
+    in(a->zm, &ca.zm, L); in(a->alat, &ca.alat, 1);
+    arrs.push_back({a->clearCounts, (void **)&ca.clearCounts, 4, 4, false, false, true});
+    out(a->uflx, &ca.uflx, L1); out(a->dflx, &ca.dflx, L1); out(a->uflxc, &ca.uflxc, L1); out(a->dflxc, &ca.dflxc, L1);
+    if (a->dudTs) { out(a->duflx_dTs, &ca.duflx_dTs, L1); out(a->duflxc_dTs, &ca.duflxc_dTs, L1); }
+    bool any_bo = false;
+    for (int b = 0; b < 16; ++b) any_bo |= a->band_output && a->band_output[b];
+    if (any_bo) {
+        // (16,ncol): untouched bands must survive the round trip, so olrb is staged in as well
+        arrs.push_back({a->olrb, (void **)&ca.olrb, 16, 8, true, true, true});
+        if (a->dudTs) arrs.push_back({a->dolrb_dTs, (void **)&ca.dolrb_dTs, 16, 8, true, true, true});
+    }
+    int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxLwArgs &c, int nc) -> int {
+        (void)nc;
+        c.flags |= RRTMGX_DEVICE_PTRS;
+        const size_t save = chunk;
+        int r = run_chunks_device(c);
+        chunk = save;
+        return r;
+    });
+    if (rc) return rc;
+    p.pending = true;
+    p.last_status = status_from(p);
+    return p.last_status;
+}
+
+int rrtmgx_heating_rate(int ncol, int nlay, const double *fnet_up_minus_down, const double *plev,
+                        double *hr_K_per_day, double grav, double cp, int flags, void *stream) {
+    if (!g.ready) return RRTMGX_ENOTINIT;
+    if (ncol <= 0 || nlay <= 0 || !fnet_up_minus_down || !plev || !hr_K_per_day || cp <= 0.) return RRTMGX_EARG;
+    const size_t n = (size_t)ncol * nlay, n1 = (size_t)ncol * (nlay + 1);
+    const int blocks = (int)((n + 255) / 256);
+    if (flags & RRTMGX_DEVICE_PTRS) {
+        cudaStream_t st = stream ? (cudaStream_t)stream : g.lw.stream;
+        RRTMGX_LAUNCH(heating_rate_kernel, blocks, 256, 0, st, ncol, nlay, fnet_up_minus_down, plev, hr_K_per_day,
+                      grav / cp);
+        if (flags & RRTMGX_NO_SYNC) return ok(cudaGetLastError()) ? 0 : RRTMGX_ECUDA;
+        return ok(cudaStreamSynchronize(st)) ? 0 : RRTMGX_ECUDA;
+    }
+    double *d = nullptr;
+    if (!ok(cudaMalloc((void **)&d, (2 * n1 + n) * sizeof(double)))) { cudaGetLastError(); return RRTMGX_ECUDA; }
+    cudaMemcpy(d, fnet_up_minus_down, n1 * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(d + n1, plev, n1 * 8, cudaMemcpyHostToDevice);
+    RRTMGX_LAUNCH(heating_rate_kernel, blocks, 256, 0, g.lw.stream, ncol, nlay, d, d + n1, d + 2 * n1, grav / cp);
+    cudaStreamSynchronize(g.lw.stream);
+    cudaError_t e = cudaMemcpy(hr_K_per_day, d + 2 * n1, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return ok(e) ? 0 : RRTMGX_ECUDA;
+}
+
+#ifndef RRTMGX_WITH_SW
+int rrtmgx_sw_run(const RrtmgxSwArgs *) { return RRTMGX_EARG; }
+#endif
+
+}  // extern "C"
+
+#ifndef RRTMGX_WITH_SW
+namespace rrtmgx {
+int sw_upload_tables(const HostTables &, const double *) { return 0; }
+}
+#endif

@@ -1,0 +1,70 @@
+// Internal host-side interface between the C ABI (api.cu) and the LW / SW kernel translation
+// units (lw.cu, sw.cu).  Not installed; the public surface is include/rrtmgx.h.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/rrtmgx.h"
+#include "common.cuh"
+#include "tables.h"
+
+namespace rrtmgx {
+
+// every kernel launch of the library goes through this counter (rrtmgx_launch_count)
+extern long long g_launches;
+#define RRTMGX_LAUNCH(kernel, grid, block, smem, stream, ...)                \
+    do {                                                                    \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);          \
+        ++::rrtmgx::g_launches;                                             \
+    } while (0)
+
+// device bump allocator over one cudaMalloc'ed scratch slab (re-grown on demand by api.cu)
+struct Slab {
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+    template <class T> T *take(size_t n) {
+        size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+        T *p = (T *)(base + used);
+        used += bytes;
+        return p;
+    }
+};
+
+// McICA state shared by LW and SW (SH/cloud_subcol_gen.F90:87-95 module variables)
+struct McicaConfig {
+    int ih = 1;
+    double corr[8] = {1.4315, 2.1219, 7., -25.584, 0.72192, 0.78996, 8.5, 40.404};
+};
+// host: jump entries for subcolumn starts; entry 2*i: i*stride draws, 2*i+1: i*stride + 2*nlay
+void kiss_jump_table(int nsub, int nlay, bool inhomo, KissJump *out /* 2*nsub */);
+McicaParams mcica_params(const McicaConfig &cfg, const double *d_xcw_beta, const double *d_xcw_gamma,
+                         int doy, const int seed_order[4]);
+
+// ---- LW ------------------------------------------------------------------------------------
+int lw_upload_tables(const HostTables &ht, const double *d_arena);   // fills __constant__ state
+size_t lw_scratch_bytes(int nc, int nlay, bool debug);
+// runs columns [col0, col0+nc) of the caller's arrays (device pointers, leading dimension
+// a->ncol); `err` is a device word receiving negative trap codes
+struct LwDebug {                  // optional device taps, chunk-local [..][nc] layouts
+    double *taug = nullptr, *pfracs = nullptr;   // [nlay][140][nc]
+};
+int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
+                 const KissJump *d_jumps, Slab &slab, int *d_err, cudaStream_t stream,
+                 cudaStream_t *side, int nside, cudaEvent_t *ev, const RrtmgxTaps *taps, int *d_negpos);
+
+// ---- SW ------------------------------------------------------------------------------------
+int sw_upload_tables(const HostTables &ht, const double *d_arena);
+size_t sw_scratch_bytes(int nc, int nlay, bool debug);
+struct SwSolar {                  // host-evaluated scalars of rrtmg_sw_sub :889-1127
+    double adjflux[14];           // adjes (* solvar) per band
+    double svar_f, svar_s, svar_i;
+    int isolvar;
+};
+int sw_run_chunk(const RrtmgxSwArgs *a, const SwSolar &sol, int col0, int nc, const McicaParams &mp,
+                 const KissJump *d_jumps, Slab &slab, int *d_err, cudaStream_t stream,
+                 cudaStream_t *side, int nside, cudaEvent_t *ev, const RrtmgxTaps *taps, int *d_negpos);
+
+// generic helpers (api.cu)
+void launch_check_negative(const double *x, size_t n, int pos, int *d_negpos, cudaStream_t s);
+
+}  // namespace rrtmgx

@@ -1,0 +1,1283 @@
+// RRTMG longwave on the device (sm_100a).
+//
+// Restates, as a different program, what these reference routines compute
+// (LW/ = GEOSirrad_GridComp/RRTMG/rrtmg_lw/gcm_model/):
+//   LW/src/rrtmg_lw_rad.F90      rrtmg_lw_part :348-610 (orchestration; no transposes here)
+//   LW/src/rrtmg_lw_setcoef.F90  setcoef :52-584                -> lw_setcoef_kernel
+//   LW/src/rrtmg_lw_cldprmc.F90  cldprmc :24-385                -> LwOptics (inside McICA)
+//   LW/src/rrtmg_lw_taumol.F90   taugb1..16 :191-3126, addAerosols :3130-3146
+//   LW/src/rrtmg_lw_rtrnmc.F90   rtrnmc :27-390                 -> lw_band_kernel (fused)
+//
+// Kernel structure.  One thread owns one column.  lw_setcoef_kernel writes the per-(layer,
+// column) interpolation state (packed indices + 23 factors) and the band Planck functions
+// once; the McICA kernel writes the optical cloud mask and cloud optical depth; then one
+// lw_band_kernel instantiation per (band, g-point sub-range) fuses gas optics and the
+// radiance sweeps: optical depths and Planck fractions live only in registers, the downward
+// sweep stores the two 14-bit transmittance-table indices per cell (4 bytes) and the upward
+// sweep re-reads them.  Every unit writes its partial flux profiles; lw_reduce_kernel adds
+// the units in a fixed order (deterministic, no floating-point atomics).
+//
+// Tables are g-point fastest ([lead][ng]): a thread reads the consecutive g-points of its
+// sub-range from one table row.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "engine.h"
+#include "mcica.cuh"
+
+namespace rrtmgx {
+
+// ---------------------------------------------------------------------------------------------
+// device-resident tables
+// ---------------------------------------------------------------------------------------------
+struct LwBandTab {
+    const double *absa, *absb, *selfref, *forref, *fracrefa, *fracrefb;
+    const double *ka_mn2, *kb_mn2, *ka_mn2o, *kb_mn2o, *ka_mo3, *kb_mo3, *ka_mco2, *kb_mco2, *ka_mco,
+        *ka_mo2, *kb_mo2;
+    const double *ccl4, *cfc11adj, *cfc12, *cfc22adj;
+};
+
+struct LwDev {
+    LwBandTab b[16];
+    const double *preflog, *tref, *chi_mls, *rat;   // rat: [6][59]
+    const double *totplnk, *totplnkderiv;           // (181,16)
+    const double *exptfn;                           // [10001][2] {exp_tbl, tfn_tbl}
+    const double *tau_tbl;                          // [10001]
+    const double *absice0, *absice1, *absice2, *absice3, *absice4, *absliq1;
+    double delwave[16];
+    int ngb[140];     // band (1-based) of each g-point
+    int ngs[16];      // cumulative g-points
+    double bpade, oneminus, fluxfac, grav, avogad;
+    // reference-atmosphere ratios used as refrat_* constants by the binary-species bands
+    double chi_1_9_over_2_9, chi_1_3_over_2_3, chi_1_13_over_2_13;   // band 3
+    double chi_1_11_over_2_11, chi_3_13_over_2_13;                   // band 4
+    double chi_1_5_over_2_5, chi_1_7_over_2_7, chi_3_43_over_2_43;   // band 5
+    double chi_1_3_over_3_3;                                         // band 7
+    double chi_1_9_over_6_9, chi_1_3_over_6_3;                       // band 9
+    double chi_1_10_over_2_10;                                       // band 12
+    double chi_1_5_over_4_5, chi_1_1_over_4_1, chi_1_3_over_4_3;     // band 13
+    double chi_4_1_over_2_1;                                         // band 15
+    double chi_1_6_over_6_6;                                         // band 16
+};
+
+__constant__ LwDev c_lw;
+
+int lw_upload_tables(const HostTables &ht, const double *d_arena) {
+    LwDev h;
+    std::memset(&h, 0, sizeof h);
+    auto dev = [&](const std::string &name) -> const double * {
+        TableRef r = ht.find(name);
+        return r.ok() ? d_arena + r.off : nullptr;
+    };
+    for (int ib = 0; ib < 16; ++ib) {
+        char pre[16];
+        std::snprintf(pre, sizeof pre, "lw.%02d.", ib + 1);
+        const std::string p(pre);
+        LwBandTab &B = h.b[ib];
+        B.absa = dev(p + "absa"); B.absb = dev(p + "absb");
+        B.selfref = dev(p + "selfref"); B.forref = dev(p + "forref");
+        B.fracrefa = dev(p + "fracrefa"); B.fracrefb = dev(p + "fracrefb");
+        B.ka_mn2 = dev(p + "ka_mn2"); B.kb_mn2 = dev(p + "kb_mn2");
+        B.ka_mn2o = dev(p + "ka_mn2o"); B.kb_mn2o = dev(p + "kb_mn2o");
+        B.ka_mo3 = dev(p + "ka_mo3"); B.kb_mo3 = dev(p + "kb_mo3");
+        B.ka_mco2 = dev(p + "ka_mco2"); B.kb_mco2 = dev(p + "kb_mco2");
+        B.ka_mco = dev(p + "ka_mco"); B.ka_mo2 = dev(p + "ka_mo2"); B.kb_mo2 = dev(p + "kb_mo2");
+        B.ccl4 = dev(p + "ccl4"); B.cfc11adj = dev(p + "cfc11adj");
+        B.cfc12 = dev(p + "cfc12"); B.cfc22adj = dev(p + "cfc22adj");
+    }
+    h.preflog = dev("lw.ref.preflog"); h.tref = dev("lw.ref.tref");
+    h.chi_mls = dev("lw.ref.chi_mls"); h.rat = dev("lw.ref.rat");
+    h.totplnk = dev("lw.wvn.totplnk"); h.totplnkderiv = dev("lw.wvn.totplnkderiv");
+    h.exptfn = dev("lw.exptfn"); h.tau_tbl = dev("lw.tau_tbl");
+    h.absice0 = dev("lw.cld.absice0"); h.absice1 = dev("lw.cld.absice1");
+    h.absice2 = dev("lw.cld.absice2"); h.absice3 = dev("lw.cld.absice3");
+    h.absice4 = dev("lw.cld.absice4"); h.absliq1 = dev("lw.cld.absliq1");
+    if (!h.preflog || !h.tref || !h.chi_mls || !h.rat || !h.totplnk || !h.totplnkderiv || !h.exptfn ||
+        !h.tau_tbl || !h.absice3 || !h.absliq1 || !h.b[0].absa || !h.b[15].absb)
+        return RRTMGX_EBLOB;
+    for (int i = 0; i < 16; ++i) { h.delwave[i] = ht.lw_delwave[i]; h.ngs[i] = ht.lw_ngs[i]; }
+    for (int i = 0; i < 140; ++i) h.ngb[i] = ht.lw_ngb[i];
+    // lwdatinit (LW/src/rrtmg_lw_init.F90:214,222), rrlw_con.F90:37-38, rrlw_tbl.F90:32
+    h.bpade = 1.0 / 0.278;
+    h.oneminus = 1. - 1.e-6;
+    h.fluxfac = 3.14159265358979323846 * 2.e4;
+    h.grav = 9.8066;
+    h.avogad = 6.02214199e+23;
+    const double *chi = ht.ptr(ht.find("lw.ref.chi_mls"));
+    auto CHI = [&](int m, int j) { return chi[(m - 1) + 7 * (j - 1)]; };
+    h.chi_1_9_over_2_9 = CHI(1, 9) / CHI(2, 9);
+    h.chi_1_3_over_2_3 = CHI(1, 3) / CHI(2, 3);
+    h.chi_1_13_over_2_13 = CHI(1, 13) / CHI(2, 13);
+    h.chi_1_11_over_2_11 = CHI(1, 11) / CHI(2, 11);
+    h.chi_3_13_over_2_13 = CHI(3, 13) / CHI(2, 13);
+    h.chi_1_5_over_2_5 = CHI(1, 5) / CHI(2, 5);
+    h.chi_1_7_over_2_7 = CHI(1, 7) / CHI(2, 7);
+    h.chi_3_43_over_2_43 = CHI(3, 43) / CHI(2, 43);
+    h.chi_1_3_over_3_3 = CHI(1, 3) / CHI(3, 3);
+    h.chi_1_9_over_6_9 = CHI(1, 9) / CHI(6, 9);
+    h.chi_1_3_over_6_3 = CHI(1, 3) / CHI(6, 3);
+    h.chi_1_10_over_2_10 = CHI(1, 10) / CHI(2, 10);
+    h.chi_1_5_over_4_5 = CHI(1, 5) / CHI(4, 5);
+    h.chi_1_1_over_4_1 = CHI(1, 1) / CHI(4, 1);
+    h.chi_1_3_over_4_3 = CHI(1, 3) / CHI(4, 3);
+    h.chi_4_1_over_2_1 = CHI(4, 1) / CHI(2, 1);
+    h.chi_1_6_over_6_6 = CHI(1, 6) / CHI(6, 6);
+    if (cudaMemcpyToSymbol(c_lw, &h, sizeof h) != cudaSuccess) return RRTMGX_ECUDA;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-(layer,column) interpolation state written by setcoef, [lay][c] with c fastest
+// ---------------------------------------------------------------------------------------------
+enum LwF {
+    F_FAC00, F_FAC01, F_FAC10, F_FAC11, F_COLH2O, F_COLCO2, F_COLO3, F_COLN2O, F_COLCH4, F_COLO2,
+    F_COLBRD, F_COLCFC11, F_COLCFC12, F_COLCFC22, F_COLCCL4, F_COLDRY, F_FORFAC, F_FORFRAC,
+    F_SELFFAC, F_SELFFRAC, F_SCALEMINOR, F_SCALEMINORN2, F_MINORFRAC, F_COUNT
+};
+
+struct LwWork {
+    int nc, nlay;
+    int *idx;                 // [nlay][nc] packed jp|jt|jt1|indfor|indself|indminor
+    double *fbase;            // [F_COUNT][nlay][nc]
+    size_t n2;                // nlay*nc
+    __host__ __device__ __forceinline__ double *f(int k) const { return fbase + (size_t)k * n2; }
+    double *planklay;         // [16][nlay][nc]
+    double *planklev;         // [16][nlay+1][nc]
+    double *plankbnd, *dplankbnd;   // [16][nc]
+    double *pwvcm;            // [nc]
+    int *laytrop;             // [nc]
+    uint32_t *seeds;          // [4][nc]
+    double *alpha, *rcorr;    // [nlay][nc]
+    uint32_t *mask;           // [nw][140][nc] optical cloud mask
+    uint32_t *cloudy_any;     // [nw][nc]
+    double *taucmc;           // [nlay][140][nc], valid where the mask bit is set
+    uint32_t *it;             // [nlay][140][nc] itgas | ittot << 16 (0xffff: clear cell)
+    double *part;             // [NUNITS][6][nlay+1][nc]
+};
+
+__device__ __forceinline__ int pack_idx(int jp, int jt, int jt1, int indfor, int indself, int indminor) {
+    return jp | (jt << 6) | (jt1 << 9) | (indfor << 12) | (indself << 14) | (indminor << 18);
+}
+
+// LW/src/rrtmg_lw_setcoef.F90:52-584.  One thread per column, layers bottom-up.
+__global__ void __launch_bounds__(128)
+lw_setcoef_kernel(int ld, int col0, LwWork W, int dudTs,
+                  const double *__restrict__ pavel, const double *__restrict__ tavel,
+                  const double *__restrict__ pz, const double *__restrict__ tz,
+                  const double *__restrict__ tbound, const double *__restrict__ semiss,
+                  const double *__restrict__ h2ovmr, const double *__restrict__ o3vmr,
+                  const double *__restrict__ co2vmr, const double *__restrict__ ch4vmr,
+                  const double *__restrict__ n2ovmr, const double *__restrict__ o2vmr,
+                  const double *__restrict__ cfc11vmr, const double *__restrict__ cfc12vmr,
+                  const double *__restrict__ cfc22vmr, const double *__restrict__ ccl4vmr, int *err) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nc = W.nc, nlay = W.nlay;
+    if (c >= nc) return;
+    const size_t col = (size_t)col0 + c;
+    const double amd = 28.9660, amw = 18.0160;
+    const double stpfac = 296. / 1013.;
+    const double grav = c_lw.grav, avogad = c_lw.avogad;
+
+    // column sums for precipitable water (:224-270); coldry is kept for the second pass
+    double amttl = 0., wvttl = 0.;
+    for (int lay = 0; lay < nlay; ++lay) {
+        const size_t i = (size_t)lay * ld + col;
+        const double h2o = h2ovmr[i];
+        const double amm = (1. - h2o) * amd + h2o * amw;
+        const double coldry = (pz[i] - pz[i + ld]) * 1.e3 * avogad / (1.e2 * grav * amm * (1. + h2o));
+        W.f(F_COLDRY)[(size_t)lay * nc + c] = coldry;
+        const double btemp = h2o * coldry;
+        amttl = amttl + coldry + btemp;
+        wvttl = wvttl + btemp;
+    }
+    const double wvsh = (amw * wvttl) / (amd * amttl);
+    W.pwvcm[c] = wvsh * (1.e3 * pz[col]) / (1.e2 * grav);
+
+    // surface / lowest-level Planck functions (:278-330)
+    {
+        const double tb = tbound[col];
+        const int indbound = clampi(f_int(tb - 159.), 1, 180);
+        const double tbndfrac = tb - 159. - (double)indbound;
+        const double t0 = tz[col];
+        const int indlev0 = clampi(f_int(t0 - 159.), 1, 180);
+        const double t0frac = t0 - 159. - (double)indlev0;
+#pragma unroll 4
+        for (int ib = 0; ib < 16; ++ib) {
+            const double *tp = c_lw.totplnk + 181 * ib;
+            const double em = semiss[(size_t)ib * ld + col];
+            double dbdtlev = tp[indbound] - tp[indbound - 1];
+            W.plankbnd[(size_t)ib * nc + c] = em * (tp[indbound - 1] + tbndfrac * dbdtlev);
+            dbdtlev = tp[indlev0] - tp[indlev0 - 1];
+            W.planklev[((size_t)ib * (nlay + 1)) * nc + c] = tp[indlev0 - 1] + t0frac * dbdtlev;
+            if (dudTs) {
+                const double *tpd = c_lw.totplnkderiv + 181 * ib;
+                dbdtlev = tpd[indbound] - tpd[indbound - 1];
+                W.dplankbnd[(size_t)ib * nc + c] = em * (tpd[indbound - 1] + tbndfrac * dbdtlev);
+            }
+        }
+    }
+
+    int laytrop = 0;
+    bool upper_found = false;
+    for (int lay = 0; lay < nlay; ++lay) {
+        const size_t i = (size_t)lay * ld + col;
+        const size_t j = (size_t)lay * nc + c;
+        const double coldry = W.f(F_COLDRY)[j];
+        const double h2o = h2ovmr[i], co2 = co2vmr[i], o3 = o3vmr[i], n2o = n2ovmr[i], ch4 = ch4vmr[i],
+                     o2 = o2vmr[i];
+        const double p = pavel[i], t = tavel[i];
+        const double summol = co2 + o3 + n2o + ch4 + o2;
+        const double wbroad = coldry * (1. - summol);
+        const double wv = h2o * coldry;
+
+        // Planck functions at the layer and at its upper level (:340-394)
+        {
+            const int indlay = clampi(f_int(t - 159.), 1, 180);
+            const double tlayfrac = t - 159. - (double)indlay;
+            const double tl = tz[i + ld];
+            const int indlev = clampi(f_int(tl - 159.), 1, 180);
+            const double tlevfrac = tl - 159. - (double)indlev;
+#pragma unroll 4
+            for (int ib = 0; ib < 16; ++ib) {
+                const double *tp = c_lw.totplnk + 181 * ib;
+                const double dbdtlev = tp[indlev] - tp[indlev - 1];
+                W.planklev[((size_t)ib * (nlay + 1) + lay + 1) * nc + c] = tp[indlev - 1] + tlevfrac * dbdtlev;
+                const double dbdtlay = tp[indlay] - tp[indlay - 1];
+                W.planklay[((size_t)ib * nlay + lay) * nc + c] = tp[indlay - 1] + tlayfrac * dbdtlay;
+            }
+        }
+
+        const double plog = log(p);
+        const int jp = clampi(f_int(36. - 5. * (plog + 0.04)), 1, 58);
+        const double fp = 5. * (c_lw.preflog[jp - 1] - plog);
+        const double tref0 = c_lw.tref[jp - 1], tref1 = c_lw.tref[jp];
+        const int jt = clampi(f_int(3. + (t - tref0) / 15.), 1, 4);
+        const double ft = ((t - tref0) / 15.) - (double)(jt - 3);
+        const int jt1 = clampi(f_int(3. + (t - tref1) / 15.), 1, 4);
+        const double ft1 = ((t - tref1) / 15.) - (double)(jt1 - 3);
+
+        const double water = wv / coldry;
+        const double scalefac = p * stpfac / t;
+        double forfac, forfrac, selffac, selffrac = 0.;
+        int indfor, indself = 1;
+        if (plog > 4.56) {
+            if (upper_found) raise(err, RRTMGX_EPRESSURE);
+            laytrop += 1;
+            forfac = scalefac / (1. + water);
+            double factor = (332. - t) / 36.;
+            indfor = clampi(f_int(factor), 1, 2);
+            forfrac = factor - (double)indfor;
+            selffac = water * forfac;
+            factor = (t - 188.) / 7.2;
+            indself = clampi(f_int(factor) - 7, 1, 9);
+            selffrac = factor - (double)(indself + 7);
+        } else {
+            upper_found = true;
+            forfac = scalefac / (1. + water);
+            const double factor = (t - 188.) / 36.;
+            indfor = 3;
+            forfrac = factor - 1.;
+            selffac = 0.;
+        }
+        const double scaleminor = p / t;
+        const double scaleminorn2 = (p / t) * (wbroad / (coldry + wv));
+        const double factor = (t - 180.8) / 7.2;
+        const int indminor = clampi(f_int(factor), 1, 18);
+        const double minorfrac = factor - (double)indminor;
+
+        const double colh2o = 1.e-20 * h2o * coldry;
+        double colco2 = 1.e-20 * co2 * coldry;
+        double colo3 = 1.e-20 * o3 * coldry;
+        double coln2o = 1.e-20 * n2o * coldry;
+        double colch4 = 1.e-20 * ch4 * coldry;
+        if (colco2 == 0.) colco2 = 1.e-32 * coldry;
+        if (colo3 == 0.) colo3 = 1.e-32 * coldry;
+        if (coln2o == 0.) coln2o = 1.e-32 * coldry;
+        if (colch4 == 0.) colch4 = 1.e-32 * coldry;
+
+        const double compfp = 1. - fp;
+        W.idx[j] = pack_idx(jp, jt, jt1, indfor, indself, indminor);
+        W.f(F_FAC10)[j] = compfp * ft;
+        W.f(F_FAC00)[j] = compfp * (1. - ft);
+        W.f(F_FAC11)[j] = fp * ft1;
+        W.f(F_FAC01)[j] = fp * (1. - ft1);
+        W.f(F_COLH2O)[j] = colh2o;
+        W.f(F_COLCO2)[j] = colco2;
+        W.f(F_COLO3)[j] = colo3;
+        W.f(F_COLN2O)[j] = coln2o;
+        W.f(F_COLCH4)[j] = colch4;
+        W.f(F_COLO2)[j] = 1.e-20 * o2 * coldry;
+        W.f(F_COLBRD)[j] = 1.e-20 * wbroad;
+        W.f(F_COLCFC11)[j] = 1.e-20 * cfc11vmr[i] * coldry;
+        W.f(F_COLCFC12)[j] = 1.e-20 * cfc12vmr[i] * coldry;
+        W.f(F_COLCFC22)[j] = 1.e-20 * cfc22vmr[i] * coldry;
+        W.f(F_COLCCL4)[j] = 1.e-20 * ccl4vmr[i] * coldry;
+        W.f(F_FORFAC)[j] = colh2o * forfac;
+        W.f(F_FORFRAC)[j] = forfrac;
+        W.f(F_SELFFAC)[j] = colh2o * selffac;
+        W.f(F_SELFFRAC)[j] = selffrac;
+        W.f(F_SCALEMINOR)[j] = scaleminor;
+        W.f(F_SCALEMINORN2)[j] = scaleminorn2;
+        W.f(F_MINORFRAC)[j] = minorfrac;
+    }
+    W.laytrop[c] = laytrop;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cloud optics inside the McICA sweep: LW/src/rrtmg_lw_cldprmc.F90:24-385
+// ---------------------------------------------------------------------------------------------
+struct LwOptics {
+    int ld, col0, nc, nlay;
+    const double *reice, *reliq;   // caller arrays (ld, nlay)
+    int iceflag, liqflag;
+    double *taucmc;                // [nlay][140][nc]
+
+    // index clamp / extrapolation traps shared by iceflag 2,3,4 and liqflag 1 (:227-268,:318-360)
+    __device__ __forceinline__ bool lookup_index(double factor, int hi, int &index) const {
+        int idx = f_int(factor);
+        if (idx >= hi) {
+            if (idx == hi) idx = hi - 1; else return false;
+        } else if (idx <= 0) {
+            if (idx == 0) idx = 1; else return false;
+        }
+        index = idx;
+        return true;
+    }
+
+    // Called for every McICA-cloudy cell.  The reference derives the radius table indices (and
+    // traps out-of-range radii) for every layer with at least one such cell, whichever phase
+    // holds water (:193-205, :227-268, :318-360), so both indices are derived here up front.
+    __device__ __forceinline__ bool cell(int lay, int ig, int c, double ciw, double clw, int *err) const {
+        const size_t i2 = (size_t)lay * ld + col0 + c;
+        const int ib = c_lw.ngb[ig];   // 1-based band
+        const double re = reice[i2];
+        const double *itab = nullptr;
+        int ilead = 0, iindex = 1;
+        double ifint = 0.;
+        if (iceflag >= 2) {
+            double factor;
+            if (iceflag == 2) { factor = (re - 2.) / 3.; ilead = 43; itab = c_lw.absice2; }
+            else if (iceflag == 3) { factor = (re - 2.) / 3.; ilead = 46; itab = c_lw.absice3; }
+            else { factor = re; ilead = 200; itab = c_lw.absice4; }
+            if (!lookup_index(factor, ilead, iindex)) { raise(err, RRTMGX_ERADIUS_ICE); iindex = 1; }
+            ifint = factor - (double)iindex;
+        }
+        const double lfactor = reliq[i2] - 1.5;
+        int lindex = 1;
+        if (!lookup_index(lfactor, 58, lindex)) { raise(err, RRTMGX_ERADIUS_LIQ); lindex = 1; }
+        const double lfint = lfactor - (double)lindex;
+
+        double tau = 0.;
+        if (ciw > 0.) {
+            double abscoice;
+            if (iceflag == 0) {
+                abscoice = c_lw.absice0[0] + c_lw.absice0[1] / re;
+            } else if (iceflag == 1) {
+                const int k = ib <= 2 ? ib : (ib <= 5 ? 3 : (ib <= 8 ? 4 : 5));   // rrlw_cld.F90 ice1b map
+                abscoice = c_lw.absice1[2 * (k - 1)] + c_lw.absice1[1 + 2 * (k - 1)] / re;
+            } else {
+                const double *cb = itab + (size_t)ilead * (ib - 1);
+                abscoice = cb[iindex - 1] + ifint * (cb[iindex] - (cb[iindex - 1]));
+            }
+            tau = ciw * abscoice;
+        }
+        if (clw > 0.) {
+            const double *cb = c_lw.absliq1 + (size_t)58 * (ib - 1);
+            const double abscoliq = cb[lindex - 1] + lfint * (cb[lindex] - (cb[lindex - 1]));
+            tau = tau + clw * abscoliq;
+        }
+        const bool optical = tau > 0.;
+        if (optical) taucmc[((size_t)lay * 140 + ig) * nc + c] = tau;
+        return optical;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// gas optics: taugb1..16 restated per (band, g sub-range)
+// ---------------------------------------------------------------------------------------------
+#define FORG _Pragma("unroll") for (int ig = 0; ig < GN; ++ig)
+
+struct Spec { double speccomb, specparm, fs; int js; };
+// binary-species parameter (e.g. LW/src/rrtmg_lw_taumol.F90:436-441)
+__device__ __forceinline__ Spec spec(double cola, double rat, double colb, double mult) {
+    Spec r;
+    r.speccomb = cola + rat * colb;
+    r.specparm = cola / r.speccomb;
+    if (r.specparm >= c_lw.oneminus) r.specparm = c_lw.oneminus;
+    const double specmult = mult * r.specparm;
+    const int k = f_int(specmult);
+    r.js = 1 + k;
+    r.fs = specmult - (double)k;   // mod(specmult, 1.) for specmult >= 0
+    return r;
+}
+
+// everything a band needs about one (layer, column)
+struct Lay {
+    int jp, jt, jt1, indfor, indself, indminor;
+    const double *fj;  // factor base + lay*nc + c
+    size_t n2;
+    __device__ __forceinline__ double f(int k) const { return fj[(size_t)k * n2]; }
+};
+
+// lower-atmosphere key-species sum for a binary band at one reference pressure
+// (e.g. taugb3 :482-511, :554-576): three-point stencils near specparm 0 and 1, else bilinear
+template <int GN>
+__device__ __forceinline__ void stencil_lower(const double *__restrict__ row /* absa row ind (1-based ind -> row ind-1), at G0 */,
+                                              int ng, double specparm, double fs, double fa, double fb,
+                                              double speccomb, double (&out)[GN]) {
+    if (specparm < 0.125) {
+        const double p = fs - 1.;
+        const double p2 = p * p, p4 = p2 * p2;
+        const double fk0 = p4, fk1 = 1. - p - 2.0 * p4, fk2 = p + p4;
+        const double w0 = fk0 * fa, w1 = fk1 * fa, w2 = fk2 * fa, w3 = fk0 * fb, w4 = fk1 * fb, w5 = fk2 * fb;
+        FORG out[ig] = speccomb * (w0 * row[ig] + w1 * row[ng + ig] + w2 * row[2 * ng + ig] +
+                                   w3 * row[9 * ng + ig] + w4 * row[10 * ng + ig] + w5 * row[11 * ng + ig]);
+    } else if (specparm > 0.875) {
+        const double p = -fs;
+        const double p2 = p * p, p4 = p2 * p2;
+        const double fk0 = p4, fk1 = 1. - p - 2.0 * p4, fk2 = p + p4;
+        const double w0 = fk2 * fa, w1 = fk1 * fa, w2 = fk0 * fa, w3 = fk2 * fb, w4 = fk1 * fb, w5 = fk0 * fb;
+        FORG out[ig] = speccomb * (w0 * row[ig - ng] + w1 * row[ig] + w2 * row[ng + ig] +
+                                   w3 * row[8 * ng + ig] + w4 * row[9 * ng + ig] + w5 * row[10 * ng + ig]);
+    } else {
+        const double w0 = (1. - fs) * fa, w1 = fs * fa, w2 = (1. - fs) * fb, w3 = fs * fb;
+        FORG out[ig] = speccomb * (w0 * row[ig] + w1 * row[ng + ig] + w2 * row[9 * ng + ig] + w3 * row[10 * ng + ig]);
+    }
+}
+
+// lerp in the first index of a [lead][ng] table: t(i) + f*(t(i+1) - t(i)), i 1-based
+template <int GN>
+__device__ __forceinline__ void lerp_rows(const double *__restrict__ t, int ng, int g0, int i, double f,
+                                          double (&out)[GN]) {
+    const double *r = t + (size_t)(i - 1) * ng + g0;
+    FORG out[ig] = r[ig] + f * (r[ng + ig] - r[ig]);
+}
+
+// binary minor species k(jm,indm,g) of shape (nj,19,ng) (e.g. taugb3 :548-552)
+template <int GN>
+__device__ __forceinline__ void minor2(const double *__restrict__ k, int ng, int g0, int nj, int jm, int indm,
+                                       double fm, double minorfrac, double (&out)[GN]) {
+    const double *a = k + ((size_t)(jm - 1) + (size_t)nj * (indm - 1)) * ng + g0;   // K(jm,indm)
+    const double *b = a + (size_t)nj * ng;                                           // K(jm,indm+1)
+    FORG {
+        const double m1 = a[ig] + fm * (a[ng + ig] - a[ig]);
+        const double m2 = b[ig] + fm * (b[ng + ig] - b[ig]);
+        out[ig] = m1 + minorfrac * (m2 - m1);
+    }
+}
+
+// adjusted minor column amount when the gas exceeds its reference abundance (e.g. :460-467)
+__device__ __forceinline__ double adjcol(double col, double coldry, double chi, double thresh, double base,
+                                         double expo) {
+    const double chi_x = col / coldry;
+    const double rat = 1.e20 * chi_x / chi;
+    if (rat > thresh) {
+        const double adjfac = base + pow(rat - base, expo);
+        return adjfac * chi * coldry * 1.e-20;
+    }
+    return col;
+}
+
+// four-point (p,T) interpolation of a single-species table: rows ind0, ind0+1, ind1, ind1+1
+template <int GN>
+__device__ __forceinline__ void key4(const double *__restrict__ tab, int ng, int g0, int ind0, int ind1,
+                                     const Lay &L, double (&out)[GN]) {
+    const double fac00 = L.f(F_FAC00), fac10 = L.f(F_FAC10), fac01 = L.f(F_FAC01), fac11 = L.f(F_FAC11);
+    const double *r0 = tab + (size_t)(ind0 - 1) * ng + g0;
+    const double *r1 = tab + (size_t)(ind1 - 1) * ng + g0;
+    FORG out[ig] = fac00 * r0[ig] + fac10 * r0[ng + ig] + fac01 * r1[ig] + fac11 * r1[ng + ig];
+}
+
+// upper-atmosphere binary key species with nspb = 5 (bands 3, 4, 5; e.g. :675-685)
+template <int GN>
+__device__ __forceinline__ void key_upper5(const double *__restrict__ tab, int ng, int g0, int ind0, int ind1,
+                                           const Spec &s0, const Spec &s1, const Lay &L, double (&out)[GN]) {
+    const double fac00 = L.f(F_FAC00), fac10 = L.f(F_FAC10), fac01 = L.f(F_FAC01), fac11 = L.f(F_FAC11);
+    const double fac000 = (1. - s0.fs) * fac00, fac010 = (1. - s0.fs) * fac10;
+    const double fac100 = s0.fs * fac00, fac110 = s0.fs * fac10;
+    const double fac001 = (1. - s1.fs) * fac01, fac011 = (1. - s1.fs) * fac11;
+    const double fac101 = s1.fs * fac01, fac111 = s1.fs * fac11;
+    const double *r0 = tab + (size_t)(ind0 - 1) * ng + g0;
+    const double *r1 = tab + (size_t)(ind1 - 1) * ng + g0;
+    FORG out[ig] = s0.speccomb * (fac000 * r0[ig] + fac100 * r0[ng + ig] + fac010 * r0[5 * ng + ig] +
+                                  fac110 * r0[6 * ng + ig]) +
+                   s1.speccomb * (fac001 * r1[ig] + fac101 * r1[ng + ig] + fac011 * r1[5 * ng + ig] +
+                                  fac111 * r1[6 * ng + ig]);
+}
+
+__device__ __forceinline__ double rat_tab(int which, int jp1 /* 1-based */) { return c_lw.rat[which * 59 + jp1 - 1]; }
+enum { R_H2OCO2 = 0, R_H2OO3 = 1, R_H2ON2O = 2, R_H2OCH4 = 3, R_N2OCO2 = 4, R_O3CO2 = 5 };
+__device__ __forceinline__ double chi_mls(int m, int j) { return c_lw.chi_mls[(m - 1) + 7 * (j - 1)]; }
+
+// Planck fraction interpolated in the binary-species parameter (e.g. :604-605)
+template <int GN>
+__device__ __forceinline__ void pfrac2(const double *__restrict__ fr, int ng, int g0, const Spec &sp,
+                                       double (&pf)[GN]) {
+    const double *r = fr + (size_t)(sp.js - 1) * ng + g0;
+    FORG pf[ig] = r[ig] + sp.fs * (r[ng + ig] - r[ig]);
+}
+template <int GN>
+__device__ __forceinline__ void pfrac1(const double *__restrict__ fr, int g0, double (&pf)[GN]) {
+    FORG pf[ig] = fr[g0 + ig];
+}
+
+// Gas optical depth (TAU = true) and Planck fraction of one layer for g-points [G0, G0+GN) of
+// BAND.  `lower` selects the lower/upper-atmosphere branch (lay <= laytrop).  The aerosol term
+// of addAerosols is added by the caller.
+template <int BAND, int G0, int GN, bool TAU>
+__device__ __forceinline__ void lw_band_layer(const Lay &L, bool lower, double pavel, double (&taug)[GN],
+                                              double (&pf)[GN]) {
+    const LwBandTab &B = c_lw.b[BAND - 1];
+    constexpr int ng = BAND == 1 ? 10 : BAND == 2 ? 12 : BAND == 3 ? 16 : BAND == 4 ? 14 : BAND == 5 ? 16
+                     : BAND == 6 ? 8 : BAND == 7 ? 12 : BAND == 8 ? 8 : BAND == 9 ? 12 : BAND == 10 ? 6
+                     : BAND == 11 ? 8 : BAND == 12 ? 8 : BAND == 13 ? 4 : 2;
+    // nspa = 1 1 9 9 9 1 9 1 9 1 1 9 9 1 9 9 ; nspb = 1 1 5 5 5 0 1 1 1 1 1 0 0 1 0 0 (rrtmg_lw_init.F90:194-195)
+    constexpr int nspa = (BAND == 3 || BAND == 4 || BAND == 5 || BAND == 7 || BAND == 9 || BAND == 12 ||
+                          BAND == 13 || BAND == 15 || BAND == 16) ? 9 : 1;
+    constexpr int nspb = (BAND == 3 || BAND == 4 || BAND == 5) ? 5 : 1;
+    const int ind0lo = ((L.jp - 1) * 5 + (L.jt - 1)) * nspa;
+    const int ind1lo = (L.jp * 5 + (L.jt1 - 1)) * nspa;
+    const int ind0up = ((L.jp - 13) * 5 + (L.jt - 1)) * nspb;
+    const int ind1up = ((L.jp - 12) * 5 + (L.jt1 - 1)) * nspb;
+    double t1[GN], t2[GN], t3[GN];
+
+    // self and foreign continuum shared by most lower-atmosphere branches
+    auto self_for = [&](double (&acc)[GN]) {   // acc += tauself + taufor, in that order
+        const double selffac = L.f(F_SELFFAC), selffrac = L.f(F_SELFFRAC);
+        const double forfac = L.f(F_FORFAC), forfrac = L.f(F_FORFRAC);
+        lerp_rows<GN>(B.selfref, ng, G0, L.indself, selffrac, t2);
+        lerp_rows<GN>(B.forref, ng, G0, L.indfor, forfrac, t3);
+        FORG acc[ig] = acc[ig] + selffac * t2[ig] + forfac * t3[ig];
+    };
+    auto for_only = [&](double (&acc)[GN]) {
+        const double forfac = L.f(F_FORFAC), forfrac = L.f(F_FORFRAC);
+        lerp_rows<GN>(B.forref, ng, G0, L.indfor, forfrac, t3);
+        FORG acc[ig] = acc[ig] + forfac * t3[ig];
+    };
+    // lower-atmosphere binary key species: tau_major + tau_major1
+    auto binary_lower = [&](const Spec &s0, const Spec &s1) {
+        const double *r0 = B.absa + (size_t)(ind0lo + s0.js - 1) * ng + G0;
+        const double *r1 = B.absa + (size_t)(ind1lo + s1.js - 1) * ng + G0;
+        stencil_lower<GN>(r0, ng, s0.specparm, s0.fs, L.f(F_FAC00), L.f(F_FAC10), s0.speccomb, t1);
+        stencil_lower<GN>(r1, ng, s1.specparm, s1.fs, L.f(F_FAC01), L.f(F_FAC11), s1.speccomb, t2);
+        FORG taug[ig] = t1[ig] + t2[ig];
+    };
+
+    if constexpr (BAND == 1) {   // :191-285  H2O (+N2 continuum)
+        if (lower) {
+            if constexpr (TAU) {
+                double corradj = 1.;
+                if (pavel < 250.) corradj = 1. - 0.15 * (250. - pavel) / 154.4;
+                const double scalen2 = L.f(F_COLBRD) * L.f(F_SCALEMINORN2), colh2o = L.f(F_COLH2O);
+                key4<GN>(B.absa, ng, G0, ind0lo + 1, ind1lo + 1, L, t1);
+                FORG taug[ig] = colh2o * t1[ig];
+                self_for(taug);
+                lerp_rows<GN>(B.ka_mn2, ng, G0, L.indminor, L.f(F_MINORFRAC), t1);
+                FORG taug[ig] = corradj * (taug[ig] + scalen2 * t1[ig]);
+            }
+            pfrac1<GN>(B.fracrefa, G0, pf);
+        } else {
+            if constexpr (TAU) {
+                const double corradj = 1. - 0.15 * (pavel / 95.6);
+                const double scalen2 = L.f(F_COLBRD) * L.f(F_SCALEMINORN2), colh2o = L.f(F_COLH2O);
+                key4<GN>(B.absb, ng, G0, ind0up + 1, ind1up + 1, L, t1);
+                FORG taug[ig] = colh2o * t1[ig];
+                for_only(taug);
+                lerp_rows<GN>(B.kb_mn2, ng, G0, L.indminor, L.f(F_MINORFRAC), t1);
+                FORG taug[ig] = corradj * (taug[ig] + scalen2 * t1[ig]);
+            }
+            pfrac1<GN>(B.fracrefb, G0, pf);
+        }
+    } else if constexpr (BAND == 2) {   // :289-363  H2O
+        if (lower) {
+            if constexpr (TAU) {
+                const double corradj = 1. - .05 * (pavel - 100.) / 900.;
+                const double colh2o = L.f(F_COLH2O);
+                key4<GN>(B.absa, ng, G0, ind0lo + 1, ind1lo + 1, L, t1);
+                FORG taug[ig] = colh2o * t1[ig];
+                self_for(taug);
+                FORG taug[ig] = corradj * taug[ig];
+            }
+            pfrac1<GN>(B.fracrefa, G0, pf);
+        } else {
+            if constexpr (TAU) {
+                const double colh2o = L.f(F_COLH2O);
+                key4<GN>(B.absb, ng, G0, ind0up + 1, ind1up + 1, L, t1);
+                FORG taug[ig] = colh2o * t1[ig];
+                for_only(taug);
+            }
+            pfrac1<GN>(B.fracrefb, G0, pf);
+        }
+    } else if constexpr (BAND == 3) {   // :367-695  H2O,CO2 (+N2O)
+        const double colh2o = L.f(F_COLH2O), colco2 = L.f(F_COLCO2);
+        if (lower) {
+            if constexpr (TAU) {
+                const Spec s0 = spec(colh2o, rat_tab(R_H2OCO2, L.jp), colco2, 8.);
+                const Spec s1 = spec(colh2o, rat_tab(R_H2OCO2, L.jp + 1), colco2, 8.);
+                const Spec sm = spec(colh2o, c_lw.chi_1_3_over_2_3, colco2, 8.);
+                const double adjcoln2o = adjcol(L.f(F_COLN2O), L.f(F_COLDRY), chi_mls(4, L.jp + 1), 1.5, 0.5, 0.65);
+                binary_lower(s0, s1);
+                self_for(taug);
+                minor2<GN>(B.ka_mn2o, ng, G0, 9, sm.js, L.indminor, sm.fs, L.f(F_MINORFRAC), t1);
+                FORG taug[ig] = taug[ig] + adjcoln2o * t1[ig];
+            }
+            pfrac2<GN>(B.fracrefa, ng, G0, spec(colh2o, c_lw.chi_1_9_over_2_9, colco2, 8.), pf);
+        } else {
+            if constexpr (TAU) {
+                const Spec s0 = spec(colh2o, rat_tab(R_H2OCO2, L.jp), colco2, 4.);
+                const Spec s1 = spec(colh2o, rat_tab(R_H2OCO2, L.jp + 1), colco2, 4.);
+                const Spec sm = spec(colh2o, c_lw.chi_1_13_over_2_13, colco2, 4.);
+                const double adjcoln2o = adjcol(L.f(F_COLN2O), L.f(F_COLDRY), chi_mls(4, L.jp + 1), 1.5, 0.5, 0.65);
+                key_upper5<GN>(B.absb, ng, G0, ind0up + s0.js, ind1up + s1.js, s0, s1, L, taug);
+                for_only(taug);
+                minor2<GN>(B.kb_mn2o, ng, G0, 5, sm.js, L.indminor, sm.fs, L.f(F_MINORFRAC), t1);
+                FORG taug[ig] = taug[ig] + adjcoln2o * t1[ig];
+            }
+            pfrac2<GN>(B.fracrefb, ng, G0, spec(colh2o, c_lw.chi_1_13_over_2_13, colco2, 4.), pf);
+        }
+    } else if constexpr (BAND == 4) {   // :699-960  H2O,CO2 / O3,CO2
+        const double colco2 = L.f(F_COLCO2);
+        if (lower) {
+            const double colh2o = L.f(F_COLH2O);
+            if constexpr (TAU) {
+                const Spec s0 = spec(colh2o, rat_tab(R_H2OCO2, L.jp), colco2, 8.);
+                const Spec s1 = spec(colh2o, rat_tab(R_H2OCO2, L.jp + 1), colco2, 8.);
+                binary_lower(s0, s1);
+                self_for(taug);
+            }
+            pfrac2<GN>(B.fracrefa, ng, G0, spec(colh2o, c_lw.chi_1_11_over_2_11, colco2, 8.), pf);
+        } else {
+            const double colo3 = L.f(F_COLO3);
+            if constexpr (TAU) {
+                const Spec s0 = spec(colo3, rat_tab(R_O3CO2, L.jp), colco2, 4.);
+                const Spec s1 = spec(colo3, rat_tab(R_O3CO2, L.jp + 1), colco2, 4.);
+                key_upper5<GN>(B.absb, ng, G0, ind0up + s0.js, ind1up + s1.js, s0, s1, L, taug);
+                // empirical stratospheric CO2 cooling-rate fix, :948-954 (g-points 8..14 of the band)
+                constexpr double fix[14] = {1., 1., 1., 1., 1., 1., 1., 0.92, 0.88, 1.07, 1.1, 0.99, 0.88, 0.943};
+                FORG if (G0 + ig >= 7) taug[ig] = taug[ig] * fix[G0 + ig];
+            }
+            pfrac2<GN>(B.fracrefb, ng, G0, spec(colo3, c_lw.chi_3_13_over_2_13, colco2, 4.), pf);
+        }
+    } else if constexpr (BAND == 5) {   // :964-1239  H2O,CO2 / O3,CO2 (+O3, CCl4)
+        const double colco2 = L.f(F_COLCO2);
+        if (lower) {
+            const double colh2o = L.f(F_COLH2O);
+            if constexpr (TAU) {
+                const Spec s0 = spec(colh2o, rat_tab(R_H2OCO2, L.jp), colco2, 8.);
+                const Spec s1 = spec(colh2o, rat_tab(R_H2OCO2, L.jp + 1), colco2, 8.);
+                const Spec sm = spec(colh2o, c_lw.chi_1_7_over_2_7, colco2, 8.);
+                const double colo3 = L.f(F_COLO3), colccl4 = L.f(F_COLCCL4);
+                binary_lower(s0, s1);
+                self_for(taug);
+                minor2<GN>(B.ka_mo3, ng, G0, 9, sm.js, L.indminor, sm.fs, L.f(F_MINORFRAC), t1);
+                FORG taug[ig] = taug[ig] + t1[ig] * colo3 + colccl4 * B.ccl4[G0 + ig];
+            }
+            pfrac2<GN>(B.fracrefa, ng, G0, spec(colh2o, c_lw.chi_1_5_over_2_5, colco2, 8.), pf);
+        } else {
+            const double colo3 = L.f(F_COLO3);
+            if constexpr (TAU) {
+                const Spec s0 = spec(colo3, rat_tab(R_O3CO2, L.jp), colco2, 4.);
+                const Spec s1 = spec(colo3, rat_tab(R_O3CO2, L.jp + 1), colco2, 4.);
+                const double colccl4 = L.f(F_COLCCL4);
+                key_upper5<GN>(B.absb, ng, G0, ind0up + s0.js, ind1up + s1.js, s0, s1, L, taug);
+                FORG taug[ig] = taug[ig] + colccl4 * B.ccl4[G0 + ig];
+            }
+            pfrac2<GN>(B.fracrefb, ng, G0, spec(colo3, c_lw.chi_3_43_over_2_43, colco2, 4.), pf);
+        }
+    } else if constexpr (BAND == 6) {   // :1243-1327  H2O (+CO2, CFC11, CFC12)
+        if constexpr (TAU) {
+            const double colcfc11 = L.f(F_COLCFC11), colcfc12 = L.f(F_COLCFC12);
+            if (lower) {
+                const double adjcolco2 = adjcol(L.f(F_COLCO2), L.f(F_COLDRY), chi_mls(2, L.jp + 1), 3.0, 2.0, 0.77);
+                const double colh2o = L.f(F_COLH2O);
+                key4<GN>(B.absa, ng, G0, ind0lo + 1, ind1lo + 1, L, t1);
+                FORG taug[ig] = colh2o * t1[ig];
+                self_for(taug);
+                lerp_rows<GN>(B.ka_mco2, ng, G0, L.indminor, L.f(F_MINORFRAC), t1);
+                FORG taug[ig] = taug[ig] + adjcolco2 * t1[ig] + colcfc11 * B.cfc11adj[G0 + ig] +
+                                colcfc12 * B.cfc12[G0 + ig];
+            } else {
+                FORG taug[ig] = 0.0 + colcfc11 * B.cfc11adj[G0 + ig] + colcfc12 * B.cfc12[G0 + ig];
+            }
+        }
+        pfrac1<GN>(B.fracrefa, G0, pf);
+    } else if constexpr (BAND == 7) {   // :1331-1603  H2O,O3 / O3 (+CO2)
+        if (lower) {
+            const double colh2o = L.f(F_COLH2O), colo3 = L.f(F_COLO3);
+            if constexpr (TAU) {
+                const Spec s0 = spec(colh2o, rat_tab(R_H2OO3, L.jp), colo3, 8.);
+                const Spec s1 = spec(colh2o, rat_tab(R_H2OO3, L.jp + 1), colo3, 8.);
+                const Spec sm = spec(colh2o, c_lw.chi_1_3_over_3_3, colo3, 8.);
+                const double adjcolco2 = adjcol(L.f(F_COLCO2), L.f(F_COLDRY), chi_mls(2, L.jp + 1), 3.0, 3.0, 0.79);
+                binary_lower(s0, s1);
+                self_for(taug);
+                minor2<GN>(B.ka_mco2, ng, G0, 9, sm.js, L.indminor, sm.fs, L.f(F_MINORFRAC), t1);
+                FORG taug[ig] = taug[ig] + adjcolco2 * t1[ig];
+            }
+            pfrac2<GN>(B.fracrefa, ng, G0, spec(colh2o, c_lw.chi_1_3_over_3_3, colo3, 8.), pf);
+        } else {
+            if constexpr (TAU) {
+                const double adjcolco2 = adjcol(L.f(F_COLCO2), L.f(F_COLDRY), chi_mls(2, L.jp + 1), 3.0, 2.0, 0.79);
+                const double colo3 = L.f(F_COLO3);
+                key4<GN>(B.absb, ng, G0, ind0up + 1, ind1up + 1, L, t1);
+                lerp_rows<GN>(B.kb_mco2, ng, G0, L.indminor, L.f(F_MINORFRAC), t2);
+                FORG taug[ig] = colo3 * t1[ig] + adjcolco2 * t2[ig];
+                // empirical stratospheric O3 cooling-rate fix, :1592-1597 (g-points 6..11)
+                constexpr double fix[12] = {1., 1., 1., 1., 1., 0.92, 0.88, 1.07, 1.1, 0.99, 0.855, 1.};
+                FORG if (G0 + ig >= 5 && G0 + ig <= 10) taug[ig] = taug[ig] * fix[G0 + ig];
+            }
+            pfrac1<GN>(B.fracrefb, G0, pf);
+        }
+    } else if constexpr (BAND == 8) {   // :1607-1728  H2O / O3 (+CO2, O3, N2O, CFC12, CFC22)
+        if constexpr (TAU) {
+            const double adjcolco2 = adjcol(L.f(F_COLCO2), L.f(F_COLDRY), chi_mls(2, L.jp + 1), 3.0, 2.0, 0.65);
+            const double colo3 = L.f(F_COLO3), coln2o = L.f(F_COLN2O), colcfc12 = L.f(F_COLCFC12),
+                         colcfc22 = L.f(F_COLCFC22), minorfrac = L.f(F_MINORFRAC);
+            if (lower) {
+                const double colh2o = L.f(F_COLH2O);
+                key4<GN>(B.absa, ng, G0, ind0lo + 1, ind1lo + 1, L, t1);
+                FORG taug[ig] = colh2o * t1[ig];
+                self_for(taug);
+                lerp_rows<GN>(B.ka_mco2, ng, G0, L.indminor, minorfrac, t1);
+                lerp_rows<GN>(B.ka_mo3, ng, G0, L.indminor, minorfrac, t2);
+                lerp_rows<GN>(B.ka_mn2o, ng, G0, L.indminor, minorfrac, t3);
+                FORG taug[ig] = taug[ig] + adjcolco2 * t1[ig] + colo3 * t2[ig] + coln2o * t3[ig] +
+                                colcfc12 * B.cfc12[G0 + ig] + colcfc22 * B.cfc22adj[G0 + ig];
+            } else {
+                key4<GN>(B.absb, ng, G0, ind0up + 1, ind1up + 1, L, t1);
+                lerp_rows<GN>(B.kb_mco2, ng, G0, L.indminor, minorfrac, t2);
+                lerp_rows<GN>(B.kb_mn2o, ng, G0, L.indminor, minorfrac, t3);
+                FORG taug[ig] = colo3 * t1[ig] + adjcolco2 * t2[ig] + coln2o * t3[ig] +
+                                colcfc12 * B.cfc12[G0 + ig] + colcfc22 * B.cfc22adj[G0 + ig];
+            }
+        }
+        if (lower) pfrac1<GN>(B.fracrefa, G0, pf); else pfrac1<GN>(B.fracrefb, G0, pf);
+    } else if constexpr (BAND == 9) {   // :1732-1994  H2O,CH4 / CH4 (+N2O)
+        if (lower) {
+            const double colh2o = L.f(F_COLH2O), colch4 = L.f(F_COLCH4);
+            if constexpr (TAU) {
+                const Spec s0 = spec(colh2o, rat_tab(R_H2OCH4, L.jp), colch4, 8.);
+                const Spec s1 = spec(colh2o, rat_tab(R_H2OCH4, L.jp + 1), colch4, 8.);
+                const Spec sm = spec(colh2o, c_lw.chi_1_3_over_6_3, colch4, 8.);
+                const double adjcoln2o = adjcol(L.f(F_COLN2O), L.f(F_COLDRY), chi_mls(4, L.jp + 1), 1.5, 0.5, 0.65);
+                binary_lower(s0, s1);
+                self_for(taug);
+                minor2<GN>(B.ka_mn2o, ng, G0, 9, sm.js, L.indminor, sm.fs, L.f(F_MINORFRAC), t1);
+                FORG taug[ig] = taug[ig] + adjcoln2o * t1[ig];
+            }
+            pfrac2<GN>(B.fracrefa, ng, G0, spec(colh2o, c_lw.chi_1_9_over_6_9, colch4, 8.), pf);
+        } else {
+            if constexpr (TAU) {
+                const double adjcoln2o = adjcol(L.f(F_COLN2O), L.f(F_COLDRY), chi_mls(4, L.jp + 1), 1.5, 0.5, 0.65);
+                const double colch4 = L.f(F_COLCH4);
+                key4<GN>(B.absb, ng, G0, ind0up + 1, ind1up + 1, L, t1);
+                lerp_rows<GN>(B.kb_mn2o, ng, G0, L.indminor, L.f(F_MINORFRAC), t2);
+                FORG taug[ig] = colch4 * t1[ig] + adjcoln2o * t2[ig];
+            }
+            pfrac1<GN>(B.fracrefb, G0, pf);
+        }
+    } else if constexpr (BAND == 10 || BAND == 11) {   // :1998-2066 H2O ; :2070-2149 H2O (+O2)
+        if constexpr (TAU) {
+            const double colh2o = L.f(F_COLH2O);
+            if (lower) {
+                key4<GN>(B.absa, ng, G0, ind0lo + 1, ind1lo + 1, L, t1);
+                FORG taug[ig] = colh2o * t1[ig];
+                self_for(taug);
+            } else {
+                key4<GN>(B.absb, ng, G0, ind0up + 1, ind1up + 1, L, t1);
+                FORG taug[ig] = colh2o * t1[ig];
+                for_only(taug);
+            }
+            if constexpr (BAND == 11) {
+                const double scaleo2 = L.f(F_COLO2) * L.f(F_SCALEMINOR);
+                lerp_rows<GN>(lower ? B.ka_mo2 : B.kb_mo2, ng, G0, L.indminor, L.f(F_MINORFRAC), t1);
+                FORG taug[ig] = taug[ig] + scaleo2 * t1[ig];
+            }
+        }
+        if (lower) pfrac1<GN>(B.fracrefa, G0, pf); else pfrac1<GN>(B.fracrefb, G0, pf);
+    } else if constexpr (BAND == 12) {   // :2153-2356  H2O,CO2 / nothing
+        if (lower) {
+            const double colh2o = L.f(F_COLH2O), colco2 = L.f(F_COLCO2);
+            if constexpr (TAU) {
+                const Spec s0 = spec(colh2o, rat_tab(R_H2OCO2, L.jp), colco2, 8.);
+                const Spec s1 = spec(colh2o, rat_tab(R_H2OCO2, L.jp + 1), colco2, 8.);
+                binary_lower(s0, s1);
+                self_for(taug);
+            }
+            pfrac2<GN>(B.fracrefa, ng, G0, spec(colh2o, c_lw.chi_1_10_over_2_10, colco2, 8.), pf);
+        } else {
+            FORG { if constexpr (TAU) taug[ig] = 0.0; pf[ig] = 0.0; }
+        }
+    } else if constexpr (BAND == 13) {   // :2360-2620  H2O,N2O (+CO2, CO) / O3 minor
+        if (lower) {
+            const double colh2o = L.f(F_COLH2O), coln2o = L.f(F_COLN2O);
+            if constexpr (TAU) {
+                const Spec s0 = spec(colh2o, rat_tab(R_H2ON2O, L.jp), coln2o, 8.);
+                const Spec s1 = spec(colh2o, rat_tab(R_H2ON2O, L.jp + 1), coln2o, 8.);
+                const Spec smco2 = spec(colh2o, c_lw.chi_1_1_over_4_1, coln2o, 8.);
+                const double coldry = L.f(F_COLDRY);
+                const double adjcolco2 = adjcol(L.f(F_COLCO2), coldry, 3.55e-4, 3.0, 2.0, 0.68);
+                const Spec smco = spec(colh2o, c_lw.chi_1_3_over_4_3, coln2o, 8.);
+                // covmr = 0 in GEOS (LW/src/rrtmg_lw_rad.F90:520) -> colco takes its 1e-32 floor
+                const double colco = 1.e-32 * coldry;
+                binary_lower(s0, s1);
+                self_for(taug);
+                minor2<GN>(B.ka_mco2, ng, G0, 9, smco2.js, L.indminor, smco2.fs, L.f(F_MINORFRAC), t1);
+                minor2<GN>(B.ka_mco, ng, G0, 9, smco.js, L.indminor, smco.fs, L.f(F_MINORFRAC), t2);
+                FORG taug[ig] = taug[ig] + adjcolco2 * t1[ig] + colco * t2[ig];
+            }
+            pfrac2<GN>(B.fracrefa, ng, G0, spec(colh2o, c_lw.chi_1_5_over_4_5, coln2o, 8.), pf);
+        } else {
+            if constexpr (TAU) {
+                const double colo3 = L.f(F_COLO3);
+                lerp_rows<GN>(B.kb_mo3, ng, G0, L.indminor, L.f(F_MINORFRAC), t1);
+                FORG taug[ig] = colo3 * t1[ig];
+            }
+            pfrac1<GN>(B.fracrefb, G0, pf);
+        }
+    } else if constexpr (BAND == 14) {   // :2624-2686  CO2
+        if constexpr (TAU) {
+            const double colco2 = L.f(F_COLCO2);
+            if (lower) {
+                key4<GN>(B.absa, ng, G0, ind0lo + 1, ind1lo + 1, L, t1);
+                FORG taug[ig] = colco2 * t1[ig];
+                self_for(taug);
+            } else {
+                key4<GN>(B.absb, ng, G0, ind0up + 1, ind1up + 1, L, t1);
+                FORG taug[ig] = colco2 * t1[ig];
+            }
+        }
+        if (lower) pfrac1<GN>(B.fracrefa, G0, pf); else pfrac1<GN>(B.fracrefb, G0, pf);
+    } else if constexpr (BAND == 15) {   // :2690-2913  N2O,CO2 (+N2) / nothing
+        if (lower) {
+            const double coln2o = L.f(F_COLN2O), colco2 = L.f(F_COLCO2);
+            const Spec sp = spec(coln2o, c_lw.chi_4_1_over_2_1, colco2, 8.);
+            if constexpr (TAU) {
+                const Spec s0 = spec(coln2o, rat_tab(R_N2OCO2, L.jp), colco2, 8.);
+                const Spec s1 = spec(coln2o, rat_tab(R_N2OCO2, L.jp + 1), colco2, 8.);
+                const double scalen2 = L.f(F_COLBRD) * L.f(F_SCALEMINOR);
+                binary_lower(s0, s1);
+                self_for(taug);
+                minor2<GN>(B.ka_mn2, ng, G0, 9, sp.js, L.indminor, sp.fs, L.f(F_MINORFRAC), t1);
+                FORG taug[ig] = taug[ig] + scalen2 * t1[ig];
+            }
+            pfrac2<GN>(B.fracrefa, ng, G0, sp, pf);
+        } else {
+            FORG { if constexpr (TAU) taug[ig] = 0.0; pf[ig] = 0.0; }
+        }
+    } else {   // BAND == 16, :2917-3126  H2O,CH4 / CH4
+        if (lower) {
+            const double colh2o = L.f(F_COLH2O), colch4 = L.f(F_COLCH4);
+            if constexpr (TAU) {
+                const Spec s0 = spec(colh2o, rat_tab(R_H2OCH4, L.jp), colch4, 8.);
+                const Spec s1 = spec(colh2o, rat_tab(R_H2OCH4, L.jp + 1), colch4, 8.);
+                binary_lower(s0, s1);
+                self_for(taug);
+            }
+            pfrac2<GN>(B.fracrefa, ng, G0, spec(colh2o, c_lw.chi_1_6_over_6_6, colch4, 8.), pf);
+        } else {
+            if constexpr (TAU) {
+                const double colch4 = L.f(F_COLCH4);
+                key4<GN>(B.absb, ng, G0, ind0up + 1, ind1up + 1, L, t1);
+                FORG taug[ig] = colch4 * t1[ig];
+            }
+            pfrac1<GN>(B.fracrefb, G0, pf);
+        }
+    }
+    (void)t1; (void)t2; (void)t3; (void)ind0lo; (void)ind1lo; (void)ind0up; (void)ind1up; (void)pavel;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused gas optics + radiance sweeps for one (band, g sub-range): LW/src/rrtmg_lw_rtrnmc.F90:27-390
+// ---------------------------------------------------------------------------------------------
+struct LwBandArgs {
+    int ld, col0;
+    LwWork W;
+    int dudTs;
+    const double *pavel;     // caller (ld,nlay)
+    const double *semiss;    // caller (ld,16)
+    const double *taua;      // caller (ld,nlay,16)
+    double *dbg_taug, *dbg_pfracs;   // optional [nlay][140][nc]
+};
+
+template <int BAND, int G0, int GN, int UNIT>
+__global__ void __launch_bounds__(128)
+lw_band_kernel(const LwBandArgs A) {
+    const LwWork &W = A.W;
+    const int nc = W.nc, nlay = W.nlay;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    const size_t col = (size_t)A.col0 + c;
+    constexpr int ib = BAND - 1;
+    const int gs = BAND == 1 ? 0 : c_lw.ngs[ib - 1];   // first g-point (0-based) of the band
+    const int g_first = gs + G0;
+    const int laytrop = W.laytrop[c];
+
+    // diffusivity angle, :177-186
+    double secdiff;
+    if (BAND == 1 || BAND == 4 || BAND >= 10) {
+        secdiff = 1.66;
+    } else {
+        constexpr double a0[9] = {1.66, 1.55, 1.58, 1.66, 1.54, 1.454, 1.89, 1.33, 1.668};
+        constexpr double a1[9] = {0.00, 0.25, 0.22, 0.00, 0.13, 0.446, -0.10, 0.40, -0.006};
+        constexpr double a2[9] = {0.00, -12.0, -11.7, 0.00, -0.72, -0.243, 0.19, -0.062, 0.414};
+        secdiff = a0[ib < 9 ? ib : 0] + a1[ib < 9 ? ib : 0] * exp(a2[ib < 9 ? ib : 0] * W.pwvcm[c]);
+        if (secdiff > 1.80) secdiff = 1.80;
+        else if (secdiff < 1.50) secdiff = 1.50;
+    }
+    const double sumfac = 0.5 * c_lw.delwave[ib] * c_lw.fluxfac;
+    const double bpade = c_lw.bpade;
+    const double tblint = 10000.0;
+    const size_t lev_stride = nc;
+    double *part = W.part + (size_t)UNIT * 6 * (nlay + 1) * nc + c;   // [f][lev][c]
+    const size_t fstride = (size_t)(nlay + 1) * nc;
+    const double *planklay = W.planklay + (size_t)ib * nlay * nc + c;
+    const double *planklev = W.planklev + (size_t)ib * (nlay + 1) * nc + c;
+
+    double radld[GN], radclrd[GN], taug[GN], pf[GN];
+    FORG { radld[ig] = 0.; radclrd[ig] = 0.; }
+    bool diverge = false;
+    part[1 * fstride + (size_t)nlay * lev_stride] = 0.;
+    part[3 * fstride + (size_t)nlay * lev_stride] = 0.;
+
+    // ---- downward sweep, :198-309 ----
+    for (int lay = nlay - 1; lay >= 0; --lay) {
+        Lay L;
+        L.fj = W.fbase + (size_t)lay * nc + c;
+        L.n2 = W.n2;
+        const int pk = W.idx[(size_t)lay * nc + c];
+        L.jp = pk & 63; L.jt = (pk >> 6) & 7; L.jt1 = (pk >> 9) & 7;
+        L.indfor = (pk >> 12) & 3; L.indself = (pk >> 14) & 15; L.indminor = (pk >> 18) & 31;
+        const double pavel = (BAND <= 2) ? A.pavel[(size_t)lay * A.ld + col] : 0.;
+        lw_band_layer<BAND, G0, GN, true>(L, lay < laytrop, pavel, taug, pf);
+        const double taer = A.taua[((size_t)ib * nlay + lay) * A.ld + col];
+        FORG taug[ig] = taug[ig] + taer;
+        if (A.dbg_taug) FORG A.dbg_taug[((size_t)lay * 140 + g_first + ig) * nc + c] = taug[ig];
+        if (A.dbg_pfracs) FORG A.dbg_pfracs[((size_t)lay * 140 + g_first + ig) * nc + c] = pf[ig];
+
+        const double blay = planklay[(size_t)lay * nc];
+        const double dplankup = planklev[(size_t)(lay + 1) * nc] - blay;
+        const double dplankdn = planklev[(size_t)lay * nc] - blay;
+        (void)dplankup;
+        const uint32_t any_word = W.cloudy_any[(size_t)(lay >> 5) * nc + c];
+        const bool layer_cloudy = (any_word >> (lay & 31)) & 1u;
+        if (!diverge && layer_cloudy) diverge = true;
+        double sumd = 0., sumdc = 0.;
+        FORG {
+            const int g = g_first + ig;
+            double odepth = secdiff * taug[ig];
+            if (odepth < 0.) odepth = 0.;
+            double tblind = odepth / (bpade + odepth);
+            const int itgas = f_int(tblint * tblind + 0.5);
+            const double2 et = reinterpret_cast<const double2 *>(c_lw.exptfn)[itgas];
+            const double agas = 1. - et.x;
+            const double bbdgas = pf[ig] * (blay + et.y * dplankdn);
+            uint32_t code = (uint32_t)itgas | 0xffff0000u;
+            bool cell_cloudy = false;
+            if (layer_cloudy) cell_cloudy = (W.mask[((size_t)(lay >> 5) * 140 + g) * nc + c] >> (lay & 31)) & 1u;
+            if (!cell_cloudy) {
+                radld[ig] = radld[ig] + (bbdgas - radld[ig]) * agas;
+            } else {
+                const double odcld = secdiff * W.taucmc[((size_t)lay * 140 + g) * nc + c];
+                const double odtot = c_lw.tau_tbl[itgas] + odcld;
+                tblind = odtot / (bpade + odtot);
+                const int ittot = f_int(tblint * tblind + 0.5);
+                const double2 ett = reinterpret_cast<const double2 *>(c_lw.exptfn)[ittot];
+                const double atot = 1. - ett.x;
+                const double bbdtot = pf[ig] * (blay + ett.y * dplankdn);
+                radld[ig] = radld[ig] + (bbdtot - radld[ig]) * atot;
+                code = (uint32_t)itgas | ((uint32_t)ittot << 16);
+            }
+            W.it[((size_t)lay * 140 + g) * nc + c] = code;
+            sumd = sumd + sumfac * radld[ig];
+            if (diverge) radclrd[ig] = radclrd[ig] + (bbdgas - radclrd[ig]) * agas;
+            else radclrd[ig] = radld[ig];
+            sumdc = sumdc + sumfac * radclrd[ig];
+        }
+        part[1 * fstride + (size_t)lay * lev_stride] = sumd;
+        part[3 * fstride + (size_t)lay * lev_stride] = sumdc;
+    }
+
+    // ---- surface, :319-333 (pf now holds the Planck fractions of layer 1) ----
+    const double plankbnd = W.plankbnd[(size_t)ib * nc + c];
+    const double reflect = 1. - A.semiss[(size_t)ib * A.ld + col];
+    double radlu[GN], radclru[GN], drad[GN], dradc[GN];
+    {
+        const double dpb = A.dudTs ? W.dplankbnd[(size_t)ib * nc + c] : 0.;
+        double su = 0., suc = 0., sd = 0.;
+        FORG {
+            const double rad0 = pf[ig] * plankbnd;
+            radlu[ig] = rad0 + reflect * radld[ig];
+            radclru[ig] = rad0 + reflect * radclrd[ig];
+            su = su + sumfac * radlu[ig];
+            suc = suc + sumfac * radclru[ig];
+            drad[ig] = pf[ig] * dpb;
+            dradc[ig] = drad[ig];
+            sd = sd + sumfac * drad[ig];
+        }
+        part[0] = su;
+        part[2 * fstride] = suc;
+        if (A.dudTs) { part[4 * fstride] = sd; part[5 * fstride] = sd; }
+    }
+
+    // ---- upward sweep, :336-379 ----
+    for (int lay = 0; lay < nlay; ++lay) {
+        Lay L;
+        L.fj = W.fbase + (size_t)lay * nc + c;
+        L.n2 = W.n2;
+        const int pk = W.idx[(size_t)lay * nc + c];
+        L.jp = pk & 63; L.jt = (pk >> 6) & 7; L.jt1 = (pk >> 9) & 7;
+        L.indfor = (pk >> 12) & 3; L.indself = (pk >> 14) & 15; L.indminor = (pk >> 18) & 31;
+        lw_band_layer<BAND, G0, GN, false>(L, lay < laytrop, 0., taug, pf);
+        const double blay = planklay[(size_t)lay * nc];
+        const double dplankup = planklev[(size_t)(lay + 1) * nc] - blay;
+        double su = 0., suc = 0., sd = 0., sdc = 0.;
+        FORG {
+            const int g = g_first + ig;
+            const uint32_t code = W.it[((size_t)lay * 140 + g) * nc + c];
+            const int itgas = code & 0xffffu, ittot = code >> 16;
+            const double2 et = reinterpret_cast<const double2 *>(c_lw.exptfn)[itgas];
+            const double agas = 1. - et.x;
+            const double bbugas = pf[ig] * (blay + et.y * dplankup);
+            if (ittot == 0xffff) {
+                radlu[ig] = radlu[ig] + (bbugas - radlu[ig]) * agas;
+                if (A.dudTs) drad[ig] = drad[ig] - drad[ig] * agas;
+            } else {
+                const double2 ett = reinterpret_cast<const double2 *>(c_lw.exptfn)[ittot];
+                const double atot = 1. - ett.x;
+                const double bbutot = pf[ig] * (blay + ett.y * dplankup);
+                radlu[ig] = radlu[ig] + (bbutot - radlu[ig]) * atot;
+                if (A.dudTs) drad[ig] = drad[ig] - drad[ig] * atot;
+            }
+            su = su + sumfac * radlu[ig];
+            if (diverge) radclru[ig] = radclru[ig] + (bbugas - radclru[ig]) * agas;
+            else radclru[ig] = radlu[ig];
+            suc = suc + sumfac * radclru[ig];
+            if (A.dudTs) {
+                if (diverge) dradc[ig] = dradc[ig] - dradc[ig] * agas;
+                else dradc[ig] = drad[ig];
+                sd = sd + sumfac * drad[ig];
+                sdc = sdc + sumfac * dradc[ig];
+            }
+        }
+        part[(size_t)(lay + 1) * lev_stride] = su;
+        part[2 * fstride + (size_t)(lay + 1) * lev_stride] = suc;
+        if (A.dudTs) {
+            part[4 * fstride + (size_t)(lay + 1) * lev_stride] = sd;
+            part[5 * fstride + (size_t)(lay + 1) * lev_stride] = sdc;
+        }
+    }
+}
+
+// units: (band, first g of the sub-range within the band, number of g-points)
+#define LW_UNITS(X)                                                                             \
+    X(1, 0, 6, 0) X(1, 6, 4, 1) X(2, 0, 6, 2) X(2, 6, 6, 3) X(3, 0, 8, 4) X(3, 8, 8, 5)         \
+    X(4, 0, 8, 6) X(4, 8, 6, 7) X(5, 0, 8, 8) X(5, 8, 8, 9) X(6, 0, 8, 10) X(7, 0, 6, 11)       \
+    X(7, 6, 6, 12) X(8, 0, 8, 13) X(9, 0, 6, 14) X(9, 6, 6, 15) X(10, 0, 6, 16) X(11, 0, 8, 17) \
+    X(12, 0, 8, 18) X(13, 0, 4, 19) X(14, 0, 2, 20) X(15, 0, 2, 21) X(16, 0, 2, 22)
+constexpr int LW_NUNITS = 23;
+__constant__ int c_unit_band[LW_NUNITS];
+static const int h_unit_band[LW_NUNITS] = {1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 7, 7, 8, 9, 9, 10, 11, 12, 13, 14, 15, 16};
+
+// fixed-order sum of the unit partials -> caller arrays; band OLR (:382-385, rad.F90:586-605)
+__global__ void lw_reduce_kernel(int ld, int col0, int nc, int nlay, int dudTs, const double *__restrict__ part,
+                                 double *__restrict__ uflx, double *__restrict__ dflx,
+                                 double *__restrict__ uflxc, double *__restrict__ dflxc,
+                                 double *__restrict__ duflx, double *__restrict__ duflxc, int band_mask,
+                                 double *__restrict__ olrb, double *__restrict__ dolrb) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lev = blockIdx.y;
+    if (c >= nc) return;
+    const size_t fstride = (size_t)(nlay + 1) * nc;
+    const size_t o = (size_t)lev * nc + c;
+    double s[6] = {0., 0., 0., 0., 0., 0.};
+    double bu = 0., bd = 0.;
+    int cur = 1;
+    const size_t col = (size_t)col0 + c;
+    const bool top = lev == nlay;
+    for (int u = 0; u < LW_NUNITS; ++u) {
+        const double *p = part + (size_t)u * 6 * fstride + o;
+        const double vu = p[0];
+        s[0] = s[0] + vu;
+        s[1] = s[1] + p[fstride];
+        s[2] = s[2] + p[2 * fstride];
+        s[3] = s[3] + p[3 * fstride];
+        double vd = 0.;
+        if (dudTs) {
+            vd = p[4 * fstride];
+            s[4] = s[4] + vd;
+            s[5] = s[5] + p[5 * fstride];
+        }
+        if (top && band_mask) {
+            const int b = c_unit_band[u];
+            if (b != cur) {
+                if ((band_mask >> (cur - 1)) & 1) { olrb[(cur - 1) + 16 * col] = bu; if (dudTs) dolrb[(cur - 1) + 16 * col] = bd; }
+                cur = b; bu = 0.; bd = 0.;
+            }
+            bu = bu + vu;
+            bd = bd + vd;
+        }
+    }
+    if (top && band_mask && ((band_mask >> (cur - 1)) & 1)) {
+        olrb[(cur - 1) + 16 * col] = bu;
+        if (dudTs) dolrb[(cur - 1) + 16 * col] = bd;
+    }
+    const size_t oo = (size_t)lev * ld + col;
+    uflx[oo] = s[0]; dflx[oo] = s[1]; uflxc[oo] = s[2]; dflxc[oo] = s[3];
+    if (dudTs) { duflx[oo] = s[4]; duflxc[oo] = s[5]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host orchestration of one chunk of columns
+// ---------------------------------------------------------------------------------------------
+static LwWork lw_carve(Slab &slab, int nc, int nlay) {
+    LwWork W;
+    W.nc = nc; W.nlay = nlay;
+    const size_t n2 = (size_t)nlay * nc, nw = (size_t)((nlay + 31) / 32);
+    W.idx = slab.take<int>(n2);
+    W.fbase = slab.take<double>((size_t)F_COUNT * n2);
+    W.n2 = n2;
+    W.planklay = slab.take<double>(16 * n2);
+    W.planklev = slab.take<double>((size_t)16 * (nlay + 1) * nc);
+    W.plankbnd = slab.take<double>((size_t)16 * nc);
+    W.dplankbnd = slab.take<double>((size_t)16 * nc);
+    W.pwvcm = slab.take<double>(nc);
+    W.laytrop = slab.take<int>(nc);
+    W.seeds = slab.take<uint32_t>((size_t)4 * nc);
+    W.alpha = slab.take<double>(n2);
+    W.rcorr = slab.take<double>(n2);
+    W.mask = slab.take<uint32_t>(nw * 140 * nc);
+    W.cloudy_any = slab.take<uint32_t>(nw * nc);
+    W.taucmc = slab.take<double>(n2 * 140);
+    W.it = slab.take<uint32_t>(n2 * 140);
+    W.part = slab.take<double>((size_t)LW_NUNITS * 6 * (nlay + 1) * nc);
+    return W;
+}
+
+size_t lw_scratch_bytes(int nc, int nlay, bool debug) {
+    Slab s;   // dry run of the carve
+    lw_carve(s, nc, nlay);
+    size_t b = s.used;
+    if (debug) b += 2 * (((size_t)nlay * 140 * nc * 8 + 255) & ~(size_t)255);
+    return b + 4096;
+}
+
+int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp, const KissJump *d_jumps,
+                 Slab &slab, int *d_err, cudaStream_t stream, cudaStream_t *side, int nside, cudaEvent_t *ev,
+                 const RrtmgxTaps *taps, int *d_negpos) {
+    (void)d_negpos;
+    static bool unit_map_uploaded = false;
+    if (!unit_map_uploaded) {
+        if (cudaMemcpyToSymbol(c_unit_band, h_unit_band, sizeof h_unit_band) != cudaSuccess) return RRTMGX_ECUDA;
+        unit_map_uploaded = true;
+    }
+    const int ld = a->ncol, nlay = a->nlay;
+    slab.used = 0;
+    LwWork W = lw_carve(slab, nc, nlay);
+    const bool want_dbg = taps && (taps->taug || taps->pfracs);
+    double *dbg_taug = nullptr, *dbg_pfracs = nullptr;
+    if (want_dbg) {
+        dbg_taug = slab.take<double>((size_t)nlay * 140 * nc);
+        dbg_pfracs = slab.take<double>((size_t)nlay * 140 * nc);
+    }
+    const int nw = (nlay + 31) / 32;
+    const dim3 blk(128), grd((nc + 127) / 128);
+
+    cudaMemsetAsync(W.cloudy_any, 0, sizeof(uint32_t) * (size_t)nw * nc, stream);
+    // clearCounts of this chunk: (ld,4) -> four strided segments
+    for (int k = 0; k < 4; ++k)
+        cudaMemsetAsync(a->clearCounts + (size_t)k * ld + col0, 0, sizeof(int32_t) * (size_t)nc, stream);
+
+    RRTMGX_LAUNCH(lw_setcoef_kernel, grd, blk, 0, stream, ld, col0, W, a->dudTs, a->play, a->tlay, a->plev,
+                  a->tlev, a->tsfc, a->emis, a->h2ovmr, a->o3vmr, a->co2vmr, a->ch4vmr, a->n2ovmr, a->o2vmr,
+                  a->cfc11vmr, a->cfc12vmr, a->cfc22vmr, a->ccl4vmr, d_err);
+    RRTMGX_LAUNCH(mcica_prep_kernel, grd, blk, 0, stream, ld, col0, nc, nlay, mp, a->zm, a->play, a->alat,
+                  W.seeds, W.alpha, W.rcorr);
+    LwOptics opt{ld, col0, nc, nlay, a->rei, a->rel, a->iceflglw, a->liqflglw, W.taucmc};
+    RRTMGX_LAUNCH(mcica_kernel<LwOptics>, dim3(grd.x, 140), blk, 0, stream, ld, col0, nc, nlay, 140, mp, d_jumps,
+                  W.seeds, W.alpha, W.rcorr, a->cldf, a->ciwp, a->clwp, 1.e-20, a->cloudLM, a->cloudMH,
+                  a->clearCounts, W.cloudy_any, W.mask, opt, d_err);
+
+    LwBandArgs A{ld, col0, W, a->dudTs, a->play, a->emis, a->tauaer, dbg_taug, dbg_pfracs};
+    // fan the independent band units out over the side streams
+    cudaEventRecord(ev[0], stream);
+    for (int s = 0; s < nside; ++s) cudaStreamWaitEvent(side[s], ev[0], 0);
+    int u = 0;
+#define X(BAND, G0, GN, UNIT)                                                              \
+    {                                                                                      \
+        cudaStream_t st = nside ? side[u % nside] : stream;                                \
+        RRTMGX_LAUNCH((lw_band_kernel<BAND, G0, GN, UNIT>), grd, blk, 0, st, A);           \
+        ++u;                                                                               \
+    }
+    LW_UNITS(X)
+#undef X
+    for (int s = 0; s < nside; ++s) {
+        cudaEventRecord(ev[1 + s], side[s]);
+        cudaStreamWaitEvent(stream, ev[1 + s], 0);
+    }
+    int band_mask = 0;
+    for (int b = 0; b < 16; ++b)
+        if (a->band_output && a->band_output[b]) band_mask |= 1 << b;
+    RRTMGX_LAUNCH(lw_reduce_kernel, dim3(grd.x, nlay + 1), blk, 0, stream, ld, col0, nc, nlay, a->dudTs, W.part,
+                  a->uflx, a->dflx, a->uflxc, a->dflxc, a->duflx_dTs, a->duflxc_dTs, band_mask, a->olrb,
+                  a->dolrb_dTs);
+
+    if (taps) {   // debug / parity taps: synchronous strided copies into the host arrays
+        if (cudaStreamSynchronize(stream) != cudaSuccess) return RRTMGX_ECUDA;
+        const size_t n2 = (size_t)nlay * nc;
+        std::vector<int> hidx(n2);
+        auto copy2d = [&](void *dst_host, const void *src_dev, size_t elem, size_t rows) {
+            // chunk-local [rows][nc] -> host [rows][ld] at column col0
+            cudaMemcpy2D((char *)dst_host + (size_t)col0 * elem, (size_t)ld * elem, src_dev, (size_t)nc * elem,
+                         (size_t)nc * elem, rows, cudaMemcpyDeviceToHost);
+        };
+        if (taps->jp || taps->jt || taps->jt1 || taps->indfor || taps->indself || taps->indminor) {
+            cudaMemcpy(hidx.data(), W.idx, n2 * sizeof(int), cudaMemcpyDeviceToHost);
+            std::vector<int> hl(nc);
+            cudaMemcpy(hl.data(), W.laytrop, nc * sizeof(int), cudaMemcpyDeviceToHost);
+            for (int lay = 0; lay < nlay; ++lay)
+                for (int c = 0; c < nc; ++c) {
+                    const int pk = hidx[(size_t)lay * nc + c];
+                    const size_t o = (size_t)lay * ld + col0 + c;
+                    const bool lower = lay < hl[c];
+                    if (taps->jp) taps->jp[o] = pk & 63;
+                    if (taps->jt) taps->jt[o] = (pk >> 6) & 7;
+                    if (taps->jt1) taps->jt1[o] = (pk >> 9) & 7;
+                    if (taps->indfor) taps->indfor[o] = (pk >> 12) & 3;
+                    // the reference leaves indself unset above the tropopause (calloc'd 0 in the oracle)
+                    if (taps->indself) taps->indself[o] = lower ? (pk >> 14) & 15 : 0;
+                    if (taps->indminor) taps->indminor[o] = (pk >> 18) & 31;
+                }
+        }
+        if (taps->laytrop) cudaMemcpy(taps->laytrop + col0, W.laytrop, nc * sizeof(int), cudaMemcpyDeviceToHost);
+        if (taps->pwvcm) cudaMemcpy(taps->pwvcm + col0, W.pwvcm, nc * sizeof(double), cudaMemcpyDeviceToHost);
+        if (taps->fac00) copy2d(taps->fac00, W.f(F_FAC00), 8, nlay);
+        if (taps->fac01) copy2d(taps->fac01, W.f(F_FAC01), 8, nlay);
+        if (taps->fac10) copy2d(taps->fac10, W.f(F_FAC10), 8, nlay);
+        if (taps->fac11) copy2d(taps->fac11, W.f(F_FAC11), 8, nlay);
+        if (taps->taug) copy2d(taps->taug, dbg_taug, 8, (size_t)nlay * 140);
+        if (taps->pfracs) copy2d(taps->pfracs, dbg_pfracs, 8, (size_t)nlay * 140);
+        if (taps->cldymc || taps->taucmc) {
+            std::vector<uint32_t> hm((size_t)nw * 140 * nc);
+            std::vector<double> ht;
+            cudaMemcpy(hm.data(), W.mask, hm.size() * 4, cudaMemcpyDeviceToHost);
+            if (taps->taucmc) {
+                ht.resize(n2 * 140);
+                cudaMemcpy(ht.data(), W.taucmc, ht.size() * 8, cudaMemcpyDeviceToHost);
+            }
+            for (int lay = 0; lay < nlay; ++lay)
+                for (int g = 0; g < 140; ++g)
+                    for (int c = 0; c < nc; ++c) {
+                        const bool on = (hm[((size_t)(lay >> 5) * 140 + g) * nc + c] >> (lay & 31)) & 1u;
+                        const size_t o = ((size_t)lay * 140 + g) * ld + col0 + c;
+                        if (taps->cldymc) taps->cldymc[o] = on;
+                        if (taps->taucmc) taps->taucmc[o] = on ? ht[((size_t)lay * 140 + g) * nc + c] : 0.;
+                    }
+        }
+        if (cudaGetLastError() != cudaSuccess) return RRTMGX_ECUDA;
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : RRTMGX_ECUDA;
+}
+
+}  // namespace rrtmgx

@@ -1,0 +1,217 @@
+// McICA stochastic subcolumn generator on the device.
+//
+// Restates GEOS_RadiationShared/cloud_subcol_gen.F90 (generate_stochastic_clouds :132-487,
+// rng_kiss :546-607, correlation_length :491-542, clearCounts_threeBand :611-769) and
+// zcw_lookup (GEOS_RadiationShared/cloud_condensate_inhomogeneity.F90:86-124).
+//
+// The reference draws one KISS stream per column: for subcolumn i and layer k the draws are
+// [cdf1(k),cdf2(k)] interleaved for k=1..nlay, then (inhomogeneous condensate) [cdf2'(k),cdf3(k)],
+// i.e. subcolumn i starts at draw i*4*nlay.  Here one thread owns one (column, subcolumn) and
+// jumps its four KISS lanes ahead in O(1) with host-precomputed jump entries (affine power for
+// the LCG, GF(2) matrix power for the xorshift, modular power for the two multiply-with-carry
+// lanes), so the integer sequence - and hence the cloud mask - is bit-identical to the
+// sequential generator.  Layers are then swept once, carrying cdf1/cdf3 in registers.
+#pragma once
+#include "common.cuh"
+
+namespace rrtmgx {
+
+__device__ __forceinline__ uint32_t mwc_step(uint32_t y, uint32_t a) { return a * (y & 65535u) + (y >> 16); }
+
+// n steps of y <- a*(y & 65535) + (y >> 16); M = a^(n-2) mod m, m = a*2^16 - 1.
+// After two explicit steps y is in [0, m+1] and y_{k+1} = a*y_k mod m holds as an equality of
+// canonical residues except at the fixed points 0 and m and the transient m+1 (handled).
+template <uint32_t A>
+__device__ __forceinline__ uint32_t mwc_jump(uint32_t y, uint32_t n, uint32_t M) {
+    constexpr uint64_t m = (uint64_t)A * 65536ull - 1ull;
+    if (n == 0) return y;
+    y = mwc_step(y, A);
+    if (n == 1) return y;
+    y = mwc_step(y, A);
+    if (n == 2) return y;
+    if (y == 0u || (uint64_t)y == m) return y;
+    uint64_t mult = M;
+    if ((uint64_t)y == m + 1ull) {          // one more explicit step, one fewer modular one
+        y = mwc_step(y, A);
+        mult = (mult * 65536ull) % m;       // times a^-1 = 2^16 (mod m)
+    }
+    return (uint32_t)((mult * (uint64_t)y) % m);
+}
+
+struct Kiss {
+    uint32_t s1, s2, s3, s4;
+    __device__ __forceinline__ void jump(const KissJump &J) {
+        s1 = J.lcg_a * s1 + J.lcg_c;
+        uint32_t r = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j)
+            if ((s2 >> j) & 1u) r ^= J.xs[j];
+        s2 = r;
+        s3 = mwc_jump<18000u>(s3, J.n, J.mwc3);
+        s4 = mwc_jump<30903u>(s4, J.n, J.mwc4);
+    }
+    // SH/cloud_subcol_gen.F90:568-575 (int32 wraparound, logical shifts)
+    __device__ __forceinline__ double draw() {
+        s1 = 69069u * s1 + 1327217885u;
+        s2 = s2 ^ (s2 << 13);
+        s2 = s2 ^ (s2 >> 17);
+        s2 = s2 ^ (s2 << 5);
+        s3 = 18000u * (s3 & 65535u) + (s3 >> 16);
+        s4 = 30903u * (s4 & 65535u) + (s4 >> 16);
+        uint32_t kiss = s1 + s2 + (s3 << 16) + s4;
+        return (double)(int32_t)kiss * 2.328306e-10 + 0.5;
+    }
+};
+
+// SH/cloud_condensate_inhomogeneity.F90:86-124
+__device__ __forceinline__ double zcw_lookup(const double *__restrict__ xcw, double cdf, double sigma_qcw) {
+    const int n1 = 1000, n2 = 140;
+    double rind1 = cdf * (double)(n1 - 1) + 1.;
+    int ind1 = clampi(f_int(rind1), 1, n1 - 1);
+    rind1 = rind1 - (double)ind1;
+    double rind2 = 40. * sigma_qcw - 3.;
+    int ind2 = clampi(f_int(rind2), 1, n2 - 1);
+    rind2 = rind2 - (double)ind2;
+    const double *c0 = xcw + (size_t)1000 * (ind2 - 1) + (ind1 - 1);
+    const double *c1 = c0 + 1000;
+    return (1.0 - rind1) * (1.0 - rind2) * __ldg(c0) + (1.0 - rind1) * rind2 * __ldg(c1) +
+           rind1 * (1.0 - rind2) * __ldg(c0 + 1) + rind1 * rind2 * __ldg(c1 + 1);
+}
+
+// Per-column preparation shared by all subcolumns: KISS seeds from the four lowest layer
+// pressures (:375-400) and the inter-layer overlap / condensate correlations (:314-321).
+// Inputs are the caller's arrays (leading dimension ld, first column col0); outputs are
+// chunk-local [..][nc].
+__global__ void mcica_prep_kernel(int ld, int col0, int nc, int nlay, McicaParams P,
+                                  const double *__restrict__ zm, const double *__restrict__ play,
+                                  const double *__restrict__ alat,
+                                  uint32_t *__restrict__ seeds,   // [4][nc]
+                                  double *__restrict__ alpha,     // [nlay][nc], k >= 1
+                                  double *__restrict__ rcorr) {   // [nlay][nc], k >= 1
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    const size_t col = (size_t)col0 + c;
+    const double r2d = 180.0 / 3.14159265358979323846;
+    double d = alat[col] * r2d - P.adl_am3;
+    double adl = (P.adl_am1 + P.adl_am2 * exp(-((d * d) / (P.adl_am4 * P.adl_am4)))) * 1.e3;
+    double rdl = 1.0;
+    if (P.inhomo) {
+        d = alat[col] * r2d - P.rdl_am3;
+        rdl = (P.rdl_am1 + P.rdl_am2 * exp(-((d * d) / (P.rdl_am4 * P.rdl_am4)))) * 1.e3;
+    }
+    double zprev = zm[col];
+    for (int k = 1; k < nlay; ++k) {
+        double z = zm[(size_t)k * ld + col];
+        double dz = fabs(z - zprev);
+        alpha[(size_t)k * nc + c] = exp(-dz / adl);
+        if (P.inhomo) rcorr[(size_t)k * nc + c] = exp(-dz / rdl);
+        zprev = z;
+    }
+    const int maximo = 2147483647 - 1;
+    // the reference tests play(1,1) > play(nlay,1) on the first column of a partition (:267);
+    // every column shares the ordering, so each column tests itself
+    const bool surface_at_one = play[col] > play[(size_t)(nlay - 1) * ld + col];
+    double pseed[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+        pseed[n] = play[(size_t)(surface_at_one ? n : nlay - 1 - n) * ld + col] * 100.;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        double p = pseed[0];
+        int so = P.seed_order[n];
+        if (so == 2) p = pseed[1];
+        if (so == 3) p = pseed[2];
+        if (so == 4) p = pseed[3];
+        seeds[(size_t)n * nc + c] = (uint32_t)f_int((p - (double)f_int(p)) * (double)maximo + 1.);
+    }
+}
+
+// One thread per (column, subcolumn).  Optics::cell(lay, isub, c, ciwp, clwp, err) turns the
+// stochastic water paths of a McICA-cloudy cell into cloud optical properties, stores them, and
+// returns whether the cell is optically cloudy.  Outputs: clearCounts (caller layout
+// (ncol,4), integer atomics, so deterministic), the optical cloud mask bit-packed over layers
+// [nw][nsub][nc] and its OR over subcolumns cloudy_any [nw][nc] (the reference's
+// cloudy(lay,col) after cldprmc).
+template <class Optics>
+__global__ void __launch_bounds__(128)
+mcica_kernel(int ld, int col0, int nc, int nlay, int nsub, McicaParams P,
+             const KissJump *__restrict__ jumps, const uint32_t *__restrict__ seeds,
+             const double *__restrict__ alpha, const double *__restrict__ rcorr,
+             const double *__restrict__ cldf, const double *__restrict__ ciwp,
+             const double *__restrict__ clwp, double cwp_tiny, int cloudLM, int cloudMH,
+             int *__restrict__ clearCounts,      // (ld,4)
+             uint32_t *__restrict__ cloudy_any,  // [nw][nc]
+             uint32_t *__restrict__ mask,        // [nw][nsub][nc]
+             Optics opt, int *err) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int isub = blockIdx.y;
+    if (c >= nc) return;
+    const size_t col = (size_t)col0 + c;
+    Kiss a, b;
+    a.s1 = seeds[c]; a.s2 = seeds[(size_t)nc + c];
+    a.s3 = seeds[(size_t)2 * nc + c]; a.s4 = seeds[(size_t)3 * nc + c];
+    b = a;
+    a.jump(jumps[2 * isub]);
+    if (P.inhomo) b.jump(jumps[2 * isub + 1]);
+
+    const bool surf1 = cloudLM < cloudMH;
+    bool any_all = false, any_low = false, any_mid = false, any_high = false;
+    double cdf1 = 0., cdf3 = 0.;
+    uint32_t word = 0;
+    for (int k = 0; k < nlay; ++k) {
+        const size_t i2 = (size_t)k * ld + col;
+        const size_t j2 = (size_t)k * nc + c;
+        double c1 = a.draw();
+        double c2 = a.draw();
+        if (k > 0 && c2 < alpha[j2]) c1 = cdf1;
+        cdf1 = c1;
+        if (P.inhomo) {
+            double c2b = b.draw();
+            double c3 = b.draw();
+            if (k > 0 && c2b < rcorr[j2]) c3 = cdf3;
+            cdf3 = c3;
+        }
+        const double cf = cldf[i2];
+        bool optical = false;
+        if (cdf1 >= 1. - cf) {
+            double ciw = ciwp[i2], clw = clwp[i2];
+            if (P.inhomo) {
+                double sigma = cf > 0.99 ? 0.5 : (cf > 0.9 ? 0.71 : 1.0);
+                double zcw = zcw_lookup(P.xcw, cdf3, sigma);
+                ciw = ciw * zcw;
+                clw = clw * zcw;
+            }
+            bool ineg = ciw <= cwp_tiny, lneg = clw <= cwp_tiny;
+            if (ineg) ciw = 0.;
+            if (lneg) clw = 0.;
+            if (!(ineg && lneg)) {
+                // McICA-cloudy cell (cldy_stoch = .true.)
+                const int lay1 = k + 1;
+                any_all = true;
+                if (surf1) {
+                    if (lay1 <= cloudLM) any_low = true;
+                    else if (lay1 <= cloudMH) any_mid = true;
+                    else any_high = true;
+                } else {
+                    if (lay1 < cloudMH) any_high = true;
+                    else if (lay1 < cloudLM) any_mid = true;
+                    else any_low = true;
+                }
+                optical = opt.cell(k, isub, c, ciw, clw, err);
+            }
+        }
+        if (optical) word |= 1u << (k & 31);
+        if ((k & 31) == 31 || k == nlay - 1) {
+            const int w = k >> 5;
+            mask[((size_t)w * nsub + isub) * nc + c] = word;
+            if (word) atomicOr(&cloudy_any[(size_t)w * nc + c], word);
+            word = 0;
+        }
+    }
+    if (!any_all) atomicAdd(&clearCounts[col], 1);
+    if (!any_high) atomicAdd(&clearCounts[(size_t)ld + col], 1);
+    if (!any_mid) atomicAdd(&clearCounts[(size_t)2 * ld + col], 1);
+    if (!any_low) atomicAdd(&clearCounts[(size_t)3 * ld + col], 1);
+}
+
+}  // namespace rrtmgx

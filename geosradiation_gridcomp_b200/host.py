@@ -1,0 +1,376 @@
+"""Host-side mirror of the reference driver interfaces, over the C ABI (include/rrtmgx.h).
+
+Function names, argument names, argument meaning, array layouts and error behaviour follow
+  rrtmg_lw      LW/src/rrtmg_lw_rad.F90:15-23,113-201
+  rrtmg_sw      SW/src/rrtmg_sw_rad.F90:68-124,130-357
+  rrtmg_lw_ini  LW/src/rrtmg_lw_init.F90:22      rrtmg_sw_ini  SW/src/rrtmg_sw_init.F90:49
+  set_inhomogeneity            GEOS_RadiationShared/cloud_condensate_inhomogeneity.F90:45
+  initialize_cloud_subcol_gen  GEOS_RadiationShared/cloud_subcol_gen.F90:108
+(LW/ = GEOSirrad_GridComp/RRTMG/rrtmg_lw/gcm_model/, SW/ = GEOSsolar_GridComp/RRTMG/rrtmg_sw/gcm_model/).
+
+Arrays are Fortran-ordered fp64 with the column index fastest, layer 1 at the surface.  Array
+arguments may be numpy arrays (host pointers; the library stages them through the GPU) or
+torch CUDA tensors / raw device addresses (``device=True``; no copies).  The compute path is
+the CUDA library only: importing this module without ``librrtmgx.so`` or calling it without
+a GPU raises - there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librrtmgx.so")
+BLOB_PATH = os.path.join(HERE, "data", "rrtmg_tables.bin")
+
+NBNDLW, NGPTLW, NBNDSW, NGPTSW = 16, 140, 14, 112
+DEVICE_PTRS, NO_SYNC, SKIP_CHECKS = 1, 2, 4
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_vp = C.c_void_p
+
+
+class RrtmgxError(RuntimeError):
+    """Raised where the reference would `error stop` (LW) or set RC /= 0 (SW)."""
+
+    def __init__(self, status, message):
+        super().__init__(f"rrtmgx status {status}: {message}")
+        self.status = status
+
+
+class Config(C.Structure):
+    _fields_ = [("table_blob", C.c_char_p), ("device", C.c_int), ("inhomogeneity", C.c_int), ("corr", _dp)]
+
+
+_LW_IN = ["play", "plev", "tlay", "tlev", "tsfc", "emis", "h2ovmr", "o3vmr", "co2vmr", "ch4vmr", "n2ovmr",
+          "o2vmr", "cfc11vmr", "cfc12vmr", "cfc22vmr", "ccl4vmr", "cldf", "ciwp", "clwp", "rei", "rel",
+          "tauaer", "zm", "alat"]
+_LW_OUT = ["uflx", "dflx", "uflxc", "dflxc", "duflx_dTs", "duflxc_dTs", "olrb", "dolrb_dTs"]
+
+
+class LwArgs(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("ncol", "nlay", "psize", "dudTs", "iceflglw", "liqflglw", "dyofyr",
+                                        "cloudLM", "cloudMH", "flags")] +
+                [("stream", _vp)] + [(n, _vp) for n in _LW_IN] + [("band_output", _vp), ("clearCounts", _vp)] +
+                [(n, _vp) for n in _LW_OUT])
+
+
+_SW_IN = ["coszen", "play", "plev", "tlay", "h2ovmr", "o3vmr", "co2vmr", "ch4vmr", "o2vmr", "cld", "ciwp",
+          "clwp", "rei", "rel", "zm", "alat", "tauaer", "ssaaer", "asmaer", "asdir", "asdif", "aldir", "aldif"]
+_SW_OUT = ["swuflx", "swdflx", "swuflxc", "swdflxc", "nirr", "nirf", "parr", "parf", "uvrr", "uvrf", "fswband",
+           "cotdtp", "cotdhp", "cotdmp", "cotdlp", "cotntp", "cotnhp", "cotnmp", "cotnlp", "drband", "dfband"]
+
+
+class SwArgs(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("ncol", "nlay", "rpart", "isolvar", "iceflgsw", "liqflgsw", "dyofyr",
+                                        "cloudLM", "cloudMH", "iaer", "normFlx", "do_drfband", "flags")] +
+                [("stream", _vp), ("scon", C.c_double), ("adjes", C.c_double), ("bndscl", _vp),
+                 ("indsolvar", _vp), ("solcycfrac", _vp)] +
+                [(n, _vp) for n in _SW_IN] + [("clearCounts", _vp)] + [(n, _vp) for n in _SW_OUT])
+
+
+_TAP_I = ["jp", "jt", "jt1", "indfor", "indself", "indminor", "laytrop"]
+_TAP_D = ["fac00", "fac01", "fac10", "fac11"]
+
+
+class Taps(C.Structure):
+    _fields_ = ([(n, _vp) for n in _TAP_I] + [(n, _vp) for n in _TAP_D] +
+                [("cldymc", _vp), ("taucmc", _vp), ("pwvcm", _vp), ("taug", _vp), ("pfracs", _vp), ("ssi", _vp)])
+
+
+_lib = None
+_initialised = False
+
+
+def lib():
+    """Load librrtmgx.so (fails loudly when the CUDA extension has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                              "(geosradiation_gridcomp_b200/csrc/build.sh); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.rrtmgx_init.argtypes = [C.POINTER(Config)]
+        L.rrtmgx_set_mcica.argtypes = [C.c_int, _dp]
+        L.rrtmgx_strerror.restype = C.c_char_p
+        L.rrtmgx_strerror.argtypes = [C.c_int]
+        L.rrtmgx_launch_count.restype = C.c_longlong
+        L.rrtmgx_lw_run.argtypes = [C.POINTER(LwArgs)]
+        L.rrtmgx_sw_run.argtypes = [C.POINTER(SwArgs)]
+        L.rrtmgx_set_taps.argtypes = [C.POINTER(Taps), C.POINTER(Taps)]
+        L.rrtmgx_table.restype = _dp
+        L.rrtmgx_table.argtypes = [C.c_char_p, C.c_char_p, C.c_int, _ip]
+        L.rrtmgx_heating_rate.argtypes = [C.c_int, C.c_int, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp]
+        _lib = L
+    return _lib
+
+
+def _check(status):
+    if status != 0:
+        raise RrtmgxError(status, lib().rrtmgx_strerror(status).decode())
+
+
+def init(device=-1, inhomogeneity=1, corr=None, table_blob=None):
+    """rrtmg_lw_ini + rrtmg_sw_ini + set_inhomogeneity + initialize_cloud_subcol_gen; idempotent."""
+    global _initialised
+    c = Config()
+    c.table_blob = (table_blob or BLOB_PATH).encode()
+    c.device = device
+    c.inhomogeneity = inhomogeneity
+    keep = None
+    if corr is not None:
+        keep = np.ascontiguousarray(corr, dtype=np.float64)
+        assert keep.size == 8
+        c.corr = keep.ctypes.data_as(_dp)
+    _check(lib().rrtmgx_init(C.byref(c)))
+    _initialised = True
+
+
+def rrtmg_lw_ini():
+    """LW/src/rrtmg_lw_init.F90:22 (GEOS calls it on every refresh; idempotent here)."""
+    init()
+
+
+def rrtmg_sw_ini():
+    """SW/src/rrtmg_sw_init.F90:49."""
+    init()
+
+
+_mcica = {"ih": 1, "corr": None}
+
+
+def set_inhomogeneity(ih):
+    """GEOS_RadiationShared/cloud_condensate_inhomogeneity.F90:45 (0 homogeneous, 1 beta, 2 gamma)."""
+    if not _initialised:
+        init()
+    _mcica["ih"] = int(ih)
+    _apply_mcica()
+
+
+def initialize_cloud_subcol_gen(adl_am1, adl_am2, adl_am30, adl_am4, rdl_am1, rdl_am2, rdl_am30, rdl_am4):
+    """GEOS_RadiationShared/cloud_subcol_gen.F90:108-129."""
+    if not _initialised:
+        init()
+    _mcica["corr"] = [adl_am1, adl_am2, adl_am30, adl_am4, rdl_am1, rdl_am2, rdl_am30, rdl_am4]
+    _apply_mcica()
+
+
+def _apply_mcica():
+    corr = _mcica["corr"]
+    p = None
+    if corr is not None:
+        arr = np.ascontiguousarray(corr, dtype=np.float64)
+        p = arr.ctypes.data_as(_dp)
+    _check(lib().rrtmgx_set_mcica(_mcica["ih"], p))
+
+
+def finalize():
+    global _initialised
+    if _lib is not None:
+        _lib.rrtmgx_finalize()
+    _initialised = False
+
+
+def launch_count():
+    return int(lib().rrtmgx_launch_count())
+
+
+def table(kind, name, band=0):
+    n = C.c_int32(0)
+    p = lib().rrtmgx_table(kind.encode(), name.encode(), band, C.byref(n))
+    if not p or n.value == 0:
+        return None
+    return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
+
+def _addr(a, device, dtype=np.float64, keep=None):
+    """Raw address of a numpy array (host) or torch CUDA tensor / int (device)."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if hasattr(a, "data_ptr"):   # torch tensor
+        if device != a.is_cuda:
+            raise ValueError("mixing host and device arrays in one call")
+        return a.data_ptr()
+    a = np.asarray(a)
+    if device:
+        raise ValueError("device=True needs torch CUDA tensors or raw addresses")
+    if a.dtype != dtype or not (a.flags.f_contiguous or a.ndim <= 1):
+        raise ValueError("arrays must be Fortran-ordered with the reference's element type")
+    if keep is not None:
+        keep.append(a)
+    return a.ctypes.data
+
+
+def _new_taps(names, ncol, nlay, ngpt):
+    t = Taps()
+    out = {}
+    for n in names:
+        if n in _TAP_I[:-1]:
+            a = np.zeros((ncol, nlay), dtype=np.int32, order="F")
+        elif n == "laytrop":
+            a = np.zeros(ncol, dtype=np.int32)
+        elif n in _TAP_D:
+            a = np.zeros((ncol, nlay), order="F")
+        elif n == "cldymc":
+            a = np.zeros((ncol, ngpt, nlay), dtype=np.uint8, order="F")   # [ilay][ig][icol] in memory
+        elif n == "pwvcm":
+            a = np.zeros(ncol)
+        elif n == "ssi":
+            a = np.zeros((ncol, ngpt), order="F")
+        else:
+            a = np.zeros((ncol, ngpt, nlay), order="F")
+        out[n] = a
+        setattr(t, n, a.ctypes.data)
+    return t, out
+
+
+def rrtmg_lw(ncol, nlay, psize, dudTs, play, plev, tlay, tlev, tsfc, emis, h2ovmr, o3vmr, co2vmr, ch4vmr,
+             n2ovmr, o2vmr, cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, cldf, ciwp, clwp, rei, rel, iceflglw,
+             liqflglw, tauaer, zm, alat, dyofyr, cloudLM, cloudMH, clearCounts, uflx, dflx, uflxc, dflxc,
+             duflx_dTs, duflxc_dTs, band_output, olrb, dolrb_dTs, *, device=False, stream=None, sync=True,
+             skip_checks=False, taps=()):
+    """Drop-in for `rrtmg_lw` (LW/src/rrtmg_lw_rad.F90:15-23): same argument order and meaning;
+    outputs are written in place.  Raises RrtmgxError where the reference stops.
+    Returns a dict of requested intermediate taps (tests only)."""
+    if not _initialised:
+        init()
+    keep = []
+    a = LwArgs()
+    a.ncol, a.nlay, a.psize, a.dudTs = int(ncol), int(nlay), int(psize), int(bool(dudTs))
+    a.iceflglw, a.liqflglw, a.dyofyr = int(iceflglw), int(liqflglw), int(dyofyr)
+    a.cloudLM, a.cloudMH = int(cloudLM), int(cloudMH)
+    a.flags = (DEVICE_PTRS if device else 0) | (0 if sync else NO_SYNC) | (SKIP_CHECKS if skip_checks else 0)
+    a.stream = stream
+    loc = locals()
+    for n in _LW_IN + _LW_OUT:
+        setattr(a, n, _addr(loc[n], device, keep=keep))
+    a.clearCounts = _addr(clearCounts, device, dtype=np.int32, keep=keep)
+    bo = np.ascontiguousarray(band_output, dtype=np.int32)   # logical(16), always host
+    a.band_output = bo.ctypes.data
+    t, tout = (None, {})
+    if taps:
+        t, tout = _new_taps(taps, ncol, nlay, NGPTLW)
+        lib().rrtmgx_set_taps(C.byref(t), None)
+    try:
+        _check(lib().rrtmgx_lw_run(C.byref(a)))
+    finally:
+        if taps:
+            lib().rrtmgx_set_taps(None, None)
+    return tout
+
+
+def rrtmg_sw(rpart, ncol, nlay, scon, adjes, coszen, isolvar, play, plev, tlay, h2ovmr, o3vmr, co2vmr, ch4vmr,
+             o2vmr, iceflgsw, liqflgsw, cld, ciwp, clwp, rei, rel, dyofyr, zm, alat, iaer, tauaer, ssaaer, asmaer,
+             asdir, asdif, aldir, aldif, cloudLM, cloudMH, normFlx, clearCounts, swuflx, swdflx, swuflxc, swdflxc,
+             nirr, nirf, parr, parf, uvrr, uvrf, fswband, cotdtp, cotdhp, cotdmp, cotdlp, cotntp, cotnhp, cotnmp,
+             cotnlp, do_drfband=False, drband=None, dfband=None, bndscl=None, indsolvar=None, solcycfrac=None, *,
+             device=False, stream=None, sync=True, skip_checks=False, taps=()):
+    """Drop-in for `rrtmg_sw` (SW/src/rrtmg_sw_rad.F90:68-124) without the MAPL handle (used by
+    the reference only for timers and asserts).  Outputs are written in place."""
+    if not _initialised:
+        init()
+    keep = []
+    a = SwArgs()
+    a.ncol, a.nlay, a.rpart, a.isolvar = int(ncol), int(nlay), int(rpart), int(isolvar)
+    a.iceflgsw, a.liqflgsw, a.dyofyr = int(iceflgsw), int(liqflgsw), int(dyofyr)
+    a.cloudLM, a.cloudMH, a.iaer = int(cloudLM), int(cloudMH), int(iaer)
+    a.normFlx, a.do_drfband = int(bool(normFlx)), int(bool(do_drfband))
+    a.flags = (DEVICE_PTRS if device else 0) | (0 if sync else NO_SYNC) | (SKIP_CHECKS if skip_checks else 0)
+    a.stream = stream
+    a.scon, a.adjes = float(scon), float(adjes)
+    for n, v, cnt in (("bndscl", bndscl, 14), ("indsolvar", indsolvar, 2), ("solcycfrac", solcycfrac, 1)):
+        if v is not None:
+            arr = np.ascontiguousarray(np.atleast_1d(v), dtype=np.float64)
+            assert arr.size == cnt
+            keep.append(arr)
+            setattr(a, n, arr.ctypes.data)
+    loc = locals()
+    for n in _SW_IN + _SW_OUT:
+        setattr(a, n, _addr(loc[n], device, keep=keep))
+    a.clearCounts = _addr(clearCounts, device, dtype=np.int32, keep=keep)
+    t, tout = (None, {})
+    if taps:
+        t, tout = _new_taps(taps, ncol, nlay, NGPTSW)
+        lib().rrtmgx_set_taps(None, C.byref(t))
+    try:
+        _check(lib().rrtmgx_sw_run(C.byref(a)))
+    finally:
+        if taps:
+            lib().rrtmgx_set_taps(None, None)
+    return tout
+
+
+def lw_status():
+    return lib().rrtmgx_lw_status()
+
+
+def sw_status():
+    return lib().rrtmgx_sw_status()
+
+
+def heating_rate(fnet_up_minus_down, plev, grav=9.80665, cp=1004.68506, device=False, stream=None, out=None):
+    """GEOS_RadiationGridComp.F90:798-819 (RADLW / RADSW) in K/day; arrays (ncol,nlay+1) -> (ncol,nlay)."""
+    if not _initialised:
+        init()
+    if device:
+        ncol, nlev = fnet_up_minus_down.shape[-1], fnet_up_minus_down.shape[0]   # torch [lev][col]
+    else:
+        ncol, nlev = fnet_up_minus_down.shape
+        if out is None:
+            out = np.zeros((ncol, nlev - 1), order="F")
+    _check(lib().rrtmgx_heating_rate(ncol, nlev - 1, _addr(fnet_up_minus_down, device), _addr(plev, device),
+                                     _addr(out, device), grav, cp, DEVICE_PTRS if device else 0, stream))
+    return out
+
+
+# ---- convenience wrappers over the synthetic-state dicts of synthetic.make_columns ---------------
+def alloc_lw_outputs(ncol, nlay):
+    o = {k: np.zeros((ncol, nlay + 1), order="F") for k in
+         ("uflx", "dflx", "uflxc", "dflxc", "duflx_dTs", "duflxc_dTs")}
+    o["olrb"] = np.zeros((16, ncol), order="F")
+    o["dolrb_dTs"] = np.zeros((16, ncol), order="F")
+    o["clearCounts"] = np.zeros((ncol, 4), dtype=np.int32, order="F")
+    return o
+
+
+def run_lw(s, psize=4, dudTs=True, iceflg=3, liqflg=1, taps=(), out=None, **kw):
+    """rrtmg_lw on a synthetic.make_columns state; returns the output dict (+ taps)."""
+    o = out if out is not None else alloc_lw_outputs(s["ncol"], s["nlay"])
+    t = rrtmg_lw(s["ncol"], s["nlay"], psize, dudTs, s["play"], s["plev"], s["tlay"], s["tlev"], s["tsfc"],
+                 s["emis"], s["h2ovmr"], s["o3vmr"], s["co2vmr"], s["ch4vmr"], s["n2ovmr"], s["o2vmr"],
+                 s["cfc11vmr"], s["cfc12vmr"], s["cfc22vmr"], s["ccl4vmr"], s["cldf"], s["ciwp"], s["clwp"],
+                 s["rei"], s["rel"], iceflg, liqflg, s["tauaer_lw"], s["zm"], s["alat"], s["dyofyr"],
+                 s["cloudLM"], s["cloudMH"], o["clearCounts"], o["uflx"], o["dflx"], o["uflxc"], o["dflxc"],
+                 o["duflx_dTs"], o["duflxc_dTs"], s["band_output"], o["olrb"], o["dolrb_dTs"], taps=taps, **kw)
+    o.update(t)
+    return o
+
+
+def alloc_sw_outputs(ncol, nlay):
+    o = {k: np.zeros((ncol, nlay + 1), order="F") for k in ("swuflx", "swdflx", "swuflxc", "swdflxc")}
+    for k in ("nirr", "nirf", "parr", "parf", "uvrr", "uvrf", "cotdtp", "cotdhp", "cotdmp", "cotdlp", "cotntp",
+              "cotnhp", "cotnmp", "cotnlp"):
+        o[k] = np.zeros(ncol)
+    for k in ("fswband", "drband", "dfband"):
+        o[k] = np.zeros((ncol, 14), order="F")
+    o["clearCounts"] = np.zeros((ncol, 4), dtype=np.int32, order="F")
+    return o
+
+
+def run_sw(s, rpart=0, isolvar=0, iceflg=3, liqflg=1, iaer=10, normFlx=1, do_drfband=False, taps=(), out=None,
+           bndscl=None, indsolvar=None, solcycfrac=None, **kw):
+    """rrtmg_sw on a synthetic.make_columns state; returns the output dict (+ taps)."""
+    o = out if out is not None else alloc_sw_outputs(s["ncol"], s["nlay"])
+    t = rrtmg_sw(rpart, s["ncol"], s["nlay"], s["scon"], s["adjes"], s["coszen"], isolvar, s["play"], s["plev"],
+                 s["tlay"], s["h2ovmr"], s["o3vmr"], s["co2vmr"], s["ch4vmr"], s["o2vmr"], iceflg, liqflg,
+                 s["cldf"], s["ciwp"], s["clwp"], s["rei"], s["rel"], s["dyofyr"], s["zm"], s["alat"], iaer,
+                 s["tauaer_sw"], s["ssaaer"], s["asmaer"], s["asdir"], s["asdif"], s["aldir"], s["aldif"],
+                 s["cloudLM"], s["cloudMH"], normFlx, o["clearCounts"], o["swuflx"], o["swdflx"], o["swuflxc"],
+                 o["swdflxc"], o["nirr"], o["nirf"], o["parr"], o["parf"], o["uvrr"], o["uvrf"], o["fswband"],
+                 o["cotdtp"], o["cotdhp"], o["cotdmp"], o["cotdlp"], o["cotntp"], o["cotnhp"], o["cotnmp"],
+                 o["cotnlp"], do_drfband, o["drband"], o["dfband"], bndscl, indsolvar, solcycfrac, taps=taps, **kw)
+    o.update(t)
+    return o

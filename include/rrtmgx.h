@@ -1,0 +1,176 @@
+/*
+ * rrtmgx.h -- C ABI of the B200-native RRTMG LW + SW + McICA column path.
+ *
+ * Drop-in boundary: these entry points are what a Fortran ISO_C_BINDING shim (see
+ * geosradiation_gridcomp_b200/fortran/ and INTEGRATION.md) binds to replace the bodies of
+ *   rrtmg_lw            GEOSirrad_GridComp/RRTMG/rrtmg_lw/gcm_model/src/rrtmg_lw_rad.F90:15-23
+ *   rrtmg_sw            GEOSsolar_GridComp/RRTMG/rrtmg_sw/gcm_model/src/rrtmg_sw_rad.F90:68-124
+ *   rrtmg_lw_ini        .../rrtmg_lw/gcm_model/src/rrtmg_lw_init.F90:22
+ *   rrtmg_sw_ini        .../rrtmg_sw/gcm_model/src/rrtmg_sw_init.F90:49
+ *   set_inhomogeneity   GEOS_RadiationShared/cloud_condensate_inhomogeneity.F90:45
+ *   initialize_cloud_subcol_gen  GEOS_RadiationShared/cloud_subcol_gen.F90:108
+ * called from GEOS_IrradGridComp.F90:3381,3471, GEOS_SolarGridComp.F90:6225,6331 and
+ * GEOS_RadiationGridComp.F90:565,578.
+ *
+ * All arrays are the caller's, in the reference layout: column-major with the COLUMN index
+ * fastest, x(ncol,nlay) -> x[icol + ncol*ilay]; layer 1 at the surface; fp64 ("real" promoted
+ * to 8 bytes, the precision contract of this build).  Pointers are HOST pointers unless
+ * RRTMGX_DEVICE_PTRS is set in `flags`, in which case every array pointer is a device pointer
+ * on the current CUDA device and no copies are made.  logical arguments are int32 (0/1).
+ *
+ * Every function returns 0 on success or a negative status that mirrors the reference trap
+ * (`error stop` in LW, _ASSERT/_FAIL -> RC in SW); rrtmgx_strerror() gives the message.
+ * There is no CPU fallback: without a CUDA device rrtmgx_init fails with RRTMGX_ENODEVICE.
+ */
+#ifndef RRTMGX_H
+#define RRTMGX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    RRTMGX_NBNDLW = 16, RRTMGX_NGPTLW = 140,   /* LW/modules/parrrtm.F90:39 */
+    RRTMGX_NBNDSW = 14, RRTMGX_NGPTSW = 112    /* SW/modules/parrrsw.F90:32 */
+};
+
+/* flags */
+enum {
+    RRTMGX_DEVICE_PTRS = 1,   /* array arguments are device pointers                         */
+    RRTMGX_NO_SYNC     = 2,   /* device pointers only: return without synchronising; status  */
+                              /* traps are then reported by rrtmgx_{lw,sw}_status()           */
+    RRTMGX_SKIP_CHECKS = 4    /* skip the negative-input scans (LW :209-318, SW :365-383)    */
+};
+
+/* status codes (negative) */
+enum {
+    RRTMGX_OK = 0,
+    RRTMGX_ENODEVICE = -1,      /* no CUDA device / CUDA error                               */
+    RRTMGX_ENOTINIT = -2,       /* rrtmgx_init not called                                    */
+    RRTMGX_EBLOB = -3,          /* table blob missing or malformed                           */
+    RRTMGX_EARG = -4,           /* bad scalar argument (ncol, nlay, flags ...)               */
+    RRTMGX_ECUDA = -5,          /* CUDA runtime failure during a run                         */
+    RRTMGX_EINHOMO = -6,        /* set_inhomogeneity: unknown ih                             */
+    RRTMGX_ESEEDORDER = -11,    /* cloud_subcol_gen.F90:273-300                              */
+    RRTMGX_ESUPERLAYER = -21,   /* cloud_subcol_gen.F90:762-766 'invalid pressure super-layers' */
+    RRTMGX_EPRESSURE = -31,     /* rrtmg_lw_setcoef.F90:445-453 'RRTMG LW pressure misordering' */
+    RRTMGX_EICEFLAG = -41,      /* cldprmc: invalid iceflag                                  */
+    RRTMGX_ERADIUS_ICE = -42,   /* cldprmc: ice radius extrapolation forbidden               */
+    RRTMGX_ELIQFLAG = -51,      /* cldprmc: invalid liqflag                                  */
+    RRTMGX_ERADIUS_LIQ = -52,   /* cldprmc: liquid radius extrapolation forbidden            */
+    RRTMGX_ESOLVAR = -61,       /* rrtmg_sw_rad.F90:910,1033,1117 bad isolvar / missing optional */
+    RRTMGX_ENEGATIVE = -100     /* -(100+k): k-th checked input array has a negative value   */
+};
+
+typedef struct {
+    const char *table_blob;   /* path of rrtmg_tables.bin; NULL -> $RRTMGX_TABLES or the     */
+                              /* file next to the library                                     */
+    int device;               /* CUDA device ordinal, -1 = current                            */
+    int inhomogeneity;        /* ih: 0 homogeneous, 1 beta (GEOS default), 2 gamma            */
+    const double *corr;       /* 8 correlation-length parameters or NULL for the defaults     */
+} RrtmgxConfig;
+
+/* rrtmg_lw_ini + rrtmg_sw_ini + set_inhomogeneity + initialize_cloud_subcol_gen.
+ * Idempotent (GEOS calls the _ini routines on every refresh). */
+int rrtmgx_init(const RrtmgxConfig *cfg);
+int rrtmgx_set_mcica(int ih, const double corr[8]);
+int rrtmgx_finalize(void);
+const char *rrtmgx_strerror(int status);
+/* number of kernels launched by this library since rrtmgx_init (bench.py gpu_launches) */
+long long rrtmgx_launch_count(void);
+
+typedef struct {
+    int ncol, nlay;
+    int psize;                /* accepted and ignored (cache blocking of the CPU code)        */
+    int dudTs;                /* logical                                                      */
+    int iceflglw, liqflglw;
+    int dyofyr, cloudLM, cloudMH;
+    int flags;
+    void *stream;             /* cudaStream_t or NULL for the library's LW stream             */
+    /* inputs */
+    const double *play, *plev, *tlay, *tlev;          /* (ncol,nlay) (ncol,0:nlay) ...        */
+    const double *tsfc, *emis;                        /* (ncol) (ncol,16)                     */
+    const double *h2ovmr, *o3vmr, *co2vmr, *ch4vmr, *n2ovmr, *o2vmr;
+    const double *cfc11vmr, *cfc12vmr, *cfc22vmr, *ccl4vmr;
+    const double *cldf, *ciwp, *clwp, *rei, *rel;     /* (ncol,nlay)                          */
+    const double *tauaer;                             /* (ncol,nlay,16)                       */
+    const double *zm, *alat;                          /* (ncol,nlay) (ncol)                   */
+    const int32_t *band_output;                       /* (16) logical                         */
+    /* outputs */
+    int32_t *clearCounts;                             /* (ncol,4)                             */
+    double *uflx, *dflx, *uflxc, *dflxc;              /* (ncol,nlay+1)                        */
+    double *duflx_dTs, *duflxc_dTs;                   /* (ncol,nlay+1), written iff dudTs     */
+    double *olrb, *dolrb_dTs;                         /* (16,ncol), bands with band_output    */
+} RrtmgxLwArgs;
+
+typedef struct {
+    int ncol, nlay;
+    int rpart;                /* accepted and ignored                                         */
+    int isolvar;              /* -1,0,1,2,3 (rrtmg_sw_rad.F90:889-1127)                       */
+    int iceflgsw, liqflgsw;
+    int dyofyr, cloudLM, cloudMH;
+    int iaer;                 /* 0 or 10                                                      */
+    int normFlx;              /* logical                                                      */
+    int do_drfband;           /* logical                                                      */
+    int flags;
+    void *stream;             /* cudaStream_t or NULL for the library's SW stream             */
+    double scon, adjes;
+    const double *bndscl;     /* (14) or NULL (absent optional)                               */
+    const double *indsolvar;  /* (2) or NULL                                                  */
+    const double *solcycfrac; /* scalar or NULL                                               */
+    /* inputs */
+    const double *coszen;                             /* (ncol)                               */
+    const double *play, *plev, *tlay;                 /* (ncol,nlay) (ncol,nlay+1) (ncol,nlay)*/
+    const double *h2ovmr, *o3vmr, *co2vmr, *ch4vmr, *o2vmr;
+    const double *cld, *ciwp, *clwp, *rei, *rel;
+    const double *zm, *alat;
+    const double *tauaer, *ssaaer, *asmaer;           /* (ncol,nlay,14)                       */
+    const double *asdir, *asdif, *aldir, *aldif;      /* (ncol)                               */
+    /* outputs */
+    int32_t *clearCounts;                             /* (ncol,4)                             */
+    double *swuflx, *swdflx, *swuflxc, *swdflxc;      /* (ncol,nlay+1)                        */
+    double *nirr, *nirf, *parr, *parf, *uvrr, *uvrf;  /* (ncol)                               */
+    double *fswband;                                  /* (ncol,14)                            */
+    double *cotdtp, *cotdhp, *cotdmp, *cotdlp;        /* (ncol)                               */
+    double *cotntp, *cotnhp, *cotnmp, *cotnlp;        /* (ncol)                               */
+    double *drband, *dfband;                          /* (ncol,14), touched iff do_drfband    */
+} RrtmgxSwArgs;
+
+int rrtmgx_lw_run(const RrtmgxLwArgs *a);
+int rrtmgx_sw_run(const RrtmgxSwArgs *a);
+/* status of the last RRTMGX_NO_SYNC run on that path (synchronises its stream) */
+int rrtmgx_lw_status(void);
+int rrtmgx_sw_status(void);
+
+/* Optional taps on device intermediates for parity tests; any pointer may be NULL.  Host
+ * pointers, filled (with a synchronisation) by the next rrtmgx_{lw,sw}_run. */
+typedef struct {
+    int32_t *jp, *jt, *jt1, *indfor, *indself, *indminor;   /* (ncol,nlay) 1-based           */
+    int32_t *laytrop;                                        /* (ncol)                        */
+    double *fac00, *fac01, *fac10, *fac11;                   /* (ncol,nlay)                   */
+    uint8_t *cldymc;          /* [ilay][ig][icol] optical cloud mask (taucmc > 0)             */
+    double *taucmc;           /* [ilay][ig][icol]; 0 where clear                              */
+    double *pwvcm;            /* (ncol) LW                                                    */
+    double *taug, *pfracs;    /* [ilay][ig][icol] LW gas optical depth incl. aerosol / Planck fraction; SW taug, taur */
+    double *ssi;              /* [ig][icol] SW                                                */
+} RrtmgxTaps;
+void rrtmgx_set_taps(const RrtmgxTaps *lw_taps, const RrtmgxTaps *sw_taps);
+
+/* GEOS_RadiationGridComp.F90:798-819 heating-rate epilogue (RADLW/RADSW):
+ * hr(l) = (F(l-1) - F(l)) * grav / (cp * (plev(l-1) - plev(l)))  with F = up - down flux at
+ * levels (ncol,nlay+1), level 0 at the surface, plev in hPa; result (ncol,nlay) in K/day.
+ * grav and cp are the caller's MAPL_GRAV and MAPL_CP.  Device or host pointers per flags. */
+int rrtmgx_heating_rate(int ncol, int nlay, const double *fnet_up_minus_down, const double *plev,
+                        double *hr_K_per_day, double grav, double cp, int flags, void *stream);
+
+/* reduced (post-cmbgb) host copies of tables for tests: kind "lw"/"sw", band as in the
+ * reference (1..16 / 16..29; 0 for band-independent), g-point fastest layout [lead][ng]. */
+const double *rrtmgx_table(const char *kind, const char *name, int band, int *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
