@@ -36,6 +36,7 @@ struct Path {   // per-path (LW or SW) execution resources
     int *d_err = nullptr;      // [0] trap code, [1] first negative-input position
     int last_status = 0;
     bool pending = false;
+    cudaStream_t run_stream = nullptr;   // stream of the last run (status is read behind it)
     RrtmgxTaps taps;
     bool has_taps = false;
 };
@@ -151,8 +152,9 @@ size_t pick_chunk(int ncol, int nlay, size_t per_col_bytes) {
 
 int status_from(Path &p) {
     int h[2];
-    if (!ok(cudaMemcpyAsync(h, p.d_err, sizeof h, cudaMemcpyDeviceToHost, p.stream))) return RRTMGX_ECUDA;
-    if (!ok(cudaStreamSynchronize(p.stream))) { cudaGetLastError(); return RRTMGX_ECUDA; }
+    cudaStream_t st = p.run_stream ? p.run_stream : p.stream;
+    if (!ok(cudaMemcpyAsync(h, p.d_err, sizeof h, cudaMemcpyDeviceToHost, st))) return RRTMGX_ECUDA;
+    if (!ok(cudaStreamSynchronize(st))) { cudaGetLastError(); return RRTMGX_ECUDA; }
     p.pending = false;
     if (h[1] < (1 << 30)) return RRTMGX_ENEGATIVE - 1 - h[1];   // -(101 + position)
     return h[0];
@@ -383,8 +385,10 @@ int rrtmgx_lw_run(const RrtmgxLwArgs *a) {
     const bool dbg = taps && (taps->taug || taps->pfracs);
     const size_t per_col = lw_scratch_bytes(1024, nlay, dbg) / 1024;
     size_t chunk = pick_chunk(ncol, nlay, per_col + (devptr ? 0 : 2 * (size_t)(37 * nlay + 60) * 8));
+    if (taps) chunk = (size_t)ncol;   // taps are laid out for the whole call
     if (int rc = grow(p.slab, lw_scratch_bytes((int)chunk, nlay, dbg))) return rc;
     cudaStream_t stream = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
+    p.run_stream = stream;
     if (!ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, stream))) return RRTMGX_ECUDA;
 
     auto run_chunks_device = [&](const RrtmgxLwArgs &da) -> int {

@@ -535,7 +535,8 @@ __device__ __forceinline__ void lw_band_layer(const Lay &L, bool lower, double p
     // nspa = 1 1 9 9 9 1 9 1 9 1 1 9 9 1 9 9 ; nspb = 1 1 5 5 5 0 1 1 1 1 1 0 0 1 0 0 (rrtmg_lw_init.F90:194-195)
     constexpr int nspa = (BAND == 3 || BAND == 4 || BAND == 5 || BAND == 7 || BAND == 9 || BAND == 12 ||
                           BAND == 13 || BAND == 15 || BAND == 16) ? 9 : 1;
-    constexpr int nspb = (BAND == 3 || BAND == 4 || BAND == 5) ? 5 : 1;
+    // band 16 multiplies its upper-atmosphere index by nspb(16) = 0, i.e. always reads rows 1,2
+    constexpr int nspb = (BAND == 3 || BAND == 4 || BAND == 5) ? 5 : (BAND == 16 ? 0 : 1);
     const int ind0lo = ((L.jp - 1) * 5 + (L.jt - 1)) * nspa;
     const int ind1lo = (L.jp * 5 + (L.jt1 - 1)) * nspa;
     const int ind0up = ((L.jp - 13) * 5 + (L.jt - 1)) * nspb;

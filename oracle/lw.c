@@ -359,7 +359,9 @@ typedef struct {
 #define TAUG(ig) c->taug[(lay - 1) + (size_t)c->nlay * ((ig)-1)]
 #define PFR(ig) c->pfracs[(lay - 1) + (size_t)c->nlay * ((ig)-1)]
 #define ABSA_G(B, ig) ((B)->absa + (size_t)65 * (B)->nspa * ((ig)-1))
-#define ABSB_G(B, ig) ((B)->absb + (size_t)235 * (B)->nspb * ((ig)-1))
+/* absb(235*nspb, ng); band 16 has nspb = 0 in rrtmg_lw_init.F90:195 yet carries a 235-row kb,
+ * so its ind0/ind1 collapse to 1 while the g stride stays 235 (taugb16 :3109-3110) */
+#define ABSB_G(B, ig) ((B)->absb + (size_t)235 * ((B)->nspb ? (B)->nspb : 1) * ((ig)-1))
 #define IND0_LO(nsp) (((A(jp) - 1) * 5 + (A(jt) - 1)) * (nsp))
 #define IND1_LO(nsp) ((A(jp) * 5 + (A(jt1) - 1)) * (nsp))
 #define IND0_UP(nsp) (((A(jp) - 13) * 5 + (A(jt) - 1)) * (nsp))
