@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- columns/s of RRTMG LW+SW with McICA on synthetic C180 L72 columns.
+
+One "step" = one rrtmg_lw call + one rrtmg_sw call (McICA subcolumns, cloud optics, gas
+optics, radiative transfer) over the same batch of columns, i.e. one radiation refresh of the
+GEOS Run phase.  The workload at N=1 is BASELINE.json configs[2]: the full C180
+cube-sphere, 194 400 columns x 72 layers; at N>1 every rank owns its own 194 400-column slab
+of a larger grid (weak scaling, no data-path collective; columns are independent).
+
+  value     whole-job columns/s with every boundary array already resident in HBM
+  e2e       the same metric through the C ABI with HOST (pinned) arrays: the library stages
+            chunks host->device, computes, and copies the fluxes back inside the timed region
+  roofline  algorithmic boundary bytes per column (59 560 B at L72)
+            x columns / device time against the measured HBM copy bandwidth
+  cpu_baseline  the C oracle (oracle/, the CPU restatement of the reference Fortran; the
+            reference itself cannot be compiled here: no Fortran compiler) on a bounded sample
+
+`--impl reference` times the oracle port alone on the host cores (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "columns/s RRTMG LW+SW (C180 L72, McICA)"
+UNIT = "columns/s"
+
+
+def algorithmic_bytes_per_column(nlay):
+    """every boundary input read once, every output written once, fp64."""
+    lw = (36 * nlay + 20) * 8 + (6 * (nlay + 1) + 32) * 8 + 16
+    sw = (56 * nlay + 7) * 8 + (4 * (nlay + 1) + 28) * 8 + 16
+    return lw, sw
+
+
+def _gen_slab(args):
+    from geosradiation_gridcomp_b200.synthetic import make_columns
+    ncol, nlay, seed, col0 = args
+    return make_columns(ncol, nlay, seed=seed, col0=col0)
+
+
+def make_state(ncol, nlay, seed, col0, workers):
+    """synthetic.make_columns for [col0, col0+ncol), generated in slabs by a process pool (the
+    generator is a pure function of (seed, global column index))."""
+    from geosradiation_gridcomp_b200.synthetic import make_columns
+    slab = 8192
+    if ncol <= slab or workers <= 1:
+        return make_columns(ncol, nlay, seed=seed, col0=col0)
+    jobs = [(min(slab, ncol - c), nlay, seed, col0 + c) for c in range(0, ncol, slab)]
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
+        parts = pool.map(_gen_slab, jobs)
+    out = dict(parts[0])
+    for k, v in parts[0].items():
+        if isinstance(v, np.ndarray) and v.dtype == np.float64 and v.ndim >= 1 and v.shape[0] == parts[0]["ncol"]:
+            out[k] = np.asfortranarray(np.concatenate([p[k] for p in parts], axis=0))
+    out["ncol"] = ncol
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.2)] or \
+               [r for (_, r) in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(sample_cols, nlay, seed, with_sw):
+    """columns/s of the oracle port (all host threads) on a bounded sample of the workload."""
+    from oracle import binding as oracle
+    s = make_state(sample_cols, nlay, seed, 0, 1)
+    oracle.lib()
+    t0 = time.perf_counter()
+    r = oracle.rrtmg_lw(s)
+    assert r["rc"] == 0
+    if with_sw:
+        r = oracle.rrtmg_sw(s)
+        assert r["rc"] == 0
+    dt = time.perf_counter() - t0
+    return sample_cols / dt, oracle.num_threads(), dt
+
+
+def oracle_has_sw():
+    from oracle import binding as oracle
+    return hasattr(oracle.lib(), "oracle_rrtmg_sw") and os.path.exists(os.path.join(ROOT, "oracle", "sw.c"))
+
+
+def run_reference(a):
+    """--impl reference: the CPU implementation of the path (oracle port; the Fortran reference
+    cannot be built in this image) with all host threads, each step a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    with_sw = oracle_has_sw()
+    sample = a.cpu_sample
+    rates, secs = [], []
+    for i in range(a.warmup + a.steps):
+        r, threads, dt = cpu_oracle_rate(sample, a.nlay, a.seed + i, with_sw)
+        if i >= a.warmup:
+            rates.append(r); secs.append(dt)
+    v = sample * len(secs) / sum(secs)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a, with_sw),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} columns x L{a.nlay} per step, {'LW+SW' if with_sw else 'LW only'}, "
+                                   f"OpenMP over column partitions"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, with_sw):
+    return {"workload": f"RRTMG {'LW+SW' if with_sw else 'LW (SW not built)'} with McICA, C180 cube-sphere "
+                        f"{a.ncol} columns x L{a.nlay} per GPU, all columns sunlit, 40% clear-sky columns",
+            "ncol_per_gpu": a.ncol, "nlay": a.nlay, "ngpt_lw": 140, "ngpt_sw": 112,
+            "l2_policy": "inputs (>10 GB per step) far exceed the 126 MB L2; no explicit flush",
+            "precision": "fp64 boundary arrays and arithmetic (promoted-real contract)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ncol", type=int, default=194400, help="columns per GPU (C180 = 6*180^2)")
+    ap.add_argument("--nlay", type=int, default=72)
+    ap.add_argument("--seed", type=int, default=20260121)
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="columns in the CPU baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    if a.warmup < 3 and a.impl == "b200":
+        a.warmup = max(a.warmup, 1)
+
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import geosradiation_gridcomp_b200 as pkg
+    from geosradiation_gridcomp_b200 import devstate, host
+    pkg.init(device=local)
+    with_sw = os.path.exists(os.path.join(ROOT, "geosradiation_gridcomp_b200", "csrc", "sw.cu"))
+
+    ncol, nlay = a.ncol, a.nlay
+    workers = max(1, (os.cpu_count() or 8) // max(world, 1))
+    s = make_state(ncol, nlay, a.seed, rank * ncol, min(workers, 16))
+
+    # ---- device-resident arm ------------------------------------------------------------------
+    d = devstate.to_device(s)
+    o = devstate.alloc_outputs(ncol, nlay)
+    st_lw, st_sw = torch.cuda.Stream(), torch.cuda.Stream()
+    run_lw = devstate.lw_runner(d, o, device=True, sync=False, stream=st_lw.cuda_stream)
+    run_sw = devstate.sw_runner(d, o, device=True, sync=False, stream=st_sw.cuda_stream) if with_sw else None
+    cur = torch.cuda.current_stream()
+
+    def step():
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        st_lw.wait_event(ev)
+        run_lw()
+        if run_sw:
+            st_sw.wait_event(ev)
+            run_sw()
+        cur.wait_stream(st_lw)
+        if run_sw:
+            cur.wait_stream(st_sw)
+
+    def check():
+        rc = host.lw_status()
+        if rc:
+            raise SystemExit(f"rrtmgx_lw_run failed: {rc}")
+        if run_sw:
+            rc = host.sw_status()
+            if rc:
+                raise SystemExit(f"rrtmgx_sw_run failed: {rc}")
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    check()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = host.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record(cur)
+    for _ in range(a.steps):
+        step()
+    e1.record(cur)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    check()
+    launches = host.launch_count() - n0
+    dev_ms = e0.elapsed_time(e1)
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dev_ms = float(tmax.item())
+    clocks = sampler.stop(t0, t1) if sampler else None
+    value = world * ncol * a.steps / (dev_ms * 1e-3)
+
+    # ---- end-to-end arm: host (pinned) arrays through the C ABI --------------------------------
+    e2e = None
+    if not a.no_e2e:
+        del d
+        torch.cuda.empty_cache()
+        hp = devstate.to_device(s, pinned=True)
+        ho = devstate.alloc_outputs(ncol, nlay, pinned=True)
+        h_lw = devstate.lw_runner(hp, ho, device=False)
+        h_sw = devstate.sw_runner(hp, ho, device=False) if with_sw else None
+        th = None
+
+        def e2e_step():
+            # LW and SW calls are independent; issue them from two host threads (the library
+            # pipelines H2D / compute / D2H per path on its own streams)
+            if h_sw:
+                t = threading.Thread(target=h_sw)
+                t.start()
+                h_lw()
+                t.join()
+            else:
+                h_lw()
+        e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n_e2e = max(1, min(a.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        lwb, swb = algorithmic_bytes_per_column(nlay)
+        h2d = ((36 * nlay + 20) * 8 + ((56 * nlay + 7) * 8 if with_sw else 0)) * ncol
+        d2h = ((6 * (nlay + 1) + 32) * 8 + 16 + (((4 * (nlay + 1) + 28) * 8 + 16) if with_sw else 0)) * ncol
+        e2e = {"value": world * ncol * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
+               "how": "C-ABI calls with pinned host arrays; chunked H2D, kernels and D2H inside the timed region"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    lwb, swb = algorithmic_bytes_per_column(nlay)
+    bpc = lwb + (swb if with_sw else 0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = (value / world) * bpc / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)",
+                "kernel": "whole step (all LW+SW kernels of one refresh); per-kernel figures in profiles/",
+                "algorithmic_bytes_per_column": bpc,
+                "note": "fp64-pipe-bound path: see DESIGN.md for the FP64 roof beside the HBM roof"}
+    cpu = None
+    if not a.no_cpu:
+        r, threads, dt = cpu_oracle_rate(a.cpu_sample, nlay, a.seed, with_sw and oracle_has_sw())
+        cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{a.cpu_sample} columns x L{nlay} of the same synthetic workload, "
+                         f"{'LW+SW' if with_sw else 'LW only'}, {dt:.1f} s"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(a, with_sw),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

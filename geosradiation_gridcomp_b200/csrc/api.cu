@@ -489,6 +489,97 @@ int rrtmgx_heating_rate(int ncol, int nlay, const double *fnet_up_minus_down, co
 
 #ifndef RRTMGX_WITH_SW
 int rrtmgx_sw_run(const RrtmgxSwArgs *) { return RRTMGX_EARG; }
+#else
+int rrtmgx_sw_run(const RrtmgxSwArgs *a) {
+    if (!g.ready) return RRTMGX_ENOTINIT;
+    if (!a || a->ncol <= 0 || a->nlay <= 1 || a->nlay > 1000) return RRTMGX_EARG;
+    if (a->cloudLM == a->cloudMH) return RRTMGX_ESUPERLAYER;   // cloud_subcol_gen.F90:762-766
+    if (a->iceflgsw < 1 || a->iceflgsw > 4) return RRTMGX_EICEFLAG;
+    if (a->liqflgsw != 1) return RRTMGX_ELIQFLAG;
+    Path &p = g.sw;
+    const bool devptr = a->flags & RRTMGX_DEVICE_PTRS;
+    if ((a->flags & RRTMGX_NO_SYNC) && !devptr) return RRTMGX_EARG;
+    SwSolar sol;
+    if (int rc = sw_solar_setup(a, g.ht, &sol)) return rc;   // rrtmg_sw_sub :889-1127
+    const int ncol = a->ncol, nlay = a->nlay;
+    if (int rc = ensure_jumps(p, 112, nlay)) return rc;
+    static const int seed_order[4] = {4, 3, 2, 1};   // SW/src/rrtmg_sw_rad.F90:1395-1400
+    const McicaParams mp = mcica_params(g.mc, dev_table("mcica.xcw_beta"), dev_table("mcica.xcw_gamma"), a->dyofyr,
+                                        seed_order);
+    const RrtmgxTaps *taps = p.has_taps ? &p.taps : nullptr;
+    const bool dbg = taps && (taps->taug || taps->pfracs || taps->ssi);
+    const size_t per_col = sw_scratch_bytes(1024, nlay, dbg) / 1024;
+    size_t chunk = pick_chunk(ncol, nlay, per_col + (devptr ? 0 : 2 * (size_t)(57 * nlay + 60) * 8));
+    if (taps) chunk = (size_t)ncol;   // taps are laid out for the whole call
+    if (int rc = grow(p.slab, sw_scratch_bytes((int)chunk, nlay, dbg))) return rc;
+    cudaStream_t stream = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
+    p.run_stream = stream;
+    if (!ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, stream))) return RRTMGX_ECUDA;
+
+    auto run_chunks_device = [&](const RrtmgxSwArgs &da) -> int {
+        const int n = da.ncol;
+        if (!(da.flags & RRTMGX_SKIP_CHECKS)) {   // _ASSERTs :365-383 in the reference's order
+            const size_t n2 = (size_t)n * nlay, n2p = (size_t)n * (nlay + 1);
+            struct { const double *x; size_t cnt; } chk[] = {
+                {da.play, n2}, {da.plev, n2p}, {da.tlay, n2}, {da.h2ovmr, n2}, {da.o3vmr, n2}, {da.co2vmr, n2},
+                {da.ch4vmr, n2}, {da.o2vmr, n2}, {da.asdir, (size_t)n}, {da.aldir, (size_t)n}, {da.asdif, (size_t)n},
+                {da.aldif, (size_t)n}, {da.cld, n2}, {da.ciwp, n2}, {da.clwp, n2}, {da.rei, n2}, {da.rel, n2},
+                {da.tauaer, n2 * 14}, {da.ssaaer, n2 * 14}};
+            for (int i = 0; i < (int)(sizeof chk / sizeof chk[0]); ++i)
+                launch_check_negative(chk[i].x, chk[i].cnt, i, p.d_err + 1, stream);
+        }
+        for (size_t col0 = 0; col0 < (size_t)n; col0 += chunk) {
+            const int nc = (int)std::min(chunk, (size_t)n - col0);
+            if (int rc = sw_run_chunk(&da, sol, (int)col0, nc, mp, p.d_jumps, p.slab, p.d_err, stream, p.side, NSIDE,
+                                      p.ev, taps, p.d_err + 1))
+                return rc;
+        }
+        return 0;
+    };
+
+    if (devptr) {
+        if (int rc = run_chunks_device(*a)) return rc;
+        p.pending = true;
+        if (a->flags & RRTMGX_NO_SYNC) return 0;
+        p.last_status = status_from(p);
+        return p.last_status;
+    }
+
+    RrtmgxSwArgs ca = *a;
+    std::vector<Arr> arrs;
+    const size_t L = nlay, L1 = nlay + 1;
+    auto in = [&](const double *const &field, const double **slot, size_t rows) {
+        arrs.push_back({field, (void **)slot, rows, 8, false, true, false});
+    };
+    auto out = [&](double *const &field, double **slot, size_t rows) {
+        arrs.push_back({field, (void **)slot, rows, 8, false, false, true});
+    };
+    in(a->coszen, &ca.coszen, 1); in(a->play, &ca.play, L); in(a->plev, &ca.plev, L1); in(a->tlay, &ca.tlay, L);
+    in(a->h2ovmr, &ca.h2ovmr, L); in(a->o3vmr, &ca.o3vmr, L); in(a->co2vmr, &ca.co2vmr, L);
+    in(a->ch4vmr, &ca.ch4vmr, L); in(a->o2vmr, &ca.o2vmr, L);
+    in(a->cld, &ca.cld, L); in(a->ciwp, &ca.ciwp, L); in(a->clwp, &ca.clwp, L); in(a->rei, &ca.rei, L);
+    in(a->rel, &ca.rel, L); in(a->zm, &ca.zm, L); in(a->alat, &ca.alat, 1);
+    in(a->tauaer, &ca.tauaer, L * 14); in(a->ssaaer, &ca.ssaaer, L * 14); in(a->asmaer, &ca.asmaer, L * 14);
+    in(a->asdir, &ca.asdir, 1); in(a->asdif, &ca.asdif, 1); in(a->aldir, &ca.aldir, 1); in(a->aldif, &ca.aldif, 1);
+    arrs.push_back({a->clearCounts, (void **)&ca.clearCounts, 4, 4, false, false, true});
+    out(a->swuflx, &ca.swuflx, L1); out(a->swdflx, &ca.swdflx, L1); out(a->swuflxc, &ca.swuflxc, L1);
+    out(a->swdflxc, &ca.swdflxc, L1);
+    out(a->nirr, &ca.nirr, 1); out(a->nirf, &ca.nirf, 1); out(a->parr, &ca.parr, 1); out(a->parf, &ca.parf, 1);
+    out(a->uvrr, &ca.uvrr, 1); out(a->uvrf, &ca.uvrf, 1); out(a->fswband, &ca.fswband, 14);
+    out(a->cotdtp, &ca.cotdtp, 1); out(a->cotdhp, &ca.cotdhp, 1); out(a->cotdmp, &ca.cotdmp, 1);
+    out(a->cotdlp, &ca.cotdlp, 1); out(a->cotntp, &ca.cotntp, 1); out(a->cotnhp, &ca.cotnhp, 1);
+    out(a->cotnmp, &ca.cotnmp, 1); out(a->cotnlp, &ca.cotnlp, 1);
+    if (a->do_drfband) { out(a->drband, &ca.drband, 14); out(a->dfband, &ca.dfband, 14); }
+    int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxSwArgs &c, int nc) -> int {
+        (void)nc;
+        c.flags |= RRTMGX_DEVICE_PTRS;
+        return run_chunks_device(c);
+    });
+    if (rc) return rc;
+    p.pending = true;
+    p.last_status = status_from(p);
+    return p.last_status;
+}
 #endif
 
 }  // extern "C"

@@ -58,8 +58,11 @@ size_t sw_scratch_bytes(int nc, int nlay, bool debug);
 struct SwSolar {                  // host-evaluated scalars of rrtmg_sw_sub :889-1127
     double adjflux[14];           // adjes (* solvar) per band
     double svar_f, svar_s, svar_i;
+    double svar_bnd[14];          // isolvar == 3: one multiplier per band for all three terms
     int isolvar;
 };
+// rrtmg_sw_sub :889-1127 + NRLSSI2.F90 (host scalars only); 0 or RRTMGX_ESOLVAR
+int sw_solar_setup(const RrtmgxSwArgs *a, const HostTables &ht, SwSolar *out);
 int sw_run_chunk(const RrtmgxSwArgs *a, const SwSolar &sol, int col0, int nc, const McicaParams &mp,
                  const KissJump *d_jumps, Slab &slab, int *d_err, cudaStream_t stream,
                  cudaStream_t *side, int nside, cudaEvent_t *ev, const RrtmgxTaps *taps, int *d_negpos);

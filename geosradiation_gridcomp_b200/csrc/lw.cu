@@ -332,6 +332,8 @@ struct LwOptics {
     const double *reice, *reliq;   // caller arrays (ld, nlay)
     int iceflag, liqflag;
     double *taucmc;                // [nlay][140][nc]
+    struct State {};
+    __device__ __forceinline__ void finish(int, int, State &) const {}
 
     // index clamp / extrapolation traps shared by iceflag 2,3,4 and liqflag 1 (:227-268,:318-360)
     __device__ __forceinline__ bool lookup_index(double factor, int hi, int &index) const {
@@ -348,7 +350,7 @@ struct LwOptics {
     // Called for every McICA-cloudy cell.  The reference derives the radius table indices (and
     // traps out-of-range radii) for every layer with at least one such cell, whichever phase
     // holds water (:193-205, :227-268, :318-360), so both indices are derived here up front.
-    __device__ __forceinline__ bool cell(int lay, int ig, int c, double ciw, double clw, int *err) const {
+    __device__ __forceinline__ bool cell(int lay, int ig, int c, double ciw, double clw, int *err, State &) const {
         const size_t i2 = (size_t)lay * ld + col0 + c;
         const int ib = c_lw.ngb[ig];   // 1-based band
         const double re = reice[i2];

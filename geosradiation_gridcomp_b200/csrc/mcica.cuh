@@ -82,7 +82,7 @@ __device__ __forceinline__ double zcw_lookup(const double *__restrict__ xcw, dou
 // pressures (:375-400) and the inter-layer overlap / condensate correlations (:314-321).
 // Inputs are the caller's arrays (leading dimension ld, first column col0); outputs are
 // chunk-local [..][nc].
-__global__ void mcica_prep_kernel(int ld, int col0, int nc, int nlay, McicaParams P,
+static __global__ void mcica_prep_kernel(int ld, int col0, int nc, int nlay, McicaParams P,
                                   const double *__restrict__ zm, const double *__restrict__ play,
                                   const double *__restrict__ alat,
                                   uint32_t *__restrict__ seeds,   // [4][nc]
@@ -126,9 +126,10 @@ __global__ void mcica_prep_kernel(int ld, int col0, int nc, int nlay, McicaParam
     }
 }
 
-// One thread per (column, subcolumn).  Optics::cell(lay, isub, c, ciwp, clwp, err) turns the
-// stochastic water paths of a McICA-cloudy cell into cloud optical properties, stores them, and
-// returns whether the cell is optically cloudy.  Outputs: clearCounts (caller layout
+// One thread per (column, subcolumn).  Optics::cell(lay, isub, c, ciwp, clwp, err, state) turns
+// the stochastic water paths of a McICA-cloudy cell into cloud optical properties, stores them,
+// and returns whether the cell goes into the cloud mask; Optics::State is per-thread scratch
+// carried along the layer sweep and handed to Optics::finish(isub, c, state) at the end.  Outputs: clearCounts (caller layout
 // (ncol,4), integer atomics, so deterministic), the optical cloud mask bit-packed over layers
 // [nw][nsub][nc] and its OR over subcolumns cloudy_any [nw][nc] (the reference's
 // cloudy(lay,col) after cldprmc).
@@ -158,6 +159,7 @@ mcica_kernel(int ld, int col0, int nc, int nlay, int nsub, McicaParams P,
     bool any_all = false, any_low = false, any_mid = false, any_high = false;
     double cdf1 = 0., cdf3 = 0.;
     uint32_t word = 0;
+    typename Optics::State ost{};
     for (int k = 0; k < nlay; ++k) {
         const size_t i2 = (size_t)k * ld + col;
         const size_t j2 = (size_t)k * nc + c;
@@ -197,7 +199,7 @@ mcica_kernel(int ld, int col0, int nc, int nlay, int nsub, McicaParams P,
                     else if (lay1 < cloudLM) any_mid = true;
                     else any_low = true;
                 }
-                optical = opt.cell(k, isub, c, ciw, clw, err);
+                optical = opt.cell(k, isub, c, ciw, clw, err, ost);
             }
         }
         if (optical) word |= 1u << (k & 31);
@@ -208,6 +210,7 @@ mcica_kernel(int ld, int col0, int nc, int nlay, int nsub, McicaParams P,
             word = 0;
         }
     }
+    opt.finish(isub, c, ost);
     if (!any_all) atomicAdd(&clearCounts[col], 1);
     if (!any_high) atomicAdd(&clearCounts[(size_t)ld + col], 1);
     if (!any_mid) atomicAdd(&clearCounts[(size_t)2 * ld + col], 1);

@@ -81,6 +81,19 @@ def table(kind, name, band=0):
     return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
 
 
+_keep = []
+
+
+def _opt(v, n):
+    """optional real argument (absent -> NULL)"""
+    if v is None:
+        return None
+    a = np.ascontiguousarray(np.atleast_1d(v), dtype=np.float64)
+    assert a.size == n
+    _keep[:] = _keep[-8:] + [a]
+    return a.ctypes.data_as(_dp)
+
+
 def _make_taps(want, ncol, nlay, ngpt):
     """Allocate the requested tap arrays; returns (struct, dict of numpy arrays)."""
     if not want:
@@ -135,7 +148,7 @@ def rrtmg_lw(s, psize=4, dudTs=True, iceflg=3, liqflg=1, taps=()):
 
 
 def rrtmg_sw(s, rpart=0, isolvar=0, iceflg=3, liqflg=1, iaer=10, normFlx=1, do_drfband=False,
-             taps=()):
+             taps=(), bndscl=None, indsolvar=None, solcycfrac=None):
     ncol, nlay = s["ncol"], s["nlay"]
     o = {k: np.zeros((ncol, nlay + 1), order="F") for k in ("swuflx", "swdflx", "swuflxc", "swdflxc")}
     for k in ("nirr", "nirf", "parr", "parf", "uvrr", "uvrf", "cotdtp", "cotdhp", "cotdmp", "cotdlp",
@@ -161,7 +174,7 @@ def rrtmg_sw(s, rpart=0, isolvar=0, iceflg=3, liqflg=1, iaer=10, normFlx=1, do_d
         _d(o["parf"]), _d(o["uvrr"]), _d(o["uvrf"]), _d(o["fswband"]), _d(o["cotdtp"]),
         _d(o["cotdhp"]), _d(o["cotdmp"]), _d(o["cotdlp"]), _d(o["cotntp"]), _d(o["cotnhp"]),
         _d(o["cotnmp"]), _d(o["cotnlp"]), C.c_int(int(do_drfband)), _d(o["drband"]), _d(o["dfband"]),
-        None, None, None, C.byref(t) if t is not None else None)
+        _opt(bndscl, 14), _opt(indsolvar, 2), _opt(solcycfrac, 1), C.byref(t) if t is not None else None)
     o["rc"] = rc
     o.update(tout)
     return o
