@@ -178,3 +178,48 @@ def rrtmg_sw(s, rpart=0, isolvar=0, iceflg=3, liqflg=1, iaer=10, normFlx=1, do_d
     o["rc"] = rc
     o.update(tout)
     return o
+
+
+def rng_kiss(seeds, n):
+    """n draws of the reference KISS generator (SH/cloud_subcol_gen.F90:546-607) from 4 int32 seeds;
+    returns (draws, final seeds)."""
+    L = lib()
+    s = [C.c_int(int(np.int32(v))) for v in seeds]
+    out = np.zeros(n)
+    r = C.c_double(0.)
+    for i in range(n):
+        L.oracle_rng_kiss(C.byref(s[0]), C.byref(s[1]), C.byref(s[2]), C.byref(s[3]), C.byref(r))
+        out[i] = r.value
+    return out, [v.value for v in s]
+
+
+def generate_stochastic_clouds(zmid, alat, doy, play, cldfrac, ciwp, clwp, nsubcol, seed_order=(1, 2, 3, 4),
+                               cwp_tiny=1e-20):
+    """Stand-alone McICA generator on (nlay,ncol) partition-layout arrays; returns
+    (cldy_stoch uint8, ciwp_stoch, clwp_stoch), each (nlay,nsubcol,ncol) Fortran order."""
+    nlay, ncol = play.shape
+    cl = np.zeros((nlay, nsubcol, ncol), dtype=np.uint8, order="F")
+    ci = np.zeros((nlay, nsubcol, ncol), order="F")
+    cw = np.zeros((nlay, nsubcol, ncol), order="F")
+    so = np.ascontiguousarray(seed_order, dtype=np.int32)
+    f = lambda a: np.asfortranarray(a, dtype=np.float64)
+    zmid, play, cldfrac, ciwp, clwp = map(f, (zmid, play, cldfrac, ciwp, clwp))
+    alat = np.ascontiguousarray(alat, dtype=np.float64)
+    rc = lib().oracle_generate_stochastic_clouds(
+        C.c_int(ncol), C.c_int(ncol), C.c_int(nsubcol), C.c_int(nlay), _d(zmid), alat.ctypes.data_as(_dp),
+        C.c_int(doy), _d(play), _d(cldfrac), _d(ciwp), _d(clwp), C.c_double(cwp_tiny),
+        cl.ctypes.data_as(_up), _d(ci), _d(cw), so.ctypes.data_as(_ip))
+    if rc:
+        raise RuntimeError(f"generate_stochastic_clouds: {rc}")
+    return cl, ci, cw
+
+
+def clear_counts(cldy_stoch, cloudLM, cloudMH):
+    nlay, nsub, ncol = cldy_stoch.shape
+    out = np.zeros((4, ncol), dtype=np.int32, order="F")
+    rc = lib().oracle_clearCounts_threeBand(C.c_int(ncol), C.c_int(ncol), C.c_int(nsub), C.c_int(nlay),
+                                            C.c_int(cloudLM), C.c_int(cloudMH),
+                                            np.asfortranarray(cldy_stoch).ctypes.data_as(_up), out.ctypes.data_as(_ip))
+    if rc:
+        raise RuntimeError(f"clearCounts_threeBand: {rc}")
+    return out

@@ -1,0 +1,85 @@
+"""The C-ABI library loads and exports every symbol include/rrtmgx.h declares; without a GPU the
+product path refuses to run (no CPU fallback).  No compute calls are made here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "rrtmgx.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rrtmgx_[a-z_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported():
+    from geosradiation_gridcomp_b200 import host
+    lib = host.lib()
+    names = declared_functions()
+    assert {"rrtmgx_init", "rrtmgx_lw_run", "rrtmgx_sw_run", "rrtmgx_finalize", "rrtmgx_set_mcica",
+            "rrtmgx_heating_rate", "rrtmgx_strerror", "rrtmgx_launch_count"} <= set(names)
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_struct_mirrors_match_header_field_order():
+    """host.LwArgs / host.SwArgs must list the fields in the header's order (ctypes mirrors)."""
+    from geosradiation_gridcomp_b200 import host
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for cname, mirror in (("RrtmgxLwArgs", host.LwArgs), ("RrtmgxSwArgs", host.SwArgs), ("RrtmgxTaps", host.Taps)):
+        body = re.search(r"typedef struct \{((?:(?!typedef struct).)*?)\} %s;" % cname, src, flags=re.S).group(1)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            decl = re.sub(r"^(const\s+)?(double|int32_t|int|void|uint8_t)\s*", "", decl)
+            fields += [f.strip().lstrip("*").strip() for f in decl.split(",")]
+        assert fields == [f[0] for f in mirror._fields_], cname
+
+
+def test_no_cpu_fallback():
+    import torch
+    from geosradiation_gridcomp_b200 import host
+    lib = host.lib()
+    assert lib.rrtmgx_strerror(-1).decode().startswith("no usable CUDA device")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the refusal path cannot be exercised")
+    args = host.LwArgs()
+    assert lib.rrtmgx_lw_run(C.byref(args)) == -2          # RRTMGX_ENOTINIT
+    sargs = host.SwArgs()
+    assert lib.rrtmgx_sw_run(C.byref(sargs)) == -2
+    cfg = host.Config()
+    cfg.device = -1
+    cfg.inhomogeneity = 1
+    assert lib.rrtmgx_init(C.byref(cfg)) == -1              # RRTMGX_ENODEVICE
+    with pytest.raises(host.RrtmgxError):
+        host.init()
+
+
+def test_host_mirror_rejects_wrong_layout():
+    from geosradiation_gridcomp_b200 import host
+    a = np.zeros((4, 3))                                    # C order, not the reference layout
+    with pytest.raises(ValueError):
+        host._addr(a, False)
+    with pytest.raises(ValueError):
+        host._addr(np.zeros((4, 3), dtype=np.float32, order="F"), False)
+    with pytest.raises(ValueError):
+        host._addr(np.zeros(4), True)                       # device=True needs device memory
+    assert host._addr(np.zeros((4, 3), order="F"), False) != 0
+
+
+def test_product_does_not_import_the_oracle():
+    """Nothing under the package may import, include, link or call the CPU oracle."""
+    pkg = os.path.join(ROOT, "geosradiation_gridcomp_b200")
+    bad = re.compile(r"import\s+oracle|from\s+oracle|from\s+\.\.?oracle|#include\s+\"[^\"]*oracle|liboracle|\boracle_[a-z]+\s*\(")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".sh")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not bad.search(txt), os.path.join(dirpath, f)
