@@ -141,8 +141,8 @@ size_t pick_chunk(int ncol, int nlay, size_t per_col_bytes) {
     if (g.chunk_cols) return std::min<size_t>(g.chunk_cols, (size_t)ncol);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    // scratch budget: a quarter of what is free, at most 12 GiB
-    size_t budget = std::min<size_t>(free_b / 4, (size_t)12 << 30);
+    // scratch budget per path: 30% of what is free, at most 40 GiB (B200: 180 GB of HBM3e)
+    size_t budget = std::min<size_t>(free_b / 10 * 3, (size_t)40 << 30);
     size_t nc = std::max<size_t>(1024, budget / std::max<size_t>(per_col_bytes, 1));
     nc = std::min<size_t>(nc, 65536);
     nc &= ~(size_t)127;

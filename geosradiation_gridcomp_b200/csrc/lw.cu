@@ -153,7 +153,7 @@ struct LwWork {
     uint32_t *cloudy_any;     // [nw][nc]
     double *taucmc;           // [nlay][140][nc], valid where the mask bit is set
     uint32_t *it;             // [nlay][140][nc] itgas | ittot << 16 (0xffff: clear cell)
-    double *part;             // [NUNITS][6][nlay+1][nc]
+    double *part;             // [16][LP_COUNT][nlay+1][nc]
 };
 
 __device__ __forceinline__ int pack_idx(int jp, int jt, int jt1, int indfor, int indself, int indminor) {
@@ -525,11 +525,11 @@ __device__ __forceinline__ void pfrac1(const double *__restrict__ fr, int g0, do
 }
 
 // Gas optical depth (TAU = true) and Planck fraction of one layer for g-points [G0, G0+GN) of
-// BAND.  `lower` selects the lower/upper-atmosphere branch (lay <= laytrop).  The aerosol term
+// BAND (G0 is the thread's first g-point within the band).  `lower` selects the lower/upper-atmosphere branch (lay <= laytrop).  The aerosol term
 // of addAerosols is added by the caller.
-template <int BAND, int G0, int GN, bool TAU>
-__device__ __forceinline__ void lw_band_layer(const Lay &L, bool lower, double pavel, double (&taug)[GN],
-                                              double (&pf)[GN]) {
+template <int BAND, int GN, bool TAU>
+__device__ __forceinline__ void lw_band_layer(const Lay &L, bool lower, double pavel, const int G0,
+                                              double (&taug)[GN], double (&pf)[GN]) {
     const LwBandTab &B = c_lw.b[BAND - 1];
     constexpr int ng = BAND == 1 ? 10 : BAND == 2 ? 12 : BAND == 3 ? 16 : BAND == 4 ? 14 : BAND == 5 ? 16
                      : BAND == 6 ? 8 : BAND == 7 ? 12 : BAND == 8 ? 8 : BAND == 9 ? 12 : BAND == 10 ? 6
@@ -904,18 +904,63 @@ struct LwBandArgs {
     double *dbg_taug, *dbg_pfracs;   // optional [nlay][140][nc]
 };
 
-template <int BAND, int G0, int GN, int UNIT>
-__global__ void __launch_bounds__(128)
+// Sum v[q] over the threads of a block that share a column lane (threadIdx.y runs over the
+// g-point groups of the band) in ascending g order and store the Q totals at dst + q*qstride.
+// `red` holds Q*NY*32 doubles; callers alternate two buffers so one barrier per call suffices.
+template <int Q, int NY>
+__device__ __forceinline__ void block_sum_store(const double (&v)[Q], double *__restrict__ red,
+                                                double *__restrict__ dst, size_t qstride, bool active) {
+    const int lane = threadIdx.x, ty = threadIdx.y;
+    if (NY == 1) {
+        if (active) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) dst[q * qstride] = v[q];
+        }
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) red[(q * NY + ty) * 32 + lane] = v[q];
+    __syncthreads();
+    for (int q = ty; q < Q; q += NY) {
+        double s = red[(q * NY) * 32 + lane];
+#pragma unroll
+        for (int y = 1; y < NY; ++y) s = s + red[(q * NY + y) * 32 + lane];
+        if (active) dst[q * qstride] = s;
+    }
+}
+
+template <int BAND> struct LwBandInfo {
+    static constexpr int ng = BAND == 1 ? 10 : BAND == 2 ? 12 : BAND == 3 ? 16 : BAND == 4 ? 14 : BAND == 5 ? 16
+                            : BAND == 6 ? 8 : BAND == 7 ? 12 : BAND == 8 ? 8 : BAND == 9 ? 12 : BAND == 10 ? 6
+                            : BAND == 11 ? 8 : BAND == 12 ? 8 : BAND == 13 ? 4 : 2;
+};
+
+// partial flux profiles of a band: part[band][LP_*][lev][c]
+enum LwPart { LP_U, LP_UC, LP_DU, LP_DUC, LP_D, LP_DC, LP_COUNT };
+
+// Block = 32 columns x (ng/GN) g-point groups of BAND: a warp is 32 consecutive columns at one
+// g-point group (coalesced on the column-fastest arrays), the warps of a block share the
+// columns' setcoef state through L1, and the g-point sums of every level are formed in the
+// block (block_sum_store) in ascending g order, like the reference's sequential accumulation.
+template <int BAND, int GN>
+__global__ void __launch_bounds__(32 * (LwBandInfo<BAND>::ng / GN))
 lw_band_kernel(const LwBandArgs A) {
+    constexpr int NY = LwBandInfo<BAND>::ng / GN;
+    static_assert(NY * GN == LwBandInfo<BAND>::ng, "GN must divide the band's g-points");
+    __shared__ double red_buf[NY > 1 ? 2 * 4 * NY * 32 : 1];
     const LwWork &W = A.W;
     const int nc = W.nc, nlay = W.nlay;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nc) return;
+    const int c0 = blockIdx.x * 32 + threadIdx.x;
+    const bool active = c0 < nc;
+    const int c = active ? c0 : nc - 1;   // idle lanes shadow the last column and never store
     const size_t col = (size_t)A.col0 + c;
     constexpr int ib = BAND - 1;
     const int gs = BAND == 1 ? 0 : c_lw.ngs[ib - 1];   // first g-point (0-based) of the band
+    const int G0 = threadIdx.y * GN;
     const int g_first = gs + G0;
     const int laytrop = W.laytrop[c];
+    int flip = 0;
+    auto red = [&]() { flip ^= 1; return red_buf + (NY > 1 ? flip * 4 * NY * 32 : 0); };
 
     // diffusivity angle, :177-186
     double secdiff;
@@ -932,17 +977,18 @@ lw_band_kernel(const LwBandArgs A) {
     const double sumfac = 0.5 * c_lw.delwave[ib] * c_lw.fluxfac;
     const double bpade = c_lw.bpade;
     const double tblint = 10000.0;
-    const size_t lev_stride = nc;
-    double *part = W.part + (size_t)UNIT * 6 * (nlay + 1) * nc + c;   // [f][lev][c]
     const size_t fstride = (size_t)(nlay + 1) * nc;
+    double *part = W.part + (size_t)ib * LP_COUNT * fstride + c;   // [f][lev][c]
     const double *planklay = W.planklay + (size_t)ib * nlay * nc + c;
     const double *planklev = W.planklev + (size_t)ib * (nlay + 1) * nc + c;
 
     double radld[GN], radclrd[GN], taug[GN], pf[GN];
     FORG { radld[ig] = 0.; radclrd[ig] = 0.; }
     bool diverge = false;
-    part[1 * fstride + (size_t)nlay * lev_stride] = 0.;
-    part[3 * fstride + (size_t)nlay * lev_stride] = 0.;
+    if (active && threadIdx.y == 0) {
+        part[LP_D * fstride + (size_t)nlay * nc] = 0.;
+        part[LP_DC * fstride + (size_t)nlay * nc] = 0.;
+    }
 
     // ---- downward sweep, :198-309 ----
     for (int lay = nlay - 1; lay >= 0; --lay) {
@@ -953,20 +999,18 @@ lw_band_kernel(const LwBandArgs A) {
         L.jp = pk & 63; L.jt = (pk >> 6) & 7; L.jt1 = (pk >> 9) & 7;
         L.indfor = (pk >> 12) & 3; L.indself = (pk >> 14) & 15; L.indminor = (pk >> 18) & 31;
         const double pavel = (BAND <= 2) ? A.pavel[(size_t)lay * A.ld + col] : 0.;
-        lw_band_layer<BAND, G0, GN, true>(L, lay < laytrop, pavel, taug, pf);
+        lw_band_layer<BAND, GN, true>(L, lay < laytrop, pavel, G0, taug, pf);
         const double taer = A.taua[((size_t)ib * nlay + lay) * A.ld + col];
         FORG taug[ig] = taug[ig] + taer;
-        if (A.dbg_taug) FORG A.dbg_taug[((size_t)lay * 140 + g_first + ig) * nc + c] = taug[ig];
-        if (A.dbg_pfracs) FORG A.dbg_pfracs[((size_t)lay * 140 + g_first + ig) * nc + c] = pf[ig];
+        if (A.dbg_taug && active) FORG A.dbg_taug[((size_t)lay * 140 + g_first + ig) * nc + c] = taug[ig];
+        if (A.dbg_pfracs && active) FORG A.dbg_pfracs[((size_t)lay * 140 + g_first + ig) * nc + c] = pf[ig];
 
         const double blay = planklay[(size_t)lay * nc];
-        const double dplankup = planklev[(size_t)(lay + 1) * nc] - blay;
         const double dplankdn = planklev[(size_t)lay * nc] - blay;
-        (void)dplankup;
         const uint32_t any_word = W.cloudy_any[(size_t)(lay >> 5) * nc + c];
         const bool layer_cloudy = (any_word >> (lay & 31)) & 1u;
         if (!diverge && layer_cloudy) diverge = true;
-        double sumd = 0., sumdc = 0.;
+        double sums[2] = {0., 0.};
         FORG {
             const int g = g_first + ig;
             double odepth = secdiff * taug[ig];
@@ -992,14 +1036,13 @@ lw_band_kernel(const LwBandArgs A) {
                 radld[ig] = radld[ig] + (bbdtot - radld[ig]) * atot;
                 code = (uint32_t)itgas | ((uint32_t)ittot << 16);
             }
-            W.it[((size_t)lay * 140 + g) * nc + c] = code;
-            sumd = sumd + sumfac * radld[ig];
+            if (active) W.it[((size_t)lay * 140 + g) * nc + c] = code;
+            sums[0] = sums[0] + sumfac * radld[ig];
             if (diverge) radclrd[ig] = radclrd[ig] + (bbdgas - radclrd[ig]) * agas;
             else radclrd[ig] = radld[ig];
-            sumdc = sumdc + sumfac * radclrd[ig];
+            sums[1] = sums[1] + sumfac * radclrd[ig];
         }
-        part[1 * fstride + (size_t)lay * lev_stride] = sumd;
-        part[3 * fstride + (size_t)lay * lev_stride] = sumdc;
+        block_sum_store<2, NY>(sums, red(), part + LP_D * fstride + (size_t)lay * nc, fstride, active);
     }
 
     // ---- surface, :319-333 (pf now holds the Planck fractions of layer 1) ----
@@ -1008,20 +1051,19 @@ lw_band_kernel(const LwBandArgs A) {
     double radlu[GN], radclru[GN], drad[GN], dradc[GN];
     {
         const double dpb = A.dudTs ? W.dplankbnd[(size_t)ib * nc + c] : 0.;
-        double su = 0., suc = 0., sd = 0.;
+        double sums[4] = {0., 0., 0., 0.};
         FORG {
             const double rad0 = pf[ig] * plankbnd;
             radlu[ig] = rad0 + reflect * radld[ig];
             radclru[ig] = rad0 + reflect * radclrd[ig];
-            su = su + sumfac * radlu[ig];
-            suc = suc + sumfac * radclru[ig];
+            sums[0] = sums[0] + sumfac * radlu[ig];
+            sums[1] = sums[1] + sumfac * radclru[ig];
             drad[ig] = pf[ig] * dpb;
             dradc[ig] = drad[ig];
-            sd = sd + sumfac * drad[ig];
+            sums[2] = sums[2] + sumfac * drad[ig];
         }
-        part[0] = su;
-        part[2 * fstride] = suc;
-        if (A.dudTs) { part[4 * fstride] = sd; part[5 * fstride] = sd; }
+        sums[3] = sums[2];
+        block_sum_store<4, NY>(sums, red(), part, fstride, active);
     }
 
     // ---- upward sweep, :336-379 ----
@@ -1032,10 +1074,10 @@ lw_band_kernel(const LwBandArgs A) {
         const int pk = W.idx[(size_t)lay * nc + c];
         L.jp = pk & 63; L.jt = (pk >> 6) & 7; L.jt1 = (pk >> 9) & 7;
         L.indfor = (pk >> 12) & 3; L.indself = (pk >> 14) & 15; L.indminor = (pk >> 18) & 31;
-        lw_band_layer<BAND, G0, GN, false>(L, lay < laytrop, 0., taug, pf);
+        lw_band_layer<BAND, GN, false>(L, lay < laytrop, 0., G0, taug, pf);
         const double blay = planklay[(size_t)lay * nc];
         const double dplankup = planklev[(size_t)(lay + 1) * nc] - blay;
-        double su = 0., suc = 0., sd = 0., sdc = 0.;
+        double sums[4] = {0., 0., 0., 0.};
         FORG {
             const int g = g_first + ig;
             const uint32_t code = W.it[((size_t)lay * 140 + g) * nc + c];
@@ -1053,37 +1095,27 @@ lw_band_kernel(const LwBandArgs A) {
                 radlu[ig] = radlu[ig] + (bbutot - radlu[ig]) * atot;
                 if (A.dudTs) drad[ig] = drad[ig] - drad[ig] * atot;
             }
-            su = su + sumfac * radlu[ig];
+            sums[0] = sums[0] + sumfac * radlu[ig];
             if (diverge) radclru[ig] = radclru[ig] + (bbugas - radclru[ig]) * agas;
             else radclru[ig] = radlu[ig];
-            suc = suc + sumfac * radclru[ig];
+            sums[1] = sums[1] + sumfac * radclru[ig];
             if (A.dudTs) {
                 if (diverge) dradc[ig] = dradc[ig] - dradc[ig] * agas;
                 else dradc[ig] = drad[ig];
-                sd = sd + sumfac * drad[ig];
-                sdc = sdc + sumfac * dradc[ig];
+                sums[2] = sums[2] + sumfac * drad[ig];
+                sums[3] = sums[3] + sumfac * dradc[ig];
             }
         }
-        part[(size_t)(lay + 1) * lev_stride] = su;
-        part[2 * fstride + (size_t)(lay + 1) * lev_stride] = suc;
-        if (A.dudTs) {
-            part[4 * fstride + (size_t)(lay + 1) * lev_stride] = sd;
-            part[5 * fstride + (size_t)(lay + 1) * lev_stride] = sdc;
-        }
+        block_sum_store<4, NY>(sums, red(), part + (size_t)(lay + 1) * nc, fstride, active);
     }
 }
 
-// units: (band, first g of the sub-range within the band, number of g-points)
-#define LW_UNITS(X)                                                                             \
-    X(1, 0, 6, 0) X(1, 6, 4, 1) X(2, 0, 6, 2) X(2, 6, 6, 3) X(3, 0, 8, 4) X(3, 8, 8, 5)         \
-    X(4, 0, 8, 6) X(4, 8, 6, 7) X(5, 0, 8, 8) X(5, 8, 8, 9) X(6, 0, 8, 10) X(7, 0, 6, 11)       \
-    X(7, 6, 6, 12) X(8, 0, 8, 13) X(9, 0, 6, 14) X(9, 6, 6, 15) X(10, 0, 6, 16) X(11, 0, 8, 17) \
-    X(12, 0, 8, 18) X(13, 0, 4, 19) X(14, 0, 2, 20) X(15, 0, 2, 21) X(16, 0, 2, 22)
-constexpr int LW_NUNITS = 23;
-__constant__ int c_unit_band[LW_NUNITS];
-static const int h_unit_band[LW_NUNITS] = {1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 7, 7, 8, 9, 9, 10, 11, 12, 13, 14, 15, 16};
+// g-points per thread for each band (must divide the band's g-points)
+#define LW_BANDS(X)                                                                              \
+    X(1, 1) X(2, 1) X(3, 1) X(4, 1) X(5, 1) X(6, 1) X(7, 1) X(8, 1) X(9, 1) X(10, 1) X(11, 1)    \
+    X(12, 1) X(13, 1) X(14, 1) X(15, 1) X(16, 1)
 
-// fixed-order sum of the unit partials -> caller arrays; band OLR (:382-385, rad.F90:586-605)
+// fixed-order sum of the band partials -> caller arrays; band OLR (:382-385, rad.F90:586-605)
 __global__ void lw_reduce_kernel(int ld, int col0, int nc, int nlay, int dudTs, const double *__restrict__ part,
                                  double *__restrict__ uflx, double *__restrict__ dflx,
                                  double *__restrict__ uflxc, double *__restrict__ dflxc,
@@ -1094,41 +1126,30 @@ __global__ void lw_reduce_kernel(int ld, int col0, int nc, int nlay, int dudTs, 
     if (c >= nc) return;
     const size_t fstride = (size_t)(nlay + 1) * nc;
     const size_t o = (size_t)lev * nc + c;
-    double s[6] = {0., 0., 0., 0., 0., 0.};
-    double bu = 0., bd = 0.;
-    int cur = 1;
+    double s[LP_COUNT] = {0., 0., 0., 0., 0., 0.};
     const size_t col = (size_t)col0 + c;
     const bool top = lev == nlay;
-    for (int u = 0; u < LW_NUNITS; ++u) {
-        const double *p = part + (size_t)u * 6 * fstride + o;
-        const double vu = p[0];
-        s[0] = s[0] + vu;
-        s[1] = s[1] + p[fstride];
-        s[2] = s[2] + p[2 * fstride];
-        s[3] = s[3] + p[3 * fstride];
+    for (int b = 0; b < 16; ++b) {
+        const double *p = part + (size_t)b * LP_COUNT * fstride + o;
+        const double vu = p[LP_U * fstride];
+        s[LP_U] = s[LP_U] + vu;
+        s[LP_UC] = s[LP_UC] + p[LP_UC * fstride];
+        s[LP_D] = s[LP_D] + p[LP_D * fstride];
+        s[LP_DC] = s[LP_DC] + p[LP_DC * fstride];
         double vd = 0.;
         if (dudTs) {
-            vd = p[4 * fstride];
-            s[4] = s[4] + vd;
-            s[5] = s[5] + p[5 * fstride];
+            vd = p[LP_DU * fstride];
+            s[LP_DU] = s[LP_DU] + vd;
+            s[LP_DUC] = s[LP_DUC] + p[LP_DUC * fstride];
         }
-        if (top && band_mask) {
-            const int b = c_unit_band[u];
-            if (b != cur) {
-                if ((band_mask >> (cur - 1)) & 1) { olrb[(cur - 1) + 16 * col] = bu; if (dudTs) dolrb[(cur - 1) + 16 * col] = bd; }
-                cur = b; bu = 0.; bd = 0.;
-            }
-            bu = bu + vu;
-            bd = bd + vd;
+        if (top && ((band_mask >> b) & 1)) {
+            olrb[b + 16 * col] = vu;
+            if (dudTs) dolrb[b + 16 * col] = vd;
         }
-    }
-    if (top && band_mask && ((band_mask >> (cur - 1)) & 1)) {
-        olrb[(cur - 1) + 16 * col] = bu;
-        if (dudTs) dolrb[(cur - 1) + 16 * col] = bd;
     }
     const size_t oo = (size_t)lev * ld + col;
-    uflx[oo] = s[0]; dflx[oo] = s[1]; uflxc[oo] = s[2]; dflxc[oo] = s[3];
-    if (dudTs) { duflx[oo] = s[4]; duflxc[oo] = s[5]; }
+    uflx[oo] = s[LP_U]; dflx[oo] = s[LP_D]; uflxc[oo] = s[LP_UC]; dflxc[oo] = s[LP_DC];
+    if (dudTs) { duflx[oo] = s[LP_DU]; duflxc[oo] = s[LP_DUC]; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1154,7 +1175,7 @@ static LwWork lw_carve(Slab &slab, int nc, int nlay) {
     W.cloudy_any = slab.take<uint32_t>(nw * nc);
     W.taucmc = slab.take<double>(n2 * 140);
     W.it = slab.take<uint32_t>(n2 * 140);
-    W.part = slab.take<double>((size_t)LW_NUNITS * 6 * (nlay + 1) * nc);
+    W.part = slab.take<double>((size_t)16 * LP_COUNT * (nlay + 1) * nc);
     return W;
 }
 
@@ -1170,11 +1191,6 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
                  Slab &slab, int *d_err, cudaStream_t stream, cudaStream_t *side, int nside, cudaEvent_t *ev,
                  const RrtmgxTaps *taps, int *d_negpos) {
     (void)d_negpos;
-    static bool unit_map_uploaded = false;
-    if (!unit_map_uploaded) {
-        if (cudaMemcpyToSymbol(c_unit_band, h_unit_band, sizeof h_unit_band) != cudaSuccess) return RRTMGX_ECUDA;
-        unit_map_uploaded = true;
-    }
     const int ld = a->ncol, nlay = a->nlay;
     slab.used = 0;
     LwWork W = lw_carve(slab, nc, nlay);
@@ -1207,13 +1223,14 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
     cudaEventRecord(ev[0], stream);
     for (int s = 0; s < nside; ++s) cudaStreamWaitEvent(side[s], ev[0], 0);
     int u = 0;
-#define X(BAND, G0, GN, UNIT)                                                              \
-    {                                                                                      \
-        cudaStream_t st = nside ? side[u % nside] : stream;                                \
-        RRTMGX_LAUNCH((lw_band_kernel<BAND, G0, GN, UNIT>), grd, blk, 0, st, A);           \
-        ++u;                                                                               \
+    const int gx = (nc + 31) / 32;
+#define X(BAND, GN)                                                                          \
+    {                                                                                        \
+        cudaStream_t st = nside ? side[u % nside] : stream;                                  \
+        RRTMGX_LAUNCH((lw_band_kernel<BAND, GN>), dim3(gx), dim3(32, LwBandInfo<BAND>::ng / GN), 0, st, A); \
+        ++u;                                                                                 \
     }
-    LW_UNITS(X)
+    LW_BANDS(X)
 #undef X
     for (int s = 0; s < nside; ++s) {
         cudaEventRecord(ev[1 + s], side[s]);
