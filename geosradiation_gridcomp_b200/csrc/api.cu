@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -19,6 +20,18 @@
 namespace rrtmgx {
 
 long long g_launches = 0;
+bool g_profile = false;
+namespace {
+struct ProfEntry { long long n = 0; double ms = 0.; };
+std::map<std::string, ProfEntry> g_prof;
+std::mutex g_prof_mu;
+}  // namespace
+void profile_add(const char *name, float ms) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    ProfEntry &e = g_prof[name];
+    e.n += 1;
+    e.ms += ms;
+}
 
 namespace {
 
@@ -330,6 +343,28 @@ const char *rrtmgx_strerror(int status) {
 }
 
 long long rrtmgx_launch_count(void) { return g_launches; }
+
+void rrtmgx_profile(int enable) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    g_profile = enable != 0;
+    if (enable) g_prof.clear();
+}
+
+size_t rrtmgx_profile_report(char *buf, size_t cap) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    std::string out;
+    char line[256];
+    for (const auto &kv : g_prof) {
+        std::snprintf(line, sizeof line, "%s\t%lld\t%.6f\n", kv.first.c_str(), kv.second.n, kv.second.ms);
+        out += line;
+    }
+    if (buf && cap) {
+        const size_t n = std::min(cap - 1, out.size());
+        std::memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return out.size() + 1;
+}
 
 void rrtmgx_set_taps(const RrtmgxTaps *lw_taps, const RrtmgxTaps *sw_taps) {
     g.lw.has_taps = lw_taps != nullptr;

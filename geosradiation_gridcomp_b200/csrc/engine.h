@@ -10,13 +10,43 @@
 
 namespace rrtmgx {
 
-// every kernel launch of the library goes through this counter (rrtmgx_launch_count)
+// every kernel launch of the library goes through this counter (rrtmgx_launch_count); with
+// profiling switched on (rrtmgx_profile) each launch is bracketed by CUDA events on its own
+// stream and waited for, which serialises the step and attributes device time per kernel
 extern long long g_launches;
-#define RRTMGX_LAUNCH(kernel, grid, block, smem, stream, ...)                \
+extern bool g_profile;
+void profile_add(const char *name, float ms);
+struct ProfScope {
+    const char *name;
+    cudaStream_t stream;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ProfScope(const char *n, cudaStream_t s) : name(n), stream(s) {
+        if (g_profile) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, stream);
+        }
+    }
+    ~ProfScope() {
+        if (e0) {
+            cudaEventRecord(e1, stream);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            profile_add(name, ms);
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
+    }
+};
+#define RRTMGX_LAUNCH_TAG(tag, kernel, grid, block, smem, stream, ...)      \
     do {                                                                    \
+        ::rrtmgx::ProfScope prof_scope_(tag, stream);                       \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);          \
         ++::rrtmgx::g_launches;                                             \
     } while (0)
+#define RRTMGX_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    RRTMGX_LAUNCH_TAG(#kernel, kernel, grid, block, smem, stream, __VA_ARGS__)
 
 // device bump allocator over one cudaMalloc'ed scratch slab (re-grown on demand by api.cu)
 struct Slab {

@@ -20,6 +20,7 @@
 // Tables are g-point fastest ([lead][ng]): a thread reads the consecutive g-points of its
 // sub-range from one table row.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -133,7 +134,10 @@ int lw_upload_tables(const HostTables &ht, const double *d_arena) {
 enum LwF {
     F_FAC00, F_FAC01, F_FAC10, F_FAC11, F_COLH2O, F_COLCO2, F_COLO3, F_COLN2O, F_COLCH4, F_COLO2,
     F_COLBRD, F_COLCFC11, F_COLCFC12, F_COLCFC22, F_COLCCL4, F_COLDRY, F_FORFAC, F_FORFRAC,
-    F_SELFFAC, F_SELFFRAC, F_SCALEMINOR, F_SCALEMINORN2, F_MINORFRAC, F_COUNT
+    F_SELFFAC, F_SELFFRAC, F_SCALEMINOR, F_SCALEMINORN2, F_MINORFRAC,
+    // minor-gas column amounts adjusted for abundances above the reference (taumol :460-467 etc.),
+    // formed once per (layer, column) here instead of once per g-point thread
+    F_ADJN2O, F_ADJCO2_6, F_ADJCO2_7, F_ADJCO2_8, F_ADJCO2_13, F_COUNT
 };
 
 struct LwWork {
@@ -159,6 +163,19 @@ struct LwWork {
 __device__ __forceinline__ int pack_idx(int jp, int jt, int jt1, int indfor, int indself, int indminor) {
     return jp | (jt << 6) | (jt1 << 9) | (indfor << 12) | (indself << 14) | (indminor << 18);
 }
+
+// adjusted minor column amount when the gas exceeds its reference abundance (e.g. taumol :460-467)
+__device__ __forceinline__ double adjcol(double col, double coldry, double chi, double thresh, double base,
+                                         double expo) {
+    const double chi_x = col / coldry;
+    const double rat = 1.e20 * chi_x / chi;
+    if (rat > thresh) {
+        const double adjfac = base + pow(rat - base, expo);
+        return adjfac * chi * coldry * 1.e-20;
+    }
+    return col;
+}
+__device__ __forceinline__ double chi_mls(int m, int j) { return c_lw.chi_mls[(m - 1) + 7 * (j - 1)]; }
 
 // LW/src/rrtmg_lw_setcoef.F90:52-584.  One thread per column, layers bottom-up.
 __global__ void __launch_bounds__(128)
@@ -320,6 +337,15 @@ lw_setcoef_kernel(int ld, int col0, LwWork W, int dudTs,
         W.f(F_SCALEMINOR)[j] = scaleminor;
         W.f(F_SCALEMINORN2)[j] = scaleminorn2;
         W.f(F_MINORFRAC)[j] = minorfrac;
+        {
+            const bool lower = plog > 4.56;
+            const double chi_n2o = chi_mls(4, jp + 1), chi_co2 = chi_mls(2, jp + 1);
+            W.f(F_ADJN2O)[j] = adjcol(coln2o, coldry, chi_n2o, 1.5, 0.5, 0.65);          // bands 3, 9
+            W.f(F_ADJCO2_6)[j] = adjcol(colco2, coldry, chi_co2, 3.0, 2.0, 0.77);        // band 6
+            W.f(F_ADJCO2_7)[j] = adjcol(colco2, coldry, chi_co2, 3.0, lower ? 3.0 : 2.0, 0.79);   // band 7
+            W.f(F_ADJCO2_8)[j] = adjcol(colco2, coldry, chi_co2, 3.0, 2.0, 0.65);        // band 8
+            W.f(F_ADJCO2_13)[j] = adjcol(colco2, coldry, 3.55e-4, 3.0, 2.0, 0.68);       // band 13
+        }
     }
     W.laytrop[c] = laytrop;
 }
@@ -469,18 +495,6 @@ __device__ __forceinline__ void minor2(const double *__restrict__ k, int ng, int
     }
 }
 
-// adjusted minor column amount when the gas exceeds its reference abundance (e.g. :460-467)
-__device__ __forceinline__ double adjcol(double col, double coldry, double chi, double thresh, double base,
-                                         double expo) {
-    const double chi_x = col / coldry;
-    const double rat = 1.e20 * chi_x / chi;
-    if (rat > thresh) {
-        const double adjfac = base + pow(rat - base, expo);
-        return adjfac * chi * coldry * 1.e-20;
-    }
-    return col;
-}
-
 // four-point (p,T) interpolation of a single-species table: rows ind0, ind0+1, ind1, ind1+1
 template <int GN>
 __device__ __forceinline__ void key4(const double *__restrict__ tab, int ng, int g0, int ind0, int ind1,
@@ -510,8 +524,6 @@ __device__ __forceinline__ void key_upper5(const double *__restrict__ tab, int n
 
 __device__ __forceinline__ double rat_tab(int which, int jp1 /* 1-based */) { return c_lw.rat[which * 59 + jp1 - 1]; }
 enum { R_H2OCO2 = 0, R_H2OO3 = 1, R_H2ON2O = 2, R_H2OCH4 = 3, R_N2OCO2 = 4, R_O3CO2 = 5 };
-__device__ __forceinline__ double chi_mls(int m, int j) { return c_lw.chi_mls[(m - 1) + 7 * (j - 1)]; }
-
 // Planck fraction interpolated in the binary-species parameter (e.g. :604-605)
 template <int GN>
 __device__ __forceinline__ void pfrac2(const double *__restrict__ fr, int ng, int g0, const Spec &sp,
@@ -619,7 +631,7 @@ __device__ __forceinline__ void lw_band_layer(const Lay &L, bool lower, double p
                 const Spec s0 = spec(colh2o, rat_tab(R_H2OCO2, L.jp), colco2, 8.);
                 const Spec s1 = spec(colh2o, rat_tab(R_H2OCO2, L.jp + 1), colco2, 8.);
                 const Spec sm = spec(colh2o, c_lw.chi_1_3_over_2_3, colco2, 8.);
-                const double adjcoln2o = adjcol(L.f(F_COLN2O), L.f(F_COLDRY), chi_mls(4, L.jp + 1), 1.5, 0.5, 0.65);
+                const double adjcoln2o = L.f(F_ADJN2O);
                 binary_lower(s0, s1);
                 self_for(taug);
                 minor2<GN>(B.ka_mn2o, ng, G0, 9, sm.js, L.indminor, sm.fs, L.f(F_MINORFRAC), t1);
@@ -631,7 +643,7 @@ __device__ __forceinline__ void lw_band_layer(const Lay &L, bool lower, double p
                 const Spec s0 = spec(colh2o, rat_tab(R_H2OCO2, L.jp), colco2, 4.);
                 const Spec s1 = spec(colh2o, rat_tab(R_H2OCO2, L.jp + 1), colco2, 4.);
                 const Spec sm = spec(colh2o, c_lw.chi_1_13_over_2_13, colco2, 4.);
-                const double adjcoln2o = adjcol(L.f(F_COLN2O), L.f(F_COLDRY), chi_mls(4, L.jp + 1), 1.5, 0.5, 0.65);
+                const double adjcoln2o = L.f(F_ADJN2O);
                 key_upper5<GN>(B.absb, ng, G0, ind0up + s0.js, ind1up + s1.js, s0, s1, L, taug);
                 for_only(taug);
                 minor2<GN>(B.kb_mn2o, ng, G0, 5, sm.js, L.indminor, sm.fs, L.f(F_MINORFRAC), t1);
@@ -692,7 +704,7 @@ __device__ __forceinline__ void lw_band_layer(const Lay &L, bool lower, double p
         if constexpr (TAU) {
             const double colcfc11 = L.f(F_COLCFC11), colcfc12 = L.f(F_COLCFC12);
             if (lower) {
-                const double adjcolco2 = adjcol(L.f(F_COLCO2), L.f(F_COLDRY), chi_mls(2, L.jp + 1), 3.0, 2.0, 0.77);
+                const double adjcolco2 = L.f(F_ADJCO2_6);
                 const double colh2o = L.f(F_COLH2O);
                 key4<GN>(B.absa, ng, G0, ind0lo + 1, ind1lo + 1, L, t1);
                 FORG taug[ig] = colh2o * t1[ig];
@@ -712,7 +724,7 @@ __device__ __forceinline__ void lw_band_layer(const Lay &L, bool lower, double p
                 const Spec s0 = spec(colh2o, rat_tab(R_H2OO3, L.jp), colo3, 8.);
                 const Spec s1 = spec(colh2o, rat_tab(R_H2OO3, L.jp + 1), colo3, 8.);
                 const Spec sm = spec(colh2o, c_lw.chi_1_3_over_3_3, colo3, 8.);
-                const double adjcolco2 = adjcol(L.f(F_COLCO2), L.f(F_COLDRY), chi_mls(2, L.jp + 1), 3.0, 3.0, 0.79);
+                const double adjcolco2 = L.f(F_ADJCO2_7);
                 binary_lower(s0, s1);
                 self_for(taug);
                 minor2<GN>(B.ka_mco2, ng, G0, 9, sm.js, L.indminor, sm.fs, L.f(F_MINORFRAC), t1);
@@ -721,7 +733,7 @@ __device__ __forceinline__ void lw_band_layer(const Lay &L, bool lower, double p
             pfrac2<GN>(B.fracrefa, ng, G0, spec(colh2o, c_lw.chi_1_3_over_3_3, colo3, 8.), pf);
         } else {
             if constexpr (TAU) {
-                const double adjcolco2 = adjcol(L.f(F_COLCO2), L.f(F_COLDRY), chi_mls(2, L.jp + 1), 3.0, 2.0, 0.79);
+                const double adjcolco2 = L.f(F_ADJCO2_7);
                 const double colo3 = L.f(F_COLO3);
                 key4<GN>(B.absb, ng, G0, ind0up + 1, ind1up + 1, L, t1);
                 lerp_rows<GN>(B.kb_mco2, ng, G0, L.indminor, L.f(F_MINORFRAC), t2);
@@ -734,7 +746,7 @@ __device__ __forceinline__ void lw_band_layer(const Lay &L, bool lower, double p
         }
     } else if constexpr (BAND == 8) {   // :1607-1728  H2O / O3 (+CO2, O3, N2O, CFC12, CFC22)
         if constexpr (TAU) {
-            const double adjcolco2 = adjcol(L.f(F_COLCO2), L.f(F_COLDRY), chi_mls(2, L.jp + 1), 3.0, 2.0, 0.65);
+            const double adjcolco2 = L.f(F_ADJCO2_8);
             const double colo3 = L.f(F_COLO3), coln2o = L.f(F_COLN2O), colcfc12 = L.f(F_COLCFC12),
                          colcfc22 = L.f(F_COLCFC22), minorfrac = L.f(F_MINORFRAC);
             if (lower) {
@@ -763,7 +775,7 @@ __device__ __forceinline__ void lw_band_layer(const Lay &L, bool lower, double p
                 const Spec s0 = spec(colh2o, rat_tab(R_H2OCH4, L.jp), colch4, 8.);
                 const Spec s1 = spec(colh2o, rat_tab(R_H2OCH4, L.jp + 1), colch4, 8.);
                 const Spec sm = spec(colh2o, c_lw.chi_1_3_over_6_3, colch4, 8.);
-                const double adjcoln2o = adjcol(L.f(F_COLN2O), L.f(F_COLDRY), chi_mls(4, L.jp + 1), 1.5, 0.5, 0.65);
+                const double adjcoln2o = L.f(F_ADJN2O);
                 binary_lower(s0, s1);
                 self_for(taug);
                 minor2<GN>(B.ka_mn2o, ng, G0, 9, sm.js, L.indminor, sm.fs, L.f(F_MINORFRAC), t1);
@@ -772,7 +784,7 @@ __device__ __forceinline__ void lw_band_layer(const Lay &L, bool lower, double p
             pfrac2<GN>(B.fracrefa, ng, G0, spec(colh2o, c_lw.chi_1_9_over_6_9, colch4, 8.), pf);
         } else {
             if constexpr (TAU) {
-                const double adjcoln2o = adjcol(L.f(F_COLN2O), L.f(F_COLDRY), chi_mls(4, L.jp + 1), 1.5, 0.5, 0.65);
+                const double adjcoln2o = L.f(F_ADJN2O);
                 const double colch4 = L.f(F_COLCH4);
                 key4<GN>(B.absb, ng, G0, ind0up + 1, ind1up + 1, L, t1);
                 lerp_rows<GN>(B.kb_mn2o, ng, G0, L.indminor, L.f(F_MINORFRAC), t2);
@@ -820,7 +832,7 @@ __device__ __forceinline__ void lw_band_layer(const Lay &L, bool lower, double p
                 const Spec s1 = spec(colh2o, rat_tab(R_H2ON2O, L.jp + 1), coln2o, 8.);
                 const Spec smco2 = spec(colh2o, c_lw.chi_1_1_over_4_1, coln2o, 8.);
                 const double coldry = L.f(F_COLDRY);
-                const double adjcolco2 = adjcol(L.f(F_COLCO2), coldry, 3.55e-4, 3.0, 2.0, 0.68);
+                const double adjcolco2 = L.f(F_ADJCO2_13);
                 const Spec smco = spec(colh2o, c_lw.chi_1_3_over_4_3, coln2o, 8.);
                 // covmr = 0 in GEOS (LW/src/rrtmg_lw_rad.F90:520) -> colco takes its 1e-32 floor
                 const double colco = 1.e-32 * coldry;
@@ -942,8 +954,8 @@ enum LwPart { LP_U, LP_UC, LP_DU, LP_DUC, LP_D, LP_DC, LP_COUNT };
 // g-point group (coalesced on the column-fastest arrays), the warps of a block share the
 // columns' setcoef state through L1, and the g-point sums of every level are formed in the
 // block (block_sum_store) in ascending g order, like the reference's sequential accumulation.
-template <int BAND, int GN>
-__global__ void __launch_bounds__(32 * (LwBandInfo<BAND>::ng / GN))
+template <int BAND, int GN, int REGS>
+__global__ void __launch_bounds__(32 * (LwBandInfo<BAND>::ng / GN), min_blocks(32 * (LwBandInfo<BAND>::ng / GN), REGS))
 lw_band_kernel(const LwBandArgs A) {
     constexpr int NY = LwBandInfo<BAND>::ng / GN;
     static_assert(NY * GN == LwBandInfo<BAND>::ng, "GN must divide the band's g-points");
@@ -1110,10 +1122,27 @@ lw_band_kernel(const LwBandArgs A) {
     }
 }
 
-// g-points per thread for each band (must divide the band's g-points)
-#define LW_BANDS(X)                                                                              \
-    X(1, 1) X(2, 1) X(3, 1) X(4, 1) X(5, 1) X(6, 1) X(7, 1) X(8, 1) X(9, 1) X(10, 1) X(11, 1)    \
-    X(12, 1) X(13, 1) X(14, 1) X(15, 1) X(16, 1)
+// Four compiled variants per band: (g-points per thread, register budget per thread; 0 = none).
+// The one used is picked per band from lw_variant[] (tuned on B200; RRTMGX_LW_GN="vvv..." overrides).
+#define LW_BANDS(X)                                                                                      \
+    X(1, 1, 2, 5, 2) X(2, 1, 2, 4, 2) X(3, 1, 2, 4, 2) X(4, 1, 2, 7, 2) X(5, 1, 2, 4, 2) X(6, 1, 2, 4, 2)   \
+    X(7, 1, 2, 4, 2) X(8, 1, 2, 4, 2) X(9, 1, 2, 6, 2) X(10, 1, 2, 3, 2) X(11, 1, 2, 4, 2) X(12, 1, 2, 4, 2) \
+    X(13, 1, 2, 4, 2) X(14, 1, 2, 2, 2) X(15, 1, 2, 2, 2) X(16, 1, 2, 2, 2)
+constexpr int LW_REGS3 = 64;   // register budget of variant 3
+
+typedef void (*LwBandLauncher)(int, cudaStream_t, const LwBandArgs &);
+template <int BAND, int GN, int REGS>
+static void lw_launch_band(int gx, cudaStream_t st, const LwBandArgs &A) {
+    static char tag[48] = "";
+    if (!tag[0]) std::snprintf(tag, sizeof tag, "lw_band_kernel<%d,gn%d,r%d>", BAND, GN, REGS);
+    RRTMGX_LAUNCH_TAG(tag, (lw_band_kernel<BAND, GN, REGS>), dim3(gx), dim3(32, LwBandInfo<BAND>::ng / GN), 0, st, A);
+}
+#define X(BAND, A0, A1, A2, A3)                                                                   \
+    {lw_launch_band<BAND, A0, 0>, lw_launch_band<BAND, A1, 0>, lw_launch_band<BAND, A2, 0>,       \
+     lw_launch_band<BAND, A3, LW_REGS3>},
+static const LwBandLauncher lw_launchers[16][4] = {LW_BANDS(X)};
+#undef X
+static int lw_variant[16] = {3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 0, 0, 0};   // profiles/r1_gn_tuning.txt
 
 // fixed-order sum of the band partials -> caller arrays; band OLR (:382-385, rad.F90:586-605)
 __global__ void lw_reduce_kernel(int ld, int col0, int nc, int nlay, int dudTs, const double *__restrict__ part,
@@ -1222,16 +1251,18 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
     // fan the independent band units out over the side streams
     cudaEventRecord(ev[0], stream);
     for (int s = 0; s < nside; ++s) cudaStreamWaitEvent(side[s], ev[0], 0);
-    int u = 0;
-    const int gx = (nc + 31) / 32;
-#define X(BAND, GN)                                                                          \
-    {                                                                                        \
-        cudaStream_t st = nside ? side[u % nside] : stream;                                  \
-        RRTMGX_LAUNCH((lw_band_kernel<BAND, GN>), dim3(gx), dim3(32, LwBandInfo<BAND>::ng / GN), 0, st, A); \
-        ++u;                                                                                 \
+    static bool variants_read = false;
+    if (!variants_read) {
+        if (const char *e = std::getenv("RRTMGX_LW_GN")) {
+            int b = 0;
+            for (const char *q = e; *q && b < 16; ++q)
+                if (*q >= '0' && *q <= '3') lw_variant[b++] = *q - '0';
+            for (; b > 0 && b < 16; ++b) lw_variant[b] = lw_variant[b - 1];
+        }
+        variants_read = true;
     }
-    LW_BANDS(X)
-#undef X
+    const int gx = (nc + 31) / 32;
+    for (int b = 0; b < 16; ++b) lw_launchers[b][lw_variant[b]](gx, nside ? side[b % nside] : stream, A);
     for (int s = 0; s < nside; ++s) {
         cudaEventRecord(ev[1 + s], side[s]);
         cudaStreamWaitEvent(stream, ev[1 + s], 0);

@@ -96,6 +96,10 @@ def lib():
         L.rrtmgx_strerror.restype = C.c_char_p
         L.rrtmgx_strerror.argtypes = [C.c_int]
         L.rrtmgx_launch_count.restype = C.c_longlong
+        L.rrtmgx_profile.argtypes = [C.c_int]
+        L.rrtmgx_profile.restype = None
+        L.rrtmgx_profile_report.argtypes = [C.c_char_p, C.c_size_t]
+        L.rrtmgx_profile_report.restype = C.c_size_t
         L.rrtmgx_lw_run.argtypes = [C.POINTER(LwArgs)]
         L.rrtmgx_sw_run.argtypes = [C.POINTER(SwArgs)]
         L.rrtmgx_set_taps.argtypes = [C.POINTER(Taps), C.POINTER(Taps)]
@@ -174,6 +178,23 @@ def finalize():
 
 def launch_count():
     return int(lib().rrtmgx_launch_count())
+
+
+def profile(enable):
+    """Switch per-kernel CUDA-event timing on (clears totals) or off; profiled steps are serialised."""
+    lib().rrtmgx_profile(1 if enable else 0)
+
+
+def profile_report():
+    """{kernel name: (launches, total device ms)} accumulated since profile(True)."""
+    n = lib().rrtmgx_profile_report(None, 0)
+    buf = C.create_string_buffer(int(n) + 16)
+    lib().rrtmgx_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split("\t")
+        out[name] = (int(cnt), float(ms))
+    return out
 
 
 def table(kind, name, band=0):

@@ -81,6 +81,14 @@ int rrtmgx_finalize(void);
 const char *rrtmgx_strerror(int status);
 /* number of kernels launched by this library since rrtmgx_init (bench.py gpu_launches) */
 long long rrtmgx_launch_count(void);
+/* Per-kernel device timing (the reference brackets its stages with MAPL timers,
+ * SW/src/rrtmg_sw_rad.F90:1181-1200): while enabled every kernel launch is bracketed by CUDA
+ * events on its stream and waited for, so a profiled step is serialised and slower.
+ * rrtmgx_profile(1) clears the totals and starts, rrtmgx_profile(0) stops;
+ * rrtmgx_profile_report writes "name<TAB>launches<TAB>total_ms" lines into buf (NUL terminated,
+ * truncated to cap) and returns the size needed. */
+void rrtmgx_profile(int enable);
+size_t rrtmgx_profile_report(char *buf, size_t cap);
 
 typedef struct {
     int ncol, nlay;
