@@ -111,8 +111,12 @@ class ClockSampler:
 def cpu_oracle_rate(sample_cols, nlay, seed, with_sw):
     """columns/s of the oracle port (all host threads) on a bounded sample of the workload."""
     from oracle import binding as oracle
-    s = make_state(sample_cols, nlay, seed, 0, 1)
+    s = make_state(sample_cols, nlay, seed, 0, min(16, os.cpu_count() or 1))
     oracle.lib()
+    warm = make_state(min(1024, sample_cols), nlay, seed, 0, 1)   # page in tables, spin up the OpenMP team
+    oracle.rrtmg_lw(warm)
+    if with_sw:
+        oracle.rrtmg_sw(warm)
     t0 = time.perf_counter()
     r = oracle.rrtmg_lw(s)
     assert r["rc"] == 0
@@ -173,7 +177,7 @@ def main():
     ap.add_argument("--ncol", type=int, default=194400, help="columns per GPU (C180 = 6*180^2)")
     ap.add_argument("--nlay", type=int, default=72)
     ap.add_argument("--seed", type=int, default=20260121)
-    ap.add_argument("--cpu-sample", type=int, default=4096, help="columns in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=65536, help="columns in the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
@@ -261,6 +265,21 @@ def main():
     clocks = sampler.stop(t0, t1) if sampler else None
     value = world * ncol * a.steps / (dev_ms * 1e-3)
 
+    # one extra, untimed step with the library's per-kernel CUDA-event timing (events on each
+    # kernel's own stream; serialises the step) to attribute device time to kernels
+    kernels = None
+    if rank == 0:
+        host.profile(True)
+        step()
+        torch.cuda.synchronize()
+        host.profile(False)
+        rep = host.profile_report()
+        tot = sum(ms for _, ms in rep.values()) or 1.0
+        top = sorted(rep.items(), key=lambda kv: -kv[1][1])[:6]
+        kernels = {"serialised_step_ms": tot,
+                   "top": [{"name": k, "launches_per_step": n, "avg_launch_ms": ms / n, "share": ms / tot}
+                           for k, (n, ms) in top]}
+
     # ---- end-to-end arm: host (pinned) arrays through the C ABI --------------------------------
     e2e = None
     if not a.no_e2e:
@@ -317,10 +336,19 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = (value / world) * bpc / 1e9
+    traffic = None
+    try:   # measured DRAM bytes per step of this workload from the committed ncu capture, if any
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("nlay") == nlay:
+            traffic = tj["dram_bytes_per_column"] * ncol
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None,
+                "traffic": traffic, "kernels": kernels,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)",
-                "kernel": "whole step (all LW+SW kernels of one refresh); per-kernel figures in profiles/",
+                "kernel": "whole step: the fixed pipeline of LW+SW kernels of one refresh (algorithmic bytes = "
+                          "boundary inputs read once + outputs written once, SURVEY.md 8d); `kernels` attributes "
+                          "device time per kernel from CUDA events; `traffic` = measured DRAM bytes per step (ncu)",
                 "algorithmic_bytes_per_column": bpc,
                 "note": "fp64-pipe-bound path: see DESIGN.md for the FP64 roof beside the HBM roof"}
     cpu = None

@@ -1,0 +1,116 @@
+! rrtmgx_c.F90 -- ISO_C_BINDING view of include/rrtmgx.h (the B200 RRTMG LW + SW + McICA library).
+!
+! Source only: no Fortran compiler exists in the build image, so this shim is exercised through
+! the same C ABI from the C++/Python tests.  A GEOS build adds this directory to the
+! GEOSirrad_GridComp / GEOSsolar_GridComp CMake targets in place of the RRTMG src/ trees and
+! links librrtmgx.so (see INTEGRATION.md).
+!
+! `real` here must be 8 bytes (build GEOS radiation with -fdefault-real-8 / -r8, the fp64
+! contract of this library); rrtmgx_real_kind checks it at compile time.
+module rrtmgx_c
+   use, intrinsic :: iso_c_binding
+   implicit none
+   public
+
+   integer, parameter :: rrtmgx_real_kind = kind(1.0)
+   ! compile-time trap: the array size is negative unless default real is c_double
+   integer, parameter, private :: real_is_c_double(2*merge(1, -1, rrtmgx_real_kind == c_double) - 1) = 0
+
+   integer(c_int), parameter :: RRTMGX_DEVICE_PTRS = 1, RRTMGX_NO_SYNC = 2, RRTMGX_SKIP_CHECKS = 4
+
+   type, bind(C) :: rrtmgx_config
+      type(c_ptr)    :: table_blob = c_null_ptr
+      integer(c_int) :: device = -1
+      integer(c_int) :: inhomogeneity = 1
+      type(c_ptr)    :: corr = c_null_ptr
+   end type
+
+   ! field order == RrtmgxLwArgs in include/rrtmgx.h
+   type, bind(C) :: rrtmgx_lw_args
+      integer(c_int) :: ncol, nlay, psize, dudTs, iceflglw, liqflglw, dyofyr, cloudLM, cloudMH, flags
+      type(c_ptr) :: stream
+      type(c_ptr) :: play, plev, tlay, tlev, tsfc, emis
+      type(c_ptr) :: h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr
+      type(c_ptr) :: cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr
+      type(c_ptr) :: cldf, ciwp, clwp, rei, rel
+      type(c_ptr) :: tauaer, zm, alat
+      type(c_ptr) :: band_output
+      type(c_ptr) :: clearCounts
+      type(c_ptr) :: uflx, dflx, uflxc, dflxc, duflx_dTs, duflxc_dTs, olrb, dolrb_dTs
+   end type
+
+   ! field order == RrtmgxSwArgs in include/rrtmgx.h
+   type, bind(C) :: rrtmgx_sw_args
+      integer(c_int) :: ncol, nlay, rpart, isolvar, iceflgsw, liqflgsw, dyofyr, cloudLM, cloudMH
+      integer(c_int) :: iaer, normFlx, do_drfband, flags
+      type(c_ptr) :: stream
+      real(c_double) :: scon, adjes
+      type(c_ptr) :: bndscl, indsolvar, solcycfrac
+      type(c_ptr) :: coszen, play, plev, tlay
+      type(c_ptr) :: h2ovmr, o3vmr, co2vmr, ch4vmr, o2vmr
+      type(c_ptr) :: cld, ciwp, clwp, rei, rel, zm, alat
+      type(c_ptr) :: tauaer, ssaaer, asmaer
+      type(c_ptr) :: asdir, asdif, aldir, aldif
+      type(c_ptr) :: clearCounts
+      type(c_ptr) :: swuflx, swdflx, swuflxc, swdflxc
+      type(c_ptr) :: nirr, nirf, parr, parf, uvrr, uvrf
+      type(c_ptr) :: fswband
+      type(c_ptr) :: cotdtp, cotdhp, cotdmp, cotdlp, cotntp, cotnhp, cotnmp, cotnlp
+      type(c_ptr) :: drband, dfband
+   end type
+
+   interface
+      integer(c_int) function rrtmgx_init(cfg) bind(C, name='rrtmgx_init')
+         import :: c_int, rrtmgx_config
+         type(rrtmgx_config), intent(in) :: cfg
+      end function
+      integer(c_int) function rrtmgx_set_mcica(ih, corr) bind(C, name='rrtmgx_set_mcica')
+         import :: c_int, c_double
+         integer(c_int), value :: ih
+         real(c_double), intent(in) :: corr(8)
+      end function
+      integer(c_int) function rrtmgx_finalize() bind(C, name='rrtmgx_finalize')
+         import :: c_int
+      end function
+      integer(c_int) function rrtmgx_lw_run(a) bind(C, name='rrtmgx_lw_run')
+         import :: c_int, rrtmgx_lw_args
+         type(rrtmgx_lw_args), intent(in) :: a
+      end function
+      integer(c_int) function rrtmgx_sw_run(a) bind(C, name='rrtmgx_sw_run')
+         import :: c_int, rrtmgx_sw_args
+         type(rrtmgx_sw_args), intent(in) :: a
+      end function
+      integer(c_int) function rrtmgx_heating_rate(ncol, nlay, fnet, plev, hr, grav, cp, flags, stream) &
+            bind(C, name='rrtmgx_heating_rate')
+         import :: c_int, c_double, c_ptr
+         integer(c_int), value :: ncol, nlay, flags
+         real(c_double), intent(in) :: fnet(*), plev(*)
+         real(c_double), intent(out) :: hr(*)
+         real(c_double), value :: grav, cp
+         type(c_ptr), value :: stream
+      end function
+      type(c_ptr) function rrtmgx_strerror(status) bind(C, name='rrtmgx_strerror')
+         import :: c_int, c_ptr
+         integer(c_int), value :: status
+      end function
+   end interface
+
+contains
+
+   ! message text of a status code as a Fortran string
+   function rrtmgx_message(status) result(msg)
+      integer(c_int), intent(in) :: status
+      character(len=:), allocatable :: msg
+      character(kind=c_char), pointer :: p(:)
+      integer :: n
+      call c_f_pointer(rrtmgx_strerror(status), p, [256])
+      n = 0
+      do while (n < 256)
+         if (p(n+1) == c_null_char) exit
+         n = n + 1
+      end do
+      allocate(character(len=n) :: msg)
+      msg = transfer(p(1:n), msg)
+   end function
+
+end module rrtmgx_c

@@ -83,3 +83,17 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".sh")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not bad.search(txt), os.path.join(dirpath, f)
+
+
+def test_fortran_shim_types_match_header_field_order():
+    """The ISO_C_BINDING derived types of the Fortran shim list the fields in the header's order."""
+    from geosradiation_gridcomp_b200 import host
+    f90 = open(os.path.join(ROOT, "geosradiation_gridcomp_b200", "fortran", "rrtmgx_c.F90")).read()
+    for tname, mirror in (("rrtmgx_lw_args", host.LwArgs), ("rrtmgx_sw_args", host.SwArgs)):
+        body = re.search(r"type, bind\(C\) :: %s\n(.*?)end type" % tname, f90, flags=re.S).group(1)
+        fields = []
+        for line in body.splitlines():
+            line = line.split("!")[0]
+            if "::" in line:
+                fields += [f.strip() for f in line.split("::")[1].split(",")]
+        assert [f.lower() for f in fields] == [f[0].lower() for f in mirror._fields_], tname
