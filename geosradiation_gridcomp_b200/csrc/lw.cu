@@ -1243,7 +1243,8 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
     RRTMGX_LAUNCH(mcica_prep_kernel, grd, blk, 0, stream, ld, col0, nc, nlay, mp, a->zm, a->play, a->alat,
                   W.seeds, W.alpha, W.rcorr);
     LwOptics opt{ld, col0, nc, nlay, a->rei, a->rel, a->iceflglw, a->liqflglw, W.taucmc};
-    RRTMGX_LAUNCH(mcica_kernel<LwOptics>, dim3(grd.x, 140), blk, 0, stream, ld, col0, nc, nlay, 140, mp, d_jumps,
+    RRTMGX_LAUNCH(mcica_kernel<LwOptics>, dim3((140 + MCICA_SUBS - 1) / MCICA_SUBS, (nc + 31) / 32), dim3(32, MCICA_SUBS), 0, stream, ld, col0,
+                  nc, nlay, 140, mp, d_jumps,
                   W.seeds, W.alpha, W.rcorr, a->cldf, a->ciwp, a->clwp, 1.e-20, a->cloudLM, a->cloudMH,
                   a->clearCounts, W.cloudy_any, W.mask, opt, d_err);
 

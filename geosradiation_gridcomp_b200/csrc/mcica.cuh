@@ -133,8 +133,10 @@ static __global__ void mcica_prep_kernel(int ld, int col0, int nc, int nlay, Mci
 // (ncol,4), integer atomics, so deterministic), the optical cloud mask bit-packed over layers
 // [nw][nsub][nc] and its OR over subcolumns cloudy_any [nw][nc] (the reference's
 // cloudy(lay,col) after cldprmc).
+constexpr int MCICA_SUBS = 7;   // divides 140 (LW) and 112 (SW)
+
 template <class Optics>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * MCICA_SUBS)
 mcica_kernel(int ld, int col0, int nc, int nlay, int nsub, McicaParams P,
              const KissJump *__restrict__ jumps, const uint32_t *__restrict__ seeds,
              const double *__restrict__ alpha, const double *__restrict__ rcorr,
@@ -144,9 +146,13 @@ mcica_kernel(int ld, int col0, int nc, int nlay, int nsub, McicaParams P,
              uint32_t *__restrict__ cloudy_any,  // [nw][nc]
              uint32_t *__restrict__ mask,        // [nw][nsub][nc]
              Optics opt, int *err) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int isub = blockIdx.y;
-    if (c >= nc) return;
+    // block = 32 columns x MCICA_SUBS subcolumns: the warps of a block sweep the same columns, so
+    // cldf/ciwp/clwp/alpha/rcorr come from L1 after the first warp touched them
+    // (subcolumn groups vary fastest across the grid so that the blocks sweeping the same columns
+    // run back to back and find the column's inputs in L2)
+    const int c = blockIdx.y * 32 + threadIdx.x;
+    const int isub = blockIdx.x * blockDim.y + threadIdx.y;
+    if (c >= nc || isub >= nsub) return;
     const size_t col = (size_t)col0 + c;
     Kiss a, b;
     a.s1 = seeds[c]; a.s2 = seeds[(size_t)nc + c];
