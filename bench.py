@@ -295,10 +295,19 @@ def main():
             # LW and SW calls are independent; issue them from two host threads (the library
             # pipelines H2D / compute / D2H per path on its own streams)
             if h_sw:
-                t = threading.Thread(target=h_sw)
+                err = []
+
+                def sw_call():
+                    try:
+                        h_sw()
+                    except BaseException as e:   # re-raised on the main thread below
+                        err.append(e)
+                t = threading.Thread(target=sw_call)
                 t.start()
                 h_lw()
                 t.join()
+                if err:
+                    raise err[0]
             else:
                 h_lw()
         e2e_step()

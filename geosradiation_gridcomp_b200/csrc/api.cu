@@ -390,6 +390,7 @@ const double *rrtmgx_table(const char *kind, const char *name, int band, int *n)
 
 int rrtmgx_lw_status(void) {
     if (!g.ready) return RRTMGX_ENOTINIT;
+    cudaSetDevice(g.device);
     if (!g.lw.pending) return g.lw.last_status;
     g.lw.last_status = status_from(g.lw);
     return g.lw.last_status;
@@ -397,6 +398,7 @@ int rrtmgx_lw_status(void) {
 
 int rrtmgx_sw_status(void) {
     if (!g.ready) return RRTMGX_ENOTINIT;
+    cudaSetDevice(g.device);
     if (!g.sw.pending) return g.sw.last_status;
     g.sw.last_status = status_from(g.sw);
     return g.sw.last_status;
@@ -404,6 +406,8 @@ int rrtmgx_sw_status(void) {
 
 int rrtmgx_lw_run(const RrtmgxLwArgs *a) {
     if (!g.ready) return RRTMGX_ENOTINIT;
+    // the CUDA current device is per host thread: callers may run LW and SW from different threads
+    if (!ok(cudaSetDevice(g.device))) { cudaGetLastError(); return RRTMGX_ENODEVICE; }
     if (!a || a->ncol <= 0 || a->nlay <= 0 || a->nlay > 1000) return RRTMGX_EARG;
     if (a->cloudLM == a->cloudMH) return RRTMGX_ESUPERLAYER;   // cloud_subcol_gen.F90:762-766
     if (a->iceflglw < 0 || a->iceflglw > 4) return RRTMGX_EICEFLAG;
@@ -502,6 +506,7 @@ int rrtmgx_heating_rate(int ncol, int nlay, const double *fnet_up_minus_down, co
                         double *hr_K_per_day, double grav, double cp, int flags, void *stream) {
     if (!g.ready) return RRTMGX_ENOTINIT;
     if (ncol <= 0 || nlay <= 0 || !fnet_up_minus_down || !plev || !hr_K_per_day || cp <= 0.) return RRTMGX_EARG;
+    cudaSetDevice(g.device);
     const size_t n = (size_t)ncol * nlay, n1 = (size_t)ncol * (nlay + 1);
     const int blocks = (int)((n + 255) / 256);
     if (flags & RRTMGX_DEVICE_PTRS) {
@@ -527,6 +532,8 @@ int rrtmgx_sw_run(const RrtmgxSwArgs *) { return RRTMGX_EARG; }
 #else
 int rrtmgx_sw_run(const RrtmgxSwArgs *a) {
     if (!g.ready) return RRTMGX_ENOTINIT;
+    // the CUDA current device is per host thread: callers may run LW and SW from different threads
+    if (!ok(cudaSetDevice(g.device))) { cudaGetLastError(); return RRTMGX_ENODEVICE; }
     if (!a || a->ncol <= 0 || a->nlay <= 1 || a->nlay > 1000) return RRTMGX_EARG;
     if (a->cloudLM == a->cloudMH) return RRTMGX_ESUPERLAYER;   // cloud_subcol_gen.F90:762-766
     if (a->iceflgsw < 1 || a->iceflgsw > 4) return RRTMGX_EICEFLAG;

@@ -947,6 +947,35 @@ template <int BAND> struct LwBandInfo {
                             : BAND == 11 ? 8 : BAND == 12 ? 8 : BAND == 13 ? 4 : 2;
 };
 
+// factor arrays (LwF) a band's gas optics read, for the next-layer prefetch
+__host__ __device__ constexpr unsigned lw_fbit(int k) { return 1u << k; }
+constexpr unsigned LW_FAC4 = lw_fbit(F_FAC00) | lw_fbit(F_FAC01) | lw_fbit(F_FAC10) | lw_fbit(F_FAC11);
+constexpr unsigned LW_SELFFOR = lw_fbit(F_SELFFAC) | lw_fbit(F_SELFFRAC) | lw_fbit(F_FORFAC) | lw_fbit(F_FORFRAC);
+template <int BAND> __host__ __device__ constexpr unsigned lw_band_fmask() {
+    constexpr unsigned base = LW_FAC4 | LW_SELFFOR;
+    return BAND == 1 ? base | lw_fbit(F_COLH2O) | lw_fbit(F_COLBRD) | lw_fbit(F_SCALEMINORN2) | lw_fbit(F_MINORFRAC)
+         : BAND == 2 ? base | lw_fbit(F_COLH2O)
+         : BAND == 3 ? base | lw_fbit(F_COLH2O) | lw_fbit(F_COLCO2) | lw_fbit(F_ADJN2O) | lw_fbit(F_MINORFRAC)
+         : BAND == 4 ? base | lw_fbit(F_COLH2O) | lw_fbit(F_COLCO2) | lw_fbit(F_COLO3)
+         : BAND == 5 ? base | lw_fbit(F_COLH2O) | lw_fbit(F_COLCO2) | lw_fbit(F_COLO3) | lw_fbit(F_COLCCL4) | lw_fbit(F_MINORFRAC)
+         : BAND == 6 ? base | lw_fbit(F_COLH2O) | lw_fbit(F_COLCFC11) | lw_fbit(F_COLCFC12) | lw_fbit(F_ADJCO2_6) | lw_fbit(F_MINORFRAC)
+         : BAND == 7 ? base | lw_fbit(F_COLH2O) | lw_fbit(F_COLO3) | lw_fbit(F_ADJCO2_7) | lw_fbit(F_MINORFRAC)
+         : BAND == 8 ? base | lw_fbit(F_COLH2O) | lw_fbit(F_COLO3) | lw_fbit(F_COLN2O) | lw_fbit(F_COLCFC12) | lw_fbit(F_COLCFC22) | lw_fbit(F_ADJCO2_8) | lw_fbit(F_MINORFRAC)
+         : BAND == 9 ? base | lw_fbit(F_COLH2O) | lw_fbit(F_COLCH4) | lw_fbit(F_ADJN2O) | lw_fbit(F_MINORFRAC)
+         : BAND == 10 ? base | lw_fbit(F_COLH2O)
+         : BAND == 11 ? base | lw_fbit(F_COLH2O) | lw_fbit(F_COLO2) | lw_fbit(F_SCALEMINOR) | lw_fbit(F_MINORFRAC)
+         : BAND == 12 ? base | lw_fbit(F_COLH2O) | lw_fbit(F_COLCO2)
+         : BAND == 13 ? base | lw_fbit(F_COLH2O) | lw_fbit(F_COLN2O) | lw_fbit(F_COLO3) | lw_fbit(F_COLDRY) | lw_fbit(F_ADJCO2_13) | lw_fbit(F_MINORFRAC)
+         : BAND == 14 ? base | lw_fbit(F_COLCO2)
+         : BAND == 15 ? base | lw_fbit(F_COLN2O) | lw_fbit(F_COLCO2) | lw_fbit(F_COLBRD) | lw_fbit(F_SCALEMINOR) | lw_fbit(F_MINORFRAC)
+         : base | lw_fbit(F_COLH2O) | lw_fbit(F_COLCH4);
+}
+// Planck fractions of the binary-species bands need the two key columns in the upward sweep too
+template <int BAND> __host__ __device__ constexpr unsigned lw_band_fmask_up() {
+    return lw_band_fmask<BAND>() & (lw_fbit(F_COLH2O) | lw_fbit(F_COLCO2) | lw_fbit(F_COLO3) | lw_fbit(F_COLN2O) |
+                                    lw_fbit(F_COLCH4));
+}
+
 // partial flux profiles of a band: part[band][LP_*][lev][c]
 enum LwPart { LP_U, LP_UC, LP_DU, LP_DUC, LP_D, LP_DC, LP_COUNT };
 
@@ -1004,6 +1033,17 @@ lw_band_kernel(const LwBandArgs A) {
 
     // ---- downward sweep, :198-309 ----
     for (int lay = nlay - 1; lay >= 0; --lay) {
+        if (lay > 0 && threadIdx.y == 0) {   // next layer's per-(layer, column) state -> L1 while this one computes
+            const size_t jn = (size_t)(lay - 1) * nc + c;
+            prefetch_l1(W.idx + jn);
+            constexpr unsigned fm = lw_band_fmask<BAND>();
+#pragma unroll
+            for (int k = 0; k < F_COUNT; ++k)
+                if ((fm >> k) & 1u) prefetch_l1(W.fbase + (size_t)k * W.n2 + jn);
+            prefetch_l1(planklay + (size_t)(lay - 1) * nc);
+            prefetch_l1(planklev + (size_t)(lay - 1) * nc);
+            prefetch_l1(A.taua + ((size_t)ib * nlay + lay - 1) * A.ld + col);
+        }
         Lay L;
         L.fj = W.fbase + (size_t)lay * nc + c;
         L.n2 = W.n2;
@@ -1080,6 +1120,19 @@ lw_band_kernel(const LwBandArgs A) {
 
     // ---- upward sweep, :336-379 ----
     for (int lay = 0; lay < nlay; ++lay) {
+        if (lay + 1 < nlay) {
+            FORG prefetch_l1(W.it + ((size_t)(lay + 1) * 140 + g_first + ig) * nc + c);
+            if (threadIdx.y == 0) {
+                const size_t jn = (size_t)(lay + 1) * nc + c;
+                prefetch_l1(W.idx + jn);
+                constexpr unsigned fm = lw_band_fmask_up<BAND>();
+#pragma unroll
+                for (int k = 0; k < F_COUNT; ++k)
+                    if ((fm >> k) & 1u) prefetch_l1(W.fbase + (size_t)k * W.n2 + jn);
+                prefetch_l1(planklay + (size_t)(lay + 1) * nc);
+                prefetch_l1(planklev + (size_t)(lay + 2) * nc);
+            }
+        }
         Lay L;
         L.fj = W.fbase + (size_t)lay * nc + c;
         L.n2 = W.n2;
