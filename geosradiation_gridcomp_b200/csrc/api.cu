@@ -62,6 +62,7 @@ struct Ctx {
     McicaConfig mc;
     Path lw, sw;
     size_t chunk_cols = 0;   // 0: automatic
+    size_t host_chunk_cols = 16384;
     std::mutex mu;
 };
 
@@ -150,7 +151,7 @@ __global__ void check_negative_kernel(const double *__restrict__ x, size_t n, in
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicMin(negpos, pos);
 }
 
-size_t pick_chunk(int ncol, int nlay, size_t per_col_bytes) {
+size_t pick_chunk(int ncol, int nlay, size_t per_col_bytes, bool host_mode) {
     if (g.chunk_cols) return std::min<size_t>(g.chunk_cols, (size_t)ncol);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
@@ -158,6 +159,8 @@ size_t pick_chunk(int ncol, int nlay, size_t per_col_bytes) {
     size_t budget = std::min<size_t>(free_b / 10 * 3, (size_t)40 << 30);
     size_t nc = std::max<size_t>(1024, budget / std::max<size_t>(per_col_bytes, 1));
     nc = std::min<size_t>(nc, 65536);
+    // host arrays: smaller chunks shorten the fill/drain of the H2D -> kernels -> D2H pipeline
+    if (host_mode) nc = std::min<size_t>(nc, g.host_chunk_cols);
     nc &= ~(size_t)127;
     (void)nlay;
     return std::min<size_t>(nc, (size_t)ncol);
@@ -294,6 +297,7 @@ int rrtmgx_init(const RrtmgxConfig *cfg) {
         if (cfg->corr) std::memcpy(g.mc.corr, cfg->corr, sizeof g.mc.corr);
     }
     if (const char *e = std::getenv("RRTMGX_CHUNK")) g.chunk_cols = (size_t)std::atoll(e);
+    if (const char *e = std::getenv("RRTMGX_HOST_CHUNK")) g.host_chunk_cols = std::max<size_t>(1024, (size_t)std::atoll(e));
     g.ready = true;
     return 0;
 }
@@ -423,7 +427,7 @@ int rrtmgx_lw_run(const RrtmgxLwArgs *a) {
     const RrtmgxTaps *taps = p.has_taps ? &p.taps : nullptr;
     const bool dbg = taps && (taps->taug || taps->pfracs);
     const size_t per_col = lw_scratch_bytes(1024, nlay, dbg) / 1024;
-    size_t chunk = pick_chunk(ncol, nlay, per_col + (devptr ? 0 : 2 * (size_t)(37 * nlay + 60) * 8));
+    size_t chunk = pick_chunk(ncol, nlay, per_col + (devptr ? 0 : 2 * (size_t)(37 * nlay + 60) * 8), !devptr);
     if (taps) chunk = (size_t)ncol;   // taps are laid out for the whole call
     if (int rc = grow(p.slab, lw_scratch_bytes((int)chunk, nlay, dbg))) return rc;
     cudaStream_t stream = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
@@ -551,7 +555,7 @@ int rrtmgx_sw_run(const RrtmgxSwArgs *a) {
     const RrtmgxTaps *taps = p.has_taps ? &p.taps : nullptr;
     const bool dbg = taps && (taps->taug || taps->pfracs || taps->ssi);
     const size_t per_col = sw_scratch_bytes(1024, nlay, dbg) / 1024;
-    size_t chunk = pick_chunk(ncol, nlay, per_col + (devptr ? 0 : 2 * (size_t)(57 * nlay + 60) * 8));
+    size_t chunk = pick_chunk(ncol, nlay, per_col + (devptr ? 0 : 2 * (size_t)(57 * nlay + 60) * 8), !devptr);
     if (taps) chunk = (size_t)ncol;   // taps are laid out for the whole call
     if (int rc = grow(p.slab, sw_scratch_bytes((int)chunk, nlay, dbg))) return rc;
     cudaStream_t stream = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;

@@ -1175,13 +1175,10 @@ lw_band_kernel(const LwBandArgs A) {
     }
 }
 
-// Four compiled variants per band: (g-points per thread, register budget per thread; 0 = none).
+// Four compiled variants per band, (g-points per thread, register budget per thread; 0 = none):
+// v0 (1, none)  v1 (1, 64)  v2 (2, 48)  v3 (2, 64); bands with 2 g-points use 1 per thread throughout.
 // The one used is picked per band from lw_variant[] (tuned on B200; RRTMGX_LW_GN="vvv..." overrides).
-#define LW_BANDS(X)                                                                                      \
-    X(1, 1, 2, 5, 2) X(2, 1, 2, 4, 2) X(3, 1, 2, 4, 2) X(4, 1, 2, 7, 2) X(5, 1, 2, 4, 2) X(6, 1, 2, 4, 2)   \
-    X(7, 1, 2, 4, 2) X(8, 1, 2, 4, 2) X(9, 1, 2, 6, 2) X(10, 1, 2, 3, 2) X(11, 1, 2, 4, 2) X(12, 1, 2, 4, 2) \
-    X(13, 1, 2, 4, 2) X(14, 1, 2, 2, 2) X(15, 1, 2, 2, 2) X(16, 1, 2, 2, 2)
-constexpr int LW_REGS3 = 64;   // register budget of variant 3
+#define LW_BANDS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
 
 typedef void (*LwBandLauncher)(int, cudaStream_t, const LwBandArgs &);
 template <int BAND, int GN, int REGS>
@@ -1190,12 +1187,12 @@ static void lw_launch_band(int gx, cudaStream_t st, const LwBandArgs &A) {
     if (!tag[0]) std::snprintf(tag, sizeof tag, "lw_band_kernel<%d,gn%d,r%d>", BAND, GN, REGS);
     RRTMGX_LAUNCH_TAG(tag, (lw_band_kernel<BAND, GN, REGS>), dim3(gx), dim3(32, LwBandInfo<BAND>::ng / GN), 0, st, A);
 }
-#define X(BAND, A0, A1, A2, A3)                                                                   \
-    {lw_launch_band<BAND, A0, 0>, lw_launch_band<BAND, A1, 0>, lw_launch_band<BAND, A2, 0>,       \
-     lw_launch_band<BAND, A3, LW_REGS3>},
+#define X(BAND)                                                                                              \
+    {lw_launch_band<BAND, 1, 0>, lw_launch_band<BAND, 1, 64>, lw_launch_band<BAND, (BAND >= 14 ? 1 : 2), 48>,    \
+     lw_launch_band<BAND, (BAND >= 14 ? 1 : 2), 64>},
 static const LwBandLauncher lw_launchers[16][4] = {LW_BANDS(X)};
 #undef X
-static int lw_variant[16] = {3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 0, 0, 0};   // profiles/r1_gn_tuning.txt
+static int lw_variant[16] = {2, 2, 3, 3, 3, 2, 2, 3, 2, 3, 3, 3, 1, 0, 0, 0};   // profiles/r1_gn_tuning.txt
 
 // fixed-order sum of the band partials -> caller arrays; band OLR (:382-385, rad.F90:586-605)
 __global__ void lw_reduce_kernel(int ld, int col0, int nc, int nlay, int dudTs, const double *__restrict__ part,
