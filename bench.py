@@ -56,7 +56,8 @@ def make_state(ncol, nlay, seed, col0, workers):
         return make_columns(ncol, nlay, seed=seed, col0=col0)
     jobs = [(min(slab, ncol - c), nlay, seed, col0 + c) for c in range(0, ncol, slab)]
     import multiprocessing as mp
-    with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
+    # spawn, not fork: callers may already hold a CUDA context and helper threads
+    with mp.get_context("spawn").Pool(min(workers, len(jobs))) as pool:
         parts = pool.map(_gen_slab, jobs)
     out = dict(parts[0])
     for k, v in parts[0].items():
