@@ -153,6 +153,9 @@ struct LwWork {
     int *laytrop;             // [nc]
     uint32_t *seeds;          // [4][nc]
     double *alpha, *rcorr;    // [nlay][nc]
+    long long *t_alpha, *t_rcorr, *t_cld;   // [nlay][nc] integer thresholds of the McICA comparisons
+    double *abscoice, *abscoliq;   // [16][nlay][nc] cloud absorption coefficients per band (cloudy layers)
+    unsigned char *cldtrap;   // [nlay][nc] bit0: ice radius out of range, bit1: liquid radius out of range
     uint32_t *mask;           // [nw][140][nc] optical cloud mask
     uint32_t *cloudy_any;     // [nw][nc]
     double *taucmc;           // [nlay][140][nc], valid where the mask bit is set
@@ -353,16 +356,21 @@ lw_setcoef_kernel(int ld, int col0, LwWork W, int dudTs,
 // ---------------------------------------------------------------------------------------------
 // cloud optics inside the McICA sweep: LW/src/rrtmg_lw_cldprmc.F90:24-385
 // ---------------------------------------------------------------------------------------------
-struct LwOptics {
-    int ld, col0, nc, nlay;
-    const double *reice, *reliq;   // caller arrays (ld, nlay)
-    int iceflag, liqflag;
-    double *taucmc;                // [nlay][140][nc]
-    struct State {};
-    __device__ __forceinline__ void finish(int, int, State &) const {}
-
-    // index clamp / extrapolation traps shared by iceflag 2,3,4 and liqflag 1 (:227-268,:318-360)
-    __device__ __forceinline__ bool lookup_index(double factor, int hi, int &index) const {
+// Absorption coefficients per (band, layer, column), formed once instead of once per subcolumn:
+// ice by iceflag 0-4 (:227-268), liquid by liqflag 1 (:318-360).  Radii outside the table range
+// are flagged; the trap fires only if a McICA-cloudy cell uses the layer, as in the reference.
+__global__ void lw_cldcoef_kernel(int ld, int col0, int nc, int nlay, int iceflag,
+                                  const double *__restrict__ cldf, const double *__restrict__ reice,
+                                  const double *__restrict__ reliq, double *__restrict__ abscoice,
+                                  double *__restrict__ abscoliq, unsigned char *__restrict__ cldtrap) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lay = blockIdx.y;
+    if (c >= nc) return;
+    const size_t i2 = (size_t)lay * ld + col0 + c;
+    const size_t j = (size_t)lay * nc + c, n2 = (size_t)nlay * nc;
+    if (!(cldf[i2] > 0.)) return;   // no subcolumn of this layer can be cloudy
+    // index clamp / extrapolation traps shared by iceflag 2,3,4 and liqflag 1
+    auto lookup_index = [](double factor, int hi, int &index) {
         int idx = f_int(factor);
         if (idx >= hi) {
             if (idx == hi) idx = hi - 1; else return false;
@@ -371,50 +379,61 @@ struct LwOptics {
         }
         index = idx;
         return true;
+    };
+    unsigned char trap = 0;
+    const double re = reice[i2];
+    const double *itab = nullptr;
+    int ilead = 0, iindex = 1;
+    double ifint = 0.;
+    if (iceflag >= 2) {
+        double factor;
+        if (iceflag == 2) { factor = (re - 2.) / 3.; ilead = 43; itab = c_lw.absice2; }
+        else if (iceflag == 3) { factor = (re - 2.) / 3.; ilead = 46; itab = c_lw.absice3; }
+        else { factor = re; ilead = 200; itab = c_lw.absice4; }
+        if (!lookup_index(factor, ilead, iindex)) { trap |= 1; iindex = 1; }
+        ifint = factor - (double)iindex;
     }
+    const double lfactor = reliq[i2] - 1.5;
+    int lindex = 1;
+    if (!lookup_index(lfactor, 58, lindex)) { trap |= 2; lindex = 1; }
+    const double lfint = lfactor - (double)lindex;
+    cldtrap[j] = trap;
+    for (int ib = 1; ib <= 16; ++ib) {
+        double ai;
+        if (iceflag == 0) {
+            ai = c_lw.absice0[0] + c_lw.absice0[1] / re;
+        } else if (iceflag == 1) {
+            const int k = ib <= 2 ? ib : (ib <= 5 ? 3 : (ib <= 8 ? 4 : 5));   // rrlw_cld.F90 ice1b map
+            ai = c_lw.absice1[2 * (k - 1)] + c_lw.absice1[1 + 2 * (k - 1)] / re;
+        } else {
+            const double *cb = itab + (size_t)ilead * (ib - 1);
+            ai = cb[iindex - 1] + ifint * (cb[iindex] - (cb[iindex - 1]));
+        }
+        const double *cl = c_lw.absliq1 + (size_t)58 * (ib - 1);
+        abscoice[(size_t)(ib - 1) * n2 + j] = ai;
+        abscoliq[(size_t)(ib - 1) * n2 + j] = cl[lindex - 1] + lfint * (cl[lindex] - (cl[lindex - 1]));
+    }
+}
 
-    // Called for every McICA-cloudy cell.  The reference derives the radius table indices (and
-    // traps out-of-range radii) for every layer with at least one such cell, whichever phase
-    // holds water (:193-205, :227-268, :318-360), so both indices are derived here up front.
+struct LwOptics {
+    int nc, nlay;
+    const double *abscoice, *abscoliq;   // [16][nlay][nc]
+    const unsigned char *cldtrap;        // [nlay][nc]
+    double *taucmc;                      // [nlay][140][nc]
+    struct State {};
+    __device__ __forceinline__ void finish(int, int, State &) const {}
+
+    // Called for every McICA-cloudy cell: taucmc = ciwp*abscoice + clwp*abscoliq (:362-383).  The
+    // reference derives both radius indices (and traps) for every layer holding such a cell,
+    // whichever phase holds water (:193-205).
     __device__ __forceinline__ bool cell(int lay, int ig, int c, double ciw, double clw, int *err, State &) const {
-        const size_t i2 = (size_t)lay * ld + col0 + c;
+        const size_t j = (size_t)lay * nc + c, n2 = (size_t)nlay * nc;
         const int ib = c_lw.ngb[ig];   // 1-based band
-        const double re = reice[i2];
-        const double *itab = nullptr;
-        int ilead = 0, iindex = 1;
-        double ifint = 0.;
-        if (iceflag >= 2) {
-            double factor;
-            if (iceflag == 2) { factor = (re - 2.) / 3.; ilead = 43; itab = c_lw.absice2; }
-            else if (iceflag == 3) { factor = (re - 2.) / 3.; ilead = 46; itab = c_lw.absice3; }
-            else { factor = re; ilead = 200; itab = c_lw.absice4; }
-            if (!lookup_index(factor, ilead, iindex)) { raise(err, RRTMGX_ERADIUS_ICE); iindex = 1; }
-            ifint = factor - (double)iindex;
-        }
-        const double lfactor = reliq[i2] - 1.5;
-        int lindex = 1;
-        if (!lookup_index(lfactor, 58, lindex)) { raise(err, RRTMGX_ERADIUS_LIQ); lindex = 1; }
-        const double lfint = lfactor - (double)lindex;
-
+        const unsigned char trap = cldtrap[j];
+        if (trap) raise(err, (trap & 1) ? RRTMGX_ERADIUS_ICE : RRTMGX_ERADIUS_LIQ);
         double tau = 0.;
-        if (ciw > 0.) {
-            double abscoice;
-            if (iceflag == 0) {
-                abscoice = c_lw.absice0[0] + c_lw.absice0[1] / re;
-            } else if (iceflag == 1) {
-                const int k = ib <= 2 ? ib : (ib <= 5 ? 3 : (ib <= 8 ? 4 : 5));   // rrlw_cld.F90 ice1b map
-                abscoice = c_lw.absice1[2 * (k - 1)] + c_lw.absice1[1 + 2 * (k - 1)] / re;
-            } else {
-                const double *cb = itab + (size_t)ilead * (ib - 1);
-                abscoice = cb[iindex - 1] + ifint * (cb[iindex] - (cb[iindex - 1]));
-            }
-            tau = ciw * abscoice;
-        }
-        if (clw > 0.) {
-            const double *cb = c_lw.absliq1 + (size_t)58 * (ib - 1);
-            const double abscoliq = cb[lindex - 1] + lfint * (cb[lindex] - (cb[lindex - 1]));
-            tau = tau + clw * abscoliq;
-        }
+        if (ciw > 0.) tau = ciw * abscoice[(size_t)(ib - 1) * n2 + j];
+        if (clw > 0.) tau = tau + clw * abscoliq[(size_t)(ib - 1) * n2 + j];
         const bool optical = tau > 0.;
         if (optical) taucmc[((size_t)lay * 140 + ig) * nc + c] = tau;
         return optical;
@@ -1250,6 +1269,12 @@ static LwWork lw_carve(Slab &slab, int nc, int nlay) {
     W.seeds = slab.take<uint32_t>((size_t)4 * nc);
     W.alpha = slab.take<double>(n2);
     W.rcorr = slab.take<double>(n2);
+    W.t_alpha = slab.take<long long>(n2);
+    W.t_rcorr = slab.take<long long>(n2);
+    W.t_cld = slab.take<long long>(n2);
+    W.abscoice = slab.take<double>(16 * n2);
+    W.abscoliq = slab.take<double>(16 * n2);
+    W.cldtrap = slab.take<unsigned char>(n2);
     W.mask = slab.take<uint32_t>(nw * 140 * nc);
     W.cloudy_any = slab.take<uint32_t>(nw * nc);
     W.taucmc = slab.take<double>(n2 * 140);
@@ -1292,11 +1317,14 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
                   a->cfc11vmr, a->cfc12vmr, a->cfc22vmr, a->ccl4vmr, d_err);
     RRTMGX_LAUNCH(mcica_prep_kernel, grd, blk, 0, stream, ld, col0, nc, nlay, mp, a->zm, a->play, a->alat,
                   W.seeds, W.alpha, W.rcorr);
-    LwOptics opt{ld, col0, nc, nlay, a->rei, a->rel, a->iceflglw, a->liqflglw, W.taucmc};
-    RRTMGX_LAUNCH(mcica_kernel<LwOptics>, dim3((140 + MCICA_SUBS - 1) / MCICA_SUBS, (nc + 31) / 32), dim3(32, MCICA_SUBS), 0, stream, ld, col0,
-                  nc, nlay, 140, mp, d_jumps,
-                  W.seeds, W.alpha, W.rcorr, a->cldf, a->ciwp, a->clwp, 1.e-20, a->cloudLM, a->cloudMH,
-                  a->clearCounts, W.cloudy_any, W.mask, opt, d_err);
+    RRTMGX_LAUNCH(mcica_threshold_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, nc, nlay, mp.inhomo, W.alpha,
+                  W.rcorr, a->cldf, W.t_alpha, W.t_rcorr, W.t_cld);
+    RRTMGX_LAUNCH(lw_cldcoef_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, nc, nlay, a->iceflglw, a->cldf,
+                  a->rei, a->rel, W.abscoice, W.abscoliq, W.cldtrap);
+    LwOptics opt{nc, nlay, W.abscoice, W.abscoliq, W.cldtrap, W.taucmc};
+    RRTMGX_LAUNCH(mcica_kernel<LwOptics>, dim3((140 + MCICA_SUBS - 1) / MCICA_SUBS, (nc + 31) / 32), dim3(32, MCICA_SUBS),
+                  0, stream, ld, col0, nc, nlay, 140, mp, d_jumps, W.seeds, W.t_alpha, W.t_rcorr, W.t_cld, a->cldf,
+                  a->ciwp, a->clwp, 1.e-20, a->cloudLM, a->cloudMH, a->clearCounts, W.cloudy_any, W.mask, opt, d_err);
 
     LwBandArgs A{ld, col0, W, a->dudTs, a->play, a->emis, a->tauaer, dbg_taug, dbg_pfracs};
     // fan the independent band units out over the side streams

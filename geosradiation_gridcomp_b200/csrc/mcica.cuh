@@ -50,18 +50,52 @@ struct Kiss {
         s3 = mwc_jump<18000u>(s3, J.n, J.mwc3);
         s4 = mwc_jump<30903u>(s4, J.n, J.mwc4);
     }
-    // SH/cloud_subcol_gen.F90:568-575 (int32 wraparound, logical shifts)
-    __device__ __forceinline__ double draw() {
+    // SH/cloud_subcol_gen.F90:568-574 (int32 wraparound, logical shifts): the integer `kiss`
+    __device__ __forceinline__ int32_t draw_int() {
         s1 = 69069u * s1 + 1327217885u;
         s2 = s2 ^ (s2 << 13);
         s2 = s2 ^ (s2 >> 17);
         s2 = s2 ^ (s2 << 5);
         s3 = 18000u * (s3 & 65535u) + (s3 >> 16);
         s4 = 30903u * (s4 & 65535u) + (s4 >> 16);
-        uint32_t kiss = s1 + s2 + (s3 << 16) + s4;
-        return (double)(int32_t)kiss * 2.328306e-10 + 0.5;
+        return (int32_t)(s1 + s2 + (s3 << 16) + s4);
     }
 };
+
+// ran_num of an integer draw, SH/cloud_subcol_gen.F90:575 (the literal is not 2^-32)
+__device__ __forceinline__ double kiss_value(int32_t kiss) { return (double)kiss * 2.328306e-10 + 0.5; }
+
+// kiss_value is monotone non-decreasing in the integer (exact conversion, one rounded multiply by
+// a positive constant, one rounded add), so every comparison the generator makes between a random
+// number and a real threshold t is equivalent to an integer comparison with
+//   K(t) = min{ k in [-2^31, 2^31) : kiss_value(k) >= t }   (2^31 when no k qualifies):
+//   ran < t  <=>  kiss < K(t),      ran >= t  <=>  kiss >= K(t).
+// K is found with the same floating-point operations, so the cloud masks stay bit-identical.
+__device__ __forceinline__ long long kiss_threshold(double t) {
+    long long lo = -2147483648LL, hi = 2147483648LL;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;   // floor
+        if (kiss_value((int32_t)mid) >= t) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// integer thresholds of the three comparisons of the layer sweep, one thread per (layer, column)
+static __global__ void mcica_threshold_kernel(int ld, int col0, int nc, int nlay, int inhomo,
+                                              const double *__restrict__ alpha, const double *__restrict__ rcorr,
+                                              const double *__restrict__ cldf,
+                                              long long *__restrict__ t_alpha, long long *__restrict__ t_rcorr,
+                                              long long *__restrict__ t_cld) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (c >= nc) return;
+    const size_t j = (size_t)k * nc + c;
+    if (k > 0) {
+        t_alpha[j] = kiss_threshold(alpha[j]);                 // cdf2 < alpha(k), :411
+        if (inhomo) t_rcorr[j] = kiss_threshold(rcorr[j]);     // cdf2 < rcorr(k), :424
+    }
+    t_cld[j] = kiss_threshold(1. - cldf[(size_t)k * ld + col0 + c]);   // cdf1 >= 1 - cldfrac, :435
+}
 
 // SH/cloud_condensate_inhomogeneity.F90:86-124
 __device__ __forceinline__ double zcw_lookup(const double *__restrict__ xcw, double cdf, double sigma_qcw) {
@@ -139,8 +173,8 @@ template <class Optics>
 __global__ void __launch_bounds__(32 * MCICA_SUBS)
 mcica_kernel(int ld, int col0, int nc, int nlay, int nsub, McicaParams P,
              const KissJump *__restrict__ jumps, const uint32_t *__restrict__ seeds,
-             const double *__restrict__ alpha, const double *__restrict__ rcorr,
-             const double *__restrict__ cldf, const double *__restrict__ ciwp,
+             const long long *__restrict__ t_alpha, const long long *__restrict__ t_rcorr,
+             const long long *__restrict__ t_cld, const double *__restrict__ cldf, const double *__restrict__ ciwp,
              const double *__restrict__ clwp, double cwp_tiny, int cloudLM, int cloudMH,
              int *__restrict__ clearCounts,      // (ld,4)
              uint32_t *__restrict__ cloudy_any,  // [nw][nc]
@@ -163,29 +197,27 @@ mcica_kernel(int ld, int col0, int nc, int nlay, int nsub, McicaParams P,
 
     const bool surf1 = cloudLM < cloudMH;
     bool any_all = false, any_low = false, any_mid = false, any_high = false;
-    double cdf1 = 0., cdf3 = 0.;
+    int32_t k1 = 0, k3 = 0;   // integer draws behind cdf1 / cdf3, carried down the column
     uint32_t word = 0;
     typename Optics::State ost{};
     for (int k = 0; k < nlay; ++k) {
-        const size_t i2 = (size_t)k * ld + col;
         const size_t j2 = (size_t)k * nc + c;
-        double c1 = a.draw();
-        double c2 = a.draw();
-        if (k > 0 && c2 < alpha[j2]) c1 = cdf1;
-        cdf1 = c1;
+        const int32_t d1 = a.draw_int();
+        const int32_t d2 = a.draw_int();
+        if (!(k > 0 && (long long)d2 < t_alpha[j2])) k1 = d1;          // else cdf1(k) = cdf1(k-1)
         if (P.inhomo) {
-            double c2b = b.draw();
-            double c3 = b.draw();
-            if (k > 0 && c2b < rcorr[j2]) c3 = cdf3;
-            cdf3 = c3;
+            const int32_t e2 = b.draw_int();
+            const int32_t e3 = b.draw_int();
+            if (!(k > 0 && (long long)e2 < t_rcorr[j2])) k3 = e3;      // else cdf3(k) = cdf3(k-1)
         }
-        const double cf = cldf[i2];
         bool optical = false;
-        if (cdf1 >= 1. - cf) {
+        if ((long long)k1 >= t_cld[j2]) {
+            const size_t i2 = (size_t)k * ld + col;
             double ciw = ciwp[i2], clw = clwp[i2];
             if (P.inhomo) {
+                const double cf = cldf[i2];
                 double sigma = cf > 0.99 ? 0.5 : (cf > 0.9 ? 0.71 : 1.0);
-                double zcw = zcw_lookup(P.xcw, cdf3, sigma);
+                double zcw = zcw_lookup(P.xcw, kiss_value(k3), sigma);
                 ciw = ciw * zcw;
                 clw = clw * zcw;
             }
