@@ -15,6 +15,9 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_partition.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
 #include "engine.h"
 
 namespace rrtmgx {
@@ -253,6 +256,35 @@ __global__ void heating_rate_kernel(int ncol, int nlay, const double *__restrict
 }
 
 }  // namespace
+
+namespace {
+__global__ void cloudy_flag_kernel(int ld, int col0, int nc, int nlay, const double *__restrict__ cldf,
+                                   unsigned char *__restrict__ flag) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    bool any = false;
+    for (int k = 0; k < nlay; ++k) any |= cldf[(size_t)k * ld + col0 + c] > 0.;
+    flag[c] = any ? 1 : 0;
+}
+}  // namespace
+
+size_t cloud_partition_tmp_bytes(int nc) {
+    size_t bytes = 0;
+    thrust::counting_iterator<int> it(0);
+    cub::DevicePartition::Flagged(nullptr, bytes, it, (const unsigned char *)nullptr, (int *)nullptr, (int *)nullptr, nc);
+    return bytes + 256;
+}
+
+int build_cloud_partition(int ld, int col0, int nc, int nlay, const double *cldf, int *perm, unsigned char *flags,
+                          void *tmp, size_t tmp_bytes, cudaStream_t stream) {
+    RRTMGX_LAUNCH(cloudy_flag_kernel, (nc + 255) / 256, 256, 0, stream, ld, col0, nc, nlay, cldf, flags);
+    thrust::counting_iterator<int> it(0);
+    int *d_nsel = (int *)tmp;   // first 256 bytes of tmp hold the selected count
+    size_t bytes = tmp_bytes - 256;
+    ++g_launches;
+    return cub::DevicePartition::Flagged((char *)tmp + 256, bytes, it, flags, perm, d_nsel, nc, stream) == cudaSuccess
+               ? 0 : RRTMGX_ECUDA;
+}
 
 void launch_check_negative(const double *x, size_t n, int pos, int *d_negpos, cudaStream_t s) {
     if (!x || !n) return;

@@ -156,6 +156,9 @@ struct LwWork {
     long long *t_alpha, *t_rcorr, *t_cld;   // [nlay][nc] integer thresholds of the McICA comparisons
     double *abscoice, *abscoliq;   // [16][nlay][nc] cloud absorption coefficients per band (cloudy layers)
     unsigned char *cldtrap;   // [nlay][nc] bit0: ice radius out of range, bit1: liquid radius out of range
+    int *perm;                // [nc] cloudy columns first (build_cloud_partition)
+    unsigned char *pflags;    // [nc]
+    char *ptmp; size_t ptmp_bytes;
     uint32_t *mask;           // [nw][140][nc] optical cloud mask
     uint32_t *cloudy_any;     // [nw][nc]
     double *taucmc;           // [nlay][140][nc], valid where the mask bit is set
@@ -182,7 +185,7 @@ __device__ __forceinline__ double chi_mls(int m, int j) { return c_lw.chi_mls[(m
 
 // LW/src/rrtmg_lw_setcoef.F90:52-584.  One thread per column, layers bottom-up.
 __global__ void __launch_bounds__(128)
-lw_setcoef_kernel(int ld, int col0, LwWork W, int dudTs,
+lw_setcoef_kernel(int ld, int col0, const int *__restrict__ perm, LwWork W, int dudTs,
                   const double *__restrict__ pavel, const double *__restrict__ tavel,
                   const double *__restrict__ pz, const double *__restrict__ tz,
                   const double *__restrict__ tbound, const double *__restrict__ semiss,
@@ -194,7 +197,7 @@ lw_setcoef_kernel(int ld, int col0, LwWork W, int dudTs,
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int nc = W.nc, nlay = W.nlay;
     if (c >= nc) return;
-    const size_t col = (size_t)col0 + c;
+    const size_t col = gcol(col0, perm, c);
     const double amd = 28.9660, amw = 18.0160;
     const double stpfac = 296. / 1013.;
     const double grav = c_lw.grav, avogad = c_lw.avogad;
@@ -359,14 +362,14 @@ lw_setcoef_kernel(int ld, int col0, LwWork W, int dudTs,
 // Absorption coefficients per (band, layer, column), formed once instead of once per subcolumn:
 // ice by iceflag 0-4 (:227-268), liquid by liqflag 1 (:318-360).  Radii outside the table range
 // are flagged; the trap fires only if a McICA-cloudy cell uses the layer, as in the reference.
-__global__ void lw_cldcoef_kernel(int ld, int col0, int nc, int nlay, int iceflag,
+__global__ void lw_cldcoef_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, int iceflag,
                                   const double *__restrict__ cldf, const double *__restrict__ reice,
                                   const double *__restrict__ reliq, double *__restrict__ abscoice,
                                   double *__restrict__ abscoliq, unsigned char *__restrict__ cldtrap) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int lay = blockIdx.y;
     if (c >= nc) return;
-    const size_t i2 = (size_t)lay * ld + col0 + c;
+    const size_t i2 = (size_t)lay * ld + gcol(col0, perm, c);
     const size_t j = (size_t)lay * nc + c, n2 = (size_t)nlay * nc;
     if (!(cldf[i2] > 0.)) return;   // no subcolumn of this layer can be cloudy
     // index clamp / extrapolation traps shared by iceflag 2,3,4 and liqflag 1
@@ -927,6 +930,7 @@ __device__ __forceinline__ void lw_band_layer(const Lay &L, bool lower, double p
 // ---------------------------------------------------------------------------------------------
 struct LwBandArgs {
     int ld, col0;
+    const int *perm;         // optional column grouping of the chunk
     LwWork W;
     int dudTs;
     const double *pavel;     // caller (ld,nlay)
@@ -1013,7 +1017,7 @@ lw_band_kernel(const LwBandArgs A) {
     const int c0 = blockIdx.x * 32 + threadIdx.x;
     const bool active = c0 < nc;
     const int c = active ? c0 : nc - 1;   // idle lanes shadow the last column and never store
-    const size_t col = (size_t)A.col0 + c;
+    const size_t col = gcol(A.col0, A.perm, c);
     constexpr int ib = BAND - 1;
     const int gs = BAND == 1 ? 0 : c_lw.ngs[ib - 1];   // first g-point (0-based) of the band
     const int G0 = threadIdx.y * GN;
@@ -1214,7 +1218,7 @@ static const LwBandLauncher lw_launchers[16][4] = {LW_BANDS(X)};
 static int lw_variant[16] = {2, 2, 3, 3, 3, 2, 2, 3, 2, 3, 3, 3, 1, 0, 0, 0};   // profiles/r1_gn_tuning.txt
 
 // fixed-order sum of the band partials -> caller arrays; band OLR (:382-385, rad.F90:586-605)
-__global__ void lw_reduce_kernel(int ld, int col0, int nc, int nlay, int dudTs, const double *__restrict__ part,
+__global__ void lw_reduce_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, int dudTs, const double *__restrict__ part,
                                  double *__restrict__ uflx, double *__restrict__ dflx,
                                  double *__restrict__ uflxc, double *__restrict__ dflxc,
                                  double *__restrict__ duflx, double *__restrict__ duflxc, int band_mask,
@@ -1225,7 +1229,7 @@ __global__ void lw_reduce_kernel(int ld, int col0, int nc, int nlay, int dudTs, 
     const size_t fstride = (size_t)(nlay + 1) * nc;
     const size_t o = (size_t)lev * nc + c;
     double s[LP_COUNT] = {0., 0., 0., 0., 0., 0.};
-    const size_t col = (size_t)col0 + c;
+    const size_t col = gcol(col0, perm, c);
     const bool top = lev == nlay;
     for (int b = 0; b < 16; ++b) {
         const double *p = part + (size_t)b * LP_COUNT * fstride + o;
@@ -1275,6 +1279,10 @@ static LwWork lw_carve(Slab &slab, int nc, int nlay) {
     W.abscoice = slab.take<double>(16 * n2);
     W.abscoliq = slab.take<double>(16 * n2);
     W.cldtrap = slab.take<unsigned char>(n2);
+    W.perm = slab.take<int>(nc);
+    W.pflags = slab.take<unsigned char>(nc);
+    W.ptmp_bytes = cloud_partition_tmp_bytes(nc);
+    W.ptmp = slab.take<char>(W.ptmp_bytes);
     W.mask = slab.take<uint32_t>(nw * 140 * nc);
     W.cloudy_any = slab.take<uint32_t>(nw * nc);
     W.taucmc = slab.take<double>(n2 * 140);
@@ -1312,21 +1320,28 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
     for (int k = 0; k < 4; ++k)
         cudaMemsetAsync(a->clearCounts + (size_t)k * ld + col0, 0, sizeof(int32_t) * (size_t)nc, stream);
 
-    RRTMGX_LAUNCH(lw_setcoef_kernel, grd, blk, 0, stream, ld, col0, W, a->dudTs, a->play, a->tlay, a->plev,
+    // group cloudy and cloud-free columns (not under debug taps, whose layouts assume identity order)
+    const int *perm = nullptr;
+    if (!taps) {
+        if (int rc = build_cloud_partition(ld, col0, nc, nlay, a->cldf, W.perm, W.pflags, W.ptmp, W.ptmp_bytes, stream))
+            return rc;
+        perm = W.perm;
+    }
+    RRTMGX_LAUNCH(lw_setcoef_kernel, grd, blk, 0, stream, ld, col0, perm, W, a->dudTs, a->play, a->tlay, a->plev,
                   a->tlev, a->tsfc, a->emis, a->h2ovmr, a->o3vmr, a->co2vmr, a->ch4vmr, a->n2ovmr, a->o2vmr,
                   a->cfc11vmr, a->cfc12vmr, a->cfc22vmr, a->ccl4vmr, d_err);
-    RRTMGX_LAUNCH(mcica_prep_kernel, grd, blk, 0, stream, ld, col0, nc, nlay, mp, a->zm, a->play, a->alat,
+    RRTMGX_LAUNCH(mcica_prep_kernel, grd, blk, 0, stream, ld, col0, perm, nc, nlay, mp, a->zm, a->play, a->alat,
                   W.seeds, W.alpha, W.rcorr);
-    RRTMGX_LAUNCH(mcica_threshold_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, nc, nlay, mp.inhomo, W.alpha,
+    RRTMGX_LAUNCH(mcica_threshold_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, perm, nc, nlay, mp.inhomo, W.alpha,
                   W.rcorr, a->cldf, W.t_alpha, W.t_rcorr, W.t_cld);
-    RRTMGX_LAUNCH(lw_cldcoef_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, nc, nlay, a->iceflglw, a->cldf,
+    RRTMGX_LAUNCH(lw_cldcoef_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, perm, nc, nlay, a->iceflglw, a->cldf,
                   a->rei, a->rel, W.abscoice, W.abscoliq, W.cldtrap);
     LwOptics opt{nc, nlay, W.abscoice, W.abscoliq, W.cldtrap, W.taucmc};
     RRTMGX_LAUNCH(mcica_kernel<LwOptics>, dim3((140 + MCICA_SUBS - 1) / MCICA_SUBS, (nc + 31) / 32), dim3(32, MCICA_SUBS),
-                  0, stream, ld, col0, nc, nlay, 140, mp, d_jumps, W.seeds, W.t_alpha, W.t_rcorr, W.t_cld, a->cldf,
+                  0, stream, ld, col0, perm, nc, nlay, 140, mp, d_jumps, W.seeds, W.t_alpha, W.t_rcorr, W.t_cld, a->cldf,
                   a->ciwp, a->clwp, 1.e-20, a->cloudLM, a->cloudMH, a->clearCounts, W.cloudy_any, W.mask, opt, d_err);
 
-    LwBandArgs A{ld, col0, W, a->dudTs, a->play, a->emis, a->tauaer, dbg_taug, dbg_pfracs};
+    LwBandArgs A{ld, col0, perm, W, a->dudTs, a->play, a->emis, a->tauaer, dbg_taug, dbg_pfracs};
     // fan the independent band units out over the side streams
     cudaEventRecord(ev[0], stream);
     for (int s = 0; s < nside; ++s) cudaStreamWaitEvent(side[s], ev[0], 0);
@@ -1349,7 +1364,7 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
     int band_mask = 0;
     for (int b = 0; b < 16; ++b)
         if (a->band_output && a->band_output[b]) band_mask |= 1 << b;
-    RRTMGX_LAUNCH(lw_reduce_kernel, dim3(grd.x, nlay + 1), blk, 0, stream, ld, col0, nc, nlay, a->dudTs, W.part,
+    RRTMGX_LAUNCH(lw_reduce_kernel, dim3(grd.x, nlay + 1), blk, 0, stream, ld, col0, perm, nc, nlay, a->dudTs, W.part,
                   a->uflx, a->dflx, a->uflxc, a->dflxc, a->duflx_dTs, a->duflxc_dTs, band_mask, a->olrb,
                   a->dolrb_dTs);
 

@@ -81,7 +81,7 @@ __device__ __forceinline__ long long kiss_threshold(double t) {
 }
 
 // integer thresholds of the three comparisons of the layer sweep, one thread per (layer, column)
-static __global__ void mcica_threshold_kernel(int ld, int col0, int nc, int nlay, int inhomo,
+static __global__ void mcica_threshold_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, int inhomo,
                                               const double *__restrict__ alpha, const double *__restrict__ rcorr,
                                               const double *__restrict__ cldf,
                                               long long *__restrict__ t_alpha, long long *__restrict__ t_rcorr,
@@ -94,7 +94,7 @@ static __global__ void mcica_threshold_kernel(int ld, int col0, int nc, int nlay
         t_alpha[j] = kiss_threshold(alpha[j]);                 // cdf2 < alpha(k), :411
         if (inhomo) t_rcorr[j] = kiss_threshold(rcorr[j]);     // cdf2 < rcorr(k), :424
     }
-    t_cld[j] = kiss_threshold(1. - cldf[(size_t)k * ld + col0 + c]);   // cdf1 >= 1 - cldfrac, :435
+    t_cld[j] = kiss_threshold(1. - cldf[(size_t)k * ld + gcol(col0, perm, c)]);   // cdf1 >= 1 - cldfrac, :435
 }
 
 // SH/cloud_condensate_inhomogeneity.F90:86-124
@@ -116,7 +116,7 @@ __device__ __forceinline__ double zcw_lookup(const double *__restrict__ xcw, dou
 // pressures (:375-400) and the inter-layer overlap / condensate correlations (:314-321).
 // Inputs are the caller's arrays (leading dimension ld, first column col0); outputs are
 // chunk-local [..][nc].
-static __global__ void mcica_prep_kernel(int ld, int col0, int nc, int nlay, McicaParams P,
+static __global__ void mcica_prep_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, McicaParams P,
                                   const double *__restrict__ zm, const double *__restrict__ play,
                                   const double *__restrict__ alat,
                                   uint32_t *__restrict__ seeds,   // [4][nc]
@@ -124,7 +124,7 @@ static __global__ void mcica_prep_kernel(int ld, int col0, int nc, int nlay, Mci
                                   double *__restrict__ rcorr) {   // [nlay][nc], k >= 1
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nc) return;
-    const size_t col = (size_t)col0 + c;
+    const size_t col = gcol(col0, perm, c);
     const double r2d = 180.0 / 3.14159265358979323846;
     double d = alat[col] * r2d - P.adl_am3;
     double adl = (P.adl_am1 + P.adl_am2 * exp(-((d * d) / (P.adl_am4 * P.adl_am4)))) * 1.e3;
@@ -171,7 +171,7 @@ constexpr int MCICA_SUBS = 7;   // divides 140 (LW) and 112 (SW)
 
 template <class Optics>
 __global__ void __launch_bounds__(32 * MCICA_SUBS)
-mcica_kernel(int ld, int col0, int nc, int nlay, int nsub, McicaParams P,
+mcica_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, int nsub, McicaParams P,
              const KissJump *__restrict__ jumps, const uint32_t *__restrict__ seeds,
              const long long *__restrict__ t_alpha, const long long *__restrict__ t_rcorr,
              const long long *__restrict__ t_cld, const double *__restrict__ cldf, const double *__restrict__ ciwp,
@@ -187,7 +187,7 @@ mcica_kernel(int ld, int col0, int nc, int nlay, int nsub, McicaParams P,
     const int c = blockIdx.y * 32 + threadIdx.x;
     const int isub = blockIdx.x * blockDim.y + threadIdx.y;
     if (c >= nc || isub >= nsub) return;
-    const size_t col = (size_t)col0 + c;
+    const size_t col = gcol(col0, perm, c);
     Kiss a, b;
     a.s1 = seeds[c]; a.s2 = seeds[(size_t)nc + c];
     a.s3 = seeds[(size_t)2 * nc + c]; a.s4 = seeds[(size_t)3 * nc + c];
