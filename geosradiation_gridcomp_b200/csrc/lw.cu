@@ -438,7 +438,7 @@ struct LwOptics {
         if (ciw > 0.) tau = ciw * abscoice[(size_t)(ib - 1) * n2 + j];
         if (clw > 0.) tau = tau + clw * abscoliq[(size_t)(ib - 1) * n2 + j];
         const bool optical = tau > 0.;
-        if (optical) taucmc[((size_t)lay * 140 + ig) * nc + c] = tau;
+        if (optical) __stcs(&taucmc[((size_t)lay * 140 + ig) * nc + c], tau);
         return optical;
     }
 };
@@ -1101,7 +1101,7 @@ lw_band_kernel(const LwBandArgs A) {
             if (!cell_cloudy) {
                 radld[ig] = radld[ig] + (bbdgas - radld[ig]) * agas;
             } else {
-                const double odcld = secdiff * W.taucmc[((size_t)lay * 140 + g) * nc + c];
+                const double odcld = secdiff * __ldcs(&W.taucmc[((size_t)lay * 140 + g) * nc + c]);
                 const double odtot = c_lw.tau_tbl[itgas] + odcld;
                 tblind = odtot / (bpade + odtot);
                 const int ittot = f_int(tblint * tblind + 0.5);
@@ -1111,7 +1111,7 @@ lw_band_kernel(const LwBandArgs A) {
                 radld[ig] = radld[ig] + (bbdtot - radld[ig]) * atot;
                 code = (uint32_t)itgas | ((uint32_t)ittot << 16);
             }
-            if (active) W.it[((size_t)lay * 140 + g) * nc + c] = code;
+            if (active) __stcs(&W.it[((size_t)lay * 140 + g) * nc + c], code);
             sums[0] = sums[0] + sumfac * radld[ig];
             if (diverge) radclrd[ig] = radclrd[ig] + (bbdgas - radclrd[ig]) * agas;
             else radclrd[ig] = radld[ig];
@@ -1168,7 +1168,7 @@ lw_band_kernel(const LwBandArgs A) {
         double sums[4] = {0., 0., 0., 0.};
         FORG {
             const int g = g_first + ig;
-            const uint32_t code = W.it[((size_t)lay * 140 + g) * nc + c];
+            const uint32_t code = __ldcs(&W.it[((size_t)lay * 140 + g) * nc + c]);
             const int itgas = code & 0xffffu, ittot = code >> 16;
             const double2 et = reinterpret_cast<const double2 *>(c_lw.exptfn)[itgas];
             const double agas = 1. - et.x;
