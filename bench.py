@@ -139,6 +139,9 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 per rank; rank 0 alone runs this arm, with every host thread
+    if "RANK" in os.environ or "OMP_NUM_THREADS" not in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     with_sw = oracle_has_sw()
     sample = a.cpu_sample
     rates, secs = [], []
@@ -362,7 +365,7 @@ def main():
                 "algorithmic_bytes_per_column": bpc,
                 "note": "fp64-pipe-bound path: see DESIGN.md for the FP64 roof beside the HBM roof"}
     cpu = None
-    if not a.no_cpu:
+    if not a.no_cpu and world == 1:
         r, threads, dt = cpu_oracle_rate(a.cpu_sample, nlay, a.seed, with_sw and oracle_has_sw())
         cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{a.cpu_sample} columns x L{nlay} of the same synthetic workload, "
