@@ -16,6 +16,7 @@
 #include <vector>
 
 #include <cub/device/device_partition.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
 #include "engine.h"
@@ -154,18 +155,21 @@ __global__ void check_negative_kernel(const double *__restrict__ x, size_t n, in
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicMin(negpos, pos);
 }
 
+// the band kernels address the per-(layer, column) planes of a chunk with 32-bit element offsets
+// (at most 32 planes of nlay*nc elements)
+size_t chunk_cap(int nlay) { return (((size_t)1 << 31) - 1) / ((size_t)32 * std::max(nlay, 1)); }
+
 size_t pick_chunk(int ncol, int nlay, size_t per_col_bytes, bool host_mode) {
-    if (g.chunk_cols) return std::min<size_t>(g.chunk_cols, (size_t)ncol);
+    if (g.chunk_cols) return std::min<size_t>(std::min<size_t>(g.chunk_cols, chunk_cap(nlay)), (size_t)ncol);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     // scratch budget per path: 30% of what is free, at most 40 GiB (B200: 180 GB of HBM3e)
     size_t budget = std::min<size_t>(free_b / 10 * 3, (size_t)40 << 30);
     size_t nc = std::max<size_t>(1024, budget / std::max<size_t>(per_col_bytes, 1));
-    nc = std::min<size_t>(nc, 65536);
+    nc = std::min<size_t>(std::min<size_t>(nc, 65536), chunk_cap(nlay));
     // host arrays: smaller chunks shorten the fill/drain of the H2D -> kernels -> D2H pipeline
     if (host_mode) nc = std::min<size_t>(nc, g.host_chunk_cols);
     nc &= ~(size_t)127;
-    (void)nlay;
     return std::min<size_t>(nc, (size_t)ncol);
 }
 
@@ -255,6 +259,18 @@ __global__ void heating_rate_kernel(int ncol, int nlay, const double *__restrict
     hr[i] = (fnet[i] - fnet[i + ncol]) * gcp / ((plev[i] - plev[i + ncol]) * 100.) * 86400.;
 }
 
+// the band kernels' branch-free division and reciprocal beside the compiler's IEEE ones
+__global__ void debug_divide_kernel(size_t n, const double *__restrict__ a, const double *__restrict__ b,
+                                    double *__restrict__ q_fast, double *__restrict__ q_ieee,
+                                    double *__restrict__ r_fast, double *__restrict__ r_ieee) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    q_fast[i] = ddiv(a[i], b[i]);
+    q_ieee[i] = a[i] / b[i];
+    r_fast[i] = drcp(b[i]);
+    r_ieee[i] = 1. / b[i];
+}
+
 }  // namespace
 
 namespace {
@@ -266,23 +282,67 @@ __global__ void cloudy_flag_kernel(int ld, int col0, int nc, int nlay, const dou
     for (int k = 0; k < nlay; ++k) any |= cldf[(size_t)k * ld + col0 + c] > 0.;
     flag[c] = any ? 1 : 0;
 }
+
+// sort key of a column: cloudy columns first, then by the pressure of layer 1 (monotone map of the
+// positive float onto 31 bits)
+__global__ void column_key_kernel(int ld, int col0, int nc, int nlay, const double *__restrict__ cldf,
+                                  const double *__restrict__ pkey, unsigned char *__restrict__ flag,
+                                  uint32_t *__restrict__ key, int *__restrict__ iota, int *__restrict__ ncloudy) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    bool any = false;
+    if (c < nc) {
+        for (int k = 0; k < nlay; ++k) any |= cldf[(size_t)k * ld + col0 + c] > 0.;
+        flag[c] = any ? 1 : 0;
+        const float p = (float)pkey[(size_t)col0 + c];
+        key[c] = (any ? 0u : 0x80000000u) | (__float_as_uint(p > 0.f ? p : 0.f) >> 1);
+        iota[c] = c;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, any);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(ncloudy, __popc(m));
+}
+
+// RRTMGX_SORT=0 keeps the columns of a chunk in the caller's order within the cloudy / cloud-free groups
+bool sort_columns() {
+    static const bool on = [] { const char *e = std::getenv("RRTMGX_SORT"); return !(e && e[0] == '0'); }();
+    return on;
+}
+size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 }  // namespace
 
 size_t cloud_partition_tmp_bytes(int nc) {
-    size_t bytes = 0;
+    size_t part = 0, sort = 0;
     thrust::counting_iterator<int> it(0);
-    cub::DevicePartition::Flagged(nullptr, bytes, it, (const unsigned char *)nullptr, (int *)nullptr, (int *)nullptr, nc);
-    return bytes + 256;
+    cub::DevicePartition::Flagged(nullptr, part, it, (const unsigned char *)nullptr, (int *)nullptr, (int *)nullptr, nc);
+    cub::DeviceRadixSort::SortPairs(nullptr, sort, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const int *)nullptr,
+                                    (int *)nullptr, nc);
+    return 256 + 3 * align256((size_t)nc * 4) + std::max(part, sort) + 256;
 }
 
-int build_cloud_partition(int ld, int col0, int nc, int nlay, const double *cldf, int *perm, unsigned char *flags,
-                          void *tmp, size_t tmp_bytes, cudaStream_t stream) {
+// perm[0 .. nc): the chunk's columns, those holding cloud in any layer first (count left at
+// (int*)tmp), each group ordered by the pressure of layer 1 when `pkey` is given.  Columns are
+// independent, so the order changes no result; it makes the warps of the band kernels walk the same
+// rows of the k-tables (jp follows the pressure) the way neighbouring columns of a real model state do.
+int build_cloud_partition(int ld, int col0, int nc, int nlay, const double *cldf, const double *pkey, int *perm,
+                          unsigned char *flags, void *tmp, size_t tmp_bytes, cudaStream_t stream) {
+    int *d_nsel = (int *)tmp;   // first 256 bytes of tmp hold the selected count
+    const size_t arr = align256((size_t)nc * 4);
+    char *base = (char *)tmp + 256;
+    if (pkey && sort_columns()) {
+        uint32_t *key_in = (uint32_t *)base, *key_out = (uint32_t *)(base + arr);
+        int *iota = (int *)(base + 2 * arr);
+        size_t bytes = tmp_bytes - 256 - 3 * arr;
+        cudaMemsetAsync(d_nsel, 0, sizeof(int), stream);
+        RRTMGX_LAUNCH(column_key_kernel, (nc + 255) / 256, 256, 0, stream, ld, col0, nc, nlay, cldf, pkey, flags, key_in,
+                      iota, d_nsel);
+        ++g_launches;
+        return cub::DeviceRadixSort::SortPairs(base + 3 * arr, bytes, key_in, key_out, iota, perm, nc, 0, 32, stream) ==
+                       cudaSuccess ? 0 : RRTMGX_ECUDA;
+    }
     RRTMGX_LAUNCH(cloudy_flag_kernel, (nc + 255) / 256, 256, 0, stream, ld, col0, nc, nlay, cldf, flags);
     thrust::counting_iterator<int> it(0);
-    int *d_nsel = (int *)tmp;   // first 256 bytes of tmp hold the selected count
-    size_t bytes = tmp_bytes - 256;
+    size_t bytes = tmp_bytes - 256 - 3 * arr;
     ++g_launches;
-    return cub::DevicePartition::Flagged((char *)tmp + 256, bytes, it, flags, perm, d_nsel, nc, stream) == cudaSuccess
+    return cub::DevicePartition::Flagged(base + 3 * arr, bytes, it, flags, perm, d_nsel, nc, stream) == cudaSuccess
                ? 0 : RRTMGX_ECUDA;
 }
 
@@ -460,7 +520,10 @@ int rrtmgx_lw_run(const RrtmgxLwArgs *a) {
     const bool dbg = taps && (taps->taug || taps->pfracs);
     const size_t per_col = lw_scratch_bytes(1024, nlay, dbg) / 1024;
     size_t chunk = pick_chunk(ncol, nlay, per_col + (devptr ? 0 : 2 * (size_t)(37 * nlay + 60) * 8), !devptr);
-    if (taps) chunk = (size_t)ncol;   // taps are laid out for the whole call
+    if (taps) {   // taps are laid out for the whole call
+        if ((size_t)ncol > chunk_cap(nlay)) return RRTMGX_EARG;
+        chunk = (size_t)ncol;
+    }
     if (int rc = grow(p.slab, lw_scratch_bytes((int)chunk, nlay, dbg))) return rc;
     cudaStream_t stream = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
     p.run_stream = stream;
@@ -563,6 +626,26 @@ int rrtmgx_heating_rate(int ncol, int nlay, const double *fnet_up_minus_down, co
     return ok(e) ? 0 : RRTMGX_ECUDA;
 }
 
+int rrtmgx_debug_divide(size_t n, const double *a, const double *b, double *q_fast, double *q_ieee,
+                        double *r_fast, double *r_ieee) {
+    if (!g.ready) return RRTMGX_ENOTINIT;
+    if (!n || !a || !b || !q_fast || !q_ieee || !r_fast || !r_ieee) return RRTMGX_EARG;
+    cudaSetDevice(g.device);
+    double *d = nullptr;
+    if (!ok(cudaMalloc((void **)&d, 6 * n * sizeof(double)))) { cudaGetLastError(); return RRTMGX_ECUDA; }
+    cudaMemcpy(d, a, n * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(d + n, b, n * 8, cudaMemcpyHostToDevice);
+    RRTMGX_LAUNCH(debug_divide_kernel, (unsigned)((n + 255) / 256), 256, 0, g.lw.stream, n, d, d + n, d + 2 * n,
+                  d + 3 * n, d + 4 * n, d + 5 * n);
+    cudaStreamSynchronize(g.lw.stream);
+    cudaMemcpy(q_fast, d + 2 * n, n * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(q_ieee, d + 3 * n, n * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(r_fast, d + 4 * n, n * 8, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(r_ieee, d + 5 * n, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return ok(e) ? 0 : RRTMGX_ECUDA;
+}
+
 #ifndef RRTMGX_WITH_SW
 int rrtmgx_sw_run(const RrtmgxSwArgs *) { return RRTMGX_EARG; }
 #else
@@ -588,7 +671,10 @@ int rrtmgx_sw_run(const RrtmgxSwArgs *a) {
     const bool dbg = taps && (taps->taug || taps->pfracs || taps->ssi);
     const size_t per_col = sw_scratch_bytes(1024, nlay, dbg) / 1024;
     size_t chunk = pick_chunk(ncol, nlay, per_col + (devptr ? 0 : 2 * (size_t)(57 * nlay + 60) * 8), !devptr);
-    if (taps) chunk = (size_t)ncol;   // taps are laid out for the whole call
+    if (taps) {   // taps are laid out for the whole call
+        if ((size_t)ncol > chunk_cap(nlay)) return RRTMGX_EARG;
+        chunk = (size_t)ncol;
+    }
     if (int rc = grow(p.slab, sw_scratch_bytes((int)chunk, nlay, dbg))) return rc;
     cudaStream_t stream = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
     p.run_stream = stream;

@@ -453,7 +453,7 @@ struct Spec { double speccomb, specparm, fs; int js; };
 __device__ __forceinline__ Spec spec(double cola, double rat, double colb, double mult) {
     Spec r;
     r.speccomb = cola + rat * colb;
-    r.specparm = cola / r.speccomb;
+    r.specparm = ddiv(cola, r.speccomb);
     if (r.specparm >= c_lw.oneminus) r.specparm = c_lw.oneminus;
     const double specmult = mult * r.specparm;
     const int k = f_int(specmult);
@@ -466,8 +466,8 @@ __device__ __forceinline__ Spec spec(double cola, double rat, double colb, doubl
 struct Lay {
     int jp, jt, jt1, indfor, indself, indminor;
     const double *fj;  // factor base + lay*nc + c
-    size_t n2;
-    __device__ __forceinline__ double f(int k) const { return fj[(size_t)k * n2]; }
+    int n2;            // plane stride (F_COUNT * n2 < 2^31: chunk_cap, api.cu)
+    __device__ __forceinline__ double f(int k) const { return fj[k * n2]; }
 };
 
 // lower-atmosphere key-species sum for a binary band at one reference pressure
@@ -500,7 +500,7 @@ __device__ __forceinline__ void stencil_lower(const double *__restrict__ row /* 
 template <int GN>
 __device__ __forceinline__ void lerp_rows(const double *__restrict__ t, int ng, int g0, int i, double f,
                                           double (&out)[GN]) {
-    const double *r = t + (size_t)(i - 1) * ng + g0;
+    const double *r = t + ((i - 1) * ng + g0);
     FORG out[ig] = r[ig] + f * (r[ng + ig] - r[ig]);
 }
 
@@ -508,8 +508,8 @@ __device__ __forceinline__ void lerp_rows(const double *__restrict__ t, int ng, 
 template <int GN>
 __device__ __forceinline__ void minor2(const double *__restrict__ k, int ng, int g0, int nj, int jm, int indm,
                                        double fm, double minorfrac, double (&out)[GN]) {
-    const double *a = k + ((size_t)(jm - 1) + (size_t)nj * (indm - 1)) * ng + g0;   // K(jm,indm)
-    const double *b = a + (size_t)nj * ng;                                           // K(jm,indm+1)
+    const double *a = k + (((jm - 1) + nj * (indm - 1)) * ng + g0);   // K(jm,indm)
+    const double *b = a + nj * ng;                                                   // K(jm,indm+1)
     FORG {
         const double m1 = a[ig] + fm * (a[ng + ig] - a[ig]);
         const double m2 = b[ig] + fm * (b[ng + ig] - b[ig]);
@@ -522,8 +522,8 @@ template <int GN>
 __device__ __forceinline__ void key4(const double *__restrict__ tab, int ng, int g0, int ind0, int ind1,
                                      const Lay &L, double (&out)[GN]) {
     const double fac00 = L.f(F_FAC00), fac10 = L.f(F_FAC10), fac01 = L.f(F_FAC01), fac11 = L.f(F_FAC11);
-    const double *r0 = tab + (size_t)(ind0 - 1) * ng + g0;
-    const double *r1 = tab + (size_t)(ind1 - 1) * ng + g0;
+    const double *r0 = tab + ((ind0 - 1) * ng + g0);
+    const double *r1 = tab + ((ind1 - 1) * ng + g0);
     FORG out[ig] = fac00 * r0[ig] + fac10 * r0[ng + ig] + fac01 * r1[ig] + fac11 * r1[ng + ig];
 }
 
@@ -536,8 +536,8 @@ __device__ __forceinline__ void key_upper5(const double *__restrict__ tab, int n
     const double fac100 = s0.fs * fac00, fac110 = s0.fs * fac10;
     const double fac001 = (1. - s1.fs) * fac01, fac011 = (1. - s1.fs) * fac11;
     const double fac101 = s1.fs * fac01, fac111 = s1.fs * fac11;
-    const double *r0 = tab + (size_t)(ind0 - 1) * ng + g0;
-    const double *r1 = tab + (size_t)(ind1 - 1) * ng + g0;
+    const double *r0 = tab + ((ind0 - 1) * ng + g0);
+    const double *r1 = tab + ((ind1 - 1) * ng + g0);
     FORG out[ig] = s0.speccomb * (fac000 * r0[ig] + fac100 * r0[ng + ig] + fac010 * r0[5 * ng + ig] +
                                   fac110 * r0[6 * ng + ig]) +
                    s1.speccomb * (fac001 * r1[ig] + fac101 * r1[ng + ig] + fac011 * r1[5 * ng + ig] +
@@ -550,7 +550,7 @@ enum { R_H2OCO2 = 0, R_H2OO3 = 1, R_H2ON2O = 2, R_H2OCH4 = 3, R_N2OCO2 = 4, R_O3
 template <int GN>
 __device__ __forceinline__ void pfrac2(const double *__restrict__ fr, int ng, int g0, const Spec &sp,
                                        double (&pf)[GN]) {
-    const double *r = fr + (size_t)(sp.js - 1) * ng + g0;
+    const double *r = fr + ((sp.js - 1) * ng + g0);
     FORG pf[ig] = r[ig] + sp.fs * (r[ng + ig] - r[ig]);
 }
 template <int GN>
@@ -594,8 +594,8 @@ __device__ __forceinline__ void lw_band_layer(const Lay &L, bool lower, double p
     };
     // lower-atmosphere binary key species: tau_major + tau_major1
     auto binary_lower = [&](const Spec &s0, const Spec &s1) {
-        const double *r0 = B.absa + (size_t)(ind0lo + s0.js - 1) * ng + G0;
-        const double *r1 = B.absa + (size_t)(ind1lo + s1.js - 1) * ng + G0;
+        const double *r0 = B.absa + ((ind0lo + s0.js - 1) * ng + G0);
+        const double *r1 = B.absa + ((ind1lo + s1.js - 1) * ng + G0);
         stencil_lower<GN>(r0, ng, s0.specparm, s0.fs, L.f(F_FAC00), L.f(F_FAC10), s0.speccomb, t1);
         stencil_lower<GN>(r1, ng, s1.specparm, s1.fs, L.f(F_FAC01), L.f(F_FAC11), s1.speccomb, t2);
         FORG taug[ig] = t1[ig] + t2[ig];
@@ -941,8 +941,8 @@ struct LwBandArgs {
 
 // Sum v[q] over the threads of a block that share a column lane (threadIdx.y runs over the
 // g-point groups of the band) in ascending g order and store the Q totals at dst + q*qstride.
-// `red` holds Q*NY*32 doubles; callers alternate two buffers so one barrier per call suffices.
-template <int Q, int NY>
+// `red` holds Q*NY*CB doubles; callers alternate two buffers so one barrier per call suffices.
+template <int Q, int NY, int CB>
 __device__ __forceinline__ void block_sum_store(const double (&v)[Q], double *__restrict__ red,
                                                 double *__restrict__ dst, size_t qstride, bool active) {
     const int lane = threadIdx.x, ty = threadIdx.y;
@@ -954,12 +954,12 @@ __device__ __forceinline__ void block_sum_store(const double (&v)[Q], double *__
         return;
     }
 #pragma unroll
-    for (int q = 0; q < Q; ++q) red[(q * NY + ty) * 32 + lane] = v[q];
+    for (int q = 0; q < Q; ++q) red[(q * NY + ty) * CB + lane] = v[q];
     __syncthreads();
     for (int q = ty; q < Q; q += NY) {
-        double s = red[(q * NY) * 32 + lane];
+        double s = red[(q * NY) * CB + lane];
 #pragma unroll
-        for (int y = 1; y < NY; ++y) s = s + red[(q * NY + y) * 32 + lane];
+        for (int y = 1; y < NY; ++y) s = s + red[(q * NY + y) * CB + lane];
         if (active) dst[q * qstride] = s;
     }
 }
@@ -1002,19 +1002,22 @@ template <int BAND> __host__ __device__ constexpr unsigned lw_band_fmask_up() {
 // partial flux profiles of a band: part[band][LP_*][lev][c]
 enum LwPart { LP_U, LP_UC, LP_DU, LP_DUC, LP_D, LP_DC, LP_COUNT };
 
-// Block = 32 columns x (ng/GN) g-point groups of BAND: a warp is 32 consecutive columns at one
-// g-point group (coalesced on the column-fastest arrays), the warps of a block share the
-// columns' setcoef state through L1, and the g-point sums of every level are formed in the
-// block (block_sum_store) in ascending g order, like the reference's sequential accumulation.
-template <int BAND, int GN, int REGS>
-__global__ void __launch_bounds__(32 * (LwBandInfo<BAND>::ng / GN), min_blocks(32 * (LwBandInfo<BAND>::ng / GN), REGS))
+// Block = CB columns x (ng/GN) g-point groups of BAND, column fastest: a warp is CB consecutive
+// columns x 32/CB consecutive g-point groups.  With CB = 32 a warp's k-table gathers hit 32
+// scattered rows (one L1 wavefront each: the L1 data pipe was the limiter, profiles/r1_c_*); with
+// CB = 8 or 4 they fall on CB rows of adjacent g-points (the tables are g-point fastest) while the
+// column-fastest arrays are still read in whole 32-byte sectors.  The warps of a block share the
+// columns' setcoef state through L1, and the g-point sums of every level are formed in the block
+// (block_sum_store) in ascending g order, like the reference's sequential accumulation.
+template <int BAND, int GN, int REGS, int CB>
+__global__ void __launch_bounds__(CB * (LwBandInfo<BAND>::ng / GN), min_blocks(CB * (LwBandInfo<BAND>::ng / GN), REGS))
 lw_band_kernel(const LwBandArgs A) {
     constexpr int NY = LwBandInfo<BAND>::ng / GN;
     static_assert(NY * GN == LwBandInfo<BAND>::ng, "GN must divide the band's g-points");
-    __shared__ double red_buf[NY > 1 ? 2 * 4 * NY * 32 : 1];
+    __shared__ double red_buf[NY > 1 ? 2 * 4 * NY * CB : 1];
     const LwWork &W = A.W;
     const int nc = W.nc, nlay = W.nlay;
-    const int c0 = blockIdx.x * 32 + threadIdx.x;
+    const int c0 = blockIdx.x * CB + threadIdx.x;
     const bool active = c0 < nc;
     const int c = active ? c0 : nc - 1;   // idle lanes shadow the last column and never store
     const size_t col = gcol(A.col0, A.perm, c);
@@ -1024,7 +1027,7 @@ lw_band_kernel(const LwBandArgs A) {
     const int g_first = gs + G0;
     const int laytrop = W.laytrop[c];
     int flip = 0;
-    auto red = [&]() { flip ^= 1; return red_buf + (NY > 1 ? flip * 4 * NY * 32 : 0); };
+    auto red = [&]() { flip ^= 1; return red_buf + (NY > 1 ? flip * 4 * NY * CB : 0); };
 
     // diffusivity angle, :177-186
     double secdiff;
@@ -1053,57 +1056,69 @@ lw_band_kernel(const LwBandArgs A) {
         part[LP_D * fstride + (size_t)nlay * nc] = 0.;
         part[LP_DC * fstride + (size_t)nlay * nc] = 0.;
     }
+    // running addresses: per-(layer, column) planes by 32-bit offsets from the column's pointer,
+    // the thread's cell of the [lay][140][nc] scratch by one 64-bit offset
+    const int n2 = (int)W.n2;
+    const int *pidx = W.idx + c;
+    const double *pfac = W.fbase + c;
+    const size_t lay_cell = (size_t)140 * nc;
+    size_t koff = (size_t)(nlay - 1) * lay_cell + (size_t)g_first * nc + c;   // cell (nlay-1, g_first)
+    size_t aoff = ((size_t)ib * nlay + nlay - 1) * A.ld + col;                // aerosol at layer nlay-1
+    const uint32_t *pmask = W.mask + (size_t)g_first * nc + c;                // [nw][140][nc]
+    uint32_t any_word = 0u, mword[GN];
+    FORG mword[ig] = 0u;
 
     // ---- downward sweep, :198-309 ----
     for (int lay = nlay - 1; lay >= 0; --lay) {
+        const int jl = lay * nc;
         if (lay > 0 && threadIdx.y == 0) {   // next layer's per-(layer, column) state -> L1 while this one computes
-            const size_t jn = (size_t)(lay - 1) * nc + c;
-            prefetch_l1(W.idx + jn);
+            prefetch_l1(pidx + jl - nc);
             constexpr unsigned fm = lw_band_fmask<BAND>();
 #pragma unroll
             for (int k = 0; k < F_COUNT; ++k)
-                if ((fm >> k) & 1u) prefetch_l1(W.fbase + (size_t)k * W.n2 + jn);
-            prefetch_l1(planklay + (size_t)(lay - 1) * nc);
-            prefetch_l1(planklev + (size_t)(lay - 1) * nc);
-            prefetch_l1(A.taua + ((size_t)ib * nlay + lay - 1) * A.ld + col);
+                if ((fm >> k) & 1u) prefetch_l1(pfac + k * n2 + jl - nc);
+            prefetch_l1(planklay + jl - nc);
+            prefetch_l1(planklev + jl - nc);
+            prefetch_l1(A.taua + aoff - A.ld);
+        }
+        if ((lay & 31) == 31 || lay == nlay - 1) {   // cloud words of the next (up to) 32 layers
+            any_word = W.cloudy_any[(lay >> 5) * nc + c];
+            FORG mword[ig] = any_word ? pmask[(size_t)(lay >> 5) * lay_cell + ig * nc] : 0u;
         }
         Lay L;
-        L.fj = W.fbase + (size_t)lay * nc + c;
-        L.n2 = W.n2;
-        const int pk = W.idx[(size_t)lay * nc + c];
+        L.fj = pfac + jl;
+        L.n2 = n2;
+        const int pk = pidx[jl];
         L.jp = pk & 63; L.jt = (pk >> 6) & 7; L.jt1 = (pk >> 9) & 7;
         L.indfor = (pk >> 12) & 3; L.indself = (pk >> 14) & 15; L.indminor = (pk >> 18) & 31;
         const double pavel = (BAND <= 2) ? A.pavel[(size_t)lay * A.ld + col] : 0.;
         lw_band_layer<BAND, GN, true>(L, lay < laytrop, pavel, G0, taug, pf);
-        const double taer = A.taua[((size_t)ib * nlay + lay) * A.ld + col];
+        const double taer = A.taua[aoff];
+        aoff -= A.ld;
         FORG taug[ig] = taug[ig] + taer;
         if (A.dbg_taug && active) FORG A.dbg_taug[((size_t)lay * 140 + g_first + ig) * nc + c] = taug[ig];
         if (A.dbg_pfracs && active) FORG A.dbg_pfracs[((size_t)lay * 140 + g_first + ig) * nc + c] = pf[ig];
 
-        const double blay = planklay[(size_t)lay * nc];
-        const double dplankdn = planklev[(size_t)lay * nc] - blay;
-        const uint32_t any_word = W.cloudy_any[(size_t)(lay >> 5) * nc + c];
+        const double blay = planklay[jl];
+        const double dplankdn = planklev[jl] - blay;
         const bool layer_cloudy = (any_word >> (lay & 31)) & 1u;
         if (!diverge && layer_cloudy) diverge = true;
         double sums[2] = {0., 0.};
         FORG {
-            const int g = g_first + ig;
             double odepth = secdiff * taug[ig];
             if (odepth < 0.) odepth = 0.;
-            double tblind = odepth / (bpade + odepth);
+            double tblind = ddiv(odepth, bpade + odepth);
             const int itgas = f_int(tblint * tblind + 0.5);
             const double2 et = reinterpret_cast<const double2 *>(c_lw.exptfn)[itgas];
             const double agas = 1. - et.x;
             const double bbdgas = pf[ig] * (blay + et.y * dplankdn);
             uint32_t code = (uint32_t)itgas | 0xffff0000u;
-            bool cell_cloudy = false;
-            if (layer_cloudy) cell_cloudy = (W.mask[((size_t)(lay >> 5) * 140 + g) * nc + c] >> (lay & 31)) & 1u;
-            if (!cell_cloudy) {
+            if (!((mword[ig] >> (lay & 31)) & 1u)) {
                 radld[ig] = radld[ig] + (bbdgas - radld[ig]) * agas;
             } else {
-                const double odcld = secdiff * __ldcs(&W.taucmc[((size_t)lay * 140 + g) * nc + c]);
+                const double odcld = secdiff * __ldcs(W.taucmc + koff + ig * nc);
                 const double odtot = c_lw.tau_tbl[itgas] + odcld;
-                tblind = odtot / (bpade + odtot);
+                tblind = ddiv(odtot, bpade + odtot);
                 const int ittot = f_int(tblint * tblind + 0.5);
                 const double2 ett = reinterpret_cast<const double2 *>(c_lw.exptfn)[ittot];
                 const double atot = 1. - ett.x;
@@ -1111,14 +1126,16 @@ lw_band_kernel(const LwBandArgs A) {
                 radld[ig] = radld[ig] + (bbdtot - radld[ig]) * atot;
                 code = (uint32_t)itgas | ((uint32_t)ittot << 16);
             }
-            if (active) __stcs(&W.it[((size_t)lay * 140 + g) * nc + c], code);
+            if (active) __stcs(W.it + koff + ig * nc, code);
             sums[0] = sums[0] + sumfac * radld[ig];
             if (diverge) radclrd[ig] = radclrd[ig] + (bbdgas - radclrd[ig]) * agas;
             else radclrd[ig] = radld[ig];
             sums[1] = sums[1] + sumfac * radclrd[ig];
         }
-        block_sum_store<2, NY>(sums, red(), part + LP_D * fstride + (size_t)lay * nc, fstride, active);
+        block_sum_store<2, NY, CB>(sums, red(), part + LP_D * fstride + jl, fstride, active);
+        koff -= lay_cell;
     }
+    koff += lay_cell;   // back on layer 0
 
     // ---- surface, :319-333 (pf now holds the Planck fractions of layer 1) ----
     const double plankbnd = W.plankbnd[(size_t)ib * nc + c];
@@ -1138,37 +1155,36 @@ lw_band_kernel(const LwBandArgs A) {
             sums[2] = sums[2] + sumfac * drad[ig];
         }
         sums[3] = sums[2];
-        block_sum_store<4, NY>(sums, red(), part, fstride, active);
+        block_sum_store<4, NY, CB>(sums, red(), part, fstride, active);
     }
 
     // ---- upward sweep, :336-379 ----
     for (int lay = 0; lay < nlay; ++lay) {
+        const int jl = lay * nc;
         if (lay + 1 < nlay) {
-            FORG prefetch_l1(W.it + ((size_t)(lay + 1) * 140 + g_first + ig) * nc + c);
+            FORG prefetch_l1(W.it + koff + lay_cell + ig * nc);
             if (threadIdx.y == 0) {
-                const size_t jn = (size_t)(lay + 1) * nc + c;
-                prefetch_l1(W.idx + jn);
+                prefetch_l1(pidx + jl + nc);
                 constexpr unsigned fm = lw_band_fmask_up<BAND>();
 #pragma unroll
                 for (int k = 0; k < F_COUNT; ++k)
-                    if ((fm >> k) & 1u) prefetch_l1(W.fbase + (size_t)k * W.n2 + jn);
-                prefetch_l1(planklay + (size_t)(lay + 1) * nc);
-                prefetch_l1(planklev + (size_t)(lay + 2) * nc);
+                    if ((fm >> k) & 1u) prefetch_l1(pfac + k * n2 + jl + nc);
+                prefetch_l1(planklay + jl + nc);
+                prefetch_l1(planklev + jl + 2 * nc);
             }
         }
         Lay L;
-        L.fj = W.fbase + (size_t)lay * nc + c;
-        L.n2 = W.n2;
-        const int pk = W.idx[(size_t)lay * nc + c];
+        L.fj = pfac + jl;
+        L.n2 = n2;
+        const int pk = pidx[jl];
         L.jp = pk & 63; L.jt = (pk >> 6) & 7; L.jt1 = (pk >> 9) & 7;
         L.indfor = (pk >> 12) & 3; L.indself = (pk >> 14) & 15; L.indminor = (pk >> 18) & 31;
         lw_band_layer<BAND, GN, false>(L, lay < laytrop, 0., G0, taug, pf);
-        const double blay = planklay[(size_t)lay * nc];
-        const double dplankup = planklev[(size_t)(lay + 1) * nc] - blay;
+        const double blay = planklay[jl];
+        const double dplankup = planklev[jl + nc] - blay;
         double sums[4] = {0., 0., 0., 0.};
         FORG {
-            const int g = g_first + ig;
-            const uint32_t code = __ldcs(&W.it[((size_t)lay * 140 + g) * nc + c]);
+            const uint32_t code = __ldcs(W.it + koff + ig * nc);
             const int itgas = code & 0xffffu, ittot = code >> 16;
             const double2 et = reinterpret_cast<const double2 *>(c_lw.exptfn)[itgas];
             const double agas = 1. - et.x;
@@ -1194,28 +1210,29 @@ lw_band_kernel(const LwBandArgs A) {
                 sums[3] = sums[3] + sumfac * dradc[ig];
             }
         }
-        block_sum_store<4, NY>(sums, red(), part + (size_t)(lay + 1) * nc, fstride, active);
+        block_sum_store<4, NY, CB>(sums, red(), part + jl + nc, fstride, active);
+        koff += lay_cell;
     }
 }
 
-// Four compiled variants per band, (g-points per thread, register budget per thread; 0 = none):
-// v0 (1, none)  v1 (1, 64)  v2 (2, 48)  v3 (2, 64); bands with 2 g-points use 1 per thread throughout.
-// The one used is picked per band from lw_variant[] (tuned on B200; RRTMGX_LW_GN="vvv..." overrides).
-#define LW_BANDS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
-
+// Compiled variants per band: the (g-points per thread, register budget; 0 = none) pair tuned for the
+// band (profiles/r1_gn_tuning.txt) at CB = 32, 16, 8, 4 columns per block row.  The one used is picked
+// per band from lw_variant[] (tuned on B200; RRTMGX_LW_GN="vvv..." overrides).
 typedef void (*LwBandLauncher)(int, cudaStream_t, const LwBandArgs &);
-template <int BAND, int GN, int REGS>
-static void lw_launch_band(int gx, cudaStream_t st, const LwBandArgs &A) {
+template <int BAND, int GN, int REGS, int CB>
+static void lw_launch_band(int nc, cudaStream_t st, const LwBandArgs &A) {
     static char tag[48] = "";
-    if (!tag[0]) std::snprintf(tag, sizeof tag, "lw_band_kernel<%d,gn%d,r%d>", BAND, GN, REGS);
-    RRTMGX_LAUNCH_TAG(tag, (lw_band_kernel<BAND, GN, REGS>), dim3(gx), dim3(32, LwBandInfo<BAND>::ng / GN), 0, st, A);
+    if (!tag[0]) std::snprintf(tag, sizeof tag, "lw_band_kernel<%d,gn%d,r%d,c%d>", BAND, GN, REGS, CB);
+    RRTMGX_LAUNCH_TAG(tag, (lw_band_kernel<BAND, GN, REGS, CB>), dim3((nc + CB - 1) / CB),
+                      dim3(CB, LwBandInfo<BAND>::ng / GN), 0, st, A);
 }
-#define X(BAND)                                                                                              \
-    {lw_launch_band<BAND, 1, 0>, lw_launch_band<BAND, 1, 64>, lw_launch_band<BAND, (BAND >= 14 ? 1 : 2), 48>,    \
-     lw_launch_band<BAND, (BAND >= 14 ? 1 : 2), 64>},
-static const LwBandLauncher lw_launchers[16][4] = {LW_BANDS(X)};
+#define X(BAND, G, R) \
+    {lw_launch_band<BAND, G, R, 32>, lw_launch_band<BAND, G, R, 16>, lw_launch_band<BAND, G, R, 8>, lw_launch_band<BAND, G, R, 4>},
+static const LwBandLauncher lw_launchers[16][4] = {
+    X(1, 2, 48) X(2, 2, 48) X(3, 2, 64) X(4, 2, 64) X(5, 2, 64) X(6, 2, 48) X(7, 2, 48) X(8, 2, 64)
+    X(9, 2, 48) X(10, 2, 64) X(11, 2, 64) X(12, 2, 64) X(13, 1, 64) X(14, 1, 0) X(15, 1, 0) X(16, 1, 0)};
 #undef X
-static int lw_variant[16] = {2, 2, 3, 3, 3, 2, 2, 3, 2, 3, 3, 3, 1, 0, 0, 0};   // profiles/r1_gn_tuning.txt
+static int lw_variant[16] = {0, 0, 2, 2, 2, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, 0};   // CB = 8 where the k-tables are widest (profiles/r2_cb_tuning.txt)
 
 // fixed-order sum of the band partials -> caller arrays; band OLR (:382-385, rad.F90:586-605)
 __global__ void lw_reduce_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, int dudTs, const double *__restrict__ part,
@@ -1323,7 +1340,7 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
     // group cloudy and cloud-free columns (not under debug taps, whose layouts assume identity order)
     const int *perm = nullptr;
     if (!taps) {
-        if (int rc = build_cloud_partition(ld, col0, nc, nlay, a->cldf, W.perm, W.pflags, W.ptmp, W.ptmp_bytes, stream))
+        if (int rc = build_cloud_partition(ld, col0, nc, nlay, a->cldf, a->play, W.perm, W.pflags, W.ptmp, W.ptmp_bytes, stream))
             return rc;
         perm = W.perm;
     }
@@ -1339,7 +1356,7 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
     LwOptics opt{nc, nlay, W.abscoice, W.abscoliq, W.cldtrap, W.taucmc};
     RRTMGX_LAUNCH(mcica_kernel<LwOptics>, dim3((140 + MCICA_SUBS - 1) / MCICA_SUBS, (nc + 31) / 32), dim3(32, MCICA_SUBS),
                   0, stream, ld, col0, perm, nc, nlay, 140, mp, d_jumps, W.seeds, W.t_alpha, W.t_rcorr, W.t_cld, a->cldf,
-                  a->ciwp, a->clwp, 1.e-20, a->cloudLM, a->cloudMH, a->clearCounts, W.cloudy_any, W.mask, opt, d_err);
+                  a->ciwp, a->clwp, 1.e-20, a->cloudLM, a->cloudMH, perm ? (const int *)W.ptmp : nullptr, a->clearCounts, W.cloudy_any, W.mask, opt, d_err);
 
     LwBandArgs A{ld, col0, perm, W, a->dudTs, a->play, a->emis, a->tauaer, dbg_taug, dbg_pfracs};
     // fan the independent band units out over the side streams
@@ -1355,8 +1372,7 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
         }
         variants_read = true;
     }
-    const int gx = (nc + 31) / 32;
-    for (int b = 0; b < 16; ++b) lw_launchers[b][lw_variant[b]](gx, nside ? side[b % nside] : stream, A);
+    for (int b = 0; b < 16; ++b) lw_launchers[b][lw_variant[b]](nc, nside ? side[b % nside] : stream, A);
     for (int s = 0; s < nside; ++s) {
         cudaEventRecord(ev[1 + s], side[s]);
         cudaStreamWaitEvent(stream, ev[1 + s], 0);

@@ -176,6 +176,7 @@ mcica_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, i
              const long long *__restrict__ t_alpha, const long long *__restrict__ t_rcorr,
              const long long *__restrict__ t_cld, const double *__restrict__ cldf, const double *__restrict__ ciwp,
              const double *__restrict__ clwp, double cwp_tiny, int cloudLM, int cloudMH,
+             const int *__restrict__ ncloudy,    // columns c >= *ncloudy hold no cloud at all (null: unknown)
              int *__restrict__ clearCounts,      // (ld,4)
              uint32_t *__restrict__ cloudy_any,  // [nw][nc]
              uint32_t *__restrict__ mask,        // [nw][nsub][nc]
@@ -188,6 +189,15 @@ mcica_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, i
     const int isub = blockIdx.x * blockDim.y + threadIdx.y;
     if (c >= nc || isub >= nsub) return;
     const size_t col = gcol(col0, perm, c);
+    if (ncloudy && c >= *ncloudy) {
+        // cldfrac = 0 in every layer: cdf1 >= 1 - cldfrac never holds (ran_num < 1), so whatever the
+        // generator draws the subcolumn is clear everywhere (:435); nothing to draw
+        const int nw = (nlay + 31) >> 5;
+        for (int w = 0; w < nw; ++w) mask[((size_t)w * nsub + isub) * nc + c] = 0u;
+        if (isub == 0)
+            for (int q = 0; q < 4; ++q) atomicAdd(&clearCounts[(size_t)q * ld + col], nsub);
+        return;
+    }
     Kiss a, b;
     a.s1 = seeds[c]; a.s2 = seeds[(size_t)nc + c];
     a.s3 = seeds[(size_t)2 * nc + c]; a.s4 = seeds[(size_t)3 * nc + c];

@@ -105,6 +105,7 @@ def lib():
         L.rrtmgx_set_taps.argtypes = [C.POINTER(Taps), C.POINTER(Taps)]
         L.rrtmgx_table.restype = _dp
         L.rrtmgx_table.argtypes = [C.c_char_p, C.c_char_p, C.c_int, _ip]
+        L.rrtmgx_debug_divide.argtypes = [C.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp]
         L.rrtmgx_heating_rate.argtypes = [C.c_int, C.c_int, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp]
         _lib = L
     return _lib
@@ -345,6 +346,17 @@ def heating_rate(fnet_up_minus_down, plev, grav=9.80665, cp=1004.68506, device=F
     _check(lib().rrtmgx_heating_rate(ncol, nlev - 1, _addr(fnet_up_minus_down, device), _addr(plev, device),
                                      _addr(out, device), grav, cp, DEVICE_PTRS if device else 0, stream))
     return out
+
+
+def debug_divide(a, b):
+    """Test hook (include/rrtmgx.h): the band kernels' branch-free a/b and 1/b beside the IEEE ones."""
+    if not _initialised:
+        init()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    out = [np.empty_like(a) for _ in range(4)]
+    _check(lib().rrtmgx_debug_divide(a.size, _addr(a, False), _addr(b, False), *[_addr(o, False) for o in out]))
+    return tuple(out)
 
 
 # ---- convenience wrappers over the synthetic-state dicts of synthetic.make_columns ---------------

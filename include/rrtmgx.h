@@ -174,6 +174,12 @@ void rrtmgx_set_taps(const RrtmgxTaps *lw_taps, const RrtmgxTaps *sw_taps);
 int rrtmgx_heating_rate(int ncol, int nlay, const double *fnet_up_minus_down, const double *plev,
                         double *hr_K_per_day, double grav, double cp, int flags, void *stream);
 
+/* Test hook: the band kernels replace the compiler's IEEE fp64 division by its own fast-path
+ * instruction sequence without the range test (csrc/common.cuh ddiv/drcp).  Evaluates both on the
+ * device for n host pairs (a, b): q_* = a/b, r_* = 1/b, so a test can pin them bit for bit. */
+int rrtmgx_debug_divide(size_t n, const double *a, const double *b, double *q_fast, double *q_ieee,
+                        double *r_fast, double *r_ieee);
+
 /* reduced (post-cmbgb) host copies of tables for tests: kind "lw"/"sw", band as in the
  * reference (1..16 / 16..29; 0 for band-independent), g-point fastest layout [lead][ng]. */
 const double *rrtmgx_table(const char *kind, const char *name, int band, int *n);

@@ -148,3 +148,28 @@ def test_heating_rate(rx, oracle):
     got = rx.heating_rate(np.asfortranarray(g["uflx"] - g["dflx"]), s["plev"], grav, cp)
     assert np.max(np.abs(got - hr(o))) <= HR_ATOL
     assert np.max(np.abs(got - hr(g))) <= 1e-9
+
+
+def test_branch_free_division_equals_ieee(rx):
+    """The band kernels' division (csrc/common.cuh ddiv/drcp: the compiler's fast-path sequence without
+    its range test) against IEEE a/b and 1/b on the device, bit for bit, over the operand ranges of the
+    band kernels: optical depths and column amounts over ~40 decades, denominators 1 - R*R' close to 1,
+    and the zero numerators of aerosol-free layers."""
+    rng = np.random.default_rng(20260118)
+    n = 1 << 21
+    a = np.concatenate([
+        10.0 ** rng.uniform(-25, 15, n) * rng.choice([-1.0, 1.0], n),
+        rng.uniform(0, 1, n),
+        np.zeros(1 << 16),
+        10.0 ** rng.uniform(-200, -100, 1 << 16),      # below the compiler's 2^-120 fast-path bound
+    ])
+    b = np.concatenate([
+        10.0 ** rng.uniform(-25, 15, n),
+        1.0 - rng.uniform(0, 1, n) * rng.uniform(0, 1, n) * (1 - 1e-9),
+        10.0 ** rng.uniform(-10, 10, 1 << 16),
+        10.0 ** rng.uniform(-10, 10, 1 << 16),
+    ])
+    qf, qi, rf, ri = rx.debug_divide(a, b)
+    np.testing.assert_array_equal(qi, a / b)            # the device's IEEE division is numpy's
+    np.testing.assert_array_equal(qf, qi)
+    np.testing.assert_array_equal(rf, ri)
