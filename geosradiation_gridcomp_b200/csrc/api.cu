@@ -16,7 +16,6 @@
 #include <vector>
 
 #include <cub/device/device_partition.cuh>
-#include <cub/device/device_radix_sort.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
 #include "engine.h"
@@ -283,66 +282,28 @@ __global__ void cloudy_flag_kernel(int ld, int col0, int nc, int nlay, const dou
     flag[c] = any ? 1 : 0;
 }
 
-// sort key of a column: cloudy columns first, then by the pressure of layer 1 (monotone map of the
-// positive float onto 31 bits)
-__global__ void column_key_kernel(int ld, int col0, int nc, int nlay, const double *__restrict__ cldf,
-                                  const double *__restrict__ pkey, unsigned char *__restrict__ flag,
-                                  uint32_t *__restrict__ key, int *__restrict__ iota, int *__restrict__ ncloudy) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    bool any = false;
-    if (c < nc) {
-        for (int k = 0; k < nlay; ++k) any |= cldf[(size_t)k * ld + col0 + c] > 0.;
-        flag[c] = any ? 1 : 0;
-        const float p = (float)pkey[(size_t)col0 + c];
-        key[c] = (any ? 0u : 0x80000000u) | (__float_as_uint(p > 0.f ? p : 0.f) >> 1);
-        iota[c] = c;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, any);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(ncloudy, __popc(m));
-}
-
-// RRTMGX_SORT=0 keeps the columns of a chunk in the caller's order within the cloudy / cloud-free groups
-bool sort_columns() {
-    static const bool on = [] { const char *e = std::getenv("RRTMGX_SORT"); return !(e && e[0] == '0'); }();
-    return on;
-}
-size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 }  // namespace
 
 size_t cloud_partition_tmp_bytes(int nc) {
-    size_t part = 0, sort = 0;
+    size_t bytes = 0;
     thrust::counting_iterator<int> it(0);
-    cub::DevicePartition::Flagged(nullptr, part, it, (const unsigned char *)nullptr, (int *)nullptr, (int *)nullptr, nc);
-    cub::DeviceRadixSort::SortPairs(nullptr, sort, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const int *)nullptr,
-                                    (int *)nullptr, nc);
-    return 256 + 3 * align256((size_t)nc * 4) + std::max(part, sort) + 256;
+    cub::DevicePartition::Flagged(nullptr, bytes, it, (const unsigned char *)nullptr, (int *)nullptr, (int *)nullptr, nc);
+    return bytes + 256;
 }
 
-// perm[0 .. nc): the chunk's columns, those holding cloud in any layer first (count left at
-// (int*)tmp), each group ordered by the pressure of layer 1 when `pkey` is given.  Columns are
-// independent, so the order changes no result; it makes the warps of the band kernels walk the same
-// rows of the k-tables (jp follows the pressure) the way neighbouring columns of a real model state do.
-int build_cloud_partition(int ld, int col0, int nc, int nlay, const double *cldf, const double *pkey, int *perm,
-                          unsigned char *flags, void *tmp, size_t tmp_bytes, cudaStream_t stream) {
-    int *d_nsel = (int *)tmp;   // first 256 bytes of tmp hold the selected count
-    const size_t arr = align256((size_t)nc * 4);
-    char *base = (char *)tmp + 256;
-    if (pkey && sort_columns()) {
-        uint32_t *key_in = (uint32_t *)base, *key_out = (uint32_t *)(base + arr);
-        int *iota = (int *)(base + 2 * arr);
-        size_t bytes = tmp_bytes - 256 - 3 * arr;
-        cudaMemsetAsync(d_nsel, 0, sizeof(int), stream);
-        RRTMGX_LAUNCH(column_key_kernel, (nc + 255) / 256, 256, 0, stream, ld, col0, nc, nlay, cldf, pkey, flags, key_in,
-                      iota, d_nsel);
-        ++g_launches;
-        return cub::DeviceRadixSort::SortPairs(base + 3 * arr, bytes, key_in, key_out, iota, perm, nc, 0, 32, stream) ==
-                       cudaSuccess ? 0 : RRTMGX_ECUDA;
-    }
+// perm[0 .. nc): the chunk's columns, those holding cloud in any layer first (their count is left at
+// (int*)tmp); both groups keep the caller's order, so neighbouring columns stay neighbours and the
+// boundary arrays are still read in whole sectors.  (Ordering each group by surface pressure as well,
+// so that a warp walks the same k-table rows, was measured: no gain on distinct columns and 5 % off
+// the host-array path, profiles/r2_cb_tuning.txt.)
+int build_cloud_partition(int ld, int col0, int nc, int nlay, const double *cldf, int *perm, unsigned char *flags,
+                          void *tmp, size_t tmp_bytes, cudaStream_t stream) {
     RRTMGX_LAUNCH(cloudy_flag_kernel, (nc + 255) / 256, 256, 0, stream, ld, col0, nc, nlay, cldf, flags);
     thrust::counting_iterator<int> it(0);
-    size_t bytes = tmp_bytes - 256 - 3 * arr;
+    int *d_nsel = (int *)tmp;   // first 256 bytes of tmp hold the selected count
+    size_t bytes = tmp_bytes - 256;
     ++g_launches;
-    return cub::DevicePartition::Flagged(base + 3 * arr, bytes, it, flags, perm, d_nsel, nc, stream) == cudaSuccess
+    return cub::DevicePartition::Flagged((char *)tmp + 256, bytes, it, flags, perm, d_nsel, nc, stream) == cudaSuccess
                ? 0 : RRTMGX_ECUDA;
 }
 

@@ -99,8 +99,8 @@ int sw_run_chunk(const RrtmgxSwArgs *a, const SwSolar &sol, int col0, int nc, co
 
 // generic helpers (api.cu)
 // perm[0..nc): the chunk's columns with any cldf > 0 first, the cloud-free ones after (device)
-int build_cloud_partition(int ld, int col0, int nc, int nlay, const double *cldf, const double *pkey, int *perm,
-                          unsigned char *flags, void *tmp, size_t tmp_bytes, cudaStream_t stream);
+int build_cloud_partition(int ld, int col0, int nc, int nlay, const double *cldf, int *perm, unsigned char *flags,
+                          void *tmp, size_t tmp_bytes, cudaStream_t stream);
 size_t cloud_partition_tmp_bytes(int nc);
 void launch_check_negative(const double *x, size_t n, int pos, int *d_negpos, cudaStream_t s);
 

@@ -1340,7 +1340,7 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
     // group cloudy and cloud-free columns (not under debug taps, whose layouts assume identity order)
     const int *perm = nullptr;
     if (!taps) {
-        if (int rc = build_cloud_partition(ld, col0, nc, nlay, a->cldf, a->play, W.perm, W.pflags, W.ptmp, W.ptmp_bytes, stream))
+        if (int rc = build_cloud_partition(ld, col0, nc, nlay, a->cldf, W.perm, W.pflags, W.ptmp, W.ptmp_bytes, stream))
             return rc;
         perm = W.perm;
     }

@@ -19,14 +19,7 @@ def main():
     nlay = int(sys.argv[2]) if len(sys.argv) > 2 else 72
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     pkg.init()
-    base = make_columns(min(ncol, 8192), nlay, seed=20260121)
-    if ncol > base["ncol"]:   # tile the slab: timing only, columns repeat
-        n0 = base["ncol"]
-        reps = -(-ncol // n0)
-        for k, v in list(base.items()):
-            if isinstance(v, np.ndarray) and v.dtype == np.float64 and v.ndim >= 1 and v.shape[0] == n0:
-                base[k] = np.asfortranarray(np.concatenate([v] * reps, axis=0)[:ncol])
-        base["ncol"] = ncol
+    base = make_columns(ncol, nlay, seed=20260121)   # all columns distinct (a tiled slab would repeat table rows)
     d = devstate.to_device(base)
     o = devstate.alloc_outputs(ncol, nlay)
     lw, sw = devstate.lw_runner(d, o), devstate.sw_runner(d, o)
