@@ -19,6 +19,7 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include "engine.h"
+#include "glue.cuh"
 
 namespace rrtmgx {
 
@@ -47,6 +48,7 @@ struct Path {   // per-path (LW or SW) execution resources
     cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_free[2] = {};
     Slab slab;            // kernel scratch
     Slab stage[2];        // host-pointer mode: device copies of one chunk's boundary arrays
+    Slab glue;            // fused Run-phase glue: the RRTMG argument arrays of one chunk
     KissJump *d_jumps = nullptr;
     int jumps_nlay = -1, jumps_inhomo = -1;
     int *d_err = nullptr;      // [0] trap code, [1] first negative-input position
@@ -488,7 +490,9 @@ int rrtmgx_lw_run(const RrtmgxLwArgs *a) {
     if (int rc = grow(p.slab, lw_scratch_bytes((int)chunk, nlay, dbg))) return rc;
     cudaStream_t stream = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
     p.run_stream = stream;
-    if (!ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, stream))) return RRTMGX_ECUDA;
+    if (!(devptr && (a->flags & RRTMGX_KEEP_STATUS)) &&
+        !ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, stream)))
+        return RRTMGX_ECUDA;
 
     auto run_chunks_device = [&](const RrtmgxLwArgs &da) -> int {
         const int n = da.ncol;
@@ -639,7 +643,9 @@ int rrtmgx_sw_run(const RrtmgxSwArgs *a) {
     if (int rc = grow(p.slab, sw_scratch_bytes((int)chunk, nlay, dbg))) return rc;
     cudaStream_t stream = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
     p.run_stream = stream;
-    if (!ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, stream))) return RRTMGX_ECUDA;
+    if (!(devptr && (a->flags & RRTMGX_KEEP_STATUS)) &&
+        !ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, stream)))
+        return RRTMGX_ECUDA;
 
     auto run_chunks_device = [&](const RrtmgxSwArgs &da) -> int {
         const int n = da.ncol;
@@ -708,6 +714,318 @@ int rrtmgx_sw_run(const RrtmgxSwArgs *a) {
 #endif
 
 }  // extern "C"
+
+// ---- fused Run-phase glue (include/rrtmgx.h; kernels in glue.cuh) -------------------------------
+namespace {
+// the argument arrays of one rrtmg_lw / rrtmg_sw call over nc columns, carved from a slab
+void carve_lw_args(Slab &s, int nc, int L, RrtmgxLwArgs &a) {
+    const size_t n2 = (size_t)nc * L, n2p = (size_t)nc * (L + 1);
+    auto D = [&](size_t n) { return s.take<double>(n); };
+    a.play = D(n2); a.plev = D(n2p); a.tlay = D(n2); a.tlev = D(n2p); a.tsfc = D(nc); a.emis = D((size_t)nc * 16);
+    a.h2ovmr = D(n2); a.o3vmr = D(n2); a.co2vmr = D(n2); a.ch4vmr = D(n2); a.n2ovmr = D(n2); a.o2vmr = D(n2);
+    a.cfc11vmr = D(n2); a.cfc12vmr = D(n2); a.cfc22vmr = D(n2); a.ccl4vmr = D(n2);
+    a.cldf = D(n2); a.ciwp = D(n2); a.clwp = D(n2); a.rei = D(n2); a.rel = D(n2);
+    a.tauaer = D(n2 * 16); a.zm = D(n2); a.alat = D(nc);
+    a.clearCounts = s.take<int32_t>((size_t)nc * 4);
+    a.uflx = D(n2p); a.dflx = D(n2p); a.uflxc = D(n2p); a.dflxc = D(n2p); a.duflx_dTs = D(n2p); a.duflxc_dTs = D(n2p);
+    a.olrb = D((size_t)nc * 16); a.dolrb_dTs = D((size_t)nc * 16);
+}
+void carve_sw_args(Slab &s, int nc, int L, RrtmgxSwArgs &a) {
+    const size_t n2 = (size_t)nc * L, n2p = (size_t)nc * (L + 1);
+    auto D = [&](size_t n) { return s.take<double>(n); };
+    a.coszen = D(nc); a.play = D(n2); a.plev = D(n2p); a.tlay = D(n2);
+    a.h2ovmr = D(n2); a.o3vmr = D(n2); a.co2vmr = D(n2); a.ch4vmr = D(n2); a.o2vmr = D(n2);
+    a.cld = D(n2); a.ciwp = D(n2); a.clwp = D(n2); a.rei = D(n2); a.rel = D(n2); a.zm = D(n2); a.alat = D(nc);
+    a.tauaer = D(n2 * 14); a.ssaaer = D(n2 * 14); a.asmaer = D(n2 * 14);
+    a.asdir = D(nc); a.asdif = D(nc); a.aldir = D(nc); a.aldif = D(nc);
+    a.clearCounts = s.take<int32_t>((size_t)nc * 4);
+    a.swuflx = D(n2p); a.swdflx = D(n2p); a.swuflxc = D(n2p); a.swdflxc = D(n2p);
+    a.nirr = D(nc); a.nirf = D(nc); a.parr = D(nc); a.parf = D(nc); a.uvrr = D(nc); a.uvrf = D(nc);
+    a.fswband = D((size_t)nc * 14);
+    a.cotdtp = D(nc); a.cotdhp = D(nc); a.cotdmp = D(nc); a.cotdlp = D(nc);
+    a.cotntp = D(nc); a.cotnhp = D(nc); a.cotnmp = D(nc); a.cotnlp = D(nc);
+    a.drband = nullptr; a.dfband = nullptr;
+}
+template <class A, class Carve> size_t carve_bytes(int nc, int L, Carve carve) {
+    Slab s;
+    A a{};
+    carve(s, nc, L, a);
+    return s.used + 4096;
+}
+
+void lw_scalars(const RrtmgxIrradArgs &S, int nc, RrtmgxLwArgs &L) {
+    L.ncol = nc; L.nlay = S.lm; L.psize = 0; L.dudTs = 1;            // Ts_derivs = .true., IRR:3232
+    L.iceflglw = S.iceflg; L.liqflglw = S.liqflg; L.dyofyr = S.doy;
+    L.cloudMH = S.lm - S.lcldmh + 1; L.cloudLM = S.lm - S.lcldlm + 1;   // IRR:3239-3240
+    L.band_output = S.band_output;
+}
+void sw_scalars(const RrtmgxSolarArgs &S, int nc, RrtmgxSwArgs &L) {
+    L.ncol = nc; L.nlay = S.lm; L.rpart = 0; L.isolvar = S.isolvar;
+    L.iceflgsw = S.iceflg; L.liqflgsw = S.liqflg; L.dyofyr = S.doy;
+    L.cloudLM = S.lm - S.lcldlm + 1; L.cloudMH = S.lm - S.lcldmh + 1;   // SOL:6347
+    L.iaer = 10; L.normFlx = 1; L.do_drfband = 0;                       // SOL:6234-6240
+    L.scon = S.sc; L.adjes = S.dist; L.bndscl = nullptr; L.indsolvar = nullptr; L.solcycfrac = S.solcycfrac;
+}
+int band_mask_of(const int32_t *bo) {
+    int m = 0;
+    for (int b = 0; b < 16; ++b) m |= (bo && bo[b]) ? 1 << b : 0;
+    return m;
+}
+
+// one chunk, everything on the device: native arrays `S` (leading dimension lds, first column col0)
+// -> prepare -> rrtmg_lw -> finish -> native outputs
+int irrad_chunk(const RrtmgxIrradArgs &S, int lds, int col0, int nc, cudaStream_t st) {
+    Path &p = g.lw;
+    if (int rc = grow(p.glue, carve_bytes<RrtmgxLwArgs>(nc, S.lm, carve_lw_args))) return rc;
+    p.glue.used = 0;
+    RrtmgxLwArgs L{};
+    lw_scalars(S, nc, L);
+    carve_lw_args(p.glue, nc, S.lm, L);
+    L.flags = RRTMGX_DEVICE_PTRS | RRTMGX_NO_SYNC | RRTMGX_KEEP_STATUS | (S.flags & RRTMGX_SKIP_CHECKS);
+    L.stream = st;
+    RRTMGX_LAUNCH(irrad_prepare_kernel, (nc + 127) / 128, 128, 0, st, nc, lds, col0, S, L);
+    if (int rc = rrtmgx_lw_run(&L)) return rc;
+    RRTMGX_LAUNCH(irrad_finish_kernel, (nc + 127) / 128, 128, 0, st, nc, lds, col0, S, L, band_mask_of(S.band_output));
+    return ok(cudaGetLastError()) ? 0 : RRTMGX_ECUDA;
+}
+#ifdef RRTMGX_WITH_SW
+int solar_chunk(const RrtmgxSolarArgs &S, int lds, int col0, int nc, cudaStream_t st) {
+    Path &p = g.sw;
+    if (int rc = grow(p.glue, carve_bytes<RrtmgxSwArgs>(nc, S.lm, carve_sw_args))) return rc;
+    p.glue.used = 0;
+    RrtmgxSwArgs L{};
+    sw_scalars(S, nc, L);
+    carve_sw_args(p.glue, nc, S.lm, L);
+    L.flags = RRTMGX_DEVICE_PTRS | RRTMGX_NO_SYNC | RRTMGX_KEEP_STATUS | (S.flags & RRTMGX_SKIP_CHECKS);
+    L.stream = st;
+    RRTMGX_LAUNCH(solar_prepare_kernel, (nc + 127) / 128, 128, 0, st, nc, lds, col0, S, L);
+    if (int rc = rrtmgx_sw_run(&L)) return rc;
+    RRTMGX_LAUNCH(solar_finish_kernel, (nc + 127) / 128, 128, 0, st, nc, lds, col0, S, L);
+    return ok(cudaGetLastError()) ? 0 : RRTMGX_ECUDA;
+}
+#endif
+constexpr size_t kGlueChunk = 131072;   // columns per pass of the device-pointer refresh (workspace ~25-35 KB each)
+
+template <class A> bool glue_args_ok(const A *a) {
+    return a && a->ncol > 0 && a->lm >= 2 && a->lm <= 1000 && a->ple && a->pl && a->t && a->q && a->o3 && a->ch4 &&
+           a->qliq && a->qice && a->rliq && a->rice && a->ts && a->lats;
+}
+}  // namespace
+
+extern "C" {
+
+int rrtmgx_irrad_refresh(const RrtmgxIrradArgs *a) {
+    if (!g.ready) return RRTMGX_ENOTINIT;
+    if (!ok(cudaSetDevice(g.device))) { cudaGetLastError(); return RRTMGX_ENODEVICE; }
+    if (!glue_args_ok(a) || !a->n2o || !a->cfc11 || !a->cfc12 || !a->hcfc22 || !a->fcld || !a->t2m || !a->emis ||
+        !a->flxu || !a->flxd || !a->flcu || !a->flcd || !a->dfdts || !a->dfdtsc || !a->sfcem || (!a->taua != !a->ssaa))
+        return RRTMGX_EARG;
+    Path &p = g.lw;
+    const bool devptr = a->flags & RRTMGX_DEVICE_PTRS;
+    if ((a->flags & RRTMGX_NO_SYNC) && !devptr) return RRTMGX_EARG;
+    const int ncol = a->ncol;
+    cudaStream_t st = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
+    if (!ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, st))) return RRTMGX_ECUDA;
+    if (devptr) {
+        for (size_t col0 = 0; col0 < (size_t)ncol; col0 += kGlueChunk)
+            if (int rc = irrad_chunk(*a, ncol, (int)col0, (int)std::min(kGlueChunk, (size_t)ncol - col0), st)) return rc;
+        p.pending = true;
+        if (a->flags & RRTMGX_NO_SYNC) return 0;
+        return p.last_status = status_from(p);
+    }
+    RrtmgxIrradArgs ca = *a;
+    std::vector<Arr> arrs;
+    const size_t L = a->lm, L1 = a->lm + 1;
+    auto in = [&](const double *const &f, const double **slot, size_t rows) {
+        arrs.push_back({f, (void **)slot, rows, 8, false, true, false});
+    };
+    auto out = [&](double *const &f, double **slot, size_t rows) {
+        arrs.push_back({f, (void **)slot, rows, 8, false, false, true});
+    };
+    in(a->ple, &ca.ple, L1); in(a->pl, &ca.pl, L); in(a->t, &ca.t, L); in(a->q, &ca.q, L); in(a->o3, &ca.o3, L);
+    in(a->ch4, &ca.ch4, L); in(a->n2o, &ca.n2o, L); in(a->co2, &ca.co2, L); in(a->cfc11, &ca.cfc11, L);
+    in(a->cfc12, &ca.cfc12, L); in(a->hcfc22, &ca.hcfc22, L); in(a->fcld, &ca.fcld, L);
+    in(a->qliq, &ca.qliq, L); in(a->qice, &ca.qice, L); in(a->rliq, &ca.rliq, L); in(a->rice, &ca.rice, L);
+    in(a->ts, &ca.ts, 1); in(a->t2m, &ca.t2m, 1); in(a->emis, &ca.emis, 1); in(a->lats, &ca.lats, 1);
+    in(a->taua, &ca.taua, L * 16); in(a->ssaa, &ca.ssaa, L * 16);
+    out(a->flxu, &ca.flxu, L1); out(a->flxd, &ca.flxd, L1); out(a->flcu, &ca.flcu, L1); out(a->flcd, &ca.flcd, L1);
+    out(a->dfdts, &ca.dfdts, L1); out(a->dfdtsc, &ca.dfdtsc, L1); out(a->sfcem, &ca.sfcem, 1);
+    out(a->cldtt, &ca.cldtt, 1); out(a->cldhi, &ca.cldhi, 1); out(a->cldmd, &ca.cldmd, 1); out(a->cldlo, &ca.cldlo, 1);
+    if (band_mask_of(a->band_output)) {   // (16,ncol): untouched bands survive the round trip
+        arrs.push_back({a->olrb, (void **)&ca.olrb, 16, 8, true, true, true});
+        arrs.push_back({a->dolrb_dts, (void **)&ca.dolrb_dts, 16, 8, true, true, true});
+    } else {
+        ca.olrb = nullptr; ca.dolrb_dts = nullptr;
+    }
+    const size_t chunk = std::min<size_t>(g.host_chunk_cols, (size_t)ncol);
+    int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxIrradArgs &c, int nc) -> int {
+        return irrad_chunk(c, nc, 0, nc, p.stream);
+    });
+    if (rc) return rc;
+    p.pending = true;
+    return p.last_status = status_from(p);
+}
+
+int rrtmgx_irrad_prepare(const RrtmgxIrradArgs *a, RrtmgxLwArgs *lw) {
+    if (!g.ready) return RRTMGX_ENOTINIT;
+    if (!ok(cudaSetDevice(g.device))) { cudaGetLastError(); return RRTMGX_ENODEVICE; }
+    if (!glue_args_ok(a) || !lw || !a->n2o || !a->cfc11 || !a->cfc12 || !a->hcfc22 || !a->fcld || !a->t2m || !a->emis)
+        return RRTMGX_EARG;
+    Path &p = g.lw;
+    const int nc = a->ncol, L = a->lm;
+    lw_scalars(*a, nc, *lw);
+    if (a->flags & RRTMGX_DEVICE_PTRS) {
+        cudaStream_t st = a->stream ? (cudaStream_t)a->stream : p.stream;
+        RRTMGX_LAUNCH(irrad_prepare_kernel, (nc + 127) / 128, 128, 0, st, nc, nc, 0, *a, *lw);
+        if (a->flags & RRTMGX_NO_SYNC) return ok(cudaGetLastError()) ? 0 : RRTMGX_ECUDA;
+        return ok(cudaStreamSynchronize(st)) ? 0 : RRTMGX_ECUDA;
+    }
+    // host arrays: native state up, prepared arguments down (whole call at once: a test / staging utility)
+    const size_t n2 = (size_t)nc * L, n2p = (size_t)nc * (L + 1);
+    Slab nat;
+    RrtmgxIrradArgs d = *a;
+    struct In { const double **f; size_t n; } ins[] = {
+        {&d.ple, n2p}, {&d.pl, n2}, {&d.t, n2}, {&d.q, n2}, {&d.o3, n2}, {&d.ch4, n2}, {&d.n2o, n2}, {&d.co2, n2},
+        {&d.cfc11, n2}, {&d.cfc12, n2}, {&d.hcfc22, n2}, {&d.fcld, n2}, {&d.qliq, n2}, {&d.qice, n2}, {&d.rliq, n2},
+        {&d.rice, n2}, {&d.ts, (size_t)nc}, {&d.t2m, (size_t)nc}, {&d.emis, (size_t)nc}, {&d.lats, (size_t)nc},
+        {&d.taua, n2 * 16}, {&d.ssaa, n2 * 16}};
+    size_t bytes = 4096;
+    for (auto &i : ins) bytes += *i.f ? ((i.n * 8 + 255) & ~(size_t)255) : 0;
+    if (int rc = grow(nat, bytes)) return rc;
+    for (auto &i : ins)
+        if (*i.f) {
+            double *dev = nat.take<double>(i.n);
+            cudaMemcpyAsync(dev, *i.f, i.n * 8, cudaMemcpyHostToDevice, p.stream);
+            *i.f = dev;
+        }
+    int rc = grow(p.glue, carve_bytes<RrtmgxLwArgs>(nc, L, carve_lw_args));
+    if (!rc) {
+        p.glue.used = 0;
+        RrtmgxLwArgs D = *lw;
+        carve_lw_args(p.glue, nc, L, D);
+        RRTMGX_LAUNCH(irrad_prepare_kernel, (nc + 127) / 128, 128, 0, p.stream, nc, nc, 0, d, D);
+        struct Out { const double *src; const double *dst; size_t n; } outs[] = {
+            {D.play, lw->play, n2}, {D.plev, lw->plev, n2p}, {D.tlay, lw->tlay, n2}, {D.tlev, lw->tlev, n2p},
+            {D.tsfc, lw->tsfc, (size_t)nc}, {D.emis, lw->emis, (size_t)nc * 16}, {D.h2ovmr, lw->h2ovmr, n2},
+            {D.o3vmr, lw->o3vmr, n2}, {D.co2vmr, lw->co2vmr, n2}, {D.ch4vmr, lw->ch4vmr, n2}, {D.n2ovmr, lw->n2ovmr, n2},
+            {D.o2vmr, lw->o2vmr, n2}, {D.cfc11vmr, lw->cfc11vmr, n2}, {D.cfc12vmr, lw->cfc12vmr, n2},
+            {D.cfc22vmr, lw->cfc22vmr, n2}, {D.ccl4vmr, lw->ccl4vmr, n2}, {D.cldf, lw->cldf, n2}, {D.ciwp, lw->ciwp, n2},
+            {D.clwp, lw->clwp, n2}, {D.rei, lw->rei, n2}, {D.rel, lw->rel, n2}, {D.tauaer, lw->tauaer, n2 * 16},
+            {D.zm, lw->zm, n2}, {D.alat, lw->alat, (size_t)nc}};
+        for (auto &o : outs)
+            if (o.dst) cudaMemcpyAsync(const_cast<double *>(o.dst), o.src, o.n * 8, cudaMemcpyDeviceToHost, p.stream);
+        if (!ok(cudaStreamSynchronize(p.stream))) rc = RRTMGX_ECUDA;
+    }
+    cudaFree(nat.base);
+    return rc;
+}
+
+#ifndef RRTMGX_WITH_SW
+int rrtmgx_solar_refresh(const RrtmgxSolarArgs *) { return RRTMGX_EARG; }
+int rrtmgx_solar_prepare(const RrtmgxSolarArgs *, RrtmgxSwArgs *) { return RRTMGX_EARG; }
+#else
+int rrtmgx_solar_refresh(const RrtmgxSolarArgs *a) {
+    if (!g.ready) return RRTMGX_ENOTINIT;
+    if (!ok(cudaSetDevice(g.device))) { cudaGetLastError(); return RRTMGX_ENODEVICE; }
+    if (!glue_args_ok(a) || !a->cl || !a->zt || !a->albvr || !a->albvf || !a->albnr || !a->albnf || !a->fsw || !a->fsc ||
+        !a->fswu || !a->fscu || (!a->taua != !a->ssaa) || (!a->taua != !a->asya))
+        return RRTMGX_EARG;
+    Path &p = g.sw;
+    const bool devptr = a->flags & RRTMGX_DEVICE_PTRS;
+    if ((a->flags & RRTMGX_NO_SYNC) && !devptr) return RRTMGX_EARG;
+    const int ncol = a->ncol;
+    cudaStream_t st = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
+    if (!ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, st))) return RRTMGX_ECUDA;
+    if (devptr) {
+        for (size_t col0 = 0; col0 < (size_t)ncol; col0 += kGlueChunk)
+            if (int rc = solar_chunk(*a, ncol, (int)col0, (int)std::min(kGlueChunk, (size_t)ncol - col0), st)) return rc;
+        p.pending = true;
+        if (a->flags & RRTMGX_NO_SYNC) return 0;
+        return p.last_status = status_from(p);
+    }
+    RrtmgxSolarArgs ca = *a;
+    std::vector<Arr> arrs;
+    const size_t L = a->lm, L1 = a->lm + 1;
+    auto in = [&](const double *const &f, const double **slot, size_t rows) {
+        arrs.push_back({f, (void **)slot, rows, 8, false, true, false});
+    };
+    auto out = [&](double *const &f, double **slot, size_t rows) {
+        arrs.push_back({f, (void **)slot, rows, 8, false, false, true});
+    };
+    in(a->ple, &ca.ple, L1); in(a->pl, &ca.pl, L); in(a->t, &ca.t, L); in(a->q, &ca.q, L); in(a->o3, &ca.o3, L);
+    in(a->ch4, &ca.ch4, L); in(a->cl, &ca.cl, L); in(a->qliq, &ca.qliq, L); in(a->qice, &ca.qice, L);
+    in(a->rliq, &ca.rliq, L); in(a->rice, &ca.rice, L); in(a->ts, &ca.ts, 1); in(a->zt, &ca.zt, 1);
+    in(a->lats, &ca.lats, 1); in(a->albvr, &ca.albvr, 1); in(a->albvf, &ca.albvf, 1); in(a->albnr, &ca.albnr, 1);
+    in(a->albnf, &ca.albnf, 1); in(a->taua, &ca.taua, L * 14); in(a->ssaa, &ca.ssaa, L * 14); in(a->asya, &ca.asya, L * 14);
+    out(a->fsw, &ca.fsw, L1); out(a->fsc, &ca.fsc, L1); out(a->fswu, &ca.fswu, L1); out(a->fscu, &ca.fscu, L1);
+    out(a->nirr, &ca.nirr, 1); out(a->nirf, &ca.nirf, 1); out(a->parr, &ca.parr, 1); out(a->parf, &ca.parf, 1);
+    out(a->uvrr, &ca.uvrr, 1); out(a->uvrf, &ca.uvrf, 1); out(a->fswband, &ca.fswband, 14);
+    out(a->cldts, &ca.cldts, 1); out(a->cldhs, &ca.cldhs, 1); out(a->cldms, &ca.cldms, 1); out(a->cldls, &ca.cldls, 1);
+    out(a->cottp, &ca.cottp, 1); out(a->cothp, &ca.cothp, 1); out(a->cotmp, &ca.cotmp, 1); out(a->cotlp, &ca.cotlp, 1);
+    const size_t chunk = std::min<size_t>(g.host_chunk_cols, (size_t)ncol);
+    int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxSolarArgs &c, int nc) -> int {
+        return solar_chunk(c, nc, 0, nc, p.stream);
+    });
+    if (rc) return rc;
+    p.pending = true;
+    return p.last_status = status_from(p);
+}
+
+int rrtmgx_solar_prepare(const RrtmgxSolarArgs *a, RrtmgxSwArgs *sw) {
+    if (!g.ready) return RRTMGX_ENOTINIT;
+    if (!ok(cudaSetDevice(g.device))) { cudaGetLastError(); return RRTMGX_ENODEVICE; }
+    if (!glue_args_ok(a) || !sw || !a->cl || !a->zt || !a->albvr || !a->albvf || !a->albnr || !a->albnf) return RRTMGX_EARG;
+    Path &p = g.sw;
+    const int nc = a->ncol, L = a->lm;
+    sw_scalars(*a, nc, *sw);
+    if (a->flags & RRTMGX_DEVICE_PTRS) {
+        cudaStream_t st = a->stream ? (cudaStream_t)a->stream : p.stream;
+        RRTMGX_LAUNCH(solar_prepare_kernel, (nc + 127) / 128, 128, 0, st, nc, nc, 0, *a, *sw);
+        if (a->flags & RRTMGX_NO_SYNC) return ok(cudaGetLastError()) ? 0 : RRTMGX_ECUDA;
+        return ok(cudaStreamSynchronize(st)) ? 0 : RRTMGX_ECUDA;
+    }
+    const size_t n2 = (size_t)nc * L, n2p = (size_t)nc * (L + 1);
+    Slab nat;
+    RrtmgxSolarArgs d = *a;
+    struct In { const double **f; size_t n; } ins[] = {
+        {&d.ple, n2p}, {&d.pl, n2}, {&d.t, n2}, {&d.q, n2}, {&d.o3, n2}, {&d.ch4, n2}, {&d.cl, n2}, {&d.qliq, n2},
+        {&d.qice, n2}, {&d.rliq, n2}, {&d.rice, n2}, {&d.ts, (size_t)nc}, {&d.zt, (size_t)nc}, {&d.lats, (size_t)nc},
+        {&d.albvr, (size_t)nc}, {&d.albvf, (size_t)nc}, {&d.albnr, (size_t)nc}, {&d.albnf, (size_t)nc},
+        {&d.taua, n2 * 14}, {&d.ssaa, n2 * 14}, {&d.asya, n2 * 14}};
+    size_t bytes = 4096;
+    for (auto &i : ins) bytes += *i.f ? ((i.n * 8 + 255) & ~(size_t)255) : 0;
+    if (int rc = grow(nat, bytes)) return rc;
+    for (auto &i : ins)
+        if (*i.f) {
+            double *dev = nat.take<double>(i.n);
+            cudaMemcpyAsync(dev, *i.f, i.n * 8, cudaMemcpyHostToDevice, p.stream);
+            *i.f = dev;
+        }
+    int rc = grow(p.glue, carve_bytes<RrtmgxSwArgs>(nc, L, carve_sw_args));
+    if (!rc) {
+        p.glue.used = 0;
+        RrtmgxSwArgs D = *sw;
+        carve_sw_args(p.glue, nc, L, D);
+        RRTMGX_LAUNCH(solar_prepare_kernel, (nc + 127) / 128, 128, 0, p.stream, nc, nc, 0, d, D);
+        struct Out { const double *src; const double *dst; size_t n; } outs[] = {
+            {D.coszen, sw->coszen, (size_t)nc}, {D.play, sw->play, n2}, {D.plev, sw->plev, n2p}, {D.tlay, sw->tlay, n2},
+            {D.h2ovmr, sw->h2ovmr, n2}, {D.o3vmr, sw->o3vmr, n2}, {D.co2vmr, sw->co2vmr, n2}, {D.ch4vmr, sw->ch4vmr, n2},
+            {D.o2vmr, sw->o2vmr, n2}, {D.cld, sw->cld, n2}, {D.ciwp, sw->ciwp, n2}, {D.clwp, sw->clwp, n2},
+            {D.rei, sw->rei, n2}, {D.rel, sw->rel, n2}, {D.zm, sw->zm, n2}, {D.alat, sw->alat, (size_t)nc},
+            {D.tauaer, sw->tauaer, n2 * 14}, {D.ssaaer, sw->ssaaer, n2 * 14}, {D.asmaer, sw->asmaer, n2 * 14},
+            {D.asdir, sw->asdir, (size_t)nc}, {D.asdif, sw->asdif, (size_t)nc}, {D.aldir, sw->aldir, (size_t)nc},
+            {D.aldif, sw->aldif, (size_t)nc}};
+        for (auto &o : outs)
+            if (o.dst) cudaMemcpyAsync(const_cast<double *>(o.dst), o.src, o.n * 8, cudaMemcpyDeviceToHost, p.stream);
+        if (!ok(cudaStreamSynchronize(p.stream))) rc = RRTMGX_ECUDA;
+    }
+    cudaFree(nat.base);
+    return rc;
+}
+#endif
+
+}  // extern "C"
+
 
 #ifndef RRTMGX_WITH_SW
 namespace rrtmgx {

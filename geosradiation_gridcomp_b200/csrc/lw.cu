@@ -470,6 +470,30 @@ struct Lay {
     __device__ __forceinline__ double f(int k) const { return fj[k * n2]; }
 };
 
+// GN consecutive g-points of one table row.  The tables are g-point fastest and 16-byte aligned in
+// the arena, ng and the thread's first g-point are even when GN is, so a row slice is read with
+// 16-byte loads: half the load instructions - and half the L1 wavefronts, which is what these
+// kernels are bound by (profiles/r2_d_*) - of one 8-byte gather per g-point.
+template <int GN> struct GRow {
+    double v[GN];
+    __device__ __forceinline__ double operator[](int i) const { return v[i]; }
+};
+template <int GN>
+__device__ __forceinline__ GRow<GN> ldrow(const double *__restrict__ p) {
+    GRow<GN> r;
+    if constexpr (GN % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < GN; i += 2) {
+            const double2 t = __ldg(reinterpret_cast<const double2 *>(p + i));
+            r.v[i] = t.x; r.v[i + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < GN; ++i) r.v[i] = __ldg(p + i);
+    }
+    return r;
+}
+
 // lower-atmosphere key-species sum for a binary band at one reference pressure
 // (e.g. taugb3 :482-511, :554-576): three-point stencils near specparm 0 and 1, else bilinear
 template <int GN>
@@ -481,18 +505,22 @@ __device__ __forceinline__ void stencil_lower(const double *__restrict__ row /* 
         const double p2 = p * p, p4 = p2 * p2;
         const double fk0 = p4, fk1 = 1. - p - 2.0 * p4, fk2 = p + p4;
         const double w0 = fk0 * fa, w1 = fk1 * fa, w2 = fk2 * fa, w3 = fk0 * fb, w4 = fk1 * fb, w5 = fk2 * fb;
-        FORG out[ig] = speccomb * (w0 * row[ig] + w1 * row[ng + ig] + w2 * row[2 * ng + ig] +
-                                   w3 * row[9 * ng + ig] + w4 * row[10 * ng + ig] + w5 * row[11 * ng + ig]);
+        const GRow<GN> r0 = ldrow<GN>(row), r1 = ldrow<GN>(row + ng), r2 = ldrow<GN>(row + 2 * ng),
+                       r9 = ldrow<GN>(row + 9 * ng), r10 = ldrow<GN>(row + 10 * ng), r11 = ldrow<GN>(row + 11 * ng);
+        FORG out[ig] = speccomb * (w0 * r0[ig] + w1 * r1[ig] + w2 * r2[ig] + w3 * r9[ig] + w4 * r10[ig] + w5 * r11[ig]);
     } else if (specparm > 0.875) {
         const double p = -fs;
         const double p2 = p * p, p4 = p2 * p2;
         const double fk0 = p4, fk1 = 1. - p - 2.0 * p4, fk2 = p + p4;
         const double w0 = fk2 * fa, w1 = fk1 * fa, w2 = fk0 * fa, w3 = fk2 * fb, w4 = fk1 * fb, w5 = fk0 * fb;
-        FORG out[ig] = speccomb * (w0 * row[ig - ng] + w1 * row[ig] + w2 * row[ng + ig] +
-                                   w3 * row[8 * ng + ig] + w4 * row[9 * ng + ig] + w5 * row[10 * ng + ig]);
+        const GRow<GN> rm = ldrow<GN>(row - ng), r0 = ldrow<GN>(row), r1 = ldrow<GN>(row + ng),
+                       r8 = ldrow<GN>(row + 8 * ng), r9 = ldrow<GN>(row + 9 * ng), r10 = ldrow<GN>(row + 10 * ng);
+        FORG out[ig] = speccomb * (w0 * rm[ig] + w1 * r0[ig] + w2 * r1[ig] + w3 * r8[ig] + w4 * r9[ig] + w5 * r10[ig]);
     } else {
         const double w0 = (1. - fs) * fa, w1 = fs * fa, w2 = (1. - fs) * fb, w3 = fs * fb;
-        FORG out[ig] = speccomb * (w0 * row[ig] + w1 * row[ng + ig] + w2 * row[9 * ng + ig] + w3 * row[10 * ng + ig]);
+        const GRow<GN> r0 = ldrow<GN>(row), r1 = ldrow<GN>(row + ng), r9 = ldrow<GN>(row + 9 * ng),
+                       r10 = ldrow<GN>(row + 10 * ng);
+        FORG out[ig] = speccomb * (w0 * r0[ig] + w1 * r1[ig] + w2 * r9[ig] + w3 * r10[ig]);
     }
 }
 
@@ -501,7 +529,8 @@ template <int GN>
 __device__ __forceinline__ void lerp_rows(const double *__restrict__ t, int ng, int g0, int i, double f,
                                           double (&out)[GN]) {
     const double *r = t + ((i - 1) * ng + g0);
-    FORG out[ig] = r[ig] + f * (r[ng + ig] - r[ig]);
+    const GRow<GN> a = ldrow<GN>(r), b = ldrow<GN>(r + ng);
+    FORG out[ig] = a[ig] + f * (b[ig] - a[ig]);
 }
 
 // binary minor species k(jm,indm,g) of shape (nj,19,ng) (e.g. taugb3 :548-552)
@@ -509,10 +538,11 @@ template <int GN>
 __device__ __forceinline__ void minor2(const double *__restrict__ k, int ng, int g0, int nj, int jm, int indm,
                                        double fm, double minorfrac, double (&out)[GN]) {
     const double *a = k + (((jm - 1) + nj * (indm - 1)) * ng + g0);   // K(jm,indm)
-    const double *b = a + nj * ng;                                                   // K(jm,indm+1)
+    const double *b = a + nj * ng;                                    // K(jm,indm+1)
+    const GRow<GN> a0 = ldrow<GN>(a), a1 = ldrow<GN>(a + ng), b0 = ldrow<GN>(b), b1 = ldrow<GN>(b + ng);
     FORG {
-        const double m1 = a[ig] + fm * (a[ng + ig] - a[ig]);
-        const double m2 = b[ig] + fm * (b[ng + ig] - b[ig]);
+        const double m1 = a0[ig] + fm * (a1[ig] - a0[ig]);
+        const double m2 = b0[ig] + fm * (b1[ig] - b0[ig]);
         out[ig] = m1 + minorfrac * (m2 - m1);
     }
 }
@@ -524,7 +554,8 @@ __device__ __forceinline__ void key4(const double *__restrict__ tab, int ng, int
     const double fac00 = L.f(F_FAC00), fac10 = L.f(F_FAC10), fac01 = L.f(F_FAC01), fac11 = L.f(F_FAC11);
     const double *r0 = tab + ((ind0 - 1) * ng + g0);
     const double *r1 = tab + ((ind1 - 1) * ng + g0);
-    FORG out[ig] = fac00 * r0[ig] + fac10 * r0[ng + ig] + fac01 * r1[ig] + fac11 * r1[ng + ig];
+    const GRow<GN> a0 = ldrow<GN>(r0), a1 = ldrow<GN>(r0 + ng), b0 = ldrow<GN>(r1), b1 = ldrow<GN>(r1 + ng);
+    FORG out[ig] = fac00 * a0[ig] + fac10 * a1[ig] + fac01 * b0[ig] + fac11 * b1[ig];
 }
 
 // upper-atmosphere binary key species with nspb = 5 (bands 3, 4, 5; e.g. :675-685)
@@ -538,10 +569,10 @@ __device__ __forceinline__ void key_upper5(const double *__restrict__ tab, int n
     const double fac101 = s1.fs * fac01, fac111 = s1.fs * fac11;
     const double *r0 = tab + ((ind0 - 1) * ng + g0);
     const double *r1 = tab + ((ind1 - 1) * ng + g0);
-    FORG out[ig] = s0.speccomb * (fac000 * r0[ig] + fac100 * r0[ng + ig] + fac010 * r0[5 * ng + ig] +
-                                  fac110 * r0[6 * ng + ig]) +
-                   s1.speccomb * (fac001 * r1[ig] + fac101 * r1[ng + ig] + fac011 * r1[5 * ng + ig] +
-                                  fac111 * r1[6 * ng + ig]);
+    const GRow<GN> a0 = ldrow<GN>(r0), a1 = ldrow<GN>(r0 + ng), a5 = ldrow<GN>(r0 + 5 * ng), a6 = ldrow<GN>(r0 + 6 * ng);
+    const GRow<GN> b0 = ldrow<GN>(r1), b1 = ldrow<GN>(r1 + ng), b5 = ldrow<GN>(r1 + 5 * ng), b6 = ldrow<GN>(r1 + 6 * ng);
+    FORG out[ig] = s0.speccomb * (fac000 * a0[ig] + fac100 * a1[ig] + fac010 * a5[ig] + fac110 * a6[ig]) +
+                   s1.speccomb * (fac001 * b0[ig] + fac101 * b1[ig] + fac011 * b5[ig] + fac111 * b6[ig]);
 }
 
 __device__ __forceinline__ double rat_tab(int which, int jp1 /* 1-based */) { return c_lw.rat[which * 59 + jp1 - 1]; }
@@ -551,11 +582,13 @@ template <int GN>
 __device__ __forceinline__ void pfrac2(const double *__restrict__ fr, int ng, int g0, const Spec &sp,
                                        double (&pf)[GN]) {
     const double *r = fr + ((sp.js - 1) * ng + g0);
-    FORG pf[ig] = r[ig] + sp.fs * (r[ng + ig] - r[ig]);
+    const GRow<GN> a = ldrow<GN>(r), b = ldrow<GN>(r + ng);
+    FORG pf[ig] = a[ig] + sp.fs * (b[ig] - a[ig]);
 }
 template <int GN>
 __device__ __forceinline__ void pfrac1(const double *__restrict__ fr, int g0, double (&pf)[GN]) {
-    FORG pf[ig] = fr[g0 + ig];
+    const GRow<GN> a = ldrow<GN>(fr + g0);
+    FORG pf[ig] = a[ig];
 }
 
 // Gas optical depth (TAU = true) and Planck fraction of one layer for g-points [G0, G0+GN) of

@@ -70,6 +70,35 @@ class SwArgs(C.Structure):
                 [(n, _vp) for n in _SW_IN] + [("clearCounts", _vp)] + [(n, _vp) for n in _SW_OUT])
 
 
+# ---- fused Run-phase glue (include/rrtmgx.h: RrtmgxIrradArgs, RrtmgxSolarArgs) ---------------------
+_IRR_IN = ["ple", "pl", "t", "q", "o3", "ch4", "n2o", "co2", "cfc11", "cfc12", "hcfc22", "fcld", "qliq", "qice",
+           "rliq", "rice", "ts", "t2m", "emis", "lats", "taua", "ssaa"]
+_IRR_OUT = ["flxu", "flxd", "flcu", "flcd", "dfdts", "dfdtsc", "sfcem", "cldtt", "cldhi", "cldmd", "cldlo", "olrb",
+            "dolrb_dts"]
+
+
+class IrradArgs(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("ncol", "lm", "iceflg", "liqflg", "doy", "lcldmh", "lcldlm", "flags")] +
+                [("stream", _vp)] +
+                [(n, C.c_double) for n in ("co2_fixed", "o2", "ccl4", "airmw", "h2omw", "o3mw", "rgas", "grav")] +
+                [(n, _vp) for n in _IRR_IN] + [("band_output", _vp)] + [(n, _vp) for n in _IRR_OUT])
+
+
+_SOL_IN = ["ple", "pl", "t", "q", "o3", "ch4", "cl", "qliq", "qice", "rliq", "rice", "ts", "zt", "lats", "albvr",
+           "albvf", "albnr", "albnf", "taua", "ssaa", "asya"]
+_SOL_OUT = ["fsw", "fsc", "fswu", "fscu", "nirr", "nirf", "parr", "parf", "uvrr", "uvrf", "fswband", "cldts", "cldhs",
+            "cldms", "cldls", "cottp", "cothp", "cotmp", "cotlp"]
+
+
+class SolarArgs(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("ncol", "lm", "iceflg", "liqflg", "doy", "isolvar", "lcldmh", "lcldlm",
+                                        "flags")] +
+                [("stream", _vp)] +
+                [(n, C.c_double) for n in ("sc", "dist", "co2", "o2", "airmw", "h2omw", "o3mw", "rgas", "grav",
+                                           "undef")] +
+                [("solcycfrac", _vp)] + [(n, _vp) for n in _SOL_IN] + [(n, _vp) for n in _SOL_OUT])
+
+
 _TAP_I = ["jp", "jt", "jt1", "indfor", "indself", "indminor", "laytrop"]
 _TAP_D = ["fac00", "fac01", "fac10", "fac11"]
 
@@ -105,6 +134,10 @@ def lib():
         L.rrtmgx_set_taps.argtypes = [C.POINTER(Taps), C.POINTER(Taps)]
         L.rrtmgx_table.restype = _dp
         L.rrtmgx_table.argtypes = [C.c_char_p, C.c_char_p, C.c_int, _ip]
+        L.rrtmgx_irrad_refresh.argtypes = [C.POINTER(IrradArgs)]
+        L.rrtmgx_irrad_prepare.argtypes = [C.POINTER(IrradArgs), C.POINTER(LwArgs)]
+        L.rrtmgx_solar_refresh.argtypes = [C.POINTER(SolarArgs)]
+        L.rrtmgx_solar_prepare.argtypes = [C.POINTER(SolarArgs), C.POINTER(SwArgs)]
         L.rrtmgx_debug_divide.argtypes = [C.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp]
         L.rrtmgx_heating_rate.argtypes = [C.c_int, C.c_int, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp]
         _lib = L
@@ -357,6 +390,128 @@ def debug_divide(a, b):
     out = [np.empty_like(a) for _ in range(4)]
     _check(lib().rrtmgx_debug_divide(a.size, _addr(a, False), _addr(b, False), *[_addr(o, False) for o in out]))
     return tuple(out)
+
+
+# ---- fused Run-phase glue: GEOS-native state in, GEOS-native fluxes out ---------------------------------
+def _irrad_args(n, iceflg, liqflg, device, keep):
+    a = IrradArgs()
+    a.ncol, a.lm, a.iceflg, a.liqflg, a.doy = int(n["ncol"]), int(n["lm"]), int(iceflg), int(liqflg), int(n["doy"])
+    a.lcldmh, a.lcldlm = int(n["lcldmh"]), int(n["lcldlm"])
+    a.flags = DEVICE_PTRS if device else 0
+    for k in ("co2_fixed", "o2", "ccl4", "airmw", "h2omw", "o3mw", "rgas", "grav"):
+        setattr(a, k, float(n[k]))
+    for k in _IRR_IN:
+        v = n.get({"taua": "taua_lw", "ssaa": "ssaa_lw"}.get(k, k))
+        setattr(a, k, _addr(v, device, keep=keep))
+    bo = np.ascontiguousarray(n["band_output"], dtype=np.int32)
+    keep.append(bo)
+    a.band_output = bo.ctypes.data
+    return a
+
+
+def irrad_prepare(n, iceflg=3, liqflg=1):
+    """The first half of the LW driver glue (GEOS_IrradGridComp.F90:3237-3371) on the device: returns the
+    rrtmg_lw input arrays (layer 1 at the surface, hPa, vmr, g/m2) of the native state `n`
+    (synthetic.make_native_state) plus cloudLM / cloudMH."""
+    if not _initialised:
+        init()
+    keep = []
+    ncol, lm = n["ncol"], n["lm"]
+    a = _irrad_args(n, iceflg, liqflg, False, keep)
+    o = {}
+    lw = LwArgs()
+    for k in _LW_IN:
+        shape = {"plev": (ncol, lm + 1), "tlev": (ncol, lm + 1), "tsfc": (ncol,), "alat": (ncol,), "emis": (ncol, 16),
+                 "tauaer": (ncol, lm, 16)}.get(k, (ncol, lm))
+        o[k] = np.zeros(shape, order="F")
+        setattr(lw, k, o[k].ctypes.data)
+    _check(lib().rrtmgx_irrad_prepare(C.byref(a), C.byref(lw)))
+    o["cloudLM"], o["cloudMH"] = lw.cloudLM, lw.cloudMH
+    return o
+
+
+def irrad_refresh(n, iceflg=3, liqflg=1, device=False, out=None):
+    """One LW refresh from the GEOS-native state: what LW_Driver does between :3237 and :3547 with RRTMG
+    (flip / units / TLEV / ZM -> rrtmg_lw -> unflip / sign / SFCEM / cloud fractions), fused on the device.
+    Returns the native outputs: FLXU_INT ... DFDTSC (ncol,0:LM) top-down, upward negative; SFCEM_INT;
+    CLDTTLW, CLDHILW, CLDMDLW, CLDLOLW; OLRB / DOLRB_DTS (16,ncol)."""
+    if not _initialised:
+        init()
+    keep = []
+    ncol, lm = n["ncol"], n["lm"]
+    a = _irrad_args(n, iceflg, liqflg, device, keep)
+    if out is None:
+        if device:
+            import torch
+            z = lambda *sh: torch.zeros(tuple(reversed(sh)), dtype=torch.float64, device="cuda")
+        else:
+            z = lambda *sh: np.zeros(sh, order="F")
+        out = {k: z(ncol, lm + 1) for k in _IRR_OUT[:6]}
+        out.update({k: z(ncol) for k in _IRR_OUT[6:11]})
+        out["olrb"], out["dolrb_dts"] = z(16, ncol), z(16, ncol)
+    for k in _IRR_OUT:
+        setattr(a, k, _addr(out[k], device, keep=keep))
+    _check(lib().rrtmgx_irrad_refresh(C.byref(a)))
+    return out
+
+
+def _solar_args(n, iceflg, liqflg, isolvar, device, keep):
+    a = SolarArgs()
+    a.ncol, a.lm, a.iceflg, a.liqflg, a.doy = int(n["ncol"]), int(n["lm"]), int(iceflg), int(liqflg), int(n["doy"])
+    a.isolvar, a.lcldmh, a.lcldlm = int(isolvar), int(n["lcldmh"]), int(n["lcldlm"])
+    a.flags = DEVICE_PTRS if device else 0
+    a.co2 = float(n["co2_fixed"])
+    for k in ("sc", "dist", "o2", "airmw", "h2omw", "o3mw", "rgas", "grav", "undef"):
+        setattr(a, k, float(n[k]))
+    for k in _SOL_IN:
+        v = n.get({"taua": "taua_sw", "ssaa": "ssaa_sw", "asya": "asya_sw", "cl": "fcld"}.get(k, k))
+        setattr(a, k, _addr(v, device, keep=keep))
+    return a
+
+
+def solar_prepare(n, iceflg=3, liqflg=1, isolvar=0):
+    """The first half of the SW driver glue (GEOS_SolarGridComp.F90:6113-6223) on the device: the rrtmg_sw
+    input arrays of the native state `n` plus cloudLM / cloudMH."""
+    if not _initialised:
+        init()
+    keep = []
+    ncol, lm = n["ncol"], n["lm"]
+    a = _solar_args(n, iceflg, liqflg, isolvar, False, keep)
+    o = {}
+    sw = SwArgs()
+    for k in _SW_IN:
+        shape = {"plev": (ncol, lm + 1), "coszen": (ncol,), "alat": (ncol,), "asdir": (ncol,), "asdif": (ncol,),
+                 "aldir": (ncol,), "aldif": (ncol,), "tauaer": (ncol, lm, 14), "ssaaer": (ncol, lm, 14),
+                 "asmaer": (ncol, lm, 14)}.get(k, (ncol, lm))
+        o[k] = np.zeros(shape, order="F")
+        setattr(sw, k, o[k].ctypes.data)
+    _check(lib().rrtmgx_solar_prepare(C.byref(a), C.byref(sw)))
+    o["cloudLM"], o["cloudMH"] = sw.cloudLM, sw.cloudMH
+    return o
+
+
+def solar_refresh(n, iceflg=3, liqflg=1, isolvar=0, device=False, out=None):
+    """One SW refresh from the GEOS-native state (SORADCORE :6113-6447 around rrtmg_sw), fused on the device.
+    Returns FSW, FSC, FSWU, FSCU (ncol,LM+1) top-down, the surface diagnostics, CLDTS..CLDLS and COTTP..COTLP
+    (MAPL_UNDEF where no cloud)."""
+    if not _initialised:
+        init()
+    keep = []
+    ncol, lm = n["ncol"], n["lm"]
+    a = _solar_args(n, iceflg, liqflg, isolvar, device, keep)
+    if out is None:
+        if device:
+            import torch
+            z = lambda *sh: torch.zeros(tuple(reversed(sh)), dtype=torch.float64, device="cuda")
+        else:
+            z = lambda *sh: np.zeros(sh, order="F")
+        out = {k: z(ncol, lm + 1) for k in _SOL_OUT[:4]}
+        out.update({k: z(ncol) for k in _SOL_OUT[4:10] + _SOL_OUT[11:]})
+        out["fswband"] = z(ncol, 14)
+    for k in _SOL_OUT:
+        setattr(a, k, _addr(out[k], device, keep=keep))
+    _check(lib().rrtmgx_solar_refresh(C.byref(a)))
+    return out
 
 
 # ---- convenience wrappers over the synthetic-state dicts of synthetic.make_columns ---------------

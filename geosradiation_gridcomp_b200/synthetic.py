@@ -127,3 +127,51 @@ def make_columns(ncol, nlay=72, seed=20260118, col0=0, lit=True):
     out["adjes"] = 1.0
     out["band_output"] = np.array([1 if b in (6, 9, 10, 11) else 0 for b in range(1, 17)], dtype=np.int32)
     return out
+
+
+# MAPL constants the GEOS drivers use in the Run-phase glue (MAPL is not in the reference tree; these
+# are the values of MAPL_Constants: MAPL_AIRMW, MAPL_H2OMW, MAPL_O3MW, MAPL_RUNIV / MAPL_AIRMW, MAPL_GRAV)
+MAPL = dict(airmw=28.965, h2omw=18.015, o3mw=47.9982, rgas=8314.47 / 28.965, grav=9.80665, undef=1.0e15)
+
+
+def make_native_state(ncol, lm=72, seed=20260118, col0=0):
+    """GEOS-native state of the same synthetic columns, as the two drivers hold it before their RRTMG glue
+    (GEOS_IrradGridComp.F90:3237-3371, GEOS_SolarGridComp.F90:6113-6223): (ncol,LM) arrays with level 1 at
+    the MODEL TOP, pressures in Pa, specific humidity and ozone mass mixing ratio, cloud water contents
+    in kg/kg, extinction / scattering (/ asymmetry-weighted) aerosol optical depths.  A few negative
+    mixing ratios and cloud fractions are planted so the drivers' clean-up of negatives is exercised."""
+    s = make_columns(ncol, lm, seed=seed, col0=col0)
+    f = lambda a: np.asfortranarray(a, dtype=np.float64)
+    flip = lambda a: a[:, ::-1]
+    ple = flip(s["plev"]) * 100.0                       # (ncol, LM+1) top-down, Pa
+    dp = ple[:, 1:] - ple[:, :-1]
+    wq = MAPL["airmw"] / MAPL["h2omw"]
+    vmr = flip(s["h2ovmr"])
+    q = (vmr / wq) / (1.0 + vmr / wq)
+    o3 = flip(s["o3vmr"]) * (MAPL["o3mw"] / MAPL["airmw"])
+    xx = 1.02 * 100 * dp
+    u = _draw(seed, col0, ncol, 40, lm)
+    neg = u < 0.002                                      # planted negatives
+    n = dict(ncol=ncol, lm=lm, doy=int(s["dyofyr"]),
+             lcldlm=lm - int(s["cloudLM"]) + 1, lcldmh=lm - int(s["cloudMH"]) + 1,
+             ple=f(ple), pl=f(flip(s["play"]) * 100.0), t=f(flip(s["tlay"])),
+             q=f(np.where(neg, -1e-9, q)), o3=f(np.where(_draw(seed, col0, ncol, 41, lm) < 0.002, -1e-10, o3)),
+             ch4=f(flip(s["ch4vmr"])), n2o=f(flip(s["n2ovmr"])), co2=f(flip(s["co2vmr"])),
+             cfc11=f(flip(s["cfc11vmr"])), cfc12=f(flip(s["cfc12vmr"])), hcfc22=f(flip(s["cfc22vmr"])),
+             fcld=f(np.where(_draw(seed, col0, ncol, 42, lm) < 0.002, -1e-3, flip(s["cldf"]))),
+             qliq=f(flip(s["clwp"]) / xx), qice=f(flip(s["ciwp"]) / xx),
+             # radii beyond the RRTMG limits on both sides, so the drivers' clamps act
+             rliq=f(flip(s["rel"]) * 2.6 - 8.0), rice=f(flip(s["rei"]) * 1.3 - 16.0),
+             ts=f(s["tsfc"]), t2m=f(s["tlev"][:, 0]), emis=f(s["emis"][:, 0]), lats=f(s["alat"]),
+             co2_fixed=4.2e-4, o2=0.209, ccl4=7.5e-11,
+             zt=f(s["coszen"]), albvr=f(s["asdir"]), albvf=f(s["asdif"]), albnr=f(s["aldir"]), albnf=f(s["aldif"]),
+             sc=float(s["scon"]), dist=float(s["adjes"]), band_output=s["band_output"])
+    # aerosol system output: extinction, un-normalised scattering (tau*ssa) and asymmetry (tau*ssa*g)
+    sca_lw = 0.45 * s["tauaer_lw"]
+    n["taua_lw"] = f((s["tauaer_lw"] + sca_lw)[:, ::-1, :])
+    n["ssaa_lw"] = f(sca_lw[:, ::-1, :])
+    n["taua_sw"] = f(s["tauaer_sw"][:, ::-1, :])
+    n["ssaa_sw"] = f((s["tauaer_sw"] * s["ssaaer"])[:, ::-1, :])
+    n["asya_sw"] = f((s["tauaer_sw"] * s["ssaaer"] * s["asmaer"])[:, ::-1, :])
+    n.update(MAPL)
+    return n

@@ -42,7 +42,9 @@ enum {
     RRTMGX_DEVICE_PTRS = 1,   /* array arguments are device pointers                         */
     RRTMGX_NO_SYNC     = 2,   /* device pointers only: return without synchronising; status  */
                               /* traps are then reported by rrtmgx_{lw,sw}_status()           */
-    RRTMGX_SKIP_CHECKS = 4    /* skip the negative-input scans (LW :209-318, SW :365-383)    */
+    RRTMGX_SKIP_CHECKS = 4,   /* skip the negative-input scans (LW :209-318, SW :365-383)    */
+    RRTMGX_KEEP_STATUS = 8    /* device pointers only: do not clear the path's status word    */
+                              /* first, so one status read covers a sequence of NO_SYNC runs  */
 };
 
 /* status codes (negative) */
@@ -173,6 +175,73 @@ void rrtmgx_set_taps(const RrtmgxTaps *lw_taps, const RrtmgxTaps *sw_taps);
  * grav and cp are the caller's MAPL_GRAV and MAPL_CP.  Device or host pointers per flags. */
 int rrtmgx_heating_rate(int ncol, int nlay, const double *fnet_up_minus_down, const double *plev,
                         double *hr_K_per_day, double grav, double cp, int flags, void *stream);
+
+/* ---- Run-phase glue fused on the device --------------------------------
+ * The two GEOS drivers reshape the model state on the host before every RRTMG call (vertical flip,
+ * Pa -> hPa, q -> vmr, content -> path, radius limits, TLEV interpolation, layer heights, negative
+ * clean-up) and reshape the fluxes afterwards (unflip, sign convention, SFCEM, FSW = down - up,
+ * clear counts -> cloud fractions, COT ratios).  These entry points take the NATIVE GEOS arrays -
+ * columns flattened (IM*JM), (ncol,LM) with level 1 at the model top, PLE (ncol,LM+1), SI units -
+ * do both reshapes in kernels around the device-resident RRTMG path, and hand back native outputs,
+ * so only the native state crosses PCIe, once.
+ *   rrtmgx_irrad_refresh   replaces GEOS_IrradGridComp.F90 LW_Driver :3237-3371, :3471-3478, :3486-3547
+ *   rrtmgx_solar_refresh   replaces GEOS_SolarGridComp.F90 SORADCORE :6113-6223, :6331-6387, :6395-6447
+ *   rrtmgx_*_prepare       only the first reshape: fills the caller-allocated arrays of an
+ *                          RrtmgxLwArgs / RrtmgxSwArgs (and its cloudLM/cloudMH), for staged use and tests
+ * Pointers are host or device pointers per `flags` as for rrtmgx_lw_run. */
+typedef struct {
+    int ncol, lm;
+    int iceflg, liqflg;       /* RRTMG_ICEFLG / RRTMG_LIQFLG resources (GEOS defaults 3, 1)           */
+    int doy;
+    int lcldmh, lcldlm;       /* GEOS (top-down) super-layer interface levels                        */
+    int flags;
+    void *stream;
+    double co2_fixed, o2, ccl4;                       /* CO2 where `co2` is NULL; uniform O2, CCl4   */
+    double airmw, h2omw, o3mw, rgas, grav;            /* MAPL_AIRMW, _H2OMW, _O3MW, _RGAS, _GRAV      */
+    const double *ple;                                /* (ncol,0:LM) Pa                              */
+    const double *pl, *t, *q, *o3, *ch4, *n2o;        /* (ncol,LM): Pa, K, kg/kg, mmr, vmr, vmr      */
+    const double *co2;                                /* (ncol,LM) vmr or NULL                       */
+    const double *cfc11, *cfc12, *hcfc22, *fcld;      /* (ncol,LM)                                   */
+    const double *qliq, *qice, *rliq, *rice;          /* CWC [kg/kg] and REFF [um], KLIQUID / KICE   */
+    const double *ts, *t2m, *emis, *lats;             /* (ncol)                                      */
+    const double *taua, *ssaa;                        /* (ncol,LM,16) extinction, scattering; or NULL */
+    const int32_t *band_output;                       /* (16) logical (host)                         */
+    /* outputs, GEOS convention: (ncol,0:LM) top-down, upward negative */
+    double *flxu, *flxd, *flcu, *flcd, *dfdts, *dfdtsc;
+    double *sfcem;                                    /* (ncol)                                      */
+    double *cldtt, *cldhi, *cldmd, *cldlo;            /* (ncol), any may be NULL                     */
+    double *olrb, *dolrb_dts;                         /* (16,ncol), bands with band_output; or NULL  */
+} RrtmgxIrradArgs;
+
+typedef struct {
+    int ncol, lm;
+    int iceflg, liqflg;
+    int doy, isolvar;
+    int lcldmh, lcldlm;
+    int flags;
+    void *stream;
+    double sc, dist;                                  /* solar constant, Earth-Sun adjustment (ADJES) */
+    double co2, o2;
+    double airmw, h2omw, o3mw, rgas, grav, undef;     /* ..., MAPL_UNDEF                              */
+    const double *solcycfrac;                         /* scalar or NULL                               */
+    const double *ple;                                /* (ncol,LM+1) Pa                               */
+    const double *pl, *t, *q, *o3, *ch4, *cl;         /* (ncol,LM)                                    */
+    const double *qliq, *qice, *rliq, *rice;          /* QQ3(:,:,2), QQ3(:,:,1), RR3(:,:,2), RR3(:,:,1) */
+    const double *ts, *zt, *lats;                     /* (ncol): TS, cos(zenith), latitude            */
+    const double *albvr, *albvf, *albnr, *albnf;      /* (ncol)                                       */
+    const double *taua, *ssaa, *asya;                 /* (ncol,LM,14) un-normalised, or NULL          */
+    /* outputs */
+    double *fsw, *fsc, *fswu, *fscu;                  /* (ncol,LM+1) top-down                         */
+    double *nirr, *nirf, *parr, *parf, *uvrr, *uvrf;  /* (ncol), any may be NULL                      */
+    double *fswband;                                  /* (ncol,14) or NULL                            */
+    double *cldts, *cldhs, *cldms, *cldls;            /* (ncol), any may be NULL                      */
+    double *cottp, *cothp, *cotmp, *cotlp;            /* (ncol), any may be NULL                      */
+} RrtmgxSolarArgs;
+
+int rrtmgx_irrad_prepare(const RrtmgxIrradArgs *g, RrtmgxLwArgs *lw);
+int rrtmgx_irrad_refresh(const RrtmgxIrradArgs *g);
+int rrtmgx_solar_prepare(const RrtmgxSolarArgs *g, RrtmgxSwArgs *sw);
+int rrtmgx_solar_refresh(const RrtmgxSolarArgs *g);
 
 /* Test hook: the band kernels replace the compiler's IEEE fp64 division by its own fast-path
  * instruction sequence without the range test (csrc/common.cuh ddiv/drcp).  Evaluates both on the

@@ -223,3 +223,142 @@ def clear_counts(cldy_stoch, cloudLM, cloudMH):
     if rc:
         raise RuntimeError(f"clearCounts_threeBand: {rc}")
     return out
+
+
+# ---- Run-phase glue (oracle/glue.c) ------------------------------------------------------------
+_IRR_STATE = ["ple", "pl", "t", "q", "o3", "ch4", "n2o", "co2", "cfc11", "cfc12", "hcfc22", "fcld", "qliq", "qice",
+              "rliq", "rice", "ts", "t2m", "emis", "lats", "taua", "ssaa"]
+_LW_INPUTS = ["play", "plev", "tlay", "tlev", "tsfc", "emis", "h2ovmr", "o3vmr", "co2vmr", "ch4vmr", "n2ovmr", "o2vmr",
+              "cfc11vmr", "cfc12vmr", "cfc22vmr", "ccl4vmr", "cldf", "ciwp", "clwp", "rei", "rel", "tauaer", "zm", "alat"]
+_SOL_STATE = ["ple", "pl", "t", "q", "o3", "ch4", "cl", "qliq", "qice", "rliq", "rice", "ts", "taua", "ssaa", "asya"]
+_SW_INPUTS = ["play", "plev", "tlay", "h2ovmr", "o3vmr", "co2vmr", "ch4vmr", "o2vmr", "cld", "ciwp", "clwp", "rei",
+              "rel", "zm", "tauaer", "ssaaer", "asmaer"]
+
+
+class IrradState(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("ncol", "lm", "iceflg", "liqflg", "lcldmh", "lcldlm")] +
+                [(n, C.c_double) for n in ("co2_fixed", "o2", "ccl4", "airmw", "h2omw", "o3mw", "rgas", "grav")] +
+                [(n, _dp) for n in _IRR_STATE])
+
+
+class LwInputs(C.Structure):
+    _fields_ = [("cloudLM", C.c_int), ("cloudMH", C.c_int)] + [(n, _dp) for n in _LW_INPUTS]
+
+
+class IrradFluxes(C.Structure):
+    _fields_ = [(n, _dp) for n in ("flxu", "flxd", "flcu", "flcd", "dfdts", "dfdtsc", "sfcem", "cldtt", "cldhi",
+                                   "cldmd", "cldlo")]
+
+
+class SolarState(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("ncol", "lm", "iceflg", "liqflg", "lcldmh", "lcldlm")] +
+                [(n, C.c_double) for n in ("co2", "o2", "airmw", "h2omw", "o3mw", "rgas", "grav")] +
+                [(n, _dp) for n in _SOL_STATE])
+
+
+class SwInputs(C.Structure):
+    _fields_ = [("cloudLM", C.c_int), ("cloudMH", C.c_int)] + [(n, _dp) for n in _SW_INPUTS]
+
+
+class SolarFluxes(C.Structure):
+    _fields_ = [(n, _dp) for n in ("fsw", "fsc", "fswu", "fscu", "cldts", "cldhs", "cldms", "cldls", "cottp", "cothp",
+                                   "cotmp", "cotlp")]
+
+
+def irrad_prepare(n, iceflg=3, liqflg=1):
+    """GEOS_IrradGridComp.F90:3237-3371 on the native state `n` (synthetic.make_native_state): returns a
+    synthetic-state dict in the layout of make_columns, ready for rrtmg_lw()."""
+    ncol, lm = n["ncol"], n["lm"]
+    s = IrradState()
+    s.ncol, s.lm, s.iceflg, s.liqflg, s.lcldmh, s.lcldlm = ncol, lm, iceflg, liqflg, n["lcldmh"], n["lcldlm"]
+    for k in ("co2_fixed", "o2", "ccl4", "airmw", "h2omw", "o3mw", "rgas", "grav"):
+        setattr(s, k, float(n[k]))
+    for k in _IRR_STATE:
+        v = n.get({"taua": "taua_lw", "ssaa": "ssaa_lw"}.get(k, k))
+        setattr(s, k, None if v is None else _d(v))
+    o = LwInputs()
+    out = {"ncol": ncol, "nlay": lm}
+    for k in _LW_INPUTS:
+        shape = {"plev": (ncol, lm + 1), "tlev": (ncol, lm + 1), "tsfc": (ncol,), "alat": (ncol,), "emis": (ncol, 16),
+                 "tauaer": (ncol, lm, 16)}.get(k, (ncol, lm))
+        out[k] = np.zeros(shape, order="F")
+        setattr(o, k, _d(out[k]))
+    rc = lib().oracle_irrad_prepare(C.byref(s), C.byref(o))
+    if rc:
+        raise RuntimeError(f"oracle_irrad_prepare: {rc}")
+    out["tauaer_lw"] = out["tauaer"]
+    out["cloudLM"], out["cloudMH"] = o.cloudLM, o.cloudMH
+    out["dyofyr"] = n["doy"]
+    out["band_output"] = n["band_output"]
+    return out
+
+
+def irrad_finish(n, o):
+    """GEOS_IrradGridComp.F90:3486-3533 on the outputs `o` of rrtmg_lw()."""
+    ncol, lm = n["ncol"], n["lm"]
+    f = IrradFluxes()
+    out = {k: np.zeros((ncol, lm + 1), order="F") for k in ("flxu", "flxd", "flcu", "flcd", "dfdts", "dfdtsc")}
+    out.update({k: np.zeros(ncol) for k in ("sfcem", "cldtt", "cldhi", "cldmd", "cldlo")})
+    for k, v in out.items():
+        setattr(f, k, _d(v))
+    L = lib()
+    L.oracle_irrad_finish.argtypes = None
+    rc = L.oracle_irrad_finish(C.c_int(ncol), C.c_int(lm), _d(n["emis"]), o["clearCounts"].ctypes.data_as(_ip),
+                               _d(o["uflx"]), _d(o["dflx"]), _d(o["uflxc"]), _d(o["dflxc"]), _d(o["duflx_dTs"]),
+                               _d(o["duflxc_dTs"]), C.byref(f))
+    if rc:
+        raise RuntimeError(f"oracle_irrad_finish: {rc}")
+    out["olrb"], out["dolrb_dts"] = o["olrb"], o["dolrb_dTs"]
+    return out
+
+
+def solar_prepare(n, iceflg=3, liqflg=1):
+    """GEOS_SolarGridComp.F90:6113-6223: returns a synthetic-state dict ready for rrtmg_sw()."""
+    ncol, lm = n["ncol"], n["lm"]
+    s = SolarState()
+    s.ncol, s.lm, s.iceflg, s.liqflg, s.lcldmh, s.lcldlm = ncol, lm, iceflg, liqflg, n["lcldmh"], n["lcldlm"]
+    s.co2 = float(n["co2_fixed"])
+    for k in ("o2", "airmw", "h2omw", "o3mw", "rgas", "grav"):
+        setattr(s, k, float(n[k]))
+    for k in _SOL_STATE:
+        v = n.get({"taua": "taua_sw", "ssaa": "ssaa_sw", "asya": "asya_sw", "cl": "fcld"}.get(k, k))
+        setattr(s, k, None if v is None else _d(v))
+    o = SwInputs()
+    out = {"ncol": ncol, "nlay": lm}
+    for k in _SW_INPUTS:
+        shape = {"plev": (ncol, lm + 1), "tauaer": (ncol, lm, 14), "ssaaer": (ncol, lm, 14),
+                 "asmaer": (ncol, lm, 14)}.get(k, (ncol, lm))
+        out[k] = np.zeros(shape, order="F")
+        setattr(o, k, _d(out[k]))
+    rc = lib().oracle_solar_prepare(C.byref(s), C.byref(o))
+    if rc:
+        raise RuntimeError(f"oracle_solar_prepare: {rc}")
+    out["tauaer_sw"] = out["tauaer"]
+    out["cldf"] = out["cld"]
+    out["cloudLM"], out["cloudMH"] = o.cloudLM, o.cloudMH
+    out["dyofyr"], out["scon"], out["adjes"] = n["doy"], n["sc"], n["dist"]
+    out["coszen"], out["alat"] = n["zt"], n["lats"]
+    out["asdir"], out["asdif"], out["aldir"], out["aldif"] = n["albvr"], n["albvf"], n["albnr"], n["albnf"]
+    return out
+
+
+def solar_finish(n, o):
+    """GEOS_SolarGridComp.F90:6395-6447 on the outputs `o` of rrtmg_sw()."""
+    ncol, lm = n["ncol"], n["lm"]
+    f = SolarFluxes()
+    out = {k: np.zeros((ncol, lm + 1), order="F") for k in ("fsw", "fsc", "fswu", "fscu")}
+    out.update({k: np.zeros(ncol) for k in ("cldts", "cldhs", "cldms", "cldls", "cottp", "cothp", "cotmp", "cotlp")})
+    for k, v in out.items():
+        setattr(f, k, _d(v))
+    cotd = (_dp * 4)(*[_d(o[k]) for k in ("cotdtp", "cotdhp", "cotdmp", "cotdlp")])
+    cotn = (_dp * 4)(*[_d(o[k]) for k in ("cotntp", "cotnhp", "cotnmp", "cotnlp")])
+    L = lib()
+    L.oracle_solar_finish.argtypes = None
+    rc = L.oracle_solar_finish(C.c_int(ncol), C.c_int(lm), C.c_double(n["undef"]), o["clearCounts"].ctypes.data_as(_ip),
+                               _d(o["swuflx"]), _d(o["swdflx"]), _d(o["swuflxc"]), _d(o["swdflxc"]), cotd, cotn,
+                               C.byref(f))
+    if rc:
+        raise RuntimeError(f"oracle_solar_finish: {rc}")
+    for k in ("nirr", "nirf", "parr", "parf", "uvrr", "uvrf", "fswband"):
+        out[k] = o[k]
+    return out

@@ -97,6 +97,54 @@ int oracle_clearCounts_threeBand(int dncol, int ncol, int nsubcol, int nlay, int
                                  int cloudMH, const unsigned char *cldy_stoch, int *clearCnts);
 void oracle_rng_kiss(int *s1, int *s2, int *s3, int *s4, double *ran);
 
+/* ---- Run-phase glue around the RRTMG calls (oracle/glue.c) ----
+ * GEOS-native state: (ncol,LM) arrays with level 1 at the model top, PLE (ncol,LM+1). */
+typedef struct {
+    int ncol, lm, iceflg, liqflg, lcldmh, lcldlm;   /* lcld*: GEOS top-down interface levels */
+    double co2_fixed, o2, ccl4;
+    double airmw, h2omw, o3mw, rgas, grav;          /* MAPL_AIRMW, _H2OMW, _O3MW, _RGAS, _GRAV */
+    const double *ple, *pl, *t, *q, *o3, *ch4, *n2o, *co2 /* (ncol,LM) or NULL */, *cfc11, *cfc12, *hcfc22, *fcld;
+    const double *qliq, *qice, *rliq, *rice;        /* CWC / REFF, KLIQUID and KICE */
+    const double *ts, *t2m, *emis, *lats;           /* (ncol) */
+    const double *taua, *ssaa;                      /* (ncol,LM,16) or NULL */
+} OracleIrradState;
+typedef struct {                                     /* the arguments of rrtmg_lw, caller-allocated */
+    int cloudLM, cloudMH;
+    double *play, *plev, *tlay, *tlev, *tsfc, *emis, *h2ovmr, *o3vmr, *co2vmr, *ch4vmr, *n2ovmr, *o2vmr,
+        *cfc11vmr, *cfc12vmr, *cfc22vmr, *ccl4vmr, *cldf, *ciwp, *clwp, *rei, *rel, *tauaer, *zm, *alat;
+} OracleLwInputs;
+typedef struct {                                     /* GEOS convention: (ncol,0:LM) top-down, upward negative */
+    double *flxu, *flxd, *flcu, *flcd, *dfdts, *dfdtsc, *sfcem;
+    double *cldtt, *cldhi, *cldmd, *cldlo;           /* any may be NULL */
+} OracleIrradFluxes;
+int oracle_irrad_prepare(const OracleIrradState *s, OracleLwInputs *o);   /* IRR:3237-3371 */
+int oracle_irrad_finish(int ncol, int lm, const double *emis, const int *clearCounts, const double *uflx,
+                        const double *dflx, const double *uflxc, const double *dflxc, const double *duflx_dTs,
+                        const double *duflxc_dTs, OracleIrradFluxes *f);  /* IRR:3486-3533 */
+
+typedef struct {
+    int ncol, lm, iceflg, liqflg, lcldmh, lcldlm;
+    double co2, o2;
+    double airmw, h2omw, o3mw, rgas, grav;
+    const double *ple, *pl, *t, *q, *o3, *ch4, *cl;
+    const double *qliq, *qice, *rliq, *rice;        /* QQ3(:,:,2), QQ3(:,:,1), RR3(:,:,2), RR3(:,:,1) */
+    const double *ts;                               /* (ncol) */
+    const double *taua, *ssaa, *asya;               /* (ncol,LM,14) un-normalised, or NULL */
+} OracleSolarState;
+typedef struct {
+    int cloudLM, cloudMH;
+    double *play, *plev, *tlay, *h2ovmr, *o3vmr, *co2vmr, *ch4vmr, *o2vmr, *cld, *ciwp, *clwp, *rei, *rel, *zm,
+        *tauaer, *ssaaer, *asmaer;
+} OracleSwInputs;
+typedef struct {
+    double *fsw, *fsc, *fswu, *fscu;                 /* (ncol,LM+1) top-down */
+    double *cldts, *cldhs, *cldms, *cldls, *cottp, *cothp, *cotmp, *cotlp;   /* (ncol), any may be NULL */
+} OracleSolarFluxes;
+int oracle_solar_prepare(const OracleSolarState *s, OracleSwInputs *o);   /* SOL:6113-6223 */
+int oracle_solar_finish(int ncol, int lm, double undef, const int *clearCounts, const double *swuflx,
+                        const double *swdflx, const double *swuflxc, const double *swdflxc, const double *cotd[4],
+                        const double *cotn[4], OracleSolarFluxes *f);     /* SOL:6395-6444 */
+
 /* reduced (post-cmbgb) tables and lookup tables, for tests of the init restatement */
 const double *oracle_lw_table(const char *name, int band, int *n);
 const double *oracle_sw_table(const char *name, int band, int *n);

@@ -1,0 +1,9 @@
+# launch list + full ncu capture of the top band / McICA kernels (one ncu use per call)
+CMD="python bench.py --steps 1 --warmup 1 --ncol 65536 --no-e2e --no-cpu"
+$CMD > gpurun_out/r2d_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
+    --log-file gpurun_out/r2d_launches.csv $CMD > gpurun_out/r2d_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+    -k 'regex:(sw_band_kernel<\(int\)(17|20),)|(lw_band_kernel<\(int\)(3|9),)|(mcica_kernel<rrtmgx::SwOptics)' -c 5 \
+    -f -o gpurun_out/r2d_top $CMD > gpurun_out/r2d_ncu_full.log 2>&1
+ls -la gpurun_out/ | tail -5
