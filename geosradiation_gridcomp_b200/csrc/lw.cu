@@ -1387,7 +1387,7 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
     RRTMGX_LAUNCH(lw_cldcoef_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, perm, nc, nlay, a->iceflglw, a->cldf,
                   a->rei, a->rel, W.abscoice, W.abscoliq, W.cldtrap);
     LwOptics opt{nc, nlay, W.abscoice, W.abscoliq, W.cldtrap, W.taucmc};
-    RRTMGX_LAUNCH(mcica_kernel<LwOptics>, dim3((140 + MCICA_SUBS - 1) / MCICA_SUBS, (nc + 31) / 32), dim3(32, MCICA_SUBS),
+    RRTMGX_LAUNCH(mcica_kernel<LwOptics>, dim3(140 / MCICA_XS, (nc + MCICA_YC - 1) / MCICA_YC), dim3(MCICA_XS, MCICA_YC),
                   0, stream, ld, col0, perm, nc, nlay, 140, mp, d_jumps, W.seeds, W.t_alpha, W.t_rcorr, W.t_cld, a->cldf,
                   a->ciwp, a->clwp, 1.e-20, a->cloudLM, a->cloudMH, perm ? (const int *)W.ptmp : nullptr, a->clearCounts, W.cloudy_any, W.mask, opt, d_err);
 

@@ -167,10 +167,17 @@ static __global__ void mcica_prep_kernel(int ld, int col0, const int *__restrict
 // (ncol,4), integer atomics, so deterministic), the optical cloud mask bit-packed over layers
 // [nw][nsub][nc] and its OR over subcolumns cloudy_any [nw][nc] (the reference's
 // cloudy(lay,col) after cldprmc).
-constexpr int MCICA_SUBS = 7;   // divides 140 (LW) and 112 (SW)
+// Block = MCICA_XS subcolumns (x, fastest) x MCICA_YC columns: a warp is (almost) one column at 28 of its
+// subcolumns.  The subcolumns of a column share cldfrac, so at a given layer they are cloudy or clear
+// TOGETHER far more often than 32 different columns are: the cloud-optics branch runs with most lanes
+// active instead of a few, and the per-(layer, column) thresholds and water paths are one broadcast
+// load per warp.  (The cloudy-cell stores then fall 8 bytes per sector; the L2 merges them with the
+// neighbouring columns' before they reach DRAM.)
+constexpr int MCICA_XS = 28;   // divides 140 (LW) and 112 (SW)
+constexpr int MCICA_YC = 8;
 
 template <class Optics>
-__global__ void __launch_bounds__(32 * MCICA_SUBS)
+__global__ void __launch_bounds__(MCICA_XS * MCICA_YC)
 mcica_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, int nsub, McicaParams P,
              const KissJump *__restrict__ jumps, const uint32_t *__restrict__ seeds,
              const long long *__restrict__ t_alpha, const long long *__restrict__ t_rcorr,
@@ -181,12 +188,8 @@ mcica_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, i
              uint32_t *__restrict__ cloudy_any,  // [nw][nc]
              uint32_t *__restrict__ mask,        // [nw][nsub][nc]
              Optics opt, int *err) {
-    // block = 32 columns x MCICA_SUBS subcolumns: the warps of a block sweep the same columns, so
-    // cldf/ciwp/clwp/alpha/rcorr come from L1 after the first warp touched them
-    // (subcolumn groups vary fastest across the grid so that the blocks sweeping the same columns
-    // run back to back and find the column's inputs in L2)
-    const int c = blockIdx.y * 32 + threadIdx.x;
-    const int isub = blockIdx.x * blockDim.y + threadIdx.y;
+    const int isub = blockIdx.x * MCICA_XS + threadIdx.x;
+    const int c = blockIdx.y * MCICA_YC + threadIdx.y;
     if (c >= nc || isub >= nsub) return;
     const size_t col = gcol(col0, perm, c);
     if (ncloudy && c >= *ncloudy) {

@@ -16,7 +16,8 @@ module rrtmgx_c
    ! compile-time trap: the array size is negative unless default real is c_double
    integer, parameter, private :: real_is_c_double(2*merge(1, -1, rrtmgx_real_kind == c_double) - 1) = 0
 
-   integer(c_int), parameter :: RRTMGX_DEVICE_PTRS = 1, RRTMGX_NO_SYNC = 2, RRTMGX_SKIP_CHECKS = 4
+   integer(c_int), parameter :: RRTMGX_DEVICE_PTRS = 1, RRTMGX_NO_SYNC = 2, RRTMGX_SKIP_CHECKS = 4, &
+                                RRTMGX_KEEP_STATUS = 8
 
    type, bind(C) :: rrtmgx_config
       type(c_ptr)    :: table_blob = c_null_ptr
@@ -59,6 +60,40 @@ module rrtmgx_c
       type(c_ptr) :: drband, dfband
    end type
 
+   ! fused Run-phase glue; field order == RrtmgxIrradArgs in include/rrtmgx.h
+   type, bind(C) :: rrtmgx_irrad_args
+      integer(c_int) :: ncol, lm, iceflg, liqflg, doy, lcldmh, lcldlm, flags
+      type(c_ptr) :: stream
+      real(c_double) :: co2_fixed, o2, ccl4, airmw, h2omw, o3mw, rgas, grav
+      type(c_ptr) :: ple, pl, t, q, o3, ch4, n2o, co2, cfc11, cfc12, hcfc22, fcld
+      type(c_ptr) :: qliq, qice, rliq, rice
+      type(c_ptr) :: ts, t2m, emis, lats
+      type(c_ptr) :: taua, ssaa
+      type(c_ptr) :: band_output
+      type(c_ptr) :: flxu, flxd, flcu, flcd, dfdts, dfdtsc
+      type(c_ptr) :: sfcem
+      type(c_ptr) :: cldtt, cldhi, cldmd, cldlo
+      type(c_ptr) :: olrb, dolrb_dts
+   end type
+
+   ! field order == RrtmgxSolarArgs in include/rrtmgx.h
+   type, bind(C) :: rrtmgx_solar_args
+      integer(c_int) :: ncol, lm, iceflg, liqflg, doy, isolvar, lcldmh, lcldlm, flags
+      type(c_ptr) :: stream
+      real(c_double) :: sc, dist, co2, o2, airmw, h2omw, o3mw, rgas, grav, undef
+      type(c_ptr) :: solcycfrac
+      type(c_ptr) :: ple, pl, t, q, o3, ch4, cl
+      type(c_ptr) :: qliq, qice, rliq, rice
+      type(c_ptr) :: ts, zt, lats
+      type(c_ptr) :: albvr, albvf, albnr, albnf
+      type(c_ptr) :: taua, ssaa, asya
+      type(c_ptr) :: fsw, fsc, fswu, fscu
+      type(c_ptr) :: nirr, nirf, parr, parf, uvrr, uvrf
+      type(c_ptr) :: fswband
+      type(c_ptr) :: cldts, cldhs, cldms, cldls
+      type(c_ptr) :: cottp, cothp, cotmp, cotlp
+   end type
+
    interface
       integer(c_int) function rrtmgx_init(cfg) bind(C, name='rrtmgx_init')
          import :: c_int, rrtmgx_config
@@ -79,6 +114,14 @@ module rrtmgx_c
       integer(c_int) function rrtmgx_sw_run(a) bind(C, name='rrtmgx_sw_run')
          import :: c_int, rrtmgx_sw_args
          type(rrtmgx_sw_args), intent(in) :: a
+      end function
+      integer(c_int) function rrtmgx_irrad_refresh(a) bind(C, name='rrtmgx_irrad_refresh')
+         import :: c_int, rrtmgx_irrad_args
+         type(rrtmgx_irrad_args), intent(in) :: a
+      end function
+      integer(c_int) function rrtmgx_solar_refresh(a) bind(C, name='rrtmgx_solar_refresh')
+         import :: c_int, rrtmgx_solar_args
+         type(rrtmgx_solar_args), intent(in) :: a
       end function
       integer(c_int) function rrtmgx_heating_rate(ncol, nlay, fnet, plev, hr, grav, cp, flags, stream) &
             bind(C, name='rrtmgx_heating_rate')
