@@ -158,6 +158,7 @@ struct LwWork {
     unsigned char *cldtrap;   // [nlay][nc] bit0: ice radius out of range, bit1: liquid radius out of range
     int *perm;                // [nc] cloudy columns first (build_cloud_partition)
     unsigned char *pflags;    // [nc]
+    int32_t *clear_save;      // [4][nc] clear counts of the chunk, kept for RRTMGX_REUSE_CLOUDS
     char *ptmp; size_t ptmp_bytes;
     uint32_t *mask;           // [nw][140][nc] optical cloud mask
     uint32_t *cloudy_any;     // [nw][nc]
@@ -1331,6 +1332,7 @@ static LwWork lw_carve(Slab &slab, int nc, int nlay) {
     W.cldtrap = slab.take<unsigned char>(n2);
     W.perm = slab.take<int>(nc);
     W.pflags = slab.take<unsigned char>(nc);
+    W.clear_save = slab.take<int32_t>((size_t)4 * nc);
     W.ptmp_bytes = cloud_partition_tmp_bytes(nc);
     W.ptmp = slab.take<char>(W.ptmp_bytes);
     W.mask = slab.take<uint32_t>(nw * 140 * nc);
@@ -1365,31 +1367,54 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
     const int nw = (nlay + 31) / 32;
     const dim3 blk(128), grd((nc + 127) / 128);
 
-    cudaMemsetAsync(W.cloudy_any, 0, sizeof(uint32_t) * (size_t)nw * nc, stream);
-    // clearCounts of this chunk: (ld,4) -> four strided segments
-    for (int k = 0; k < 4; ++k)
-        cudaMemsetAsync(a->clearCounts + (size_t)k * ld + col0, 0, sizeof(int32_t) * (size_t)nc, stream);
-
-    // group cloudy and cloud-free columns (not under debug taps, whose layouts assume identity order)
+    // RRTMGX_REUSE_CLOUDS: the previous call left this chunk's column grouping, McICA mask, cloud optical
+    // depths and clear counts in the slab (same carve: same shape, same slab, whole call in one chunk)
+    struct CloudCache { const char *base = nullptr; int nc = 0, nlay = 0, ld = 0; bool perm = false, valid = false; };
+    static CloudCache cache;
+    const bool one_chunk = col0 == 0 && nc == ld && !taps;
+    const bool reuse = (a->flags & RRTMGX_REUSE_CLOUDS) && one_chunk && cache.valid && cache.base == slab.base &&
+                       cache.nc == nc && cache.nlay == nlay && cache.ld == ld;
     const int *perm = nullptr;
-    if (!taps) {
-        if (int rc = build_cloud_partition(ld, col0, nc, nlay, a->cldf, W.perm, W.pflags, W.ptmp, W.ptmp_bytes, stream))
-            return rc;
-        perm = W.perm;
+    if (reuse) {
+        perm = cache.perm ? W.perm : nullptr;
+        for (int k = 0; k < 4; ++k)
+            cudaMemcpyAsync(a->clearCounts + (size_t)k * ld + col0, W.clear_save + (size_t)k * nc,
+                            sizeof(int32_t) * (size_t)nc, cudaMemcpyDeviceToDevice, stream);
+    } else {
+        cache.valid = false;
+        cudaMemsetAsync(W.cloudy_any, 0, sizeof(uint32_t) * (size_t)nw * nc, stream);
+        // clearCounts of this chunk: (ld,4) -> four strided segments
+        for (int k = 0; k < 4; ++k)
+            cudaMemsetAsync(a->clearCounts + (size_t)k * ld + col0, 0, sizeof(int32_t) * (size_t)nc, stream);
+        // group cloudy and cloud-free columns (not under debug taps, whose layouts assume identity order)
+        if (!taps) {
+            if (int rc = build_cloud_partition(ld, col0, nc, nlay, a->cldf, W.perm, W.pflags, W.ptmp, W.ptmp_bytes, stream))
+                return rc;
+            perm = W.perm;
+        }
     }
     RRTMGX_LAUNCH(lw_setcoef_kernel, grd, blk, 0, stream, ld, col0, perm, W, a->dudTs, a->play, a->tlay, a->plev,
                   a->tlev, a->tsfc, a->emis, a->h2ovmr, a->o3vmr, a->co2vmr, a->ch4vmr, a->n2ovmr, a->o2vmr,
                   a->cfc11vmr, a->cfc12vmr, a->cfc22vmr, a->ccl4vmr, d_err);
-    RRTMGX_LAUNCH(mcica_prep_kernel, grd, blk, 0, stream, ld, col0, perm, nc, nlay, mp, a->zm, a->play, a->alat,
-                  W.seeds, W.alpha, W.rcorr);
-    RRTMGX_LAUNCH(mcica_threshold_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, perm, nc, nlay, mp.inhomo, W.alpha,
-                  W.rcorr, a->cldf, W.t_alpha, W.t_rcorr, W.t_cld);
-    RRTMGX_LAUNCH(lw_cldcoef_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, perm, nc, nlay, a->iceflglw, a->cldf,
-                  a->rei, a->rel, W.abscoice, W.abscoliq, W.cldtrap);
-    LwOptics opt{nc, nlay, W.abscoice, W.abscoliq, W.cldtrap, W.taucmc};
-    RRTMGX_LAUNCH(mcica_kernel<LwOptics>, dim3(140 / MCICA_XS, (nc + MCICA_YC - 1) / MCICA_YC), dim3(MCICA_XS, MCICA_YC),
-                  0, stream, ld, col0, perm, nc, nlay, 140, mp, d_jumps, W.seeds, W.t_alpha, W.t_rcorr, W.t_cld, a->cldf,
-                  a->ciwp, a->clwp, 1.e-20, a->cloudLM, a->cloudMH, perm ? (const int *)W.ptmp : nullptr, a->clearCounts, W.cloudy_any, W.mask, opt, d_err);
+    if (!reuse) {
+        RRTMGX_LAUNCH(mcica_prep_kernel, grd, blk, 0, stream, ld, col0, perm, nc, nlay, mp, a->zm, a->play, a->alat,
+                      W.seeds, W.alpha, W.rcorr);
+        RRTMGX_LAUNCH(mcica_threshold_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, perm, nc, nlay, mp.inhomo,
+                      W.alpha, W.rcorr, a->cldf, W.t_alpha, W.t_rcorr, W.t_cld);
+        RRTMGX_LAUNCH(lw_cldcoef_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, perm, nc, nlay, a->iceflglw, a->cldf,
+                      a->rei, a->rel, W.abscoice, W.abscoliq, W.cldtrap);
+        LwOptics opt{nc, nlay, W.abscoice, W.abscoliq, W.cldtrap, W.taucmc};
+        RRTMGX_LAUNCH(mcica_kernel<LwOptics>, dim3(140 / MCICA_XS, (nc + MCICA_YC - 1) / MCICA_YC),
+                      dim3(MCICA_XS, MCICA_YC), 0, stream, ld, col0, perm, nc, nlay, 140, mp, d_jumps, W.seeds, W.t_alpha,
+                      W.t_rcorr, W.t_cld, a->cldf, a->ciwp, a->clwp, 1.e-20, a->cloudLM, a->cloudMH,
+                      perm ? (const int *)W.ptmp : nullptr, a->clearCounts, W.cloudy_any, W.mask, opt, d_err);
+        if (one_chunk) {
+            for (int k = 0; k < 4; ++k)
+                cudaMemcpyAsync(W.clear_save + (size_t)k * nc, a->clearCounts + (size_t)k * ld + col0,
+                                sizeof(int32_t) * (size_t)nc, cudaMemcpyDeviceToDevice, stream);
+            cache = {slab.base, nc, nlay, ld, perm != nullptr, true};
+        }
+    }
 
     LwBandArgs A{ld, col0, perm, W, a->dudTs, a->play, a->emis, a->tauaer, dbg_taug, dbg_pfracs};
     // fan the independent band units out over the side streams

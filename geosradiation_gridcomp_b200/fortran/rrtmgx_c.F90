@@ -17,7 +17,7 @@ module rrtmgx_c
    integer, parameter, private :: real_is_c_double(2*merge(1, -1, rrtmgx_real_kind == c_double) - 1) = 0
 
    integer(c_int), parameter :: RRTMGX_DEVICE_PTRS = 1, RRTMGX_NO_SYNC = 2, RRTMGX_SKIP_CHECKS = 4, &
-                                RRTMGX_KEEP_STATUS = 8
+                                RRTMGX_KEEP_STATUS = 8, RRTMGX_REUSE_CLOUDS = 16
 
    type, bind(C) :: rrtmgx_config
       type(c_ptr)    :: table_blob = c_null_ptr

@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(HERE, "librrtmgx.so")
 BLOB_PATH = os.path.join(HERE, "data", "rrtmg_tables.bin")
 
 NBNDLW, NGPTLW, NBNDSW, NGPTSW = 16, 140, 14, 112
-DEVICE_PTRS, NO_SYNC, SKIP_CHECKS = 1, 2, 4
+DEVICE_PTRS, NO_SYNC, SKIP_CHECKS, KEEP_STATUS, REUSE_CLOUDS = 1, 2, 4, 8, 16
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -286,7 +286,7 @@ def rrtmg_lw(ncol, nlay, psize, dudTs, play, plev, tlay, tlev, tsfc, emis, h2ovm
              n2ovmr, o2vmr, cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, cldf, ciwp, clwp, rei, rel, iceflglw,
              liqflglw, tauaer, zm, alat, dyofyr, cloudLM, cloudMH, clearCounts, uflx, dflx, uflxc, dflxc,
              duflx_dTs, duflxc_dTs, band_output, olrb, dolrb_dTs, *, device=False, stream=None, sync=True,
-             skip_checks=False, taps=()):
+             skip_checks=False, reuse_clouds=False, taps=()):
     """Drop-in for `rrtmg_lw` (LW/src/rrtmg_lw_rad.F90:15-23): same argument order and meaning;
     outputs are written in place.  Raises RrtmgxError where the reference stops.
     Returns a dict of requested intermediate taps (tests only)."""
@@ -297,7 +297,8 @@ def rrtmg_lw(ncol, nlay, psize, dudTs, play, plev, tlay, tlev, tsfc, emis, h2ovm
     a.ncol, a.nlay, a.psize, a.dudTs = int(ncol), int(nlay), int(psize), int(bool(dudTs))
     a.iceflglw, a.liqflglw, a.dyofyr = int(iceflglw), int(liqflglw), int(dyofyr)
     a.cloudLM, a.cloudMH = int(cloudLM), int(cloudMH)
-    a.flags = (DEVICE_PTRS if device else 0) | (0 if sync else NO_SYNC) | (SKIP_CHECKS if skip_checks else 0)
+    a.flags = ((DEVICE_PTRS if device else 0) | (0 if sync else NO_SYNC) | (SKIP_CHECKS if skip_checks else 0) |
+               (REUSE_CLOUDS if reuse_clouds else 0))
     a.stream = stream
     loc = locals()
     for n in _LW_IN + _LW_OUT:
@@ -322,7 +323,7 @@ def rrtmg_sw(rpart, ncol, nlay, scon, adjes, coszen, isolvar, play, plev, tlay, 
              asdir, asdif, aldir, aldif, cloudLM, cloudMH, normFlx, clearCounts, swuflx, swdflx, swuflxc, swdflxc,
              nirr, nirf, parr, parf, uvrr, uvrf, fswband, cotdtp, cotdhp, cotdmp, cotdlp, cotntp, cotnhp, cotnmp,
              cotnlp, do_drfband=False, drband=None, dfband=None, bndscl=None, indsolvar=None, solcycfrac=None, *,
-             device=False, stream=None, sync=True, skip_checks=False, taps=()):
+             device=False, stream=None, sync=True, skip_checks=False, reuse_clouds=False, taps=()):
     """Drop-in for `rrtmg_sw` (SW/src/rrtmg_sw_rad.F90:68-124) without the MAPL handle (used by
     the reference only for timers and asserts).  Outputs are written in place."""
     if not _initialised:
@@ -333,7 +334,8 @@ def rrtmg_sw(rpart, ncol, nlay, scon, adjes, coszen, isolvar, play, plev, tlay, 
     a.iceflgsw, a.liqflgsw, a.dyofyr = int(iceflgsw), int(liqflgsw), int(dyofyr)
     a.cloudLM, a.cloudMH, a.iaer = int(cloudLM), int(cloudMH), int(iaer)
     a.normFlx, a.do_drfband = int(bool(normFlx)), int(bool(do_drfband))
-    a.flags = (DEVICE_PTRS if device else 0) | (0 if sync else NO_SYNC) | (SKIP_CHECKS if skip_checks else 0)
+    a.flags = ((DEVICE_PTRS if device else 0) | (0 if sync else NO_SYNC) | (SKIP_CHECKS if skip_checks else 0) |
+               (REUSE_CLOUDS if reuse_clouds else 0))
     a.stream = stream
     a.scon, a.adjes = float(scon), float(adjes)
     for n, v, cnt in (("bndscl", bndscl, 14), ("indsolvar", indsolvar, 2), ("solcycfrac", solcycfrac, 1)):

@@ -43,8 +43,16 @@ enum {
     RRTMGX_NO_SYNC     = 2,   /* device pointers only: return without synchronising; status  */
                               /* traps are then reported by rrtmgx_{lw,sw}_status()           */
     RRTMGX_SKIP_CHECKS = 4,   /* skip the negative-input scans (LW :209-318, SW :365-383)    */
-    RRTMGX_KEEP_STATUS = 8    /* device pointers only: do not clear the path's status word    */
+    RRTMGX_KEEP_STATUS = 8,   /* device pointers only: do not clear the path's status word    */
                               /* first, so one status read covers a sequence of NO_SYNC runs  */
+    RRTMGX_REUSE_CLOUDS = 16  /* the cloud inputs (cldf, ciwp, clwp, rei, rel, zm, play, alat,  */
+                              /* dyofyr, ice/liq flags, cloudLM/MH) are those of the previous   */
+                              /* call on this path: keep its McICA subcolumns, cloud optics and */
+                              /* clear counts instead of regenerating them (GEOS calls rrtmg_lw */
+                              /* once more per removed gas, IRR:3405-3468, and rrtmg_sw with    */
+                              /* and without aerosols, SOL:3249-3287, on one cloud state).      */
+                              /* Honoured when both calls cover their columns in one chunk of   */
+                              /* the same shape; otherwise the clouds are regenerated.          */
 };
 
 /* status codes (negative) */

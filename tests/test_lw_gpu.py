@@ -173,3 +173,25 @@ def test_branch_free_division_equals_ieee(rx):
     np.testing.assert_array_equal(qi, a / b)            # the device's IEEE division is numpy's
     np.testing.assert_array_equal(qf, qi)
     np.testing.assert_array_equal(rf, ri)
+
+
+def test_lw_reuse_clouds_for_removed_gas_calls(rx):
+    """GEOS calls rrtmg_lw once more per removed gas on the same cloud state (IRR:3405-3468):
+    RRTMGX_REUSE_CLOUDS keeps the McICA subcolumns, cloud optics and clear counts of the previous call and
+    gives the bits of a full call with fewer launches."""
+    s = make_columns(2048, 72, seed=31)
+    rx.run_lw(s)
+    s2 = dict(s)
+    s2["ch4vmr"] = np.zeros_like(s["ch4vmr"], order="F")
+    n0 = rx.launch_count()
+    fresh = rx.run_lw(s2)
+    n1 = rx.launch_count()
+    reused = rx.run_lw(s2, reuse_clouds=True)
+    n2 = rx.launch_count()
+    for k in FLUXES + ("olrb", "dolrb_dTs", "clearCounts"):
+        np.testing.assert_array_equal(reused[k], fresh[k], err_msg=k)
+    assert n2 - n1 <= (n1 - n0) - 5          # partition, prep, thresholds, cloud coefficients, McICA skipped
+    assert np.abs(fresh["uflx"] - rx.run_lw(s)["uflx"]).max() > 1e-3    # and the gas did matter
+    # a different shape invalidates the kept clouds: the flag is then ignored, not trusted
+    s3 = make_columns(1000, 72, seed=32)
+    np.testing.assert_array_equal(rx.run_lw(s3, reuse_clouds=True)["uflx"], rx.run_lw(s3)["uflx"])

@@ -157,3 +157,21 @@ def test_sw_heating_rate(rx, oracle):
         return (net[:, :-1] - net[:, 1:]) * (grav / cp) / ((s["plev"][:, :-1] - s["plev"][:, 1:]) * 100.0) * 86400.0
     got = rx.heating_rate(np.asfortranarray(g["swuflx"] - g["swdflx"]), s["plev"], grav, cp)
     assert np.max(np.abs(got - hr(o))) <= 1e-6      # north_star: heating rates within 1e-6 K/day
+
+
+def test_sw_reuse_clouds_with_and_without_aerosols(rx):
+    """SORADCORE is run without and then with aerosols on one cloud state (SOL:3249-3287): the second call
+    keeps the first one's McICA subcolumns and cloud optics under RRTMGX_REUSE_CLOUDS."""
+    s = make_columns(2048, 72, seed=33)
+    clean = rx.run_sw(s, iaer=0)
+    n0 = rx.launch_count()
+    fresh = rx.run_sw(s, iaer=10)
+    n1 = rx.launch_count()
+    rx.run_sw(s, iaer=0)
+    n2 = rx.launch_count()
+    reused = rx.run_sw(s, iaer=10, reuse_clouds=True)
+    n3 = rx.launch_count()
+    for k in ("swuflx", "swdflx", "swuflxc", "swdflxc", "nirr", "parf", "fswband", "cotntp", "cotdlp", "clearCounts"):
+        np.testing.assert_array_equal(reused[k], fresh[k], err_msg=k)
+    assert n3 - n2 <= (n1 - n0) - 5
+    assert np.abs(fresh["swdflx"] - clean["swdflx"]).max() > 1e-4
