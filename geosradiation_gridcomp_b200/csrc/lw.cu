@@ -64,6 +64,8 @@ struct LwDev {
 
 __constant__ LwDev c_lw;
 
+static int g_lw_ngs[16], g_lw_ngb[140];   // host copies for the debug taps
+
 int lw_upload_tables(const HostTables &ht, const double *d_arena) {
     LwDev h;
     std::memset(&h, 0, sizeof h);
@@ -99,6 +101,8 @@ int lw_upload_tables(const HostTables &ht, const double *d_arena) {
         return RRTMGX_EBLOB;
     for (int i = 0; i < 16; ++i) { h.delwave[i] = ht.lw_delwave[i]; h.ngs[i] = ht.lw_ngs[i]; }
     for (int i = 0; i < 140; ++i) h.ngb[i] = ht.lw_ngb[i];
+    for (int i = 0; i < 16; ++i) g_lw_ngs[i] = ht.lw_ngs[i];
+    for (int i = 0; i < 140; ++i) g_lw_ngb[i] = ht.lw_ngb[i];
     // lwdatinit (LW/src/rrtmg_lw_init.F90:214,222), rrlw_con.F90:37-38, rrlw_tbl.F90:32
     h.bpade = 1.0 / 0.278;
     h.oneminus = 1. - 1.e-6;
@@ -160,10 +164,10 @@ struct LwWork {
     unsigned char *pflags;    // [nc]
     int32_t *clear_save;      // [4][nc] clear counts of the chunk, kept for RRTMGX_REUSE_CLOUDS
     char *ptmp; size_t ptmp_bytes;
-    uint32_t *mask;           // [nw][140][nc] optical cloud mask
+    uint32_t *mask;           // [band][nw][nc][ng] optical cloud mask (lw_cell with nw for nlay)
     uint32_t *cloudy_any;     // [nw][nc]
-    double *taucmc;           // [nlay][140][nc], valid where the mask bit is set
-    uint32_t *it;             // [nlay][140][nc] itgas | ittot << 16 (0xffff: clear cell)
+    double *taucmc;           // per-cell layout (lw_cell), valid where the mask bit is set
+    uint32_t *it;             // per-cell layout (lw_cell): itgas | ittot << 16 (0xffff: clear cell)
     double *part;             // [16][LP_COUNT][nlay+1][nc]
 };
 
@@ -419,13 +423,27 @@ __global__ void lw_cldcoef_kernel(int ld, int col0, const int *__restrict__ perm
     }
 }
 
+// Per-cell scratch of the LW path is g-point fastest inside a band: [band][lay][nc][ng_band], i.e. the
+// g-points of one (band, layer, column) are adjacent and the columns follow.  The McICA kernel (lanes =
+// subcolumns of a column) and the band kernels (lanes = g-point groups of a few columns) then read and
+// write contiguous runs.  `first` = first g-point of the band, `ng` its count, n2 = rows * nc.
+__device__ __forceinline__ size_t lw_cell(int first, int ng, size_t n2, int nc, int row, int c, int gi) {
+    return (size_t)first * n2 + ((size_t)row * nc + c) * ng + gi;
+}
+
 struct LwOptics {
     int nc, nlay;
     const double *abscoice, *abscoliq;   // [16][nlay][nc]
     const unsigned char *cldtrap;        // [nlay][nc]
-    double *taucmc;                      // [nlay][140][nc]
+    double *taucmc;                      // lw_cell layout
     struct State {};
     __device__ __forceinline__ void finish(int, int, State &) const {}
+    __device__ __forceinline__ size_t cell_index(int rows, int row, int ig, int c) const {
+        const int ib = c_lw.ngb[ig] - 1;
+        const int first = ib ? c_lw.ngs[ib - 1] : 0;
+        return lw_cell(first, c_lw.ngs[ib] - first, (size_t)rows * nc, nc, row, c, ig - first);
+    }
+    __device__ __forceinline__ size_t mask_index(int w, int nw, int ig, int c) const { return cell_index(nw, w, ig, c); }
 
     // Called for every McICA-cloudy cell: taucmc = ciwp*abscoice + clwp*abscoliq (:362-383).  The
     // reference derives both radius indices (and traps) for every layer holding such a cell,
@@ -439,7 +457,7 @@ struct LwOptics {
         if (ciw > 0.) tau = ciw * abscoice[(size_t)(ib - 1) * n2 + j];
         if (clw > 0.) tau = tau + clw * abscoliq[(size_t)(ib - 1) * n2 + j];
         const bool optical = tau > 0.;
-        if (optical) __stcs(&taucmc[((size_t)lay * 140 + ig) * nc + c], tau);
+        if (optical) __stcs(&taucmc[cell_index(nlay, lay, ig, c)], tau);
         return optical;
     }
 };
@@ -973,13 +991,14 @@ struct LwBandArgs {
     double *dbg_taug, *dbg_pfracs;   // optional [nlay][140][nc]
 };
 
-// Sum v[q] over the threads of a block that share a column lane (threadIdx.y runs over the
-// g-point groups of the band) in ascending g order and store the Q totals at dst + q*qstride.
-// `red` holds Q*NY*CB doubles; callers alternate two buffers so one barrier per call suffices.
+// Sum v[q] over the threads of a block that share a column (threadIdx.x runs over the g-point groups
+// of the band, threadIdx.y over the block's columns) in ascending g order and store the Q totals at
+// dst + q*qstride.  `red` holds Q*CB*NY doubles; callers alternate two buffers so one barrier per call
+// suffices.
 template <int Q, int NY, int CB>
 __device__ __forceinline__ void block_sum_store(const double (&v)[Q], double *__restrict__ red,
                                                 double *__restrict__ dst, size_t qstride, bool active) {
-    const int lane = threadIdx.x, ty = threadIdx.y;
+    const int ty = threadIdx.x, lane = threadIdx.y;
     if (NY == 1) {
         if (active) {
 #pragma unroll
@@ -988,12 +1007,13 @@ __device__ __forceinline__ void block_sum_store(const double (&v)[Q], double *__
         return;
     }
 #pragma unroll
-    for (int q = 0; q < Q; ++q) red[(q * NY + ty) * CB + lane] = v[q];
+    for (int q = 0; q < Q; ++q) red[(q * CB + lane) * NY + ty] = v[q];
     __syncthreads();
     for (int q = ty; q < Q; q += NY) {
-        double s = red[(q * NY) * CB + lane];
+        const double *r = red + (q * CB + lane) * NY;
+        double s = r[0];
 #pragma unroll
-        for (int y = 1; y < NY; ++y) s = s + red[(q * NY + y) * CB + lane];
+        for (int y = 1; y < NY; ++y) s = s + r[y];
         if (active) dst[q * qstride] = s;
     }
 }
@@ -1036,28 +1056,30 @@ template <int BAND> __host__ __device__ constexpr unsigned lw_band_fmask_up() {
 // partial flux profiles of a band: part[band][LP_*][lev][c]
 enum LwPart { LP_U, LP_UC, LP_DU, LP_DUC, LP_D, LP_DC, LP_COUNT };
 
-// Block = CB columns x (ng/GN) g-point groups of BAND, column fastest: a warp is CB consecutive
-// columns x 32/CB consecutive g-point groups.  With CB = 32 a warp's k-table gathers hit 32
-// scattered rows (one L1 wavefront each: the L1 data pipe was the limiter, profiles/r1_c_*); with
-// CB = 8 or 4 they fall on CB rows of adjacent g-points (the tables are g-point fastest) while the
-// column-fastest arrays are still read in whole 32-byte sectors.  The warps of a block share the
-// columns' setcoef state through L1, and the g-point sums of every level are formed in the block
+// Block = (ng/GN) g-point groups (x, fastest) x CB columns of BAND: a warp is the g-point groups of
+// 32/(ng/GN) neighbouring columns.  The lanes of a column share jp/jt/js, so every k-table gather of a
+// warp falls on a few rows read in full (the tables are g-point fastest), the per-(layer, column) setcoef
+// state is one broadcast sector, and the per-cell scratch (lw_cell: g-point fastest inside a band) is
+// one contiguous run.  (With 32 columns per warp every gather touched 32 scattered rows: the L1 data
+// pipe was 88 % busy, profiles/r2_d_*.)  The g-point sums of every level are formed in the block
 // (block_sum_store) in ascending g order, like the reference's sequential accumulation.
 template <int BAND, int GN, int REGS, int CB>
 __global__ void __launch_bounds__(CB * (LwBandInfo<BAND>::ng / GN), min_blocks(CB * (LwBandInfo<BAND>::ng / GN), REGS))
 lw_band_kernel(const LwBandArgs A) {
     constexpr int NY = LwBandInfo<BAND>::ng / GN;
+    constexpr int NG = LwBandInfo<BAND>::ng;
     static_assert(NY * GN == LwBandInfo<BAND>::ng, "GN must divide the band's g-points");
     __shared__ double red_buf[NY > 1 ? 2 * 4 * NY * CB : 1];
     const LwWork &W = A.W;
     const int nc = W.nc, nlay = W.nlay;
-    const int c0 = blockIdx.x * CB + threadIdx.x;
+    const int ty = threadIdx.x;
+    const int c0 = blockIdx.x * CB + threadIdx.y;
     const bool active = c0 < nc;
     const int c = active ? c0 : nc - 1;   // idle lanes shadow the last column and never store
     const size_t col = gcol(A.col0, A.perm, c);
     constexpr int ib = BAND - 1;
     const int gs = BAND == 1 ? 0 : c_lw.ngs[ib - 1];   // first g-point (0-based) of the band
-    const int G0 = threadIdx.y * GN;
+    const int G0 = ty * GN;
     const int g_first = gs + G0;
     const int laytrop = W.laytrop[c];
     int flip = 0;
@@ -1086,26 +1108,26 @@ lw_band_kernel(const LwBandArgs A) {
     double radld[GN], radclrd[GN], taug[GN], pf[GN];
     FORG { radld[ig] = 0.; radclrd[ig] = 0.; }
     bool diverge = false;
-    if (active && threadIdx.y == 0) {
+    if (active && ty == 0) {
         part[LP_D * fstride + (size_t)nlay * nc] = 0.;
         part[LP_DC * fstride + (size_t)nlay * nc] = 0.;
     }
-    // running addresses: per-(layer, column) planes by 32-bit offsets from the column's pointer,
-    // the thread's cell of the [lay][140][nc] scratch by one 64-bit offset
+    // running addresses: per-(layer, column) planes by 32-bit offsets from the column's pointer, the
+    // thread's cell of the lw_cell scratch by one 64-bit offset (GN adjacent elements per thread)
     const int n2 = (int)W.n2;
     const int *pidx = W.idx + c;
     const double *pfac = W.fbase + c;
-    const size_t lay_cell = (size_t)140 * nc;
-    size_t koff = (size_t)(nlay - 1) * lay_cell + (size_t)g_first * nc + c;   // cell (nlay-1, g_first)
+    const size_t lay_cell = (size_t)NG * nc;
+    size_t koff = lw_cell(gs, NG, W.n2, nc, nlay - 1, c, G0);                 // cell (nlay-1, c, G0)
     size_t aoff = ((size_t)ib * nlay + nlay - 1) * A.ld + col;                // aerosol at layer nlay-1
-    const uint32_t *pmask = W.mask + (size_t)g_first * nc + c;                // [nw][140][nc]
+    const int nw = (nlay + 31) >> 5;
     uint32_t any_word = 0u, mword[GN];
     FORG mword[ig] = 0u;
 
     // ---- downward sweep, :198-309 ----
     for (int lay = nlay - 1; lay >= 0; --lay) {
         const int jl = lay * nc;
-        if (lay > 0 && threadIdx.y == 0) {   // next layer's per-(layer, column) state -> L1 while this one computes
+        if (lay > 0 && ty == 0) {   // next layer's per-(layer, column) state -> L1 while this one computes
             prefetch_l1(pidx + jl - nc);
             constexpr unsigned fm = lw_band_fmask<BAND>();
 #pragma unroll
@@ -1117,7 +1139,8 @@ lw_band_kernel(const LwBandArgs A) {
         }
         if ((lay & 31) == 31 || lay == nlay - 1) {   // cloud words of the next (up to) 32 layers
             any_word = W.cloudy_any[(lay >> 5) * nc + c];
-            FORG mword[ig] = any_word ? pmask[(size_t)(lay >> 5) * lay_cell + ig * nc] : 0u;
+            const uint32_t *pm = W.mask + lw_cell(gs, NG, (size_t)nw * nc, nc, lay >> 5, c, G0);
+            FORG mword[ig] = any_word ? pm[ig] : 0u;
         }
         Lay L;
         L.fj = pfac + jl;
@@ -1150,7 +1173,7 @@ lw_band_kernel(const LwBandArgs A) {
             if (!((mword[ig] >> (lay & 31)) & 1u)) {
                 radld[ig] = radld[ig] + (bbdgas - radld[ig]) * agas;
             } else {
-                const double odcld = secdiff * __ldcs(W.taucmc + koff + ig * nc);
+                const double odcld = secdiff * __ldcs(W.taucmc + koff + ig);
                 const double odtot = c_lw.tau_tbl[itgas] + odcld;
                 tblind = ddiv(odtot, bpade + odtot);
                 const int ittot = f_int(tblint * tblind + 0.5);
@@ -1160,7 +1183,7 @@ lw_band_kernel(const LwBandArgs A) {
                 radld[ig] = radld[ig] + (bbdtot - radld[ig]) * atot;
                 code = (uint32_t)itgas | ((uint32_t)ittot << 16);
             }
-            if (active) __stcs(W.it + koff + ig * nc, code);
+            if (active) __stcs(W.it + koff + ig, code);
             sums[0] = sums[0] + sumfac * radld[ig];
             if (diverge) radclrd[ig] = radclrd[ig] + (bbdgas - radclrd[ig]) * agas;
             else radclrd[ig] = radld[ig];
@@ -1196,8 +1219,8 @@ lw_band_kernel(const LwBandArgs A) {
     for (int lay = 0; lay < nlay; ++lay) {
         const int jl = lay * nc;
         if (lay + 1 < nlay) {
-            FORG prefetch_l1(W.it + koff + lay_cell + ig * nc);
-            if (threadIdx.y == 0) {
+            prefetch_l1(W.it + koff + lay_cell);
+            if (ty == 0) {
                 prefetch_l1(pidx + jl + nc);
                 constexpr unsigned fm = lw_band_fmask_up<BAND>();
 #pragma unroll
@@ -1218,7 +1241,7 @@ lw_band_kernel(const LwBandArgs A) {
         const double dplankup = planklev[jl + nc] - blay;
         double sums[4] = {0., 0., 0., 0.};
         FORG {
-            const uint32_t code = __ldcs(W.it + koff + ig * nc);
+            const uint32_t code = __ldcs(W.it + koff + ig);
             const int itgas = code & 0xffffu, ittot = code >> 16;
             const double2 et = reinterpret_cast<const double2 *>(c_lw.exptfn)[itgas];
             const double agas = 1. - et.x;
@@ -1250,7 +1273,7 @@ lw_band_kernel(const LwBandArgs A) {
 }
 
 // Compiled variants per band: the (g-points per thread, register budget; 0 = none) pair tuned for the
-// band (profiles/r1_gn_tuning.txt) at CB = 32, 16, 8, 4 columns per block row.  The one used is picked
+// band (profiles/r1_gn_tuning.txt) at CB = 32, 16, 8, 4 columns per block.  The one used is picked
 // per band from lw_variant[] (tuned on B200; RRTMGX_LW_GN="vvv..." overrides).
 typedef void (*LwBandLauncher)(int, cudaStream_t, const LwBandArgs &);
 template <int BAND, int GN, int REGS, int CB>
@@ -1258,7 +1281,7 @@ static void lw_launch_band(int nc, cudaStream_t st, const LwBandArgs &A) {
     static char tag[48] = "";
     if (!tag[0]) std::snprintf(tag, sizeof tag, "lw_band_kernel<%d,gn%d,r%d,c%d>", BAND, GN, REGS, CB);
     RRTMGX_LAUNCH_TAG(tag, (lw_band_kernel<BAND, GN, REGS, CB>), dim3((nc + CB - 1) / CB),
-                      dim3(CB, LwBandInfo<BAND>::ng / GN), 0, st, A);
+                      dim3(LwBandInfo<BAND>::ng / GN, CB), 0, st, A);
 }
 #define X(BAND, G, R) \
     {lw_launch_band<BAND, G, R, 32>, lw_launch_band<BAND, G, R, 16>, lw_launch_band<BAND, G, R, 8>, lw_launch_band<BAND, G, R, 4>},
@@ -1266,7 +1289,7 @@ static const LwBandLauncher lw_launchers[16][4] = {
     X(1, 2, 48) X(2, 2, 48) X(3, 2, 64) X(4, 2, 64) X(5, 2, 64) X(6, 2, 48) X(7, 2, 48) X(8, 2, 64)
     X(9, 2, 48) X(10, 2, 64) X(11, 2, 64) X(12, 2, 64) X(13, 1, 64) X(14, 1, 0) X(15, 1, 0) X(16, 1, 0)};
 #undef X
-static int lw_variant[16] = {0, 0, 2, 2, 2, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, 0};   // CB = 8 where the k-tables are widest (profiles/r2_cb_tuning.txt)
+static int lw_variant[16] = {0, 1, 3, 3, 3, 2, 3, 2, 3, 2, 2, 2, 2, 1, 1, 1};   // columns per block, profiles/r2_cb_tuning.txt (run r2h)
 
 // fixed-order sum of the band partials -> caller arrays; band OLR (:382-385, rad.F90:586-605)
 __global__ void lw_reduce_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, int dudTs, const double *__restrict__ part,
@@ -1488,10 +1511,14 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
             for (int lay = 0; lay < nlay; ++lay)
                 for (int g = 0; g < 140; ++g)
                     for (int c = 0; c < nc; ++c) {
-                        const bool on = (hm[((size_t)(lay >> 5) * 140 + g) * nc + c] >> (lay & 31)) & 1u;
+                        const int ib = g_lw_ngb[g] - 1, first = ib ? g_lw_ngs[ib - 1] : 0, ngb = g_lw_ngs[ib] - first;
+                        auto cell = [&](size_t rows, int row) {   // lw_cell on the host
+                            return (size_t)first * rows * nc + ((size_t)row * nc + c) * ngb + (g - first);
+                        };
+                        const bool on = (hm[cell(nw, lay >> 5)] >> (lay & 31)) & 1u;
                         const size_t o = ((size_t)lay * 140 + g) * ld + col0 + c;
                         if (taps->cldymc) taps->cldymc[o] = on;
-                        if (taps->taucmc) taps->taucmc[o] = on ? ht[((size_t)lay * 140 + g) * nc + c] : 0.;
+                        if (taps->taucmc) taps->taucmc[o] = on ? ht[cell(nlay, lay)] : 0.;
                     }
         }
         if (cudaGetLastError() != cudaSuccess) return RRTMGX_ECUDA;

@@ -165,7 +165,7 @@ static __global__ void mcica_prep_kernel(int ld, int col0, const int *__restrict
 // and returns whether the cell goes into the cloud mask; Optics::State is per-thread scratch
 // carried along the layer sweep and handed to Optics::finish(isub, c, state) at the end.  Outputs: clearCounts (caller layout
 // (ncol,4), integer atomics, so deterministic), the optical cloud mask bit-packed over layers
-// [nw][nsub][nc] and its OR over subcolumns cloudy_any [nw][nc] (the reference's
+// (laid out by Optics::mask_index) and its OR over subcolumns cloudy_any [nw][nc] (the reference's
 // cloudy(lay,col) after cldprmc).
 // Block = MCICA_XS subcolumns (x, fastest) x MCICA_YC columns: a warp is (almost) one column at 28 of its
 // subcolumns.  The subcolumns of a column share cldfrac, so at a given layer they are cloudy or clear
@@ -186,7 +186,7 @@ mcica_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, i
              const int *__restrict__ ncloudy,    // columns c >= *ncloudy hold no cloud at all (null: unknown)
              int *__restrict__ clearCounts,      // (ld,4)
              uint32_t *__restrict__ cloudy_any,  // [nw][nc]
-             uint32_t *__restrict__ mask,        // [nw][nsub][nc]
+             uint32_t *__restrict__ mask,        // indexed by Optics::mask_index(w, nw, isub, c)
              Optics opt, int *err) {
     const int isub = blockIdx.x * MCICA_XS + threadIdx.x;
     const int c = blockIdx.y * MCICA_YC + threadIdx.y;
@@ -196,7 +196,7 @@ mcica_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, i
         // cldfrac = 0 in every layer: cdf1 >= 1 - cldfrac never holds (ran_num < 1), so whatever the
         // generator draws the subcolumn is clear everywhere (:435); nothing to draw
         const int nw = (nlay + 31) >> 5;
-        for (int w = 0; w < nw; ++w) mask[((size_t)w * nsub + isub) * nc + c] = 0u;
+        for (int w = 0; w < nw; ++w) mask[opt.mask_index(w, nw, isub, c)] = 0u;
         if (isub == 0)
             for (int q = 0; q < 4; ++q) atomicAdd(&clearCounts[(size_t)q * ld + col], nsub);
         return;
@@ -256,7 +256,7 @@ mcica_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, i
         if (optical) word |= 1u << (k & 31);
         if ((k & 31) == 31 || k == nlay - 1) {
             const int w = k >> 5;
-            mask[((size_t)w * nsub + isub) * nc + c] = word;
+            mask[opt.mask_index(w, (nlay + 31) >> 5, isub, c)] = word;
             if (word) atomicOr(&cloudy_any[(size_t)w * nc + c], word);
             word = 0;
         }
