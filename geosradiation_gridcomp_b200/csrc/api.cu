@@ -920,6 +920,60 @@ int rrtmgx_irrad_prepare(const RrtmgxIrradArgs *a, RrtmgxLwArgs *lw) {
     return rc;
 }
 
+int rrtmgx_irrad_update(const RrtmgxIrradUpdateArgs *u) {
+    if (!g.ready) return RRTMGX_ENOTINIT;
+    if (!ok(cudaSetDevice(g.device))) { cudaGetLastError(); return RRTMGX_ENODEVICE; }
+    if (!u || u->ncol <= 0 || u->lm < 1 || !u->flxu_int || !u->flxd_int || !u->flcu_int || !u->flcd_int || !u->dfdts ||
+        !u->dfdtsc || !u->sfcem_int || !u->ts_int || !u->tsinst)
+        return RRTMGX_EARG;
+    Path &p = g.lw;
+    const int nc = u->ncol, L1 = u->lm + 1;
+    const dim3 grid((nc + 255) / 256, L1);
+    if (u->flags & RRTMGX_DEVICE_PTRS) {
+        cudaStream_t st = u->stream ? (cudaStream_t)u->stream : p.stream;
+        RRTMGX_LAUNCH(irrad_update_kernel, grid, 256, 0, st, *u);
+        if (u->flags & RRTMGX_NO_SYNC) return ok(cudaGetLastError()) ? 0 : RRTMGX_ECUDA;
+        return ok(cudaStreamSynchronize(st)) ? 0 : RRTMGX_ECUDA;
+    }
+    // host arrays: a handful of (ncol, LM+1) fields up, the requested exports down
+    RrtmgxIrradUpdateArgs d = *u;
+    const size_t n3 = (size_t)nc * L1, n1 = (size_t)nc;
+    struct F { const double **in; double **out; size_t n; };
+    F fields[] = {{&d.flxu_int, nullptr, n3}, {&d.flxd_int, nullptr, n3}, {&d.flcu_int, nullptr, n3},
+                  {&d.flcd_int, nullptr, n3}, {&d.dfdts, nullptr, n3}, {&d.dfdtsc, nullptr, n3},
+                  {&d.sfcem_int, nullptr, n1}, {&d.ts_int, nullptr, n1}, {&d.tsinst, nullptr, n1},
+                  {nullptr, &d.flx, n3}, {nullptr, &d.flc, n3}, {nullptr, &d.flxu, n3}, {nullptr, &d.flcu, n3},
+                  {nullptr, &d.flxd, n3}, {nullptr, &d.flcd, n3}, {nullptr, &d.olr, n1}, {nullptr, &d.olc, n1},
+                  {nullptr, &d.sfcem, n1}, {nullptr, &d.lws, n1}, {nullptr, &d.lcs, n1}, {nullptr, &d.flns, n1},
+                  {nullptr, &d.flnsc, n1}};
+    size_t bytes = 4096;
+    for (auto &f : fields) bytes += (f.n * 8 + 255) & ~(size_t)255;
+    Slab tmp;
+    if (int rc = grow(tmp, bytes)) return rc;
+    double *host_out[22] = {};
+    int k = 0;
+    for (auto &f : fields) {
+        double *dev = tmp.take<double>(f.n);
+        if (f.in) {
+            cudaMemcpyAsync(dev, *f.in, f.n * 8, cudaMemcpyHostToDevice, p.stream);
+            *f.in = dev;
+        } else if (*f.out) {
+            host_out[k] = *f.out;
+            *f.out = dev;
+        }
+        ++k;
+    }
+    RRTMGX_LAUNCH(irrad_update_kernel, grid, 256, 0, p.stream, d);
+    k = 0;
+    for (auto &f : fields) {
+        if (f.out && host_out[k]) cudaMemcpyAsync(host_out[k], *f.out, f.n * 8, cudaMemcpyDeviceToHost, p.stream);
+        ++k;
+    }
+    const bool good = ok(cudaStreamSynchronize(p.stream));
+    cudaFree(tmp.base);
+    return good ? 0 : RRTMGX_ECUDA;
+}
+
 #ifndef RRTMGX_WITH_SW
 int rrtmgx_solar_refresh(const RrtmgxSolarArgs *) { return RRTMGX_EARG; }
 int rrtmgx_solar_prepare(const RrtmgxSolarArgs *, RrtmgxSwArgs *) { return RRTMGX_EARG; }

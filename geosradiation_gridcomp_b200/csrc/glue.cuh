@@ -131,6 +131,35 @@ irrad_finish_kernel(int nc, int lds, int col0, RrtmgxIrradArgs S, RrtmgxLwArgs L
             }
 }
 
+// GEOS_IrradGridComp.F90 Update :3861, :3929-3990 (USE_RRTMG): one thread per (column, level)
+__global__ void __launch_bounds__(256)
+irrad_update_kernel(RrtmgxIrradUpdateArgs U) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int K = blockIdx.y;
+    if (c >= U.ncol) return;
+    const size_t i = (size_t)K * U.ncol + c;
+    const double delt = U.tsinst[c] - U.ts_int[c];
+    const double flx_int = U.flxd_int[i] + U.flxu_int[i];   // :3604
+    const double flc_int = U.flcd_int[i] + U.flcu_int[i];   // :3606
+    if (U.flx) U.flx[i] = flx_int + U.dfdts[i] * delt;
+    if (U.flc) U.flc[i] = flc_int + U.dfdtsc[i] * delt;
+    if (U.flxu) U.flxu[i] = U.flxu_int[i] + U.dfdts[i] * delt;
+    if (U.flcu) U.flcu[i] = U.flcu_int[i] + U.dfdtsc[i] * delt;
+    if (U.flxd) U.flxd[i] = U.flxd_int[i];
+    if (U.flcd) U.flcd[i] = U.flcd_int[i];
+    if (K == 0) {
+        if (U.olr) U.olr[c] = -(flx_int + U.dfdts[i] * delt);
+        if (U.olc) U.olc[c] = -(flc_int + U.dfdtsc[i] * delt);
+    }
+    if (K == U.lm) {
+        if (U.sfcem) U.sfcem[c] = U.sfcem_int[c] - U.dfdts[i] * delt;
+        if (U.lws) U.lws[c] = flx_int + U.sfcem_int[c];
+        if (U.lcs) U.lcs[c] = flc_int + U.sfcem_int[c];
+        if (U.flns) U.flns[c] = flx_int + U.dfdts[i] * delt;
+        if (U.flnsc) U.flnsc[c] = flc_int + U.dfdtsc[i] * delt;
+    }
+}
+
 __global__ void __launch_bounds__(128)
 solar_prepare_kernel(int nc, int lds, int col0, RrtmgxSolarArgs S, RrtmgxSwArgs L) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;

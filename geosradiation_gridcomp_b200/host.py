@@ -84,6 +84,15 @@ class IrradArgs(C.Structure):
                 [(n, _vp) for n in _IRR_IN] + [("band_output", _vp)] + [(n, _vp) for n in _IRR_OUT])
 
 
+_UPD_IN = ["flxu_int", "flxd_int", "flcu_int", "flcd_int", "dfdts", "dfdtsc", "sfcem_int", "ts_int", "tsinst"]
+_UPD_OUT = ["flx", "flc", "flxu", "flcu", "flxd", "flcd", "olr", "olc", "sfcem", "lws", "lcs", "flns", "flnsc"]
+
+
+class IrradUpdateArgs(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("ncol", "lm", "flags")] + [("stream", _vp)] +
+                [(n, _vp) for n in _UPD_IN + _UPD_OUT])
+
+
 _SOL_IN = ["ple", "pl", "t", "q", "o3", "ch4", "cl", "qliq", "qice", "rliq", "rice", "ts", "zt", "lats", "albvr",
            "albvf", "albnr", "albnf", "taua", "ssaa", "asya"]
 _SOL_OUT = ["fsw", "fsc", "fswu", "fscu", "nirr", "nirf", "parr", "parf", "uvrr", "uvrf", "fswband", "cldts", "cldhs",
@@ -136,6 +145,7 @@ def lib():
         L.rrtmgx_table.argtypes = [C.c_char_p, C.c_char_p, C.c_int, _ip]
         L.rrtmgx_irrad_refresh.argtypes = [C.POINTER(IrradArgs)]
         L.rrtmgx_irrad_prepare.argtypes = [C.POINTER(IrradArgs), C.POINTER(LwArgs)]
+        L.rrtmgx_irrad_update.argtypes = [C.POINTER(IrradUpdateArgs)]
         L.rrtmgx_solar_refresh.argtypes = [C.POINTER(SolarArgs)]
         L.rrtmgx_solar_prepare.argtypes = [C.POINTER(SolarArgs), C.POINTER(SwArgs)]
         L.rrtmgx_debug_divide.argtypes = [C.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp]
@@ -454,6 +464,33 @@ def irrad_refresh(n, iceflg=3, liqflg=1, device=False, out=None):
     for k in _IRR_OUT:
         setattr(a, k, _addr(out[k], device, keep=keep))
     _check(lib().rrtmgx_irrad_refresh(C.byref(a)))
+    return out
+
+
+def irrad_update(f, ts_int, tsinst, device=False, want=None):
+    """The between-refresh linear update of the LW exports (GEOS_IrradGridComp.F90 Update :3861, :3929-3990)
+    from the outputs `f` of irrad_refresh(); `want` selects exports (default: all)."""
+    if not _initialised:
+        init()
+    keep = []
+    if device:
+        ncol, lm1 = f["flxu"].shape[-1], f["flxu"].shape[0]
+        import torch
+        z = lambda *sh: torch.zeros(tuple(reversed(sh)), dtype=torch.float64, device="cuda")
+    else:
+        ncol, lm1 = f["flxu"].shape
+        z = lambda *sh: np.zeros(sh, order="F")
+    a = IrradUpdateArgs()
+    a.ncol, a.lm, a.flags = int(ncol), int(lm1 - 1), DEVICE_PTRS if device else 0
+    src = {"flxu_int": f["flxu"], "flxd_int": f["flxd"], "flcu_int": f["flcu"], "flcd_int": f["flcd"],
+           "dfdts": f["dfdts"], "dfdtsc": f["dfdtsc"], "sfcem_int": f["sfcem"], "ts_int": ts_int, "tsinst": tsinst}
+    for k in _UPD_IN:
+        setattr(a, k, _addr(src[k], device, keep=keep))
+    out = {}
+    for k in (want or _UPD_OUT):
+        out[k] = z(ncol, lm1) if k in _UPD_OUT[:6] else z(ncol)
+        setattr(a, k, _addr(out[k], device, keep=keep))
+    _check(lib().rrtmgx_irrad_update(C.byref(a)))
     return out
 
 

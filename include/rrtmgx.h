@@ -246,6 +246,24 @@ typedef struct {
     double *cottp, *cothp, *cotmp, *cotlp;            /* (ncol), any may be NULL                      */
 } RrtmgxSolarArgs;
 
+/* Between refreshes GEOS updates the LW exports every model step from the fluxes held since the last
+ * refresh, linearised in the surface temperature (GEOS_IrradGridComp.F90 Update, :3861 and the
+ * USE_RRTMG branch :3929-3990 with FLX_INT = FLXD_INT + FLXU_INT, :3604-3606):
+ *   DELT = TSINST - TS_INT;  FLX = FLX_INT + DFDTS*DELT;  FLXU = FLXU_INT + DFDTS*DELT;  FLXD = FLXD_INT;
+ *   OLR = -(FLX_INT(0) + DFDTS(0)*DELT);  SFCEM = SFCEM_INT - DFDTS(LM)*DELT;  LWS = FLX_INT(LM) + SFCEM_INT;
+ *   FLNS = FLX_INT(LM) + DFDTS(LM)*DELT;  and the clear-sky twins.  Inputs are the outputs of
+ * rrtmgx_irrad_refresh (they can stay on the device); any output pointer may be NULL. */
+typedef struct {
+    int ncol, lm;
+    int flags;
+    void *stream;
+    const double *flxu_int, *flxd_int, *flcu_int, *flcd_int, *dfdts, *dfdtsc;   /* (ncol,0:LM)          */
+    const double *sfcem_int, *ts_int, *tsinst;                                    /* (ncol)               */
+    double *flx, *flc, *flxu, *flcu, *flxd, *flcd;                                /* (ncol,0:LM)          */
+    double *olr, *olc, *sfcem, *lws, *lcs, *flns, *flnsc;                         /* (ncol)               */
+} RrtmgxIrradUpdateArgs;
+int rrtmgx_irrad_update(const RrtmgxIrradUpdateArgs *u);
+
 int rrtmgx_irrad_prepare(const RrtmgxIrradArgs *g, RrtmgxLwArgs *lw);
 int rrtmgx_irrad_refresh(const RrtmgxIrradArgs *g);
 int rrtmgx_solar_prepare(const RrtmgxSolarArgs *g, RrtmgxSwArgs *sw);

@@ -362,3 +362,28 @@ def solar_finish(n, o):
     for k in ("nirr", "nirf", "parr", "parf", "uvrr", "uvrf", "fswband"):
         out[k] = o[k]
     return out
+
+
+_UPD_3D = ("flx", "flc", "flxu", "flcu", "flxd", "flcd")
+_UPD_2D = ("olr", "olc", "sfcem", "lws", "lcs", "flns", "flnsc")
+
+
+class IrradExports(C.Structure):
+    _fields_ = [(n, _dp) for n in _UPD_3D + _UPD_2D]
+
+
+def irrad_update(f, ts_int, tsinst):
+    """GEOS_IrradGridComp.F90 Update (:3861, :3929-3990) on the refresh outputs `f` of irrad_finish()."""
+    ncol, lm1 = f["flxu"].shape
+    e = IrradExports()
+    out = {k: np.zeros((ncol, lm1), order="F") for k in _UPD_3D}
+    out.update({k: np.zeros(ncol) for k in _UPD_2D})
+    for k, v in out.items():
+        setattr(e, k, _d(v))
+    L = lib()
+    L.oracle_irrad_update.argtypes = None
+    rc = L.oracle_irrad_update(C.c_int(ncol), C.c_int(lm1 - 1), _d(f["flxu"]), _d(f["flxd"]), _d(f["flcu"]), _d(f["flcd"]),
+                               _d(f["dfdts"]), _d(f["dfdtsc"]), _d(f["sfcem"]), _d(ts_int), _d(tsinst), C.byref(e))
+    if rc:
+        raise RuntimeError(f"oracle_irrad_update: {rc}")
+    return out

@@ -215,3 +215,33 @@ int oracle_solar_finish(int ncol, int LM, double undef, const int *clearCounts, 
     }
     return 0;
 }
+
+/* GEOS_IrradGridComp.F90 Update: DELT :3861, FLX_INT = FLXD_INT + FLXU_INT :3604-3606, USE_RRTMG branch :3929-3990.
+ * Any output pointer may be NULL (unassociated export). */
+int oracle_irrad_update(int ncol, int LM, const double *flxu_int, const double *flxd_int, const double *flcu_int,
+                        const double *flcd_int, const double *dfdts, const double *dfdtsc, const double *sfcem_int,
+                        const double *ts_int, const double *tsinst, OracleIrradExports *e) {
+    for (int ij = 0; ij < ncol; ++ij) {
+        const double DELT = tsinst[ij] - ts_int[ij];
+        for (int K = 0; K <= LM; ++K) {
+            const double FLX_INT = G2(flxd_int, ij, K) + G2(flxu_int, ij, K);
+            const double FLC_INT = G2(flcd_int, ij, K) + G2(flcu_int, ij, K);
+            if (e->flx) G2(e->flx, ij, K) = FLX_INT + G2(dfdts, ij, K) * DELT;
+            if (e->flc) G2(e->flc, ij, K) = FLC_INT + G2(dfdtsc, ij, K) * DELT;
+            if (e->flxu) G2(e->flxu, ij, K) = G2(flxu_int, ij, K) + G2(dfdts, ij, K) * DELT;
+            if (e->flcu) G2(e->flcu, ij, K) = G2(flcu_int, ij, K) + G2(dfdtsc, ij, K) * DELT;
+            if (e->flxd) G2(e->flxd, ij, K) = G2(flxd_int, ij, K);
+            if (e->flcd) G2(e->flcd, ij, K) = G2(flcd_int, ij, K);
+        }
+        const double FLX0 = G2(flxd_int, ij, 0) + G2(flxu_int, ij, 0), FLC0 = G2(flcd_int, ij, 0) + G2(flcu_int, ij, 0);
+        const double FLXL = G2(flxd_int, ij, LM) + G2(flxu_int, ij, LM), FLCL = G2(flcd_int, ij, LM) + G2(flcu_int, ij, LM);
+        if (e->olr) e->olr[ij] = -(FLX0 + G2(dfdts, ij, 0) * DELT);
+        if (e->olc) e->olc[ij] = -(FLC0 + G2(dfdtsc, ij, 0) * DELT);
+        if (e->sfcem) e->sfcem[ij] = sfcem_int[ij] - G2(dfdts, ij, LM) * DELT;
+        if (e->lws) e->lws[ij] = FLXL + sfcem_int[ij];
+        if (e->lcs) e->lcs[ij] = FLCL + sfcem_int[ij];
+        if (e->flns) e->flns[ij] = FLXL + G2(dfdts, ij, LM) * DELT;
+        if (e->flnsc) e->flnsc[ij] = FLCL + G2(dfdtsc, ij, LM) * DELT;
+    }
+    return 0;
+}

@@ -122,6 +122,14 @@ int oracle_irrad_finish(int ncol, int lm, const double *emis, const int *clearCo
                         const double *dflx, const double *uflxc, const double *dflxc, const double *duflx_dTs,
                         const double *duflxc_dTs, OracleIrradFluxes *f);  /* IRR:3486-3533 */
 
+typedef struct {                                     /* exports of the between-refresh Update, any may be NULL */
+    double *flx, *flc, *flxu, *flcu, *flxd, *flcd;   /* (ncol,0:LM) */
+    double *olr, *olc, *sfcem, *lws, *lcs, *flns, *flnsc;   /* (ncol) */
+} OracleIrradExports;
+int oracle_irrad_update(int ncol, int lm, const double *flxu_int, const double *flxd_int, const double *flcu_int,
+                        const double *flcd_int, const double *dfdts, const double *dfdtsc, const double *sfcem_int,
+                        const double *ts_int, const double *tsinst, OracleIrradExports *e);   /* IRR:3861, 3929-3990 */
+
 typedef struct {
     int ncol, lm, iceflg, liqflg, lcldmh, lcldlm;
     double co2, o2;

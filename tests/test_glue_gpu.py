@@ -85,3 +85,21 @@ def test_refresh_device_pointers_equal_host_arrays(rx):
         np.testing.assert_array_equal(d_lw[k].cpu().numpy().T, h_lw[k], err_msg=k)
     for k in ("fsw", "fsc", "fswu", "fscu", "nirr", "cottp", "cldts", "fswband"):
         np.testing.assert_array_equal(d_sw[k].cpu().numpy().T, h_sw[k], err_msg=k)
+
+
+def test_irrad_update_bit_exact(rx, oracle):
+    """Between-refresh linear update of the LW exports (IRR Update :3861, :3929-3990): plain IEEE sums and
+    products in the reference's order, so every export is bit-identical to the oracle's."""
+    n = make_native_state(900, 72, seed=28)
+    f = rx.irrad_refresh(n)
+    rng = np.random.default_rng(5)
+    ts_int = np.asfortranarray(n["ts"])
+    tsinst = np.asfortranarray(n["ts"] + rng.normal(0, 1.5, n["ncol"]))
+    g = rx.irrad_update(f, ts_int, tsinst)
+    o = oracle.irrad_update(f, ts_int, tsinst)
+    for k, v in o.items():
+        np.testing.assert_array_equal(g[k], v, err_msg=k)
+    np.testing.assert_array_equal(g["flxd"], f["flxd"])
+    assert (g["olr"] > 0).all()
+    only = rx.irrad_update(f, ts_int, tsinst, want=("olr", "flns"))
+    np.testing.assert_array_equal(only["olr"], o["olr"])
