@@ -192,14 +192,27 @@ struct Arr {
     size_t rows, elem;
     bool inner;         // (k,ncol) layout: the chunk is contiguous
     bool in, out;
+    bool f32 = false;   // RRTMGX_F32_ARRAYS: the caller's array is real*4; widened / narrowed on the device
 };
+
+// real*4 boundary arrays (the production kind of GEOS): exact widening on the way in, one rounding on the way out
+__global__ void widen_kernel(const float *__restrict__ x, double *__restrict__ y, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        y[i] = (double)x[i];
+}
+__global__ void narrow_kernel(const double *__restrict__ x, float *__restrict__ y, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        y[i] = (float)x[i];
+}
 
 // Host-pointer mode: run `fn(chunk_args, nc)` over chunks with H2D / compute / D2H overlapped
 // on three streams and two staging sets.
 template <class Args, class Fn>
 int run_staged(Path &p, const Args &a, Args &ca, std::vector<Arr> &arrs, int ncol, size_t chunk, Fn fn) {
     size_t stage_bytes = 0;
-    for (auto &r : arrs) stage_bytes += ((r.rows * chunk * r.elem) + 255) & ~(size_t)255;
+    for (auto &r : arrs)
+        stage_bytes += (((r.rows * chunk * r.elem) + 255) & ~(size_t)255) +
+                       (r.f32 ? ((r.rows * chunk * 8 + 255) & ~(size_t)255) : 0);
     for (int s = 0; s < 2; ++s)
         if (int rc = grow(p.stage[s], stage_bytes + 4096)) return rc;
     int k = 0;
@@ -208,35 +221,48 @@ int run_staged(Path &p, const Args &a, Args &ca, std::vector<Arr> &arrs, int nco
         const size_t nc = std::min(chunk, (size_t)ncol - col0);
         Slab &st = p.stage[s];
         st.used = 0;
-        std::vector<void *> dev(arrs.size());
+        std::vector<void *> dev(arrs.size()), raw(arrs.size());
         if (k >= 2) cudaStreamWaitEvent(p.h2d, p.ev_free[s], 0);
         for (size_t i = 0; i < arrs.size(); ++i) {
             Arr &r = arrs[i];
-            dev[i] = r.host ? (void *)st.take<char>(r.rows * nc * r.elem) : nullptr;
+            raw[i] = r.host ? (void *)st.take<char>(r.rows * nc * r.elem) : nullptr;
+            dev[i] = (r.host && r.f32) ? (void *)st.take<char>(r.rows * nc * 8) : raw[i];
             if (!r.host || !r.in) continue;
             if (r.inner)
-                cudaMemcpyAsync(dev[i], (const char *)r.host + col0 * r.rows * r.elem, r.rows * nc * r.elem,
+                cudaMemcpyAsync(raw[i], (const char *)r.host + col0 * r.rows * r.elem, r.rows * nc * r.elem,
                                 cudaMemcpyHostToDevice, p.h2d);
             else
-                cudaMemcpy2DAsync(dev[i], nc * r.elem, (const char *)r.host + col0 * r.elem, (size_t)ncol * r.elem,
+                cudaMemcpy2DAsync(raw[i], nc * r.elem, (const char *)r.host + col0 * r.elem, (size_t)ncol * r.elem,
                                   nc * r.elem, r.rows, cudaMemcpyHostToDevice, p.h2d);
         }
         cudaEventRecord(p.ev_in[s], p.h2d);
         cudaStreamWaitEvent(p.stream, p.ev_in[s], 0);
+        for (size_t i = 0; i < arrs.size(); ++i)
+            if (arrs[i].host && arrs[i].f32 && arrs[i].in) {
+                const size_t n = arrs[i].rows * nc;
+                RRTMGX_LAUNCH(widen_kernel, (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, p.stream,
+                              (const float *)raw[i], (double *)dev[i], n);
+            }
         ca = a;
         ca.ncol = (int)nc;
         for (size_t i = 0; i < arrs.size(); ++i) *arrs[i].slot = dev[i];
         if (int rc = fn(ca, (int)nc)) return rc;
+        for (size_t i = 0; i < arrs.size(); ++i)
+            if (arrs[i].host && arrs[i].f32 && arrs[i].out) {
+                const size_t n = arrs[i].rows * nc;
+                RRTMGX_LAUNCH(narrow_kernel, (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, p.stream,
+                              (const double *)dev[i], (float *)raw[i], n);
+            }
         cudaEventRecord(p.ev_done[s], p.stream);
         cudaStreamWaitEvent(p.d2h, p.ev_done[s], 0);
         for (size_t i = 0; i < arrs.size(); ++i) {
             Arr &r = arrs[i];
             if (!r.host || !r.out) continue;
             if (r.inner)
-                cudaMemcpyAsync((char *)r.host + col0 * r.rows * r.elem, dev[i], r.rows * nc * r.elem,
+                cudaMemcpyAsync((char *)r.host + col0 * r.rows * r.elem, raw[i], r.rows * nc * r.elem,
                                 cudaMemcpyDeviceToHost, p.d2h);
             else
-                cudaMemcpy2DAsync((char *)r.host + col0 * r.elem, (size_t)ncol * r.elem, dev[i], nc * r.elem,
+                cudaMemcpy2DAsync((char *)r.host + col0 * r.elem, (size_t)ncol * r.elem, raw[i], nc * r.elem,
                                   nc * r.elem, r.rows, cudaMemcpyDeviceToHost, p.d2h);
         }
         cudaEventRecord(p.ev_free[s], p.d2h);
@@ -474,6 +500,7 @@ int rrtmgx_lw_run(const RrtmgxLwArgs *a) {
     Path &p = g.lw;
     const bool devptr = a->flags & RRTMGX_DEVICE_PTRS;
     if ((a->flags & RRTMGX_NO_SYNC) && !devptr) return RRTMGX_EARG;
+    if ((a->flags & RRTMGX_F32_ARRAYS) && devptr) return RRTMGX_EARG;   // real*4 arrays are widened while staged
     const int ncol = a->ncol, nlay = a->nlay;
     if (int rc = ensure_jumps(p, 140, nlay)) return rc;
     static const int seed_order[4] = {1, 2, 3, 4};   // LW/src/rrtmg_lw_rad.F90:541-546
@@ -527,12 +554,14 @@ int rrtmgx_lw_run(const RrtmgxLwArgs *a) {
     // host pointers: stage chunk by chunk
     RrtmgxLwArgs ca = *a;
     std::vector<Arr> arrs;
+    const bool f32 = a->flags & RRTMGX_F32_ARRAYS;   // the caller's real arrays are real*4
+    const size_t esz = f32 ? 4 : 8;
     const size_t L = nlay, L1 = nlay + 1;
     auto in = [&](const double *const &field, const double **slot, size_t rows) {
-        arrs.push_back({field, (void **)slot, rows, 8, false, true, false});
+        arrs.push_back({field, (void **)slot, rows, esz, false, true, false, f32});
     };
     auto out = [&](double *const &field, double **slot, size_t rows, bool inner = false) {
-        arrs.push_back({field, (void **)slot, rows, 8, inner, false, true});
+        arrs.push_back({field, (void **)slot, rows, esz, inner, false, true, f32});
     };
     in(a->play, &ca.play, L); in(a->plev, &ca.plev, L1); in(a->tlay, &ca.tlay, L); in(a->tlev, &ca.tlev, L1);
     in(a->tsfc, &ca.tsfc, 1); in(a->emis, &ca.emis, 16);
@@ -549,8 +578,8 @@ int rrtmgx_lw_run(const RrtmgxLwArgs *a) {
     for (int b = 0; b < 16; ++b) any_bo |= a->band_output && a->band_output[b];
     if (any_bo) {
         // (16,ncol): untouched bands must survive the round trip, so olrb is staged in as well
-        arrs.push_back({a->olrb, (void **)&ca.olrb, 16, 8, true, true, true});
-        if (a->dudTs) arrs.push_back({a->dolrb_dTs, (void **)&ca.dolrb_dTs, 16, 8, true, true, true});
+        arrs.push_back({a->olrb, (void **)&ca.olrb, 16, esz, true, true, true, f32});
+        if (a->dudTs) arrs.push_back({a->dolrb_dTs, (void **)&ca.dolrb_dTs, 16, esz, true, true, true, f32});
     }
     int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxLwArgs &c, int nc) -> int {
         (void)nc;
@@ -625,6 +654,7 @@ int rrtmgx_sw_run(const RrtmgxSwArgs *a) {
     Path &p = g.sw;
     const bool devptr = a->flags & RRTMGX_DEVICE_PTRS;
     if ((a->flags & RRTMGX_NO_SYNC) && !devptr) return RRTMGX_EARG;
+    if ((a->flags & RRTMGX_F32_ARRAYS) && devptr) return RRTMGX_EARG;   // real*4 arrays are widened while staged
     SwSolar sol;
     if (int rc = sw_solar_setup(a, g.ht, &sol)) return rc;   // rrtmg_sw_sub :889-1127
     const int ncol = a->ncol, nlay = a->nlay;
@@ -678,12 +708,14 @@ int rrtmgx_sw_run(const RrtmgxSwArgs *a) {
 
     RrtmgxSwArgs ca = *a;
     std::vector<Arr> arrs;
+    const bool f32 = a->flags & RRTMGX_F32_ARRAYS;   // the caller's real arrays are real*4
+    const size_t esz = f32 ? 4 : 8;
     const size_t L = nlay, L1 = nlay + 1;
     auto in = [&](const double *const &field, const double **slot, size_t rows) {
-        arrs.push_back({field, (void **)slot, rows, 8, false, true, false});
+        arrs.push_back({field, (void **)slot, rows, esz, false, true, false, f32});
     };
     auto out = [&](double *const &field, double **slot, size_t rows) {
-        arrs.push_back({field, (void **)slot, rows, 8, false, false, true});
+        arrs.push_back({field, (void **)slot, rows, esz, false, false, true, f32});
     };
     in(a->coszen, &ca.coszen, 1); in(a->play, &ca.play, L); in(a->plev, &ca.plev, L1); in(a->tlay, &ca.tlay, L);
     in(a->h2ovmr, &ca.h2ovmr, L); in(a->o3vmr, &ca.o3vmr, L); in(a->co2vmr, &ca.co2vmr, L);
@@ -823,6 +855,7 @@ int rrtmgx_irrad_refresh(const RrtmgxIrradArgs *a) {
     Path &p = g.lw;
     const bool devptr = a->flags & RRTMGX_DEVICE_PTRS;
     if ((a->flags & RRTMGX_NO_SYNC) && !devptr) return RRTMGX_EARG;
+    if ((a->flags & RRTMGX_F32_ARRAYS) && devptr) return RRTMGX_EARG;   // real*4 arrays are widened while staged
     const int ncol = a->ncol;
     cudaStream_t st = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
     if (!ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, st))) return RRTMGX_ECUDA;
@@ -835,12 +868,14 @@ int rrtmgx_irrad_refresh(const RrtmgxIrradArgs *a) {
     }
     RrtmgxIrradArgs ca = *a;
     std::vector<Arr> arrs;
+    const bool f32 = a->flags & RRTMGX_F32_ARRAYS;   // the caller's real arrays are real*4
+    const size_t esz = f32 ? 4 : 8;
     const size_t L = a->lm, L1 = a->lm + 1;
     auto in = [&](const double *const &f, const double **slot, size_t rows) {
-        arrs.push_back({f, (void **)slot, rows, 8, false, true, false});
+        arrs.push_back({f, (void **)slot, rows, esz, false, true, false, f32});
     };
     auto out = [&](double *const &f, double **slot, size_t rows) {
-        arrs.push_back({f, (void **)slot, rows, 8, false, false, true});
+        arrs.push_back({f, (void **)slot, rows, esz, false, false, true, f32});
     };
     in(a->ple, &ca.ple, L1); in(a->pl, &ca.pl, L); in(a->t, &ca.t, L); in(a->q, &ca.q, L); in(a->o3, &ca.o3, L);
     in(a->ch4, &ca.ch4, L); in(a->n2o, &ca.n2o, L); in(a->co2, &ca.co2, L); in(a->cfc11, &ca.cfc11, L);
@@ -852,8 +887,8 @@ int rrtmgx_irrad_refresh(const RrtmgxIrradArgs *a) {
     out(a->dfdts, &ca.dfdts, L1); out(a->dfdtsc, &ca.dfdtsc, L1); out(a->sfcem, &ca.sfcem, 1);
     out(a->cldtt, &ca.cldtt, 1); out(a->cldhi, &ca.cldhi, 1); out(a->cldmd, &ca.cldmd, 1); out(a->cldlo, &ca.cldlo, 1);
     if (band_mask_of(a->band_output)) {   // (16,ncol): untouched bands survive the round trip
-        arrs.push_back({a->olrb, (void **)&ca.olrb, 16, 8, true, true, true});
-        arrs.push_back({a->dolrb_dts, (void **)&ca.dolrb_dts, 16, 8, true, true, true});
+        arrs.push_back({a->olrb, (void **)&ca.olrb, 16, esz, true, true, true, f32});
+        arrs.push_back({a->dolrb_dts, (void **)&ca.dolrb_dts, 16, esz, true, true, true, f32});
     } else {
         ca.olrb = nullptr; ca.dolrb_dts = nullptr;
     }
@@ -987,6 +1022,7 @@ int rrtmgx_solar_refresh(const RrtmgxSolarArgs *a) {
     Path &p = g.sw;
     const bool devptr = a->flags & RRTMGX_DEVICE_PTRS;
     if ((a->flags & RRTMGX_NO_SYNC) && !devptr) return RRTMGX_EARG;
+    if ((a->flags & RRTMGX_F32_ARRAYS) && devptr) return RRTMGX_EARG;   // real*4 arrays are widened while staged
     const int ncol = a->ncol;
     cudaStream_t st = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
     if (!ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, st))) return RRTMGX_ECUDA;
@@ -999,12 +1035,14 @@ int rrtmgx_solar_refresh(const RrtmgxSolarArgs *a) {
     }
     RrtmgxSolarArgs ca = *a;
     std::vector<Arr> arrs;
+    const bool f32 = a->flags & RRTMGX_F32_ARRAYS;   // the caller's real arrays are real*4
+    const size_t esz = f32 ? 4 : 8;
     const size_t L = a->lm, L1 = a->lm + 1;
     auto in = [&](const double *const &f, const double **slot, size_t rows) {
-        arrs.push_back({f, (void **)slot, rows, 8, false, true, false});
+        arrs.push_back({f, (void **)slot, rows, esz, false, true, false, f32});
     };
     auto out = [&](double *const &f, double **slot, size_t rows) {
-        arrs.push_back({f, (void **)slot, rows, 8, false, false, true});
+        arrs.push_back({f, (void **)slot, rows, esz, false, false, true, f32});
     };
     in(a->ple, &ca.ple, L1); in(a->pl, &ca.pl, L); in(a->t, &ca.t, L); in(a->q, &ca.q, L); in(a->o3, &ca.o3, L);
     in(a->ch4, &ca.ch4, L); in(a->cl, &ca.cl, L); in(a->qliq, &ca.qliq, L); in(a->qice, &ca.qice, L);

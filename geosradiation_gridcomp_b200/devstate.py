@@ -12,20 +12,23 @@ _SW_OUT1 = ("nirr", "nirf", "parr", "parf", "uvrr", "uvrf", "cotdtp", "cotdhp", 
             "cotnhp", "cotnmp", "cotnlp")
 
 
-def to_device(s, device="cuda", pinned=False):
-    """Copy a synthetic.make_columns dict to the device (arrays transposed views of the same bytes)."""
+def to_device(s, device="cuda", pinned=False, real4=False):
+    """Copy a synthetic.make_columns dict to the device (arrays transposed views of the same bytes);
+    real4: as real*4 arrays (host arrays for RRTMGX_F32_ARRAYS)."""
     d = {}
     for k, v in s.items():
         if isinstance(v, np.ndarray) and v.dtype == np.float64 and v.size > 16:
             t = torch.from_numpy(np.ascontiguousarray(v.T))   # same memory order as the F array
+            if real4:
+                t = t.to(torch.float32)
             d[k] = t.pin_memory() if pinned else t.to(device)
         else:
             d[k] = v
     return d
 
 
-def alloc_outputs(ncol, nlay, device="cuda", pinned=False):
-    kw = dict(dtype=torch.float64, device="cpu" if pinned else device, pin_memory=pinned)
+def alloc_outputs(ncol, nlay, device="cuda", pinned=False, real4=False):
+    kw = dict(dtype=torch.float32 if real4 else torch.float64, device="cpu" if pinned else device, pin_memory=pinned)
     o = {k: torch.zeros((nlay + 1, ncol), **kw) for k in _LW_OUT2 + _SW_OUT2}
     for k in _SW_OUT1:
         o[k] = torch.zeros(ncol, **kw)
@@ -43,7 +46,8 @@ def _ptr(t, device):
     return t if device else t.numpy().T if t.dim() == 2 else t.numpy()
 
 
-def lw_runner(d, o=None, device=True, sync=True, skip_checks=False, dudTs=True, iceflg=3, liqflg=1, stream=None):
+def lw_runner(d, o=None, device=True, sync=True, skip_checks=False, dudTs=True, iceflg=3, liqflg=1, stream=None,
+              f32=False):
     ncol, nlay = d["ncol"], d["nlay"]
     o = o if o is not None else alloc_outputs(ncol, nlay, pinned=not device)
     p = (lambda t: t) if device else (lambda t: t.data_ptr())
@@ -56,14 +60,14 @@ def lw_runner(d, o=None, device=True, sync=True, skip_checks=False, dudTs=True, 
                       p(d["tauaer_lw"]), p(d["zm"]), p(d["alat"]), d["dyofyr"], d["cloudLM"], d["cloudMH"],
                       p(o["clearCounts_lw"]), p(o["uflx"]), p(o["dflx"]), p(o["uflxc"]), p(o["dflxc"]),
                       p(o["duflx_dTs"]), p(o["duflxc_dTs"]), d["band_output"], p(o["olrb"]), p(o["dolrb_dTs"]),
-                      device=device, sync=sync, skip_checks=skip_checks, stream=stream)
+                      device=device, sync=sync, skip_checks=skip_checks, stream=stream, f32=f32)
         return o
     run.outputs = o
     return run
 
 
 def sw_runner(d, o=None, device=True, sync=True, skip_checks=False, iceflg=3, liqflg=1, isolvar=0, iaer=10,
-              normFlx=1, stream=None):
+              normFlx=1, stream=None, f32=False):
     ncol, nlay = d["ncol"], d["nlay"]
     o = o if o is not None else alloc_outputs(ncol, nlay, pinned=not device)
     p = (lambda t: t) if device else (lambda t: t.data_ptr())
@@ -78,7 +82,7 @@ def sw_runner(d, o=None, device=True, sync=True, skip_checks=False, iceflg=3, li
                       p(o["nirr"]), p(o["nirf"]), p(o["parr"]), p(o["parf"]), p(o["uvrr"]), p(o["uvrf"]),
                       p(o["fswband"]), p(o["cotdtp"]), p(o["cotdhp"]), p(o["cotdmp"]), p(o["cotdlp"]), p(o["cotntp"]),
                       p(o["cotnhp"]), p(o["cotnmp"]), p(o["cotnlp"]), False, p(o["drband"]), p(o["dfband"]),
-                      device=device, sync=sync, skip_checks=skip_checks, stream=stream)
+                      device=device, sync=sync, skip_checks=skip_checks, stream=stream, f32=f32)
         return o
     run.outputs = o
     return run

@@ -44,7 +44,7 @@ contains
       a%dudTs = merge(1_c_int, 0_c_int, dudTs)
       a%iceflglw = iceflglw; a%liqflglw = liqflglw
       a%dyofyr = dyofyr; a%cloudLM = cloudLM; a%cloudMH = cloudMH
-      a%flags = 0                                        ! host arrays; the library stages them
+      a%flags = rrtmgx_real_flags                        ! host arrays of default real; the library stages them
       a%stream = c_null_ptr
       a%play = c_loc(play); a%plev = c_loc(plev); a%tlay = c_loc(tlay); a%tlev = c_loc(tlev)
       a%tsfc = c_loc(tsfc); a%emis = c_loc(emis)

@@ -60,19 +60,26 @@ contains
 
       type(rrtmgx_sw_args) :: a
       integer(c_int) :: status
+      real(c_double), target :: bndscl_d(14), indsolvar_d(2), solcycfrac_d   ! always double in the C ABI
 
       a%ncol = ncol; a%nlay = nlay; a%rpart = rpart      ! rpart: cache blocking of the CPU code, ignored
       a%isolvar = isolvar; a%iceflgsw = iceflgsw; a%liqflgsw = liqflgsw
       a%dyofyr = dyofyr; a%cloudLM = cloudLM; a%cloudMH = cloudMH
       a%iaer = iaer; a%normFlx = normFlx
       a%do_drfband = merge(1_c_int, 0_c_int, do_drfband)
-      a%flags = 0
+      a%flags = rrtmgx_real_flags
       a%stream = c_null_ptr
       a%scon = scon; a%adjes = adjes
       a%bndscl = c_null_ptr; a%indsolvar = c_null_ptr; a%solcycfrac = c_null_ptr   ! absent optionals -> NULL
-      if (present(bndscl)) a%bndscl = c_loc(bndscl)
-      if (present(indsolvar)) a%indsolvar = c_loc(indsolvar)
-      if (present(solcycfrac)) a%solcycfrac = c_loc(solcycfrac)
+      if (present(bndscl)) then
+         bndscl_d = bndscl; a%bndscl = c_loc(bndscl_d)
+      end if
+      if (present(indsolvar)) then
+         indsolvar_d = indsolvar; a%indsolvar = c_loc(indsolvar_d)
+      end if
+      if (present(solcycfrac)) then
+         solcycfrac_d = solcycfrac; a%solcycfrac = c_loc(solcycfrac_d)
+      end if
       a%coszen = c_loc(coszen); a%play = c_loc(play); a%plev = c_loc(plev); a%tlay = c_loc(tlay)
       a%h2ovmr = c_loc(h2ovmr); a%o3vmr = c_loc(o3vmr); a%co2vmr = c_loc(co2vmr); a%ch4vmr = c_loc(ch4vmr)
       a%o2vmr = c_loc(o2vmr)

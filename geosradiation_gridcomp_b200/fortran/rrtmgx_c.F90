@@ -5,19 +5,24 @@
 ! GEOSirrad_GridComp / GEOSsolar_GridComp CMake targets in place of the RRTMG src/ trees and
 ! links librrtmgx.so (see INTEGRATION.md).
 !
-! `real` here must be 8 bytes (build GEOS radiation with -fdefault-real-8 / -r8, the fp64
-! contract of this library); rrtmgx_real_kind checks it at compile time.
+! Default `real` may be 8 bytes (-fdefault-real-8 / -r8: the fp64 contract the parity tests hold the
+! library to) or 4 bytes (the production kind of GEOS): rrtmgx_real_flags then carries
+! RRTMGX_F32_ARRAYS, the library widens the arrays exactly while it stages them, computes in fp64 and
+! rounds the outputs once.  Any other kind is a compile-time error.
 module rrtmgx_c
    use, intrinsic :: iso_c_binding
    implicit none
    public
 
    integer, parameter :: rrtmgx_real_kind = kind(1.0)
-   ! compile-time trap: the array size is negative unless default real is c_double
-   integer, parameter, private :: real_is_c_double(2*merge(1, -1, rrtmgx_real_kind == c_double) - 1) = 0
+   ! compile-time trap: the array size is negative unless default real is c_double or c_float
+   integer, parameter, private :: real_is_c_real(2*merge(1, -1, rrtmgx_real_kind == c_double .or. &
+                                                                 rrtmgx_real_kind == c_float) - 1) = 0
 
    integer(c_int), parameter :: RRTMGX_DEVICE_PTRS = 1, RRTMGX_NO_SYNC = 2, RRTMGX_SKIP_CHECKS = 4, &
-                                RRTMGX_KEEP_STATUS = 8, RRTMGX_REUSE_CLOUDS = 16
+                                RRTMGX_KEEP_STATUS = 8, RRTMGX_REUSE_CLOUDS = 16, RRTMGX_F32_ARRAYS = 32
+   ! what every shim ORs into `flags`: the element kind of the caller's real arrays
+   integer(c_int), parameter :: rrtmgx_real_flags = merge(0_c_int, RRTMGX_F32_ARRAYS, rrtmgx_real_kind == c_double)
 
    type, bind(C) :: rrtmgx_config
       type(c_ptr)    :: table_blob = c_null_ptr

@@ -42,7 +42,7 @@ contains
 
       bo = merge(1_c_int, 0_c_int, BAND_OUTPUT)
       a%ncol = ncol; a%lm = LM; a%iceflg = ICEFLGLW; a%liqflg = LIQFLGLW; a%doy = DOY
-      a%lcldmh = LCLDMH; a%lcldlm = LCLDLM; a%flags = 0; a%stream = c_null_ptr
+      a%lcldmh = LCLDMH; a%lcldlm = LCLDLM; a%flags = rrtmgx_real_flags; a%stream = c_null_ptr
       a%co2_fixed = CO2_FIXED; a%o2 = O2; a%ccl4 = CCL4
       a%airmw = AIRMW; a%h2omw = H2OMW; a%o3mw = O3MW; a%rgas = RGAS; a%grav = GRAV
       a%ple = c_loc(PLE); a%pl = c_loc(PL); a%t = c_loc(T); a%q = c_loc(Q); a%o3 = c_loc(O3)
@@ -84,12 +84,13 @@ contains
       integer, intent(out), optional :: RC
       type(rrtmgx_solar_args) :: a
       integer(c_int) :: status
+      real(c_double), target :: solcycfrac_d
 
       a%ncol = ncol; a%lm = LM; a%iceflg = ICEFLGSW; a%liqflg = LIQFLGSW; a%doy = DOY; a%isolvar = ISOLVAR
-      a%lcldmh = LCLDMH; a%lcldlm = LCLDLM; a%flags = 0; a%stream = c_null_ptr
+      a%lcldmh = LCLDMH; a%lcldlm = LCLDLM; a%flags = rrtmgx_real_flags; a%stream = c_null_ptr
       a%sc = SC; a%dist = DIST; a%co2 = CO2; a%o2 = O2
       a%airmw = AIRMW; a%h2omw = H2OMW; a%o3mw = O3MW; a%rgas = RGAS; a%grav = GRAV; a%undef = UNDEF
-      a%solcycfrac = c_loc(SOLCYCFRAC)
+      solcycfrac_d = SOLCYCFRAC; a%solcycfrac = c_loc(solcycfrac_d)
       a%ple = c_loc(PLE); a%pl = c_loc(PL); a%t = c_loc(T); a%q = c_loc(Q); a%o3 = c_loc(O3); a%ch4 = c_loc(CH4)
       a%cl = c_loc(CL); a%qliq = c_loc(QLIQ); a%qice = c_loc(QICE); a%rliq = c_loc(RLIQ); a%rice = c_loc(RICE)
       a%ts = c_loc(TS); a%zt = c_loc(ZT); a%lats = c_loc(LATS)

@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(HERE, "librrtmgx.so")
 BLOB_PATH = os.path.join(HERE, "data", "rrtmg_tables.bin")
 
 NBNDLW, NGPTLW, NBNDSW, NGPTSW = 16, 140, 14, 112
-DEVICE_PTRS, NO_SYNC, SKIP_CHECKS, KEEP_STATUS, REUSE_CLOUDS = 1, 2, 4, 8, 16
+DEVICE_PTRS, NO_SYNC, SKIP_CHECKS, KEEP_STATUS, REUSE_CLOUDS, F32_ARRAYS = 1, 2, 4, 8, 16, 32
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -296,7 +296,7 @@ def rrtmg_lw(ncol, nlay, psize, dudTs, play, plev, tlay, tlev, tsfc, emis, h2ovm
              n2ovmr, o2vmr, cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, cldf, ciwp, clwp, rei, rel, iceflglw,
              liqflglw, tauaer, zm, alat, dyofyr, cloudLM, cloudMH, clearCounts, uflx, dflx, uflxc, dflxc,
              duflx_dTs, duflxc_dTs, band_output, olrb, dolrb_dTs, *, device=False, stream=None, sync=True,
-             skip_checks=False, reuse_clouds=False, taps=()):
+             skip_checks=False, reuse_clouds=False, f32=False, taps=()):
     """Drop-in for `rrtmg_lw` (LW/src/rrtmg_lw_rad.F90:15-23): same argument order and meaning;
     outputs are written in place.  Raises RrtmgxError where the reference stops.
     Returns a dict of requested intermediate taps (tests only)."""
@@ -308,11 +308,12 @@ def rrtmg_lw(ncol, nlay, psize, dudTs, play, plev, tlay, tlev, tsfc, emis, h2ovm
     a.iceflglw, a.liqflglw, a.dyofyr = int(iceflglw), int(liqflglw), int(dyofyr)
     a.cloudLM, a.cloudMH = int(cloudLM), int(cloudMH)
     a.flags = ((DEVICE_PTRS if device else 0) | (0 if sync else NO_SYNC) | (SKIP_CHECKS if skip_checks else 0) |
-               (REUSE_CLOUDS if reuse_clouds else 0))
+               (REUSE_CLOUDS if reuse_clouds else 0) | (F32_ARRAYS if f32 else 0))
+    rk = np.float32 if f32 else np.float64   # element kind of the caller's real arrays
     a.stream = stream
     loc = locals()
     for n in _LW_IN + _LW_OUT:
-        setattr(a, n, _addr(loc[n], device, keep=keep))
+        setattr(a, n, _addr(loc[n], device, dtype=rk, keep=keep))
     a.clearCounts = _addr(clearCounts, device, dtype=np.int32, keep=keep)
     bo = np.ascontiguousarray(band_output, dtype=np.int32)   # logical(16), always host
     a.band_output = bo.ctypes.data
@@ -333,7 +334,7 @@ def rrtmg_sw(rpart, ncol, nlay, scon, adjes, coszen, isolvar, play, plev, tlay, 
              asdir, asdif, aldir, aldif, cloudLM, cloudMH, normFlx, clearCounts, swuflx, swdflx, swuflxc, swdflxc,
              nirr, nirf, parr, parf, uvrr, uvrf, fswband, cotdtp, cotdhp, cotdmp, cotdlp, cotntp, cotnhp, cotnmp,
              cotnlp, do_drfband=False, drband=None, dfband=None, bndscl=None, indsolvar=None, solcycfrac=None, *,
-             device=False, stream=None, sync=True, skip_checks=False, reuse_clouds=False, taps=()):
+             device=False, stream=None, sync=True, skip_checks=False, reuse_clouds=False, f32=False, taps=()):
     """Drop-in for `rrtmg_sw` (SW/src/rrtmg_sw_rad.F90:68-124) without the MAPL handle (used by
     the reference only for timers and asserts).  Outputs are written in place."""
     if not _initialised:
@@ -345,7 +346,8 @@ def rrtmg_sw(rpart, ncol, nlay, scon, adjes, coszen, isolvar, play, plev, tlay, 
     a.cloudLM, a.cloudMH, a.iaer = int(cloudLM), int(cloudMH), int(iaer)
     a.normFlx, a.do_drfband = int(bool(normFlx)), int(bool(do_drfband))
     a.flags = ((DEVICE_PTRS if device else 0) | (0 if sync else NO_SYNC) | (SKIP_CHECKS if skip_checks else 0) |
-               (REUSE_CLOUDS if reuse_clouds else 0))
+               (REUSE_CLOUDS if reuse_clouds else 0) | (F32_ARRAYS if f32 else 0))
+    rk = np.float32 if f32 else np.float64   # element kind of the caller's real arrays
     a.stream = stream
     a.scon, a.adjes = float(scon), float(adjes)
     for n, v, cnt in (("bndscl", bndscl, 14), ("indsolvar", indsolvar, 2), ("solcycfrac", solcycfrac, 1)):
@@ -356,7 +358,7 @@ def rrtmg_sw(rpart, ncol, nlay, scon, adjes, coszen, isolvar, play, plev, tlay, 
             setattr(a, n, arr.ctypes.data)
     loc = locals()
     for n in _SW_IN + _SW_OUT:
-        setattr(a, n, _addr(loc[n], device, keep=keep))
+        setattr(a, n, _addr(loc[n], device, dtype=rk, keep=keep))
     a.clearCounts = _addr(clearCounts, device, dtype=np.int32, keep=keep)
     t, tout = (None, {})
     if taps:
@@ -405,16 +407,16 @@ def debug_divide(a, b):
 
 
 # ---- fused Run-phase glue: GEOS-native state in, GEOS-native fluxes out ---------------------------------
-def _irrad_args(n, iceflg, liqflg, device, keep):
+def _irrad_args(n, iceflg, liqflg, device, keep, f32=False):
     a = IrradArgs()
     a.ncol, a.lm, a.iceflg, a.liqflg, a.doy = int(n["ncol"]), int(n["lm"]), int(iceflg), int(liqflg), int(n["doy"])
     a.lcldmh, a.lcldlm = int(n["lcldmh"]), int(n["lcldlm"])
-    a.flags = DEVICE_PTRS if device else 0
+    a.flags = (DEVICE_PTRS if device else 0) | (F32_ARRAYS if f32 else 0)
     for k in ("co2_fixed", "o2", "ccl4", "airmw", "h2omw", "o3mw", "rgas", "grav"):
         setattr(a, k, float(n[k]))
     for k in _IRR_IN:
         v = n.get({"taua": "taua_lw", "ssaa": "ssaa_lw"}.get(k, k))
-        setattr(a, k, _addr(v, device, keep=keep))
+        setattr(a, k, _addr(v, device, dtype=np.float32 if f32 else np.float64, keep=keep))
     bo = np.ascontiguousarray(n["band_output"], dtype=np.int32)
     keep.append(bo)
     a.band_output = bo.ctypes.data
@@ -442,7 +444,7 @@ def irrad_prepare(n, iceflg=3, liqflg=1):
     return o
 
 
-def irrad_refresh(n, iceflg=3, liqflg=1, device=False, out=None):
+def irrad_refresh(n, iceflg=3, liqflg=1, device=False, out=None, f32=False):
     """One LW refresh from the GEOS-native state: what LW_Driver does between :3237 and :3547 with RRTMG
     (flip / units / TLEV / ZM -> rrtmg_lw -> unflip / sign / SFCEM / cloud fractions), fused on the device.
     Returns the native outputs: FLXU_INT ... DFDTSC (ncol,0:LM) top-down, upward negative; SFCEM_INT;
@@ -451,18 +453,19 @@ def irrad_refresh(n, iceflg=3, liqflg=1, device=False, out=None):
         init()
     keep = []
     ncol, lm = n["ncol"], n["lm"]
-    a = _irrad_args(n, iceflg, liqflg, device, keep)
+    a = _irrad_args(n, iceflg, liqflg, device, keep, f32)
+    rk = np.float32 if f32 else np.float64
     if out is None:
         if device:
             import torch
             z = lambda *sh: torch.zeros(tuple(reversed(sh)), dtype=torch.float64, device="cuda")
         else:
-            z = lambda *sh: np.zeros(sh, order="F")
+            z = lambda *sh: np.zeros(sh, dtype=rk, order="F")
         out = {k: z(ncol, lm + 1) for k in _IRR_OUT[:6]}
         out.update({k: z(ncol) for k in _IRR_OUT[6:11]})
         out["olrb"], out["dolrb_dts"] = z(16, ncol), z(16, ncol)
     for k in _IRR_OUT:
-        setattr(a, k, _addr(out[k], device, keep=keep))
+        setattr(a, k, _addr(out[k], device, dtype=rk, keep=keep))
     _check(lib().rrtmgx_irrad_refresh(C.byref(a)))
     return out
 

@@ -103,3 +103,18 @@ def test_irrad_update_bit_exact(rx, oracle):
     assert (g["olr"] > 0).all()
     only = rx.irrad_update(f, ts_int, tsinst, want=("olr", "flns"))
     np.testing.assert_array_equal(only["olr"], o["olr"])
+
+
+def test_irrad_refresh_real4_arrays(rx):
+    """The production kind: a real*4 native state through the fused glue gives the bits of the fp64 interface
+    on the widened state, rounded once."""
+    n = make_native_state(800, 72, seed=29)
+    n32 = {k: (np.asfortranarray(v, dtype=np.float32) if isinstance(v, np.ndarray) and v.dtype == np.float64 else v)
+           for k, v in n.items()}
+    n64 = {k: (np.asfortranarray(v, dtype=np.float64) if isinstance(v, np.ndarray) and v.dtype == np.float32 else v)
+           for k, v in n32.items()}
+    ref = rx.irrad_refresh(n64)
+    got = rx.irrad_refresh(n32, f32=True)
+    for k in ("flxu", "flxd", "flcu", "flcd", "dfdts", "dfdtsc", "sfcem", "cldtt", "cldlo"):
+        assert got[k].dtype == np.float32
+        np.testing.assert_array_equal(got[k], ref[k].astype(np.float32), err_msg=k)

@@ -195,3 +195,22 @@ def test_lw_reuse_clouds_for_removed_gas_calls(rx):
     # a different shape invalidates the kept clouds: the flag is then ignored, not trusted
     s3 = make_columns(1000, 72, seed=32)
     np.testing.assert_array_equal(rx.run_lw(s3, reuse_clouds=True)["uflx"], rx.run_lw(s3)["uflx"])
+
+
+def test_lw_real4_arrays(rx):
+    """RRTMGX_F32_ARRAYS: real*4 boundary arrays (the production kind of GEOS) are widened exactly while staged,
+    the arithmetic stays fp64, the outputs are rounded once: the same bits as the fp64 interface run on the
+    widened inputs and then rounded."""
+    s = make_columns(1500, 72, seed=41)
+    s32 = {k: (np.asfortranarray(v, dtype=np.float32) if isinstance(v, np.ndarray) and v.dtype == np.float64 else v)
+           for k, v in s.items()}
+    s64 = {k: (np.asfortranarray(v, dtype=np.float64) if isinstance(v, np.ndarray) and v.dtype == np.float32 else v)
+           for k, v in s32.items()}
+    ref = rx.run_lw(s64)
+    out = rx.alloc_lw_outputs(1500, 72)
+    out = {k: (np.asfortranarray(v, dtype=np.float32) if v.dtype == np.float64 else v) for k, v in out.items()}
+    got = rx.run_lw(s32, out=out, f32=True)
+    for k in FLUXES + ("olrb", "dolrb_dTs"):
+        assert got[k].dtype == np.float32
+        np.testing.assert_array_equal(got[k], ref[k].astype(np.float32), err_msg=k)
+    np.testing.assert_array_equal(got["clearCounts"], ref["clearCounts"])

@@ -175,3 +175,21 @@ def test_sw_reuse_clouds_with_and_without_aerosols(rx):
         np.testing.assert_array_equal(reused[k], fresh[k], err_msg=k)
     assert n3 - n2 <= (n1 - n0) - 5
     assert np.abs(fresh["swdflx"] - clean["swdflx"]).max() > 1e-4
+
+
+def test_sw_real4_arrays(rx):
+    """RRTMGX_F32_ARRAYS on the SW path: same bits as the fp64 interface on the widened inputs, rounded once."""
+    s = make_columns(1500, 72, seed=42)
+    s32 = {k: (np.asfortranarray(v, dtype=np.float32) if isinstance(v, np.ndarray) and v.dtype == np.float64 else v)
+           for k, v in s.items()}
+    s64 = {k: (np.asfortranarray(v, dtype=np.float64) if isinstance(v, np.ndarray) and v.dtype == np.float32 else v)
+           for k, v in s32.items()}
+    ref = rx.run_sw(s64)
+    out = rx.alloc_sw_outputs(1500, 72)
+    out = {k: (np.asfortranarray(v, dtype=np.float32) if v.dtype == np.float64 else v) for k, v in out.items()}
+    got = rx.run_sw(s32, out=out, f32=True)
+    for k in ("swuflx", "swdflx", "swuflxc", "swdflxc", "nirr", "nirf", "parr", "parf", "uvrr", "uvrf", "fswband",
+              "cotntp", "cotdtp"):
+        assert got[k].dtype == np.float32
+        np.testing.assert_array_equal(got[k], ref[k].astype(np.float32), err_msg=k)
+    np.testing.assert_array_equal(got["clearCounts"], ref["clearCounts"])
