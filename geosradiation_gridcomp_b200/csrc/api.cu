@@ -164,8 +164,9 @@ size_t pick_chunk(int ncol, int nlay, size_t per_col_bytes, bool host_mode) {
     if (g.chunk_cols) return std::min<size_t>(std::min<size_t>(g.chunk_cols, chunk_cap(nlay)), (size_t)ncol);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    // scratch budget per path: 30% of what is free, at most 40 GiB (B200: 180 GB of HBM3e)
-    size_t budget = std::min<size_t>(free_b / 10 * 3, (size_t)40 << 30);
+    // scratch budget per path: 45% of what is free, at most 80 GiB (B200: 180 GB of HBM3e; the SW path
+    // holds 1.1 MB per column, so this is what lets it run 65 536-column chunks: fewer, fuller launches)
+    size_t budget = std::min<size_t>(free_b / 100 * 45, (size_t)80 << 30);
     size_t nc = std::max<size_t>(1024, budget / std::max<size_t>(per_col_bytes, 1));
     nc = std::min<size_t>(std::min<size_t>(nc, 65536), chunk_cap(nlay));
     // host arrays: smaller chunks shorten the fill/drain of the H2D -> kernels -> D2H pipeline
