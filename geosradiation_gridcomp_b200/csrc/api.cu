@@ -79,6 +79,8 @@ bool ok(cudaError_t e) { return e == cudaSuccess; }
 
 int grow(Slab &s, size_t bytes) {
     if (s.cap >= bytes) return 0;
+    lw_forget_clouds();   // a re-grown slab holds nothing a later RRTMGX_REUSE_CLOUDS call could keep
+    sw_forget_clouds();
     if (s.base) cudaFree(s.base);
     s.base = nullptr;
     s.cap = 0;
@@ -399,6 +401,8 @@ int rrtmgx_finalize(void) {
     cudaDeviceSynchronize();
     path_free(g.lw);
     path_free(g.sw);
+    lw_forget_clouds();
+    sw_forget_clouds();
     if (g.d_arena) cudaFree(g.d_arena);
     g.d_arena = nullptr;
     g.ready = false;
@@ -1123,5 +1127,6 @@ int rrtmgx_solar_prepare(const RrtmgxSolarArgs *a, RrtmgxSwArgs *sw) {
 #ifndef RRTMGX_WITH_SW
 namespace rrtmgx {
 int sw_upload_tables(const HostTables &, const double *) { return 0; }
+void sw_forget_clouds() {}
 }
 #endif

@@ -97,6 +97,9 @@ int sw_run_chunk(const RrtmgxSwArgs *a, const SwSolar &sol, int col0, int nc, co
                  const KissJump *d_jumps, Slab &slab, int *d_err, cudaStream_t stream,
                  cudaStream_t *side, int nside, cudaEvent_t *ev, const RrtmgxTaps *taps, int *d_negpos);
 
+void lw_forget_clouds();   // drop what RRTMGX_REUSE_CLOUDS would reuse (slab freed or re-grown)
+void sw_forget_clouds();
+
 // generic helpers (api.cu)
 // perm[0..nc): the chunk's columns with any cldf > 0 first, the cloud-free ones after (device)
 int build_cloud_partition(int ld, int col0, int nc, int nlay, const double *cldf, int *perm, unsigned char *flags,

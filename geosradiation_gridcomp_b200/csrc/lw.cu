@@ -1374,6 +1374,11 @@ size_t lw_scratch_bytes(int nc, int nlay, bool debug) {
     return b + 4096;
 }
 
+// what RRTMGX_REUSE_CLOUDS may keep from the previous call of this path (see lw_run_chunk)
+struct CloudCache { const char *base = nullptr; int nc = 0, nlay = 0, ld = 0; bool perm = false, valid = false; };
+static CloudCache g_lw_cloud_cache;
+void lw_forget_clouds() { g_lw_cloud_cache = CloudCache(); }
+
 int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp, const KissJump *d_jumps,
                  Slab &slab, int *d_err, cudaStream_t stream, cudaStream_t *side, int nside, cudaEvent_t *ev,
                  const RrtmgxTaps *taps, int *d_negpos) {
@@ -1392,8 +1397,7 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
 
     // RRTMGX_REUSE_CLOUDS: the previous call left this chunk's column grouping, McICA mask, cloud optical
     // depths and clear counts in the slab (same carve: same shape, same slab, whole call in one chunk)
-    struct CloudCache { const char *base = nullptr; int nc = 0, nlay = 0, ld = 0; bool perm = false, valid = false; };
-    static CloudCache cache;
+    CloudCache &cache = g_lw_cloud_cache;
     const bool one_chunk = col0 == 0 && nc == ld && !taps;
     const bool reuse = (a->flags & RRTMGX_REUSE_CLOUDS) && one_chunk && cache.valid && cache.base == slab.base &&
                        cache.nc == nc && cache.nlay == nlay && cache.ld == ld;
