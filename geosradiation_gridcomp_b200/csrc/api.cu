@@ -49,6 +49,7 @@ struct Path {   // per-path (LW or SW) execution resources
     Slab slab;            // kernel scratch
     Slab stage[2];        // host-pointer mode: device copies of one chunk's boundary arrays
     Slab glue;            // fused Run-phase glue: the RRTMG argument arrays of one chunk
+    Slab zeros;           // removed-gas runs: the array that stands in for the zeroed gas
     KissJump *d_jumps = nullptr;
     int jumps_nlay = -1, jumps_inhomo = -1;
     int *d_err = nullptr;      // [0] trap code, [1] first negative-input position
@@ -119,6 +120,8 @@ void path_free(Path &p) {
     }
     if (p.slab.base) cudaFree(p.slab.base);
     for (auto &s : p.stage) if (s.base) cudaFree(s.base);
+    if (p.glue.base) cudaFree(p.glue.base);
+    if (p.zeros.base) cudaFree(p.zeros.base);
     if (p.d_jumps) cudaFree(p.d_jumps);
     if (p.d_err) cudaFree(p.d_err);
     p = Path();
@@ -494,7 +497,9 @@ int rrtmgx_sw_status(void) {
     return g.sw.last_status;
 }
 
-int rrtmgx_lw_run(const RrtmgxLwArgs *a) {
+int rrtmgx_lw_run(const RrtmgxLwArgs *a) { return rrtmgx_lw_run_variants(a, nullptr); }
+
+int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *var) {
     if (!g.ready) return RRTMGX_ENOTINIT;
     // the CUDA current device is per host thread: callers may run LW and SW from different threads
     if (!ok(cudaSetDevice(g.device))) { cudaGetLastError(); return RRTMGX_ENODEVICE; }
@@ -502,6 +507,11 @@ int rrtmgx_lw_run(const RrtmgxLwArgs *a) {
     if (a->cloudLM == a->cloudMH) return RRTMGX_ESUPERLAYER;   // cloud_subcol_gen.F90:762-766
     if (a->iceflglw < 0 || a->iceflglw > 4) return RRTMGX_EICEFLAG;
     if (a->liqflglw != 1) return RRTMGX_ELIQFLAG;
+    const int nvar = var ? var->nvar : 0;
+    if (nvar < 0 || nvar > 64 || (nvar && (!var->gas || !var->uflx || !var->dflx || (a->dudTs && !var->duflx_dTs))))
+        return RRTMGX_EARG;
+    for (int v = 0; v < nvar; ++v)
+        if (var->gas[v] < RRTMGX_GAS_H2O || var->gas[v] > RRTMGX_GAS_HCFC22) return RRTMGX_EARG;
     Path &p = g.lw;
     const bool devptr = a->flags & RRTMGX_DEVICE_PTRS;
     if ((a->flags & RRTMGX_NO_SYNC) && !devptr) return RRTMGX_EARG;
@@ -526,6 +536,18 @@ int rrtmgx_lw_run(const RrtmgxLwArgs *a) {
         !ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, stream)))
         return RRTMGX_ECUDA;
 
+    // removed-gas runs: a device array of zeros stands in for the gas (as large as one staged chunk or the whole
+    // device-resident call), d_var = the (.., nvar) flux arrays as the device sees them
+    const double *d_zero = nullptr;
+    double *d_var[3] = {nullptr, nullptr, nullptr};
+    if (nvar) {
+        const size_t nz = (size_t)(devptr ? ncol : (int)std::min<size_t>(chunk, ncol)) * nlay;
+        if (int rc = grow(p.zeros, nz * sizeof(double) + 256)) return rc;
+        if (!ok(cudaMemsetAsync(p.zeros.base, 0, nz * sizeof(double), stream))) return RRTMGX_ECUDA;
+        d_zero = (const double *)p.zeros.base;
+        d_var[0] = var->uflx; d_var[1] = var->dflx; d_var[2] = var->duflx_dTs;
+    }
+
     auto run_chunks_device = [&](const RrtmgxLwArgs &da) -> int {
         const int n = da.ncol;
         if (!(da.flags & RRTMGX_SKIP_CHECKS)) {
@@ -539,15 +561,29 @@ int rrtmgx_lw_run(const RrtmgxLwArgs *a) {
             for (int i = 0; i < (int)(sizeof chk / sizeof chk[0]); ++i)
                 launch_check_negative(chk[i].x, chk[i].cnt, i, p.d_err + 1, stream);
         }
+        // chunk by chunk: the removed-gas runs of the chunk (gas array replaced by zeros, fluxes into slab v of the
+        // variant arrays), then the run with every gas; all of them on the clouds the first one generated
+        const size_t vslab = (size_t)n * (nlay + 1);
         for (size_t col0 = 0; col0 < (size_t)n; col0 += chunk) {
             const int nc = (int)std::min(chunk, (size_t)n - col0);
-            if (int rc = lw_run_chunk(&da, (int)col0, nc, mp, p.d_jumps, p.slab, p.d_err, stream, p.side, NSIDE, p.ev,
-                                      taps, p.d_err + 1))
-                return rc;
+            for (int v = 0; v <= nvar; ++v) {
+                RrtmgxLwArgs dv = da;
+                if (v < nvar) {
+                    const double **gasp[] = {nullptr, &dv.h2ovmr, &dv.o3vmr, &dv.co2vmr, &dv.ch4vmr, &dv.n2ovmr,
+                                             &dv.cfc11vmr, &dv.cfc12vmr, &dv.cfc22vmr};
+                    // a zero array with the leading dimension of the call: rows of the gas array are n apart
+                    *gasp[var->gas[v]] = d_zero;
+                    dv.uflx = d_var[0] + v * vslab; dv.dflx = d_var[1] + v * vslab;
+                    if (da.dudTs) dv.duflx_dTs = d_var[2] + v * vslab;
+                }
+                if (v > 0) dv.flags |= RRTMGX_REUSE_CLOUDS;
+                if (int rc = lw_run_chunk(&dv, (int)col0, nc, mp, p.d_jumps, p.slab, p.d_err, stream, p.side, NSIDE, p.ev,
+                                          taps, p.d_err + 1))
+                    return rc;
+            }
         }
         return 0;
     };
-
     if (devptr) {
         if (int rc = run_chunks_device(*a)) return rc;
         p.pending = true;
@@ -586,6 +622,8 @@ int rrtmgx_lw_run(const RrtmgxLwArgs *a) {
         arrs.push_back({a->olrb, (void **)&ca.olrb, 16, esz, true, true, true, f32});
         if (a->dudTs) arrs.push_back({a->dolrb_dTs, (void **)&ca.dolrb_dTs, 16, esz, true, true, true, f32});
     }
+    for (int k = 0; k < 3 && nvar; ++k)   // (ncol, nlay+1, nvar): nvar*(nlay+1) rows of ncol
+        if (d_var[k]) arrs.push_back({d_var[k], (void **)&d_var[k], (size_t)nvar * L1, esz, false, false, true, f32});
     int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxLwArgs &c, int nc) -> int {
         (void)nc;
         c.flags |= RRTMGX_DEVICE_PTRS;

@@ -1375,7 +1375,7 @@ size_t lw_scratch_bytes(int nc, int nlay, bool debug) {
 }
 
 // what RRTMGX_REUSE_CLOUDS may keep from the previous call of this path (see lw_run_chunk)
-struct CloudCache { const char *base = nullptr; int nc = 0, nlay = 0, ld = 0; bool perm = false, valid = false; };
+struct CloudCache { const char *base = nullptr; int col0 = 0, nc = 0, nlay = 0, ld = 0; bool perm = false, valid = false; };
 static CloudCache g_lw_cloud_cache;
 void lw_forget_clouds() { g_lw_cloud_cache = CloudCache(); }
 
@@ -1398,9 +1398,10 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
     // RRTMGX_REUSE_CLOUDS: the previous call left this chunk's column grouping, McICA mask, cloud optical
     // depths and clear counts in the slab (same carve: same shape, same slab, whole call in one chunk)
     CloudCache &cache = g_lw_cloud_cache;
-    const bool one_chunk = col0 == 0 && nc == ld && !taps;
-    const bool reuse = (a->flags & RRTMGX_REUSE_CLOUDS) && one_chunk && cache.valid && cache.base == slab.base &&
-                       cache.nc == nc && cache.nlay == nlay && cache.ld == ld;
+    // the slab holds the clouds of ONE chunk: the previous run of this path must have been this very chunk
+    const bool keep = !taps;
+    const bool reuse = (a->flags & RRTMGX_REUSE_CLOUDS) && keep && cache.valid && cache.base == slab.base &&
+                       cache.col0 == col0 && cache.nc == nc && cache.nlay == nlay && cache.ld == ld;
     const int *perm = nullptr;
     if (reuse) {
         perm = cache.perm ? W.perm : nullptr;
@@ -1435,11 +1436,11 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
                       dim3(MCICA_XS, MCICA_YC), 0, stream, ld, col0, perm, nc, nlay, 140, mp, d_jumps, W.seeds, W.t_alpha,
                       W.t_rcorr, W.t_cld, a->cldf, a->ciwp, a->clwp, 1.e-20, a->cloudLM, a->cloudMH,
                       perm ? (const int *)W.ptmp : nullptr, a->clearCounts, W.cloudy_any, W.mask, opt, d_err);
-        if (one_chunk) {
+        if (keep) {
             for (int k = 0; k < 4; ++k)
                 cudaMemcpyAsync(W.clear_save + (size_t)k * nc, a->clearCounts + (size_t)k * ld + col0,
                                 sizeof(int32_t) * (size_t)nc, cudaMemcpyDeviceToDevice, stream);
-            cache = {slab.base, nc, nlay, ld, perm != nullptr, true};
+            cache = {slab.base, col0, nc, nlay, ld, perm != nullptr, true};
         }
     }
 

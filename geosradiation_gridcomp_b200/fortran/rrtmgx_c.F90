@@ -45,6 +45,13 @@ module rrtmgx_c
       type(c_ptr) :: uflx, dflx, uflxc, dflxc, duflx_dTs, duflxc_dTs, olrb, dolrb_dTs
    end type
 
+   ! field order == RrtmgxLwVariants in include/rrtmgx.h; gas: 1 H2O 2 O3 3 CO2 4 CH4 5 N2O 6 CFC11 7 CFC12 8 HCFC22
+   type, bind(C) :: rrtmgx_lw_variants
+      integer(c_int) :: nvar
+      type(c_ptr) :: gas
+      type(c_ptr) :: uflx, dflx, duflx_dTs
+   end type
+
    ! field order == RrtmgxSwArgs in include/rrtmgx.h
    type, bind(C) :: rrtmgx_sw_args
       integer(c_int) :: ncol, nlay, rpart, isolvar, iceflgsw, liqflgsw, dyofyr, cloudLM, cloudMH
@@ -115,6 +122,12 @@ module rrtmgx_c
       integer(c_int) function rrtmgx_lw_run(a) bind(C, name='rrtmgx_lw_run')
          import :: c_int, rrtmgx_lw_args
          type(rrtmgx_lw_args), intent(in) :: a
+      end function
+      ! removed-gas loop + main call in one (IRR:3405-3478); v == RrtmgxLwVariants
+      integer(c_int) function rrtmgx_lw_run_variants(a, v) bind(C, name='rrtmgx_lw_run_variants')
+         import :: c_int, rrtmgx_lw_args, rrtmgx_lw_variants
+         type(rrtmgx_lw_args), intent(in) :: a
+         type(rrtmgx_lw_variants), intent(in) :: v
       end function
       integer(c_int) function rrtmgx_sw_run(a) bind(C, name='rrtmgx_sw_run')
          import :: c_int, rrtmgx_sw_args

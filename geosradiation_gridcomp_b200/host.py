@@ -56,6 +56,12 @@ class LwArgs(C.Structure):
                 [(n, _vp) for n in _LW_OUT])
 
 
+class LwVariants(C.Structure):
+    _fields_ = [("nvar", C.c_int), ("gas", _vp), ("uflx", _vp), ("dflx", _vp), ("duflx_dTs", _vp)]
+
+
+GAS = {"H2O": 1, "O3": 2, "CO2": 3, "CH4": 4, "N2O": 5, "CFC11": 6, "CFC12": 7, "HCFC22": 8}   # RRTMGX_GAS_*
+
 _SW_IN = ["coszen", "play", "plev", "tlay", "h2ovmr", "o3vmr", "co2vmr", "ch4vmr", "o2vmr", "cld", "ciwp",
           "clwp", "rei", "rel", "zm", "alat", "tauaer", "ssaaer", "asmaer", "asdir", "asdif", "aldir", "aldif"]
 _SW_OUT = ["swuflx", "swdflx", "swuflxc", "swdflxc", "nirr", "nirf", "parr", "parf", "uvrr", "uvrf", "fswband",
@@ -143,6 +149,7 @@ def lib():
         L.rrtmgx_set_taps.argtypes = [C.POINTER(Taps), C.POINTER(Taps)]
         L.rrtmgx_table.restype = _dp
         L.rrtmgx_table.argtypes = [C.c_char_p, C.c_char_p, C.c_int, _ip]
+        L.rrtmgx_lw_run_variants.argtypes = [C.POINTER(LwArgs), C.POINTER(LwVariants)]
         L.rrtmgx_irrad_refresh.argtypes = [C.POINTER(IrradArgs)]
         L.rrtmgx_irrad_prepare.argtypes = [C.POINTER(IrradArgs), C.POINTER(LwArgs)]
         L.rrtmgx_irrad_update.argtypes = [C.POINTER(IrradUpdateArgs)]
@@ -296,10 +303,12 @@ def rrtmg_lw(ncol, nlay, psize, dudTs, play, plev, tlay, tlev, tsfc, emis, h2ovm
              n2ovmr, o2vmr, cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, cldf, ciwp, clwp, rei, rel, iceflglw,
              liqflglw, tauaer, zm, alat, dyofyr, cloudLM, cloudMH, clearCounts, uflx, dflx, uflxc, dflxc,
              duflx_dTs, duflxc_dTs, band_output, olrb, dolrb_dTs, *, device=False, stream=None, sync=True,
-             skip_checks=False, reuse_clouds=False, f32=False, taps=()):
+             skip_checks=False, reuse_clouds=False, f32=False, taps=(), rats=None):
     """Drop-in for `rrtmg_lw` (LW/src/rrtmg_lw_rad.F90:15-23): same argument order and meaning;
     outputs are written in place.  Raises RrtmgxError where the reference stops.
-    Returns a dict of requested intermediate taps (tests only)."""
+    Returns a dict of requested intermediate taps (tests only).
+    rats = (names, uflxrat, dflxrat, duflx_dt_rat): the removed-gas loop of the LW driver in the same call
+    (IRR:3405-3468), arrays (ncol,nlay+1,len(names))."""
     if not _initialised:
         init()
     keep = []
@@ -322,7 +331,15 @@ def rrtmg_lw(ncol, nlay, psize, dudTs, play, plev, tlay, tlev, tsfc, emis, h2ovm
         t, tout = _new_taps(taps, ncol, nlay, NGPTLW)
         lib().rrtmgx_set_taps(C.byref(t), None)
     try:
-        _check(lib().rrtmgx_lw_run(C.byref(a)))
+        if rats is None:
+            _check(lib().rrtmgx_lw_run(C.byref(a)))
+        else:
+            names, ur, dr, dur = rats
+            v = LwVariants()
+            gas = np.array([GAS[n] for n in names], dtype=np.int32)
+            v.nvar, v.gas = len(names), gas.ctypes.data
+            v.uflx, v.dflx, v.duflx_dTs = (_addr(x, device, dtype=rk, keep=keep) for x in (ur, dr, dur))
+            _check(lib().rrtmgx_lw_run_variants(C.byref(a), C.byref(v)))
     finally:
         if taps:
             lib().rrtmgx_set_taps(None, None)

@@ -163,6 +163,21 @@ typedef struct {
 } RrtmgxSwArgs;
 
 int rrtmgx_lw_run(const RrtmgxLwArgs *a);
+
+/* The removed-gas diagnostic loop of the LW driver in one call (GEOS_IrradGridComp.F90:3405-3468 followed by
+ * the main call :3471-3478): for n = 1..nvar rrtmg_lw is run with the gas gas[n] zeroed and its uflx, dflx and
+ * duflx_dTs written to slab n of the (ncol,nlay+1,nvar) arrays below, then once with every gas, into the arrays
+ * of `a`.  (Like the loop it replaces, the variants leave their uflxc/dflxc/duflxc_dTs/olrb/clearCounts in the
+ * arrays of `a`, where the main call overwrites them.)  The inputs cross PCIe once and every run of a chunk
+ * shares its McICA subcolumns and cloud optics; results are those of the separate calls, bit for bit. */
+enum { RRTMGX_GAS_H2O = 1, RRTMGX_GAS_O3, RRTMGX_GAS_CO2, RRTMGX_GAS_CH4, RRTMGX_GAS_N2O, RRTMGX_GAS_CFC11,
+       RRTMGX_GAS_CFC12, RRTMGX_GAS_HCFC22 };
+typedef struct {
+    int nvar;                                 /* number of removed-gas runs (0: same as rrtmgx_lw_run)        */
+    const int32_t *gas;                       /* (nvar) RRTMGX_GAS_*, host                                     */
+    double *uflx, *dflx, *duflx_dTs;          /* (ncol,nlay+1,nvar): UFLXRAT, DFLXRAT, DUFLX_DT_RAT            */
+} RrtmgxLwVariants;
+int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *v);
 int rrtmgx_sw_run(const RrtmgxSwArgs *a);
 /* status of the last RRTMGX_NO_SYNC run on that path (synchronises its stream) */
 int rrtmgx_lw_status(void);

@@ -214,3 +214,41 @@ def test_lw_real4_arrays(rx):
         assert got[k].dtype == np.float32
         np.testing.assert_array_equal(got[k], ref[k].astype(np.float32), err_msg=k)
     np.testing.assert_array_equal(got["clearCounts"], ref["clearCounts"])
+
+
+def test_lw_removed_gas_loop_in_one_call(rx):
+    """rrtmgx_lw_run_variants = the removed-gas loop of LW_Driver (IRR:3405-3468) plus the main call: the same
+    bits as the separate calls, over several chunks of host arrays and with device pointers."""
+    import torch
+    names = ("CH4", "H2O", "CFC12")
+    key = {"CH4": "ch4vmr", "H2O": "h2ovmr", "CFC12": "cfc12vmr"}
+    ncol, nlay = 20000, 72            # host arrays: two staged chunks
+    s = make_columns(ncol, nlay, seed=51)
+    sep = []
+    for n in names:
+        s2 = dict(s)
+        s2[key[n]] = np.zeros_like(s[key[n]], order="F")
+        sep.append(rx.run_lw(s2))
+    main = rx.run_lw(s)
+    rat = [np.zeros((ncol, nlay + 1, len(names)), order="F") for _ in range(3)]
+    n0 = rx.launch_count()
+    got = rx.run_lw(s, rats=(names, *rat))
+    launches = rx.launch_count() - n0
+    for k in FLUXES + ("olrb", "dolrb_dTs", "clearCounts"):
+        np.testing.assert_array_equal(got[k], main[k], err_msg=k)
+    for i, n in enumerate(names):
+        np.testing.assert_array_equal(rat[0][:, :, i], sep[i]["uflx"], err_msg=n)
+        np.testing.assert_array_equal(rat[1][:, :, i], sep[i]["dflx"], err_msg=n)
+        np.testing.assert_array_equal(rat[2][:, :, i], sep[i]["duflx_dTs"], err_msg=n)
+    assert np.abs(sep[1]["uflx"] - main["uflx"]).max() > 1.0      # removing water vapour matters
+    # device pointers
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).cuda()
+    d = {k: (dev(v) if isinstance(v, np.ndarray) and v.dtype == np.float64 else v) for k, v in s.items()}
+    o = {k: dev(v) for k, v in rx.alloc_lw_outputs(ncol, nlay).items()}
+    drat = [torch.zeros((len(names), nlay + 1, ncol), dtype=torch.float64, device="cuda") for _ in range(3)]
+    rx.run_lw(d, out=o, device=True, rats=(names, *drat))
+    np.testing.assert_array_equal(o["uflx"].cpu().numpy().T, main["uflx"])
+    for i in range(len(names)):
+        np.testing.assert_array_equal(drat[0][i].cpu().numpy().T, sep[i]["uflx"])
+        np.testing.assert_array_equal(drat[2][i].cpu().numpy().T, sep[i]["duflx_dTs"])
+    assert launches > 0
