@@ -685,8 +685,11 @@ int rrtmgx_debug_divide(size_t n, const double *a, const double *b, double *q_fa
 
 #ifndef RRTMGX_WITH_SW
 int rrtmgx_sw_run(const RrtmgxSwArgs *) { return RRTMGX_EARG; }
+int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *, const RrtmgxSwNoAerosol *) { return RRTMGX_EARG; }
 #else
-int rrtmgx_sw_run(const RrtmgxSwArgs *a) {
+int rrtmgx_sw_run(const RrtmgxSwArgs *a) { return rrtmgx_sw_run_with_clean(a, nullptr); }
+
+int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *a, const RrtmgxSwNoAerosol *na) {
     if (!g.ready) return RRTMGX_ENOTINIT;
     // the CUDA current device is per host thread: callers may run LW and SW from different threads
     if (!ok(cudaSetDevice(g.device))) { cudaGetLastError(); return RRTMGX_ENODEVICE; }
@@ -698,6 +701,9 @@ int rrtmgx_sw_run(const RrtmgxSwArgs *a) {
     const bool devptr = a->flags & RRTMGX_DEVICE_PTRS;
     if ((a->flags & RRTMGX_NO_SYNC) && !devptr) return RRTMGX_EARG;
     if ((a->flags & RRTMGX_F32_ARRAYS) && devptr) return RRTMGX_EARG;   // real*4 arrays are widened while staged
+    if (na && (!na->swuflx || !na->swdflx || !na->swuflxc || !na->swdflxc || !na->fswband)) return RRTMGX_EARG;
+    double *d_na[5] = {na ? na->swuflx : nullptr, na ? na->swdflx : nullptr, na ? na->swuflxc : nullptr,
+                       na ? na->swdflxc : nullptr, na ? na->fswband : nullptr};
     SwSolar sol;
     if (int rc = sw_solar_setup(a, g.ht, &sol)) return rc;   // rrtmg_sw_sub :889-1127
     const int ncol = a->ncol, nlay = a->nlay;
@@ -734,7 +740,17 @@ int rrtmgx_sw_run(const RrtmgxSwArgs *a) {
         }
         for (size_t col0 = 0; col0 < (size_t)n; col0 += chunk) {
             const int nc = (int)std::min(chunk, (size_t)n - col0);
-            if (int rc = sw_run_chunk(&da, sol, (int)col0, nc, mp, p.d_jumps, p.slab, p.d_err, stream, p.side, NSIDE,
+            if (na) {   // the no-aerosol run of the chunk first (SOL:3249-3258), its fluxes into the NA arrays
+                RrtmgxSwArgs dv = da;
+                dv.iaer = 0;
+                dv.swuflx = d_na[0]; dv.swdflx = d_na[1]; dv.swuflxc = d_na[2]; dv.swdflxc = d_na[3]; dv.fswband = d_na[4];
+                if (int rc = sw_run_chunk(&dv, sol, (int)col0, nc, mp, p.d_jumps, p.slab, p.d_err, stream, p.side, NSIDE,
+                                          p.ev, taps, p.d_err + 1))
+                    return rc;
+            }
+            RrtmgxSwArgs dm = da;
+            if (na) dm.flags |= RRTMGX_REUSE_CLOUDS;
+            if (int rc = sw_run_chunk(&dm, sol, (int)col0, nc, mp, p.d_jumps, p.slab, p.d_err, stream, p.side, NSIDE,
                                       p.ev, taps, p.d_err + 1))
                 return rc;
         }
@@ -776,6 +792,10 @@ int rrtmgx_sw_run(const RrtmgxSwArgs *a) {
     out(a->cotdlp, &ca.cotdlp, 1); out(a->cotntp, &ca.cotntp, 1); out(a->cotnhp, &ca.cotnhp, 1);
     out(a->cotnmp, &ca.cotnmp, 1); out(a->cotnlp, &ca.cotnlp, 1);
     if (a->do_drfband) { out(a->drband, &ca.drband, 14); out(a->dfband, &ca.dfband, 14); }
+    if (na) {
+        for (int k = 0; k < 4; ++k) arrs.push_back({d_na[k], (void **)&d_na[k], L1, esz, false, false, true, f32});
+        arrs.push_back({d_na[4], (void **)&d_na[4], 14, esz, false, false, true, f32});
+    }
     int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxSwArgs &c, int nc) -> int {
         (void)nc;
         c.flags |= RRTMGX_DEVICE_PTRS;

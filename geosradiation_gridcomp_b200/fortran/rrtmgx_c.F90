@@ -52,6 +52,11 @@ module rrtmgx_c
       type(c_ptr) :: uflx, dflx, duflx_dTs
    end type
 
+   ! field order == RrtmgxSwNoAerosol in include/rrtmgx.h
+   type, bind(C) :: rrtmgx_sw_no_aerosol
+      type(c_ptr) :: swuflx, swdflx, swuflxc, swdflxc, fswband
+   end type
+
    ! field order == RrtmgxSwArgs in include/rrtmgx.h
    type, bind(C) :: rrtmgx_sw_args
       integer(c_int) :: ncol, nlay, rpart, isolvar, iceflgsw, liqflgsw, dyofyr, cloudLM, cloudMH
@@ -140,6 +145,12 @@ module rrtmgx_c
       integer(c_int) function rrtmgx_solar_refresh(a) bind(C, name='rrtmgx_solar_refresh')
          import :: c_int, rrtmgx_solar_args
          type(rrtmgx_solar_args), intent(in) :: a
+      end function
+      ! no-aerosol + regular pass in one (SOL:3249-3287)
+      integer(c_int) function rrtmgx_sw_run_with_clean(a, na) bind(C, name='rrtmgx_sw_run_with_clean')
+         import :: c_int, rrtmgx_sw_args, rrtmgx_sw_no_aerosol
+         type(rrtmgx_sw_args), intent(in) :: a
+         type(rrtmgx_sw_no_aerosol), intent(in) :: na
       end function
       integer(c_int) function rrtmgx_heating_rate(ncol, nlay, fnet, plev, hr, grav, cp, flags, stream) &
             bind(C, name='rrtmgx_heating_rate')

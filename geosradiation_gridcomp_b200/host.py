@@ -56,6 +56,10 @@ class LwArgs(C.Structure):
                 [(n, _vp) for n in _LW_OUT])
 
 
+class SwNoAerosol(C.Structure):
+    _fields_ = [(n, _vp) for n in ("swuflx", "swdflx", "swuflxc", "swdflxc", "fswband")]
+
+
 class LwVariants(C.Structure):
     _fields_ = [("nvar", C.c_int), ("gas", _vp), ("uflx", _vp), ("dflx", _vp), ("duflx_dTs", _vp)]
 
@@ -149,6 +153,7 @@ def lib():
         L.rrtmgx_set_taps.argtypes = [C.POINTER(Taps), C.POINTER(Taps)]
         L.rrtmgx_table.restype = _dp
         L.rrtmgx_table.argtypes = [C.c_char_p, C.c_char_p, C.c_int, _ip]
+        L.rrtmgx_sw_run_with_clean.argtypes = [C.POINTER(SwArgs), C.POINTER(SwNoAerosol)]
         L.rrtmgx_lw_run_variants.argtypes = [C.POINTER(LwArgs), C.POINTER(LwVariants)]
         L.rrtmgx_irrad_refresh.argtypes = [C.POINTER(IrradArgs)]
         L.rrtmgx_irrad_prepare.argtypes = [C.POINTER(IrradArgs), C.POINTER(LwArgs)]
@@ -351,7 +356,8 @@ def rrtmg_sw(rpart, ncol, nlay, scon, adjes, coszen, isolvar, play, plev, tlay, 
              asdir, asdif, aldir, aldif, cloudLM, cloudMH, normFlx, clearCounts, swuflx, swdflx, swuflxc, swdflxc,
              nirr, nirf, parr, parf, uvrr, uvrf, fswband, cotdtp, cotdhp, cotdmp, cotdlp, cotntp, cotnhp, cotnmp,
              cotnlp, do_drfband=False, drband=None, dfband=None, bndscl=None, indsolvar=None, solcycfrac=None, *,
-             device=False, stream=None, sync=True, skip_checks=False, reuse_clouds=False, f32=False, taps=()):
+             device=False, stream=None, sync=True, skip_checks=False, reuse_clouds=False, f32=False, taps=(),
+             clean=None):
     """Drop-in for `rrtmg_sw` (SW/src/rrtmg_sw_rad.F90:68-124) without the MAPL handle (used by
     the reference only for timers and asserts).  Outputs are written in place."""
     if not _initialised:
@@ -382,7 +388,13 @@ def rrtmg_sw(rpart, ncol, nlay, scon, adjes, coszen, isolvar, play, plev, tlay, 
         t, tout = _new_taps(taps, ncol, nlay, NGPTSW)
         lib().rrtmgx_set_taps(None, C.byref(t))
     try:
-        _check(lib().rrtmgx_sw_run(C.byref(a)))
+        if clean is None:
+            _check(lib().rrtmgx_sw_run(C.byref(a)))
+        else:   # dict of the no-aerosol outputs: the two SORADCORE passes in one call (SOL:3249-3287)
+            na = SwNoAerosol()
+            for n in ("swuflx", "swdflx", "swuflxc", "swdflxc", "fswband"):
+                setattr(na, n, _addr(clean[n], device, dtype=rk, keep=keep))
+            _check(lib().rrtmgx_sw_run_with_clean(C.byref(a), C.byref(na)))
     finally:
         if taps:
             lib().rrtmgx_set_taps(None, None)

@@ -179,6 +179,16 @@ typedef struct {
 } RrtmgxLwVariants;
 int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *v);
 int rrtmgx_sw_run(const RrtmgxSwArgs *a);
+
+/* The two SORADCORE passes of one solar refresh in one call (GEOS_SolarGridComp.F90:3249-3287): rrtmg_sw without
+ * aerosols (aerosol optical depth zero), its fluxes and band fluxes into `na` (FSWNA, FSWUNA, FSCNA, FSCUNA,
+ * FSWBANDNA come from these), then the regular run into the arrays of `a`.  The inputs cross PCIe once and both
+ * runs of a chunk share the McICA subcolumns, cloud optics and setcoef state; bits of the separate calls. */
+typedef struct {
+    double *swuflx, *swdflx, *swuflxc, *swdflxc;      /* (ncol,nlay+1)                                */
+    double *fswband;                                  /* (ncol,14)                                    */
+} RrtmgxSwNoAerosol;
+int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *a, const RrtmgxSwNoAerosol *na);
 /* status of the last RRTMGX_NO_SYNC run on that path (synchronises its stream) */
 int rrtmgx_lw_status(void);
 int rrtmgx_sw_status(void);

@@ -91,7 +91,7 @@ def test_fortran_shim_types_match_header_field_order():
     f90 = open(os.path.join(ROOT, "geosradiation_gridcomp_b200", "fortran", "rrtmgx_c.F90")).read()
     for tname, mirror in (("rrtmgx_lw_args", host.LwArgs), ("rrtmgx_sw_args", host.SwArgs),
                           ("rrtmgx_irrad_args", host.IrradArgs), ("rrtmgx_solar_args", host.SolarArgs),
-                          ("rrtmgx_lw_variants", host.LwVariants)):
+                          ("rrtmgx_lw_variants", host.LwVariants), ("rrtmgx_sw_no_aerosol", host.SwNoAerosol)):
         body = re.search(r"type, bind\(C\) :: %s\n(.*?)end type" % tname, f90, flags=re.S).group(1)
         fields = []
         for line in body.splitlines():

@@ -193,3 +193,19 @@ def test_sw_real4_arrays(rx):
         assert got[k].dtype == np.float32
         np.testing.assert_array_equal(got[k], ref[k].astype(np.float32), err_msg=k)
     np.testing.assert_array_equal(got["clearCounts"], ref["clearCounts"])
+
+
+def test_sw_clean_and_full_in_one_call(rx):
+    """rrtmgx_sw_run_with_clean = the no-aerosol and the regular SORADCORE pass (SOL:3249-3287) in one call:
+    the bits of the two separate calls (iaer = 0, then 10), over two staged chunks."""
+    ncol, nlay = 20000, 72
+    s = make_columns(ncol, nlay, seed=52)
+    clean = rx.run_sw(s, iaer=0)
+    full = rx.run_sw(s, iaer=10)
+    na = {k: np.zeros_like(full[k], order="F") for k in ("swuflx", "swdflx", "swuflxc", "swdflxc", "fswband")}
+    got = rx.run_sw(s, iaer=10, clean=na)
+    for k in ("swuflx", "swdflx", "swuflxc", "swdflxc", "nirr", "parf", "fswband", "cotntp", "clearCounts"):
+        np.testing.assert_array_equal(got[k], full[k], err_msg=k)
+    for k in na:
+        np.testing.assert_array_equal(na[k], clean[k], err_msg="clean " + k)
+    assert np.abs(clean["swdflx"] - full["swdflx"]).max() > 1e-4
