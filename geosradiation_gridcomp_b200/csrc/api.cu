@@ -165,13 +165,14 @@ __global__ void check_negative_kernel(const double *__restrict__ x, size_t n, in
 // (at most 32 planes of nlay*nc elements)
 size_t chunk_cap(int nlay) { return (((size_t)1 << 31) - 1) / ((size_t)32 * std::max(nlay, 1)); }
 
-size_t pick_chunk(int ncol, int nlay, size_t per_col_bytes, bool host_mode) {
+size_t pick_chunk(int ncol, int nlay, size_t per_col_bytes, bool host_mode, size_t own_bytes) {
     if (g.chunk_cols) return std::min<size_t>(std::min<size_t>(g.chunk_cols, chunk_cap(nlay)), (size_t)ncol);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    // scratch budget per path: 45% of what is free, at most 80 GiB (B200: 180 GB of HBM3e; the SW path
+    // scratch budget per path: 55% of what is free, at most 80 GiB (B200: 180 GB of HBM3e; the SW path
     // holds 1.1 MB per column, so this is what lets it run 65 536-column chunks: fewer, fuller launches)
-    size_t budget = std::min<size_t>(free_b / 100 * 45, (size_t)80 << 30);
+    // (the path's own slab from earlier calls counts as free: the choice must not shrink once it is allocated)
+    size_t budget = std::min<size_t>((free_b + own_bytes) / 100 * 55, (size_t)80 << 30);
     size_t nc = std::max<size_t>(1024, budget / std::max<size_t>(per_col_bytes, 1));
     nc = std::min<size_t>(std::min<size_t>(nc, 65536), chunk_cap(nlay));
     // host arrays: smaller chunks shorten the fill/drain of the H2D -> kernels -> D2H pipeline
@@ -524,7 +525,7 @@ int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *var) {
     const RrtmgxTaps *taps = p.has_taps ? &p.taps : nullptr;
     const bool dbg = taps && (taps->taug || taps->pfracs);
     const size_t per_col = lw_scratch_bytes(1024, nlay, dbg) / 1024;
-    size_t chunk = pick_chunk(ncol, nlay, per_col + (devptr ? 0 : 2 * (size_t)(37 * nlay + 60) * 8), !devptr);
+    size_t chunk = pick_chunk(ncol, nlay, per_col + (devptr ? 0 : 2 * (size_t)(37 * nlay + 60) * 8), !devptr, p.slab.cap);
     if (taps) {   // taps are laid out for the whole call
         if ((size_t)ncol > chunk_cap(nlay)) return RRTMGX_EARG;
         chunk = (size_t)ncol;
@@ -714,7 +715,7 @@ int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *a, const RrtmgxSwNoAerosol *na)
     const RrtmgxTaps *taps = p.has_taps ? &p.taps : nullptr;
     const bool dbg = taps && (taps->taug || taps->pfracs || taps->ssi);
     const size_t per_col = sw_scratch_bytes(1024, nlay, dbg) / 1024;
-    size_t chunk = pick_chunk(ncol, nlay, per_col + (devptr ? 0 : 2 * (size_t)(57 * nlay + 60) * 8), !devptr);
+    size_t chunk = pick_chunk(ncol, nlay, per_col + (devptr ? 0 : 2 * (size_t)(57 * nlay + 60) * 8), !devptr, p.slab.cap);
     if (taps) {   // taps are laid out for the whole call
         if ((size_t)ncol > chunk_cap(nlay)) return RRTMGX_EARG;
         chunk = (size_t)ncol;
