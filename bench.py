@@ -172,6 +172,33 @@ def workload_config(a, with_sw):
             "precision": "fp64 boundary arrays and arithmetic (promoted-real contract)"}
 
 
+def bind_near_gpu(local):
+    """Multi-rank runs: keep this rank's host threads (and, by first touch, its pinned staging arrays) on the
+    NUMA node its GPU hangs off, so eight ranks do not pull their host arrays across the socket link.
+    Returns the node or None when the topology cannot be read."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:          # 00000000:1b:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -199,6 +226,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_near_gpu(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -405,6 +433,8 @@ def main():
         "dtype": "f64", "data": "synthetic", "config": workload_config(a, with_sw),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
     }
+    if e2e is not None and world > 1:
+        e2e["host_numa_node_rank0"] = numa   # ranks are bound to the NUMA node of their GPU (bind_near_gpu)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
