@@ -309,12 +309,14 @@ __global__ void debug_divide_kernel(size_t n, const double *__restrict__ a, cons
 
 namespace {
 __global__ void cloudy_flag_kernel(int ld, int col0, int nc, int nlay, const double *__restrict__ cldf,
-                                   unsigned char *__restrict__ flag) {
+                                   unsigned char *__restrict__ flag, int *__restrict__ ktop) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nc) return;
-    bool any = false;
-    for (int k = 0; k < nlay; ++k) any |= cldf[(size_t)k * ld + col0 + c] > 0.;
-    flag[c] = any ? 1 : 0;
+    int top = -1;   // last layer (array order) that can hold cloud
+    for (int k = 0; k < nlay; ++k)
+        if (cldf[(size_t)k * ld + col0 + c] > 0.) top = k;
+    flag[c] = top >= 0 ? 1 : 0;
+    ktop[c] = top;
 }
 
 }  // namespace
@@ -332,8 +334,8 @@ size_t cloud_partition_tmp_bytes(int nc) {
 // so that a warp walks the same k-table rows, was measured: no gain on distinct columns and 5 % off
 // the host-array path, profiles/r2_cb_tuning.txt.)
 int build_cloud_partition(int ld, int col0, int nc, int nlay, const double *cldf, int *perm, unsigned char *flags,
-                          void *tmp, size_t tmp_bytes, cudaStream_t stream) {
-    RRTMGX_LAUNCH(cloudy_flag_kernel, (nc + 255) / 256, 256, 0, stream, ld, col0, nc, nlay, cldf, flags);
+                          int *ktop, void *tmp, size_t tmp_bytes, cudaStream_t stream) {
+    RRTMGX_LAUNCH(cloudy_flag_kernel, (nc + 255) / 256, 256, 0, stream, ld, col0, nc, nlay, cldf, flags, ktop);
     thrust::counting_iterator<int> it(0);
     int *d_nsel = (int *)tmp;   // first 256 bytes of tmp hold the selected count
     size_t bytes = tmp_bytes - 256;

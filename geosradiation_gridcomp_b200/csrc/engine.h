@@ -102,8 +102,9 @@ void sw_forget_clouds();
 
 // generic helpers (api.cu)
 // perm[0..nc): the chunk's columns with any cldf > 0 first, the cloud-free ones after (device)
+// ktop[0..nc): per chunk-local column (caller's order) the last layer with cldf > 0, -1 if none
 int build_cloud_partition(int ld, int col0, int nc, int nlay, const double *cldf, int *perm, unsigned char *flags,
-                          void *tmp, size_t tmp_bytes, cudaStream_t stream);
+                          int *ktop, void *tmp, size_t tmp_bytes, cudaStream_t stream);
 size_t cloud_partition_tmp_bytes(int nc);
 void launch_check_negative(const double *x, size_t n, int pos, int *d_negpos, cudaStream_t s);
 

@@ -162,6 +162,7 @@ struct LwWork {
     unsigned char *cldtrap;   // [nlay][nc] bit0: ice radius out of range, bit1: liquid radius out of range
     int *perm;                // [nc] cloudy columns first (build_cloud_partition)
     unsigned char *pflags;    // [nc]
+    int *ktop;                // [nc] last layer with cldf > 0 per chunk-local column (caller's order)
     int32_t *clear_save;      // [4][nc] clear counts of the chunk, kept for RRTMGX_REUSE_CLOUDS
     char *ptmp; size_t ptmp_bytes;
     uint32_t *mask;           // [band][nw][nc][ng] optical cloud mask (lw_cell with nw for nlay)
@@ -1355,6 +1356,7 @@ static LwWork lw_carve(Slab &slab, int nc, int nlay) {
     W.cldtrap = slab.take<unsigned char>(n2);
     W.perm = slab.take<int>(nc);
     W.pflags = slab.take<unsigned char>(nc);
+    W.ktop = slab.take<int>(nc);
     W.clear_save = slab.take<int32_t>((size_t)4 * nc);
     W.ptmp_bytes = cloud_partition_tmp_bytes(nc);
     W.ptmp = slab.take<char>(W.ptmp_bytes);
@@ -1416,7 +1418,7 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
             cudaMemsetAsync(a->clearCounts + (size_t)k * ld + col0, 0, sizeof(int32_t) * (size_t)nc, stream);
         // group cloudy and cloud-free columns (not under debug taps, whose layouts assume identity order)
         if (!taps) {
-            if (int rc = build_cloud_partition(ld, col0, nc, nlay, a->cldf, W.perm, W.pflags, W.ptmp, W.ptmp_bytes, stream))
+            if (int rc = build_cloud_partition(ld, col0, nc, nlay, a->cldf, W.perm, W.pflags, W.ktop, W.ptmp, W.ptmp_bytes, stream))
                 return rc;
             perm = W.perm;
         }
@@ -1426,16 +1428,17 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
                   a->cfc11vmr, a->cfc12vmr, a->cfc22vmr, a->ccl4vmr, d_err);
     if (!reuse) {
         RRTMGX_LAUNCH(mcica_prep_kernel, grd, blk, 0, stream, ld, col0, perm, nc, nlay, mp, a->zm, a->play, a->alat,
-                      W.seeds, W.alpha, W.rcorr);
+                      perm ? W.ktop : nullptr, W.seeds, W.alpha, W.rcorr);
         RRTMGX_LAUNCH(mcica_threshold_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, perm, nc, nlay, mp.inhomo,
-                      W.alpha, W.rcorr, a->cldf, W.t_alpha, W.t_rcorr, W.t_cld);
+                      W.alpha, W.rcorr, a->cldf, perm ? W.ktop : nullptr, W.t_alpha, W.t_rcorr, W.t_cld);
         RRTMGX_LAUNCH(lw_cldcoef_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, perm, nc, nlay, a->iceflglw, a->cldf,
                       a->rei, a->rel, W.abscoice, W.abscoliq, W.cldtrap);
         LwOptics opt{nc, nlay, W.abscoice, W.abscoliq, W.cldtrap, W.taucmc};
         RRTMGX_LAUNCH(mcica_kernel<LwOptics>, dim3(140 / MCICA_XS, (nc + MCICA_YC - 1) / MCICA_YC),
                       dim3(MCICA_XS, MCICA_YC), 0, stream, ld, col0, perm, nc, nlay, 140, mp, d_jumps, W.seeds, W.t_alpha,
                       W.t_rcorr, W.t_cld, a->cldf, a->ciwp, a->clwp, 1.e-20, a->cloudLM, a->cloudMH,
-                      perm ? (const int *)W.ptmp : nullptr, a->clearCounts, W.cloudy_any, W.mask, opt, d_err);
+                      perm ? (const int *)W.ptmp : nullptr, perm ? W.ktop : nullptr, a->clearCounts, W.cloudy_any, W.mask,
+                      opt, d_err);
         if (keep) {
             for (int k = 0; k < 4; ++k)
                 cudaMemcpyAsync(W.clear_save + (size_t)k * nc, a->clearCounts + (size_t)k * ld + col0,

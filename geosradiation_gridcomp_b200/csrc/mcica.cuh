@@ -83,12 +83,13 @@ __device__ __forceinline__ long long kiss_threshold(double t) {
 // integer thresholds of the three comparisons of the layer sweep, one thread per (layer, column)
 static __global__ void mcica_threshold_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, int inhomo,
                                               const double *__restrict__ alpha, const double *__restrict__ rcorr,
-                                              const double *__restrict__ cldf,
+                                              const double *__restrict__ cldf, const int *__restrict__ ktop,
                                               long long *__restrict__ t_alpha, long long *__restrict__ t_rcorr,
                                               long long *__restrict__ t_cld) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     if (c >= nc) return;
+    if (ktop && k > ktop[perm[c]]) return;   // the sweep of this column stops below this layer (or never starts)
     const size_t j = (size_t)k * nc + c;
     if (k > 0) {
         t_alpha[j] = kiss_threshold(alpha[j]);                 // cdf2 < alpha(k), :411
@@ -119,11 +120,13 @@ __device__ __forceinline__ double zcw_lookup(const double *__restrict__ xcw, dou
 static __global__ void mcica_prep_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, McicaParams P,
                                   const double *__restrict__ zm, const double *__restrict__ play,
                                   const double *__restrict__ alat,
+                                  const int *__restrict__ ktop,   // by caller-order column, -1: no cloud (null: unknown)
                                   uint32_t *__restrict__ seeds,   // [4][nc]
                                   double *__restrict__ alpha,     // [nlay][nc], k >= 1
                                   double *__restrict__ rcorr) {   // [nlay][nc], k >= 1
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nc) return;
+    if (ktop && ktop[perm[c]] < 0) return;   // a cloud-free column draws nothing
     const size_t col = gcol(col0, perm, c);
     const double r2d = 180.0 / 3.14159265358979323846;
     double d = alat[col] * r2d - P.adl_am3;
@@ -184,6 +187,7 @@ mcica_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, i
              const long long *__restrict__ t_cld, const double *__restrict__ cldf, const double *__restrict__ ciwp,
              const double *__restrict__ clwp, double cwp_tiny, int cloudLM, int cloudMH,
              const int *__restrict__ ncloudy,    // columns c >= *ncloudy hold no cloud at all (null: unknown)
+             const int *__restrict__ ktop,       // by caller-order column: last layer with cldf > 0 (null: unknown)
              int *__restrict__ clearCounts,      // (ld,4)
              uint32_t *__restrict__ cloudy_any,  // [nw][nc]
              uint32_t *__restrict__ mask,        // indexed by Optics::mask_index(w, nw, isub, c)
@@ -213,7 +217,10 @@ mcica_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, i
     int32_t k1 = 0, k3 = 0;   // integer draws behind cdf1 / cdf3, carried down the column
     uint32_t word = 0;
     typename Optics::State ost{};
-    for (int k = 0; k < nlay; ++k) {
+    // above the last layer that holds cloud no draw can make a cell cloudy (cdf1 >= 1 - 0 never holds) and
+    // nothing later reads the generator: the sweep stops there
+    const int klast = ktop ? ktop[perm[c]] : nlay - 1;
+    for (int k = 0; k <= klast; ++k) {
         const size_t j2 = (size_t)k * nc + c;
         const int32_t d1 = a.draw_int();
         const int32_t d2 = a.draw_int();
@@ -254,13 +261,14 @@ mcica_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, i
             }
         }
         if (optical) word |= 1u << (k & 31);
-        if ((k & 31) == 31 || k == nlay - 1) {
+        if ((k & 31) == 31 || k == klast) {
             const int w = k >> 5;
             mask[opt.mask_index(w, (nlay + 31) >> 5, isub, c)] = word;
             if (word) atomicOr(&cloudy_any[(size_t)w * nc + c], word);
             word = 0;
         }
     }
+    for (int w = (klast >> 5) + 1; w < ((nlay + 31) >> 5); ++w) mask[opt.mask_index(w, (nlay + 31) >> 5, isub, c)] = 0u;
     opt.finish(isub, c, ost);
     if (!any_all) atomicAdd(&clearCounts[col], 1);
     if (!any_high) atomicAdd(&clearCounts[(size_t)ld + col], 1);
