@@ -153,12 +153,30 @@ int ensure_jumps(Path &p, int nsub, int nlay) {
     return 0;
 }
 
-__global__ void check_negative_kernel(const double *__restrict__ x, size_t n, int pos, int *negpos) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// The reference scans every input for negative values before it starts (LW :209-318, SW :365-383) and names
+// the first offending array.  One launch scans all arrays of a call: blockIdx.y picks the array, the blocks of
+// a row stride over it with 16-byte loads; the smallest offending array position wins.
+struct NegScan {
+    const double *x[24];
+    unsigned long long n[24];
+};
+__global__ void __launch_bounds__(256) check_negative_kernel(NegScan S, int *negpos) {
+    const int a = blockIdx.y;
+    const double *__restrict__ x = S.x[a];
+    const size_t n = S.n[a], n2 = n / 2;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     bool bad = false;
-    for (; i < n; i += stride) bad |= x[i] < 0.;
-    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicMin(negpos, pos);
+    const double2 *__restrict__ x2 = reinterpret_cast<const double2 *>(x);   // arrays are 16-byte aligned slabs
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+            const double2 v = x2[i];
+            bad |= (v.x < 0.) | (v.y < 0.);
+        }
+        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) bad |= x[n - 1] < 0.;
+    } else {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) bad |= x[i] < 0.;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicMin(negpos, a);
 }
 
 // the band kernels address the per-(layer, column) planes of a chunk with 32-bit element offsets
@@ -344,10 +362,18 @@ int build_cloud_partition(int ld, int col0, int nc, int nlay, const double *cldf
                ? 0 : RRTMGX_ECUDA;
 }
 
-void launch_check_negative(const double *x, size_t n, int pos, int *d_negpos, cudaStream_t s) {
-    if (!x || !n) return;
-    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
-    RRTMGX_LAUNCH(check_negative_kernel, blocks, 256, 0, s, x, n, pos, d_negpos);
+// arrays x[i] of cnt[i] elements, position i in the reference's order of checks; null or empty arrays are skipped
+void launch_check_negative(const double *const *x, const size_t *cnt, int narr, int *d_negpos, cudaStream_t s) {
+    NegScan S{};
+    size_t most = 0;
+    for (int i = 0; i < narr && i < 24; ++i) {
+        S.x[i] = x[i];
+        S.n[i] = x[i] ? cnt[i] : 0;
+        most = std::max<size_t>(most, S.n[i]);
+    }
+    if (!most) return;
+    const unsigned bx = (unsigned)std::min<size_t>((most / 2 + 255) / 256, 148 * 2);
+    RRTMGX_LAUNCH(check_negative_kernel, dim3(std::max(bx, 1u), narr), 256, 0, s, S, d_negpos);
 }
 
 }  // namespace rrtmgx
@@ -561,8 +587,11 @@ int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *var) {
                 {da.o2vmr, n2}, {da.cfc11vmr, n2}, {da.cfc12vmr, n2}, {da.cfc22vmr, n2}, {da.ccl4vmr, n2},
                 {da.emis, (size_t)n * 16}, {da.cldf, n2}, {da.ciwp, n2}, {da.clwp, n2}, {da.rei, n2},
                 {da.rel, n2}, {da.tauaer, n2 * 16}};
-            for (int i = 0; i < (int)(sizeof chk / sizeof chk[0]); ++i)
-                launch_check_negative(chk[i].x, chk[i].cnt, i, p.d_err + 1, stream);
+            constexpr int narr = (int)(sizeof chk / sizeof chk[0]);
+            const double *xs[narr];
+            size_t cnts[narr];
+            for (int i = 0; i < narr; ++i) { xs[i] = chk[i].x; cnts[i] = chk[i].cnt; }
+            launch_check_negative(xs, cnts, narr, p.d_err + 1, stream);
         }
         // chunk by chunk: the removed-gas runs of the chunk (gas array replaced by zeros, fluxes into slab v of the
         // variant arrays), then the run with every gas; all of them on the clouds the first one generated
@@ -738,8 +767,11 @@ int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *a, const RrtmgxSwNoAerosol *na)
                 {da.ch4vmr, n2}, {da.o2vmr, n2}, {da.asdir, (size_t)n}, {da.aldir, (size_t)n}, {da.asdif, (size_t)n},
                 {da.aldif, (size_t)n}, {da.cld, n2}, {da.ciwp, n2}, {da.clwp, n2}, {da.rei, n2}, {da.rel, n2},
                 {da.tauaer, n2 * 14}, {da.ssaaer, n2 * 14}};
-            for (int i = 0; i < (int)(sizeof chk / sizeof chk[0]); ++i)
-                launch_check_negative(chk[i].x, chk[i].cnt, i, p.d_err + 1, stream);
+            constexpr int narr = (int)(sizeof chk / sizeof chk[0]);
+            const double *xs[narr];
+            size_t cnts[narr];
+            for (int i = 0; i < narr; ++i) { xs[i] = chk[i].x; cnts[i] = chk[i].cnt; }
+            launch_check_negative(xs, cnts, narr, p.d_err + 1, stream);
         }
         for (size_t col0 = 0; col0 < (size_t)n; col0 += chunk) {
             const int nc = (int)std::min(chunk, (size_t)n - col0);

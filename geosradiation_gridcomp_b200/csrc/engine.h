@@ -106,6 +106,6 @@ void sw_forget_clouds();
 int build_cloud_partition(int ld, int col0, int nc, int nlay, const double *cldf, int *perm, unsigned char *flags,
                           int *ktop, void *tmp, size_t tmp_bytes, cudaStream_t stream);
 size_t cloud_partition_tmp_bytes(int nc);
-void launch_check_negative(const double *x, size_t n, int pos, int *d_negpos, cudaStream_t s);
+void launch_check_negative(const double *const *x, const size_t *cnt, int narr, int *d_negpos, cudaStream_t s);
 
 }  // namespace rrtmgx
