@@ -1,10 +1,10 @@
-# final round-1 evidence: tests, launch list, full ncu capture of the top band / McICA kernels
-python -m pytest tests -m gpu -x -q > gpurun_out/r2k_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2k_tests.log
+# final round-1 evidence (after the McICA early exit and the fused input scan): tests, launch list, full ncu capture
+python -m pytest tests -m gpu -x -q > gpurun_out/r2u_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2u_tests.log
 CMD="python bench.py --steps 1 --warmup 1 --ncol 65536 --no-e2e --no-cpu"
-$CMD > gpurun_out/r2k_plain.log 2>&1 &&
+$CMD > gpurun_out/r2u_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread \
-    --clock-control none --csv --log-file gpurun_out/r2k_launches.csv $CMD > gpurun_out/r2k_ncu.log 2>&1
+    --clock-control none --csv --log-file gpurun_out/r2u_launches.csv $CMD > gpurun_out/r2u_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
     -k 'regex:(sw_band_kernel<\(int\)(17|20),)|(lw_band_kernel<\(int\)(3|9),)|(mcica_kernel<rrtmgx::SwOptics)' -c 5 \
-    -f -o gpurun_out/r2k_top $CMD > gpurun_out/r2k_ncu_full.log 2>&1
+    -f -o gpurun_out/r2u_top $CMD > gpurun_out/r2u_ncu_full.log 2>&1
 ls -la gpurun_out/ | tail -4
