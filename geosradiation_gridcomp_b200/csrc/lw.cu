@@ -146,10 +146,17 @@ enum LwF {
 
 struct LwWork {
     int nc, nlay;
-    int *idx;                 // [nlay][nc] packed jp|jt|jt1|indfor|indself|indminor
-    double *fbase;            // [F_COUNT][nlay][nc]
+    int *idx;                 // [tile][nlay][32] packed jp|jt|jt1|indfor|indself|indminor
+    double *fbase;            // [tile][nlay][F_COUNT][32]: the setcoef state of a 32-column tile is contiguous
     size_t n2;                // nlay*nc
-    __host__ __device__ __forceinline__ double *f(int k) const { return fbase + (size_t)k * n2; }
+    size_t n2p;               // nlay * (nc padded to 32)
+    int ncp;                  // nc padded to 32
+    // plane k of the factors, to be indexed with tf(lay, c); packed indices are indexed with ti(lay, c)
+    __host__ __device__ __forceinline__ double *f(int k) const { return fbase + (size_t)k * 32; }
+    __host__ __device__ __forceinline__ size_t ti(int lay, int c) const { return ((size_t)(c >> 5) * nlay + lay) * 32 + (c & 31); }
+    __host__ __device__ __forceinline__ size_t tf(int lay, int c) const {
+        return ((size_t)(c >> 5) * nlay + lay) * (F_COUNT * 32) + (c & 31);
+    }
     double *planklay;         // [16][nlay][nc]
     double *planklev;         // [16][nlay+1][nc]
     double *plankbnd, *dplankbnd;   // [16][nc]
@@ -215,7 +222,7 @@ lw_setcoef_kernel(int ld, int col0, const int *__restrict__ perm, LwWork W, int 
         const double h2o = h2ovmr[i];
         const double amm = (1. - h2o) * amd + h2o * amw;
         const double coldry = (pz[i] - pz[i + ld]) * 1.e3 * avogad / (1.e2 * grav * amm * (1. + h2o));
-        W.f(F_COLDRY)[(size_t)lay * nc + c] = coldry;
+        W.f(F_COLDRY)[W.tf(lay, c)] = coldry;
         const double btemp = h2o * coldry;
         amttl = amttl + coldry + btemp;
         wvttl = wvttl + btemp;
@@ -251,7 +258,7 @@ lw_setcoef_kernel(int ld, int col0, const int *__restrict__ perm, LwWork W, int 
     bool upper_found = false;
     for (int lay = 0; lay < nlay; ++lay) {
         const size_t i = (size_t)lay * ld + col;
-        const size_t j = (size_t)lay * nc + c;
+        const size_t j = W.tf(lay, c);
         const double coldry = W.f(F_COLDRY)[j];
         const double h2o = h2ovmr[i], co2 = co2vmr[i], o3 = o3vmr[i], n2o = n2ovmr[i], ch4 = ch4vmr[i],
                      o2 = o2vmr[i];
@@ -326,7 +333,7 @@ lw_setcoef_kernel(int ld, int col0, const int *__restrict__ perm, LwWork W, int 
         if (colch4 == 0.) colch4 = 1.e-32 * coldry;
 
         const double compfp = 1. - fp;
-        W.idx[j] = pack_idx(jp, jt, jt1, indfor, indself, indminor);
+        W.idx[W.ti(lay, c)] = pack_idx(jp, jt, jt1, indfor, indself, indminor);
         W.f(F_FAC10)[j] = compfp * ft;
         W.f(F_FAC00)[j] = compfp * (1. - ft);
         W.f(F_FAC11)[j] = fp * ft1;
@@ -424,16 +431,18 @@ __global__ void lw_cldcoef_kernel(int ld, int col0, const int *__restrict__ perm
     }
 }
 
-// Per-cell scratch of the LW path is g-point fastest inside a band: [band][lay][nc][ng_band], i.e. the
-// g-points of one (band, layer, column) are adjacent and the columns follow.  The McICA kernel (lanes =
-// subcolumns of a column) and the band kernels (lanes = g-point groups of a few columns) then read and
-// write contiguous runs.  `first` = first g-point of the band, `ng` its count, n2 = rows * nc.
-__device__ __forceinline__ size_t lw_cell(int first, int ng, size_t n2, int nc, int row, int c, int gi) {
-    return (size_t)first * n2 + ((size_t)row * nc + c) * ng + gi;
+// Per-cell scratch of the LW path is g-point fastest inside a band and tiled by 32 columns:
+// [band][tile][row][32 columns][ng_band], i.e. the g-points of one (band, layer, column) are adjacent, the
+// columns of a tile follow, then the layers of the tile: what a block streams is one contiguous region.  The
+// McICA kernel (lanes = subcolumns of a column) and the band kernels (lanes = g-point groups of a few columns)
+// read and write contiguous runs.  `first` = first g-point of the band, `ng` its count, rows = layers (or
+// 32-layer mask words) per column, ncp = columns padded to 32.
+__host__ __device__ __forceinline__ size_t lw_cell(int first, int ng, int rows, int ncp, int row, int c, int gi) {
+    return (size_t)first * rows * ncp + ((((size_t)(c >> 5) * rows + row) * 32) + (c & 31)) * ng + gi;
 }
 
 struct LwOptics {
-    int nc, nlay;
+    int nc, nlay, ncp;
     const double *abscoice, *abscoliq;   // [16][nlay][nc]
     const unsigned char *cldtrap;        // [nlay][nc]
     double *taucmc;                      // lw_cell layout
@@ -442,7 +451,7 @@ struct LwOptics {
     __device__ __forceinline__ size_t cell_index(int rows, int row, int ig, int c) const {
         const int ib = c_lw.ngb[ig] - 1;
         const int first = ib ? c_lw.ngs[ib - 1] : 0;
-        return lw_cell(first, c_lw.ngs[ib] - first, (size_t)rows * nc, nc, row, c, ig - first);
+        return lw_cell(first, c_lw.ngs[ib] - first, rows, ncp, row, c, ig - first);
     }
     __device__ __forceinline__ size_t mask_index(int w, int nw, int ig, int c) const { return cell_index(nw, w, ig, c); }
 
@@ -486,8 +495,7 @@ __device__ __forceinline__ Spec spec(double cola, double rat, double colb, doubl
 struct Lay {
     int jp, jt, jt1, indfor, indself, indminor;
     const double *fj;  // factor base + lay*nc + c
-    int n2;            // plane stride (F_COUNT * n2 < 2^31: chunk_cap, api.cu)
-    __device__ __forceinline__ double f(int k) const { return fj[k * n2]; }
+    __device__ __forceinline__ double f(int k) const { return fj[k * 32]; }   // planes of a tile row are 32 apart
 };
 
 // GN consecutive g-points of one table row.  The tables are g-point fastest and 16-byte aligned in
@@ -1115,11 +1123,10 @@ lw_band_kernel(const LwBandArgs A) {
     }
     // running addresses: per-(layer, column) planes by 32-bit offsets from the column's pointer, the
     // thread's cell of the lw_cell scratch by one 64-bit offset (GN adjacent elements per thread)
-    const int n2 = (int)W.n2;
-    const int *pidx = W.idx + c;
-    const double *pfac = W.fbase + c;
-    const size_t lay_cell = (size_t)NG * nc;
-    size_t koff = lw_cell(gs, NG, W.n2, nc, nlay - 1, c, G0);                 // cell (nlay-1, c, G0)
+    const int *pidx = W.idx + W.ti(0, c);          // + 32 per layer
+    const double *pfac = W.fbase + W.tf(0, c);     // + F_COUNT*32 per layer
+    constexpr int lay_cell = 32 * NG;              // layer stride of the tiled per-cell scratch
+    size_t koff = lw_cell(gs, NG, nlay, W.ncp, nlay - 1, c, G0);              // cell (nlay-1, c, G0)
     size_t aoff = ((size_t)ib * nlay + nlay - 1) * A.ld + col;                // aerosol at layer nlay-1
     const int nw = (nlay + 31) >> 5;
     uint32_t any_word = 0u, mword[GN];
@@ -1129,24 +1136,23 @@ lw_band_kernel(const LwBandArgs A) {
     for (int lay = nlay - 1; lay >= 0; --lay) {
         const int jl = lay * nc;
         if (lay > 0 && ty == 0) {   // next layer's per-(layer, column) state -> L1 while this one computes
-            prefetch_l1(pidx + jl - nc);
+            prefetch_l1(pidx + (lay - 1) * 32);
             constexpr unsigned fm = lw_band_fmask<BAND>();
 #pragma unroll
             for (int k = 0; k < F_COUNT; ++k)
-                if ((fm >> k) & 1u) prefetch_l1(pfac + k * n2 + jl - nc);
+                if ((fm >> k) & 1u) prefetch_l1(pfac + ((lay - 1) * F_COUNT + k) * 32);
             prefetch_l1(planklay + jl - nc);
             prefetch_l1(planklev + jl - nc);
             prefetch_l1(A.taua + aoff - A.ld);
         }
         if ((lay & 31) == 31 || lay == nlay - 1) {   // cloud words of the next (up to) 32 layers
             any_word = W.cloudy_any[(lay >> 5) * nc + c];
-            const uint32_t *pm = W.mask + lw_cell(gs, NG, (size_t)nw * nc, nc, lay >> 5, c, G0);
+            const uint32_t *pm = W.mask + lw_cell(gs, NG, nw, W.ncp, lay >> 5, c, G0);
             FORG mword[ig] = any_word ? pm[ig] : 0u;
         }
         Lay L;
-        L.fj = pfac + jl;
-        L.n2 = n2;
-        const int pk = pidx[jl];
+        L.fj = pfac + lay * (F_COUNT * 32);
+        const int pk = pidx[lay * 32];
         L.jp = pk & 63; L.jt = (pk >> 6) & 7; L.jt1 = (pk >> 9) & 7;
         L.indfor = (pk >> 12) & 3; L.indself = (pk >> 14) & 15; L.indminor = (pk >> 18) & 31;
         const double pavel = (BAND <= 2) ? A.pavel[(size_t)lay * A.ld + col] : 0.;
@@ -1222,19 +1228,18 @@ lw_band_kernel(const LwBandArgs A) {
         if (lay + 1 < nlay) {
             prefetch_l1(W.it + koff + lay_cell);
             if (ty == 0) {
-                prefetch_l1(pidx + jl + nc);
+                prefetch_l1(pidx + (lay + 1) * 32);
                 constexpr unsigned fm = lw_band_fmask_up<BAND>();
 #pragma unroll
                 for (int k = 0; k < F_COUNT; ++k)
-                    if ((fm >> k) & 1u) prefetch_l1(pfac + k * n2 + jl + nc);
+                    if ((fm >> k) & 1u) prefetch_l1(pfac + ((lay + 1) * F_COUNT + k) * 32);
                 prefetch_l1(planklay + jl + nc);
                 prefetch_l1(planklev + jl + 2 * nc);
             }
         }
         Lay L;
-        L.fj = pfac + jl;
-        L.n2 = n2;
-        const int pk = pidx[jl];
+        L.fj = pfac + lay * (F_COUNT * 32);
+        const int pk = pidx[lay * 32];
         L.jp = pk & 63; L.jt = (pk >> 6) & 7; L.jt1 = (pk >> 9) & 7;
         L.indfor = (pk >> 12) & 3; L.indself = (pk >> 14) & 15; L.indminor = (pk >> 18) & 31;
         lw_band_layer<BAND, GN, false>(L, lay < laytrop, 0., G0, taug, pf);
@@ -1336,8 +1341,10 @@ static LwWork lw_carve(Slab &slab, int nc, int nlay) {
     LwWork W;
     W.nc = nc; W.nlay = nlay;
     const size_t n2 = (size_t)nlay * nc, nw = (size_t)((nlay + 31) / 32);
-    W.idx = slab.take<int>(n2);
-    W.fbase = slab.take<double>((size_t)F_COUNT * n2);
+    W.ncp = (nc + 31) & ~31;
+    W.n2p = (size_t)nlay * W.ncp;
+    W.idx = slab.take<int>(W.n2p);
+    W.fbase = slab.take<double>((size_t)F_COUNT * W.n2p);
     W.n2 = n2;
     W.planklay = slab.take<double>(16 * n2);
     W.planklev = slab.take<double>((size_t)16 * (nlay + 1) * nc);
@@ -1360,10 +1367,10 @@ static LwWork lw_carve(Slab &slab, int nc, int nlay) {
     W.clear_save = slab.take<int32_t>((size_t)4 * nc);
     W.ptmp_bytes = cloud_partition_tmp_bytes(nc);
     W.ptmp = slab.take<char>(W.ptmp_bytes);
-    W.mask = slab.take<uint32_t>(nw * 140 * nc);
+    W.mask = slab.take<uint32_t>(nw * 140 * W.ncp);
     W.cloudy_any = slab.take<uint32_t>(nw * nc);
-    W.taucmc = slab.take<double>(n2 * 140);
-    W.it = slab.take<uint32_t>(n2 * 140);
+    W.taucmc = slab.take<double>(W.n2p * 140);
+    W.it = slab.take<uint32_t>(W.n2p * 140);
     W.part = slab.take<double>((size_t)16 * LP_COUNT * (nlay + 1) * nc);
     return W;
 }
@@ -1433,7 +1440,7 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
                       W.alpha, W.rcorr, a->cldf, perm ? W.ktop : nullptr, W.t_alpha, W.t_rcorr, W.t_cld);
         RRTMGX_LAUNCH(lw_cldcoef_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, perm, nc, nlay, a->iceflglw, a->cldf,
                       a->rei, a->rel, W.abscoice, W.abscoliq, W.cldtrap);
-        LwOptics opt{nc, nlay, W.abscoice, W.abscoliq, W.cldtrap, W.taucmc};
+        LwOptics opt{nc, nlay, W.ncp, W.abscoice, W.abscoliq, W.cldtrap, W.taucmc};
         RRTMGX_LAUNCH(mcica_kernel<LwOptics>, dim3(140 / MCICA_XS, (nc + MCICA_YC - 1) / MCICA_YC),
                       dim3(MCICA_XS, MCICA_YC), 0, stream, ld, col0, perm, nc, nlay, 140, mp, d_jumps, W.seeds, W.t_alpha,
                       W.t_rcorr, W.t_cld, a->cldf, a->ciwp, a->clwp, 1.e-20, a->cloudLM, a->cloudMH,
@@ -1475,20 +1482,19 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
 
     if (taps) {   // debug / parity taps: synchronous strided copies into the host arrays
         if (cudaStreamSynchronize(stream) != cudaSuccess) return RRTMGX_ECUDA;
-        const size_t n2 = (size_t)nlay * nc;
-        std::vector<int> hidx(n2);
+        std::vector<int> hidx(W.n2p);
         auto copy2d = [&](void *dst_host, const void *src_dev, size_t elem, size_t rows) {
             // chunk-local [rows][nc] -> host [rows][ld] at column col0
             cudaMemcpy2D((char *)dst_host + (size_t)col0 * elem, (size_t)ld * elem, src_dev, (size_t)nc * elem,
                          (size_t)nc * elem, rows, cudaMemcpyDeviceToHost);
         };
         if (taps->jp || taps->jt || taps->jt1 || taps->indfor || taps->indself || taps->indminor) {
-            cudaMemcpy(hidx.data(), W.idx, n2 * sizeof(int), cudaMemcpyDeviceToHost);
+            cudaMemcpy(hidx.data(), W.idx, W.n2p * sizeof(int), cudaMemcpyDeviceToHost);
             std::vector<int> hl(nc);
             cudaMemcpy(hl.data(), W.laytrop, nc * sizeof(int), cudaMemcpyDeviceToHost);
             for (int lay = 0; lay < nlay; ++lay)
                 for (int c = 0; c < nc; ++c) {
-                    const int pk = hidx[(size_t)lay * nc + c];
+                    const int pk = hidx[W.ti(lay, c)];
                     const size_t o = (size_t)lay * ld + col0 + c;
                     const bool lower = lay < hl[c];
                     if (taps->jp) taps->jp[o] = pk & 63;
@@ -1502,27 +1508,32 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
         }
         if (taps->laytrop) cudaMemcpy(taps->laytrop + col0, W.laytrop, nc * sizeof(int), cudaMemcpyDeviceToHost);
         if (taps->pwvcm) cudaMemcpy(taps->pwvcm + col0, W.pwvcm, nc * sizeof(double), cudaMemcpyDeviceToHost);
-        if (taps->fac00) copy2d(taps->fac00, W.f(F_FAC00), 8, nlay);
-        if (taps->fac01) copy2d(taps->fac01, W.f(F_FAC01), 8, nlay);
-        if (taps->fac10) copy2d(taps->fac10, W.f(F_FAC10), 8, nlay);
-        if (taps->fac11) copy2d(taps->fac11, W.f(F_FAC11), 8, nlay);
+        if (taps->fac00 || taps->fac01 || taps->fac10 || taps->fac11) {   // de-tile on the host
+            std::vector<double> hf((size_t)F_COUNT * W.n2p);
+            cudaMemcpy(hf.data(), W.fbase, hf.size() * 8, cudaMemcpyDeviceToHost);
+            double *dst[4] = {taps->fac00, taps->fac01, taps->fac10, taps->fac11};
+            const int plane[4] = {F_FAC00, F_FAC01, F_FAC10, F_FAC11};
+            for (int q = 0; q < 4; ++q)
+                if (dst[q])
+                    for (int lay = 0; lay < nlay; ++lay)
+                        for (int c = 0; c < nc; ++c)
+                            dst[q][(size_t)lay * ld + col0 + c] = hf[W.tf(lay, c) + (size_t)plane[q] * 32];
+        }
         if (taps->taug) copy2d(taps->taug, dbg_taug, 8, (size_t)nlay * 140);
         if (taps->pfracs) copy2d(taps->pfracs, dbg_pfracs, 8, (size_t)nlay * 140);
         if (taps->cldymc || taps->taucmc) {
-            std::vector<uint32_t> hm((size_t)nw * 140 * nc);
+            std::vector<uint32_t> hm((size_t)nw * 140 * W.ncp);
             std::vector<double> ht;
             cudaMemcpy(hm.data(), W.mask, hm.size() * 4, cudaMemcpyDeviceToHost);
             if (taps->taucmc) {
-                ht.resize(n2 * 140);
+                ht.resize(W.n2p * 140);
                 cudaMemcpy(ht.data(), W.taucmc, ht.size() * 8, cudaMemcpyDeviceToHost);
             }
             for (int lay = 0; lay < nlay; ++lay)
                 for (int g = 0; g < 140; ++g)
                     for (int c = 0; c < nc; ++c) {
                         const int ib = g_lw_ngb[g] - 1, first = ib ? g_lw_ngs[ib - 1] : 0, ngb = g_lw_ngs[ib] - first;
-                        auto cell = [&](size_t rows, int row) {   // lw_cell on the host
-                            return (size_t)first * rows * nc + ((size_t)row * nc + c) * ngb + (g - first);
-                        };
+                        auto cell = [&](int rows, int row) { return lw_cell(first, ngb, rows, W.ncp, row, c, g - first); };
                         const bool on = (hm[cell(nw, lay >> 5)] >> (lay & 31)) & 1u;
                         const size_t o = ((size_t)lay * 140 + g) * ld + col0 + c;
                         if (taps->cldymc) taps->cldymc[o] = on;

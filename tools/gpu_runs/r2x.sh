@@ -1,0 +1,4 @@
+# LW per-cell scratch and setcoef state tiled by 32 columns
+python -m pytest tests -m gpu -x -q > gpurun_out/r2x_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2x_tests.log
+python tools/profile_step.py 65536 72 2 > gpurun_out/r2x_prof.json 2> gpurun_out/r2x_prof.err
+python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/r2x_bench.log 2>&1
