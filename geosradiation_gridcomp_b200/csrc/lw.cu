@@ -164,7 +164,7 @@ struct LwWork {
     int *laytrop;             // [nc]
     uint32_t *seeds;          // [4][nc]
     double *alpha, *rcorr;    // [nlay][nc]
-    long long *t_alpha, *t_rcorr, *t_cld;   // [nlay][nc] integer thresholds of the McICA comparisons
+    long long *thr;           // [tile][nlay][3][32] integer thresholds of the McICA comparisons (alpha, rcorr, cld)
     double *abscoice, *abscoliq;   // [16][nlay][nc] cloud absorption coefficients per band (cloudy layers)
     unsigned char *cldtrap;   // [nlay][nc] bit0: ice radius out of range, bit1: liquid radius out of range
     int *perm;                // [nc] cloudy columns first (build_cloud_partition)
@@ -1355,9 +1355,7 @@ static LwWork lw_carve(Slab &slab, int nc, int nlay) {
     W.seeds = slab.take<uint32_t>((size_t)4 * nc);
     W.alpha = slab.take<double>(n2);
     W.rcorr = slab.take<double>(n2);
-    W.t_alpha = slab.take<long long>(n2);
-    W.t_rcorr = slab.take<long long>(n2);
-    W.t_cld = slab.take<long long>(n2);
+    W.thr = slab.take<long long>(3 * W.n2p);
     W.abscoice = slab.take<double>(16 * n2);
     W.abscoliq = slab.take<double>(16 * n2);
     W.cldtrap = slab.take<unsigned char>(n2);
@@ -1437,13 +1435,12 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
         RRTMGX_LAUNCH(mcica_prep_kernel, grd, blk, 0, stream, ld, col0, perm, nc, nlay, mp, a->zm, a->play, a->alat,
                       perm ? W.ktop : nullptr, W.seeds, W.alpha, W.rcorr);
         RRTMGX_LAUNCH(mcica_threshold_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, perm, nc, nlay, mp.inhomo,
-                      W.alpha, W.rcorr, a->cldf, perm ? W.ktop : nullptr, W.t_alpha, W.t_rcorr, W.t_cld);
+                      W.alpha, W.rcorr, a->cldf, perm ? W.ktop : nullptr, W.thr);
         RRTMGX_LAUNCH(lw_cldcoef_kernel, dim3(grd.x, nlay), blk, 0, stream, ld, col0, perm, nc, nlay, a->iceflglw, a->cldf,
                       a->rei, a->rel, W.abscoice, W.abscoliq, W.cldtrap);
         LwOptics opt{nc, nlay, W.ncp, W.abscoice, W.abscoliq, W.cldtrap, W.taucmc};
         RRTMGX_LAUNCH(mcica_kernel<LwOptics>, dim3(140 / MCICA_XS, (nc + MCICA_YC - 1) / MCICA_YC),
-                      dim3(MCICA_XS, MCICA_YC), 0, stream, ld, col0, perm, nc, nlay, 140, mp, d_jumps, W.seeds, W.t_alpha,
-                      W.t_rcorr, W.t_cld, a->cldf, a->ciwp, a->clwp, 1.e-20, a->cloudLM, a->cloudMH,
+                      dim3(MCICA_XS, MCICA_YC), 0, stream, ld, col0, perm, nc, nlay, 140, mp, d_jumps, W.seeds, W.thr, a->cldf, a->ciwp, a->clwp, 1.e-20, a->cloudLM, a->cloudMH,
                       perm ? (const int *)W.ptmp : nullptr, perm ? W.ktop : nullptr, a->clearCounts, W.cloudy_any, W.mask,
                       opt, d_err);
         if (keep) {

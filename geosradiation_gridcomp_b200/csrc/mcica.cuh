@@ -80,22 +80,29 @@ __device__ __forceinline__ long long kiss_threshold(double t) {
     return lo;
 }
 
-// integer thresholds of the three comparisons of the layer sweep, one thread per (layer, column)
+// Per-(layer, column) scratch that one column's sweep walks layer by layer is tiled by 32 columns,
+// [tile][lay][plane][32]: consecutive layers of a column are a few hundred bytes apart instead of nc*8.
+__host__ __device__ __forceinline__ size_t tile_index(int nlay, int planes, int lay, int c) {
+    return (((size_t)(c >> 5) * nlay + lay) * planes) * 32 + (c & 31);
+}
+
+// integer thresholds of the three comparisons of the layer sweep, one thread per (layer, column):
+// thr = [tile][lay][alpha, rcorr, cld][32]
 static __global__ void mcica_threshold_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, int inhomo,
                                               const double *__restrict__ alpha, const double *__restrict__ rcorr,
                                               const double *__restrict__ cldf, const int *__restrict__ ktop,
-                                              long long *__restrict__ t_alpha, long long *__restrict__ t_rcorr,
-                                              long long *__restrict__ t_cld) {
+                                              long long *__restrict__ thr) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     if (c >= nc) return;
     if (ktop && k > ktop[perm[c]]) return;   // the sweep of this column stops below this layer (or never starts)
     const size_t j = (size_t)k * nc + c;
+    long long *t = thr + tile_index(nlay, 3, k, c);
     if (k > 0) {
-        t_alpha[j] = kiss_threshold(alpha[j]);                 // cdf2 < alpha(k), :411
-        if (inhomo) t_rcorr[j] = kiss_threshold(rcorr[j]);     // cdf2 < rcorr(k), :424
+        t[0] = kiss_threshold(alpha[j]);                 // cdf2 < alpha(k), :411
+        if (inhomo) t[32] = kiss_threshold(rcorr[j]);    // cdf2 < rcorr(k), :424
     }
-    t_cld[j] = kiss_threshold(1. - cldf[(size_t)k * ld + gcol(col0, perm, c)]);   // cdf1 >= 1 - cldfrac, :435
+    t[64] = kiss_threshold(1. - cldf[(size_t)k * ld + gcol(col0, perm, c)]);   // cdf1 >= 1 - cldfrac, :435
 }
 
 // SH/cloud_condensate_inhomogeneity.F90:86-124
@@ -183,8 +190,7 @@ template <class Optics>
 __global__ void __launch_bounds__(MCICA_XS * MCICA_YC)
 mcica_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, int nsub, McicaParams P,
              const KissJump *__restrict__ jumps, const uint32_t *__restrict__ seeds,
-             const long long *__restrict__ t_alpha, const long long *__restrict__ t_rcorr,
-             const long long *__restrict__ t_cld, const double *__restrict__ cldf, const double *__restrict__ ciwp,
+             const long long *__restrict__ thr, const double *__restrict__ cldf, const double *__restrict__ ciwp,
              const double *__restrict__ clwp, double cwp_tiny, int cloudLM, int cloudMH,
              const int *__restrict__ ncloudy,    // columns c >= *ncloudy hold no cloud at all (null: unknown)
              const int *__restrict__ ktop,       // by caller-order column: last layer with cldf > 0 (null: unknown)
@@ -221,17 +227,17 @@ mcica_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, i
     // nothing later reads the generator: the sweep stops there
     const int klast = ktop ? ktop[perm[c]] : nlay - 1;
     for (int k = 0; k <= klast; ++k) {
-        const size_t j2 = (size_t)k * nc + c;
         const int32_t d1 = a.draw_int();
         const int32_t d2 = a.draw_int();
-        if (!(k > 0 && (long long)d2 < t_alpha[j2])) k1 = d1;          // else cdf1(k) = cdf1(k-1)
+        const long long *t = thr + tile_index(nlay, 3, k, c);
+        if (!(k > 0 && (long long)d2 < t[0])) k1 = d1;                 // else cdf1(k) = cdf1(k-1)
         if (P.inhomo) {
             const int32_t e2 = b.draw_int();
             const int32_t e3 = b.draw_int();
-            if (!(k > 0 && (long long)e2 < t_rcorr[j2])) k3 = e3;      // else cdf3(k) = cdf3(k-1)
+            if (!(k > 0 && (long long)e2 < t[32])) k3 = e3;            // else cdf3(k) = cdf3(k-1)
         }
         bool optical = false;
-        if ((long long)k1 >= t_cld[j2]) {
+        if ((long long)k1 >= t[64]) {
             const size_t i2 = (size_t)k * ld + col;
             double ciw = ciwp[i2], clw = clwp[i2];
             if (P.inhomo) {
