@@ -1278,8 +1278,8 @@ lw_band_kernel(const LwBandArgs A) {
     }
 }
 
-// Compiled variants per band: the (g-points per thread, register budget; 0 = none) pair tuned for the
-// band (profiles/r1_gn_tuning.txt) at CB = 32, 16, 8, 4 columns per block.  The one used is picked
+// Compiled variants per band: the (g-points per thread, register budget) pair tuned for the band
+// (profiles/r2_cb_tuning.txt, run r3c) at CB = 32, 16, 8, 4 columns per block.  The one used is picked
 // per band from lw_variant[] (tuned on B200; RRTMGX_LW_GN="vvv..." overrides).
 typedef void (*LwBandLauncher)(int, cudaStream_t, const LwBandArgs &);
 template <int BAND, int GN, int REGS, int CB>
@@ -1292,8 +1292,8 @@ static void lw_launch_band(int nc, cudaStream_t st, const LwBandArgs &A) {
 #define X(BAND, G, R) \
     {lw_launch_band<BAND, G, R, 32>, lw_launch_band<BAND, G, R, 16>, lw_launch_band<BAND, G, R, 8>, lw_launch_band<BAND, G, R, 4>},
 static const LwBandLauncher lw_launchers[16][4] = {
-    X(1, 2, 48) X(2, 2, 48) X(3, 2, 64) X(4, 2, 64) X(5, 2, 64) X(6, 2, 48) X(7, 2, 48) X(8, 2, 64)
-    X(9, 2, 48) X(10, 2, 64) X(11, 2, 64) X(12, 2, 64) X(13, 1, 64) X(14, 1, 0) X(15, 1, 0) X(16, 1, 0)};
+    X(1, 2, 56) X(2, 2, 56) X(3, 2, 80) X(4, 2, 56) X(5, 2, 80) X(6, 2, 80) X(7, 2, 48) X(8, 2, 80)
+    X(9, 2, 56) X(10, 2, 64) X(11, 2, 80) X(12, 2, 80) X(13, 1, 80) X(14, 1, 64) X(15, 1, 80) X(16, 1, 80)};
 #undef X
 static int lw_variant[16] = {0, 1, 3, 3, 3, 2, 3, 2, 3, 2, 2, 2, 2, 1, 1, 1};   // columns per block, profiles/r2_cb_tuning.txt (run r2h)
 
