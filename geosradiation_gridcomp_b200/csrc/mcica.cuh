@@ -187,7 +187,7 @@ constexpr int MCICA_XS = 28;   // divides 140 (LW) and 112 (SW)
 constexpr int MCICA_YC = 8;
 
 template <class Optics>
-__global__ void __launch_bounds__(MCICA_XS * MCICA_YC)
+__global__ void __launch_bounds__(MCICA_XS * MCICA_YC, 5)
 mcica_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, int nsub, McicaParams P,
              const KissJump *__restrict__ jumps, const uint32_t *__restrict__ seeds,
              const long long *__restrict__ thr, const double *__restrict__ cldf, const double *__restrict__ ciwp,
