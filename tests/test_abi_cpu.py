@@ -99,3 +99,24 @@ def test_fortran_shim_types_match_header_field_order():
             if "::" in line:
                 fields += [f.strip() for f in line.split("::")[1].split(",")]
         assert [f.lower() for f in fields] == [f[0].lower() for f in mirror._fields_], tname
+
+
+def test_ctypes_mirrors_match_the_compiled_header(tmp_path):
+    """sizeof and the offset of the last field of every argument struct, as gcc lays out include/rrtmgx.h,
+    against the ctypes mirrors of host.py (a drifted mirror would shift every pointer after the drift)."""
+    import subprocess
+    from geosradiation_gridcomp_b200 import host
+    pairs = [("RrtmgxLwArgs", host.LwArgs, "dolrb_dTs"), ("RrtmgxSwArgs", host.SwArgs, "dfband"),
+             ("RrtmgxIrradArgs", host.IrradArgs, "dolrb_dts"), ("RrtmgxSolarArgs", host.SolarArgs, "cotlp"),
+             ("RrtmgxIrradUpdateArgs", host.IrradUpdateArgs, "flnsc"), ("RrtmgxLwVariants", host.LwVariants, "duflx_dTs"),
+             ("RrtmgxSwNoAerosol", host.SwNoAerosol, "fswband"), ("RrtmgxTaps", host.Taps, "ssi"),
+             ("RrtmgxConfig", host.Config, "corr")]
+    src = tmp_path / "probe.c"
+    body = "".join(f'  printf("{n} %zu %zu\\n", sizeof({n}), offsetof({n}, {last}));\n' for n, _, last in pairs)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rrtmgx.h"\nint main(void) {\n' + body + "  return 0;\n}\n")
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).split("\n")
+    got = {l.split()[0]: (int(l.split()[1]), int(l.split()[2])) for l in out if l.strip()}
+    for name, mirror, last in pairs:
+        assert got[name] == (C.sizeof(mirror), getattr(mirror, last).offset), name
