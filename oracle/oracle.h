@@ -153,6 +153,13 @@ int oracle_solar_finish(int ncol, int lm, double undef, const int *clearCounts, 
                         const double *swdflx, const double *swuflxc, const double *swdflxc, const double *cotd[4],
                         const double *cotn[4], OracleSolarFluxes *f);     /* SOL:6395-6444 */
 
+/* test hooks: reftra_sw / vrtqdr_sw alone (SW/src/rrtmg_sw_spcvmc.F90:1115-1588), arrays (nlay,ngpt,ncol) in,
+ * (nlay+1,ngpt,ncol) out, for the independent numpy restatement in tests/test_oracle_cpu.py */
+int oracle_reftra_sw(int ncol, int nlay, const double *pgg, const double *prmuz, const double *ptau,
+                     const double *pw, double *pref, double *prefd, double *ptra, double *ptrad);
+int oracle_vrtqdr_sw(int ncol, int nlay, const double *pref, const double *prefd, const double *ptra,
+                     const double *ptrad, const double *pdbt, const double *ptdbt, double *pfd, double *pfu);
+
 /* reduced (post-cmbgb) tables and lookup tables, for tests of the init restatement */
 const double *oracle_lw_table(const char *name, int band, int *n);
 const double *oracle_sw_table(const char *name, int band, int *n);

@@ -1452,3 +1452,24 @@ int oracle_rrtmg_sw(
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Test hooks: the two-stream and the adding routine on their own, so that tests/ can hold them
+ * against an independent numpy restatement of SW/src/rrtmg_sw_spcvmc.F90:1115-1588.
+ * Arrays as in the routines: inputs (nlay,ngpt,ncol), outputs and level arrays (nlay+1,ngpt,ncol).
+ * ---------------------------------------------------------------------------------------- */
+int oracle_reftra_sw(int ncol, int nlay, const double *pgg, const double *prmuz, const double *ptau,
+                     const double *pw, double *pref, double *prefd, double *ptra, double *ptrad) {
+    reftra_sw(ncol, nlay, NULL, pgg, prmuz, ptau, pw, pref, prefd, ptra, ptrad, 0);
+    return 0;
+}
+
+int oracle_vrtqdr_sw(int ncol, int nlay, const double *pref, const double *prefd, const double *ptra,
+                     const double *ptrad, const double *pdbt, const double *ptdbt, double *pfd, double *pfu) {
+    const size_t n = (size_t)(nlay + 1) * NG * (size_t)ncol;
+    double *w = (double *)malloc(4 * n * sizeof(double));
+    if (!w) return -1;
+    vrtqdr_sw(ncol, nlay, pref, prefd, ptra, ptrad, pdbt, ptdbt, pfd, pfu, w, w + n, w + 2 * n, w + 3 * n);
+    free(w);
+    return 0;
+}

@@ -185,3 +185,134 @@ def test_oracle_matches_committed_golden_vectors(oracle):
                 np.testing.assert_array_equal(got, ref, err_msg=k)
             else:
                 np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-300, err_msg=k)
+
+
+# ---- an independent restatement of the SW two-stream and adding routines ----------------------------------
+# Written straight from SW/src/rrtmg_sw_spcvmc.F90 (reftra_sw :1115-1370, vrtqdr_sw :1374-1588) in vectorised
+# numpy, on purpose without looking at oracle/sw.c: two transcriptions that agree pin the formulas against
+# slips of sign, index or branch (not the last bit: numpy's exp is not libm's).
+def _reftra_np(zto1, zw, zg, prmuz):
+    eps, od_lo, zwcrit = 1.e-08, 0.06, 0.9999995
+    zg3 = 3. * zg
+    zgamma1 = (8. - zw * (5. + zg3)) * 0.25
+    zgamma2 = 3. * (zw * (1. - zg)) * 0.25
+    zgamma3 = (2. - zg3 * prmuz) * 0.25
+    zgamma4 = 1. - zgamma3
+    zwo = zw / (1. - (1. - zw) * (zg / (1. - zg)) ** 2)
+    # conservative scattering
+    za = zgamma1 * prmuz
+    za1 = za - zgamma3
+    zgt = zgamma1 * zto1
+    ze2c = np.exp(-np.minimum(zto1 / prmuz, 500.))
+    ref_c = (zgt - za1 * (1. - ze2c)) / (1. + zgt)
+    tra_c = 1. - ref_c
+    refd_c = zgt / (1. + zgt)
+    trad_c = 1. - refd_c
+    one = ze2c == 1.
+    ref_c, tra_c = np.where(one, 0., ref_c), np.where(one, 1., tra_c)
+    refd_c, trad_c = np.where(one, 0., refd_c), np.where(one, 1., trad_c)
+    # non-conservative scattering
+    with np.errstate(invalid="ignore", divide="ignore"):
+        za1 = zgamma1 * zgamma4 + zgamma2 * zgamma3
+        za2 = zgamma1 * zgamma3 + zgamma2 * zgamma4
+        zrk = np.sqrt(zgamma1 ** 2 - zgamma2 ** 2)
+        zrp = zrk * prmuz
+        zrp1, zrm1, zrk2 = 1. + zrp, 1. - zrp, 2. * zrk
+        zrpp = 1. - zrp * zrp
+        zrkg = zrk + zgamma1
+        zr1 = zrm1 * (za2 + zrk * zgamma3)
+        zr2 = zrp1 * (za2 - zrk * zgamma3)
+        zr3 = zrk2 * (zgamma3 - za2 * prmuz)
+        zr4 = zrpp * zrkg
+        zr5 = zrpp * (zrk - zgamma1)
+        zt1 = zrp1 * (za1 + zrk * zgamma4)
+        zt2 = zrm1 * (za1 - zrk * zgamma4)
+        zt3 = zrk2 * (zgamma4 + za1 * prmuz)
+        zbeta = (zgamma1 - zrk) / zrkg
+        ze1 = np.minimum(zrk * zto1, 5.)
+        ze2 = np.minimum(zto1 / prmuz, 5.)
+        zem1 = np.where(ze1 <= od_lo, 1. - ze1 + 0.5 * ze1 * ze1, np.exp(-ze1))
+        zep1 = 1. / zem1
+        zem2 = np.where(ze2 <= od_lo, 1. - ze2 + 0.5 * ze2 * ze2, np.exp(-ze2))
+        zep2 = 1. / zem2
+        zdenr = zr4 * zep1 + zr5 * zem1
+        zdent = zr4 * zep1 + zr5 * zem1
+        small = (zdenr >= -eps) & (zdenr <= eps)
+        ref_n = np.where(small, eps, zw * (zr1 * zep1 - zr2 * zem1 - zr3 * zem2) / zdenr)
+        tra_n = np.where(small, zem2, zem2 - zem2 * zw * (zt1 * zep1 - zt2 * zem1 - zt3 * zep2) / zdent)
+        zemm = zem1 * zem1
+        zdend = 1. / ((1. - zbeta * zemm) * zrkg)
+        refd_n = zgamma2 * (1. - zemm) * zdend
+        trad_n = zrk2 * zem1 * zdend
+    cons = zwo >= zwcrit
+    return (np.where(cons, ref_c, ref_n), np.where(cons, refd_c, refd_n), np.where(cons, tra_c, tra_n),
+            np.where(cons, trad_c, trad_n))
+
+
+def _vrtqdr_np(pref, prefd, ptra, ptrad, pdbt, ptdbt):
+    """Arrays [level or layer][...], index 0 = top (jk = 1); level arrays have klev+1 entries."""
+    klev = pdbt.shape[0]
+    prup, prupd = np.empty_like(pref), np.empty_like(pref)
+    prup[klev], prupd[klev] = pref[klev], prefd[klev]
+    zreflect = 1. / (1. - prefd[klev] * prefd[klev - 1])
+    prup[klev - 1] = pref[klev - 1] + (ptrad[klev - 1] * ((ptra[klev - 1] - pdbt[klev - 1]) * prefd[klev] +
+                                                            pdbt[klev - 1] * pref[klev])) * zreflect
+    prupd[klev - 1] = prefd[klev - 1] + ptrad[klev - 1] * ptrad[klev - 1] * prefd[klev] * zreflect
+    for jk in range(1, klev):                    # do jk = 1, klev-1
+        ikp = klev + 1 - jk                      # 1-based
+        ikx = ikp - 1
+        zr = 1. / (1. - prupd[ikp - 1] * prefd[ikx - 1])
+        prup[ikx - 1] = pref[ikx - 1] + (ptrad[ikx - 1] * ((ptra[ikx - 1] - pdbt[ikx - 1]) * prupd[ikp - 1] +
+                                                            pdbt[ikx - 1] * prup[ikp - 1])) * zr
+        prupd[ikx - 1] = prefd[ikx - 1] + ptrad[ikx - 1] * ptrad[ikx - 1] * prupd[ikp - 1] * zr
+    ptdn, prdnd = np.empty_like(pref), np.empty_like(pref)
+    ptdn[0], prdnd[0] = 1., 0.
+    ptdn[1], prdnd[1] = ptra[0], prefd[0]
+    for jk in range(2, klev + 1):                # do jk = 2, klev
+        ikp = jk + 1
+        zr = 1. / (1. - prefd[jk - 1] * prdnd[jk - 1])
+        ptdn[ikp - 1] = ptdbt[jk - 1] * ptra[jk - 1] + (ptrad[jk - 1] * ((ptdn[jk - 1] - ptdbt[jk - 1]) +
+                                                                        ptdbt[jk - 1] * pref[jk - 1] * prdnd[jk - 1])) * zr
+        prdnd[ikp - 1] = prefd[jk - 1] + ptrad[jk - 1] * ptrad[jk - 1] * prdnd[jk - 1] * zr
+    zr = 1. / (1. - prdnd * prupd)
+    pfu = (ptdbt * prup + (ptdn - ptdbt) * prupd) * zr
+    pfd = ptdbt + (ptdn - ptdbt + ptdbt * prup * prdnd) * zr
+    return pfd, pfu
+
+
+def test_two_stream_and_adding_against_independent_numpy(oracle):
+    import ctypes as C
+    L = oracle.lib()
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(8)
+    ncol, nlay, ng = 6, 40, 112
+    shp = (nlay, ng, ncol)
+    tau = np.asfortranarray(10.0 ** rng.uniform(-6, 2.5, shp))
+    w = np.asfortranarray(np.where(rng.random(shp) < 0.25, 1.0 - 10.0 ** rng.uniform(-9, -5, shp), rng.uniform(0, 1, shp)))
+    g = np.asfortranarray(np.where(rng.random(shp) < 0.3, 0.0, rng.uniform(0, 0.95, shp)))
+    mu = np.ascontiguousarray(rng.uniform(0.02, 1.0, ncol))
+    out = [np.zeros((nlay + 1, ng, ncol), order="F") for _ in range(4)]
+    p = lambda a: a.ctypes.data_as(dp)
+    assert L.oracle_reftra_sw(ncol, nlay, p(g), p(mu), p(tau), p(w), *[p(o) for o in out]) == 0
+    ref = _reftra_np(tau, w, g, mu[None, None, :])
+    # reflectances and transmittances are O(1); thin layers are differences of O(1) terms, so their last
+    # bits (numpy exp vs libm exp) show up as ~1e-16 absolute, not as a relative error
+    for o, r in zip(out, ref):
+        np.testing.assert_allclose(o[:nlay], r, rtol=2e-12, atol=2e-15)
+    zwo = w / (1. - (1. - w) * (g / (1. - g)) ** 2)
+    assert (zwo >= 0.9999995).sum() > 1000 and (zwo < 0.9999995).sum() > 1000    # both branches exercised
+    # adding method on those layers (plus a surface), top = index 0
+    dbt = np.asfortranarray(np.exp(-tau / mu[None, None, :]))
+    tdbt = np.ones((nlay + 1, ng, ncol), order="F")
+    for k in range(nlay):
+        tdbt[k + 1] = tdbt[k] * dbt[k]
+    for o in out[:2]:
+        o[nlay] = rng.uniform(0.03, 0.6, (ng, ncol))          # surface albedo: pref / prefd at klev+1
+    out[2][nlay] = 0.
+    out[3][nlay] = 0.
+    pfd, pfu = np.zeros_like(tdbt), np.zeros_like(tdbt)
+    assert L.oracle_vrtqdr_sw(ncol, nlay, *[p(o) for o in out], p(dbt), p(tdbt), p(pfd), p(pfu)) == 0
+    rfd, rfu = _vrtqdr_np(out[0], out[1], out[2], out[3], dbt, tdbt)
+    np.testing.assert_allclose(pfd, rfd, rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(pfu, rfu, rtol=1e-12, atol=1e-15)
+    assert (pfd[0] == 1.0).all()            # top boundary: unit downward flux, exactly
