@@ -316,3 +316,62 @@ def test_two_stream_and_adding_against_independent_numpy(oracle):
     np.testing.assert_allclose(pfd, rfd, rtol=1e-12, atol=1e-15)
     np.testing.assert_allclose(pfu, rfu, rtol=1e-12, atol=1e-15)
     assert (pfd[0] == 1.0).all()            # top boundary: unit downward flux, exactly
+
+
+# ---- published-number sanity: AFGL mid-latitude summer, clear sky ------------------------------------------
+# The reference ships no known-answer cases; the nearest thing to one is the ICRCCM / RRTMG validation
+# literature for the AFGL standard atmospheres.  Line-by-line and RRTMG results for mid-latitude summer (MLS)
+# clear sky cluster at OLR ~ 281-284 W/m2 and surface downward LW ~ 344-348 W/m2 (CO2 ~ 355-380 ppmv; today's
+# CO2/CH4 lower the OLR by 1-2 W/m2), and the clear MLS atmosphere absorbs roughly a fifth of the incoming
+# solar beam at 60 degrees.  The bounds below are 3 % wide: they do not pin bits, they catch a wrong band
+# table, a unit slip in the column amounts or a broken continuum, which the property tests cannot see.
+_MLS = np.array([  # z km, p hPa, T K, H2O ppmv  (AFGL-TR-86-0110, model 2)
+    [0, 1013., 294.2, 18760.], [1, 902., 289.7, 13780.], [2, 802., 285.2, 9680.], [3, 710., 279.2, 5984.],
+    [4, 628., 273.2, 3813.], [5, 554., 267.2, 2225.], [6, 487., 261.2, 1510.], [7, 426., 254.7, 1020.],
+    [8, 372., 248.2, 646.], [9, 324., 241.7, 413.], [10, 281., 235.3, 247.], [11, 243., 228.8, 95.6],
+    [12, 209., 222.3, 29.4], [13, 179., 215.8, 8.0], [14, 153., 215.7, 5.0], [15, 130., 215.7, 3.4],
+    [16, 111., 215.7, 3.3], [17, 95., 215.7, 3.2], [18, 81.2, 216.8, 3.15], [19, 69.5, 217.9, 3.2],
+    [20, 59.5, 219.2, 3.3], [21, 51., 220.4, 3.45], [22, 43.7, 221.6, 3.6], [23, 37.6, 222.8, 3.85],
+    [24, 32.2, 223.9, 4.0], [25, 27.7, 225.1, 4.2], [27.5, 19.07, 228.45, 4.45], [30, 13.2, 233.7, 4.7],
+    [32.5, 9.3, 239.0, 4.85], [35, 6.52, 245.2, 4.95], [37.5, 4.64, 251.3, 5.0], [40, 3.33, 257.5, 5.1],
+    [42.5, 2.41, 263.7, 5.3], [45, 1.76, 269.9, 5.45], [47.5, 1.29, 275.2, 5.5], [50, 0.951, 275.7, 5.5]])
+
+
+def _mls_state():
+    from geosradiation_gridcomp_b200 import synthetic
+    nlay = len(_MLS) - 1
+    s = synthetic.make_columns(1, nlay=nlay, seed=1)
+    f = lambda a: np.asfortranarray(np.asarray(a, dtype=np.float64).reshape(1, -1))
+    z, p, t, w = _MLS.T
+    play = np.sqrt(p[:-1] * p[1:])                       # layer means (log-pressure midpoints)
+    s.update(plev=f(p), play=f(play), tlev=f(t), tlay=f(0.5 * (t[:-1] + t[1:])), tsfc=f([t[0]]).reshape(1),
+             h2ovmr=f(1e-6 * np.sqrt(w[:-1] * w[1:])),
+             o3vmr=f(8e-6 * np.exp(-np.log(play / 10.0) ** 2 / 3.0) + 3e-8),
+             zm=f(500.0 * (z[:-1] + z[1:])), emis=np.ones((1, 16), order="F"),
+             cldf=f(np.zeros(nlay)), ciwp=f(np.zeros(nlay)), clwp=f(np.zeros(nlay)),
+             tauaer_lw=np.zeros((1, nlay, 16), order="F"), tauaer_sw=np.zeros((1, nlay, 14), order="F"),
+             coszen=np.array([0.5]), asdir=np.array([0.2]), asdif=np.array([0.2]), aldir=np.array([0.2]),
+             aldif=np.array([0.2]), alat=np.array([0.7]), scon=1361.0, adjes=1.0)
+    s["cloudLM"] = int(np.argmax(play < 700.0))
+    s["cloudMH"] = int(np.argmax(play < 400.0))
+    return s
+
+
+def test_midlatitude_summer_clear_sky_against_published_ranges(oracle):
+    s = _mls_state()
+    lw = oracle.rrtmg_lw(s)
+    assert lw["rc"] == 0
+    olr, sfc_dn, sfc_up = lw["uflx"][0, -1], lw["dflx"][0, 0], lw["uflx"][0, 0]
+    assert abs(sfc_up - 5.670373e-8 * 294.2 ** 4) < 0.5          # black surface at 294.2 K: 424.8 W/m2
+    assert 272.0 < olr < 290.0, olr                               # literature 281-284 (older CO2/CH4)
+    assert 338.0 < sfc_dn < 356.0, sfc_dn                         # literature 344-348
+    np.testing.assert_array_equal(lw["uflx"], lw["uflxc"])       # no cloud: all-sky is clear-sky
+    sw = oracle.rrtmg_sw(s, iaer=0, normFlx=0)
+    assert sw["rc"] == 0
+    toa_dn, toa_up = sw["swdflx"][0, -1], sw["swuflx"][0, -1]
+    sfc_d, sfc_u = sw["swdflx"][0, 0], sw["swuflx"][0, 0]
+    assert abs(toa_dn - 0.5 * 1361.0) < 0.05 * 0.5                # the 14 bands integrate to the solar constant
+    absorbed = ((toa_dn - toa_up) - (sfc_d - sfc_u)) / toa_dn
+    assert 0.16 < absorbed < 0.26, absorbed                       # clear MLS at 60 deg: about one fifth
+    assert 0.68 < sfc_d / toa_dn < 0.80, sfc_d / toa_dn
+    assert abs(sfc_u / sfc_d - 0.2) < 1e-9                        # Lambertian surface, albedo 0.2 in every band
