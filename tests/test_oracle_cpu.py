@@ -375,3 +375,140 @@ def test_midlatitude_summer_clear_sky_against_published_ranges(oracle):
     assert 0.16 < absorbed < 0.26, absorbed                       # clear MLS at 60 deg: about one fifth
     assert 0.68 < sfc_d / toa_dn < 0.80, sfc_d / toa_dn
     assert abs(sfc_u / sfc_d - 0.2) < 1e-9                        # Lambertian surface, albedo 0.2 in every band
+
+
+# ---- an independent restatement of the LW radiative transfer ------------------------------------------------
+# rtrnmc (LW/src/rrtmg_lw_rtrnmc.F90:22-390), the Planck-function interpolation and precipitable water of
+# setcoef (LW/src/rrtmg_lw_setcoef.F90:204-395) and the transmittance tables of rrtmg_lw_ini
+# (LW/src/rrtmg_lw_init.F90:96-114), written from the Fortran in numpy (g-points vectorised, layers looped)
+# without reference to oracle/lw.c.  It is fed the oracle's own optical depths, Planck fractions and McICA
+# cloud (taps), so what it pins is everything downstream of the gas optics.
+def _lw_tables_np():
+    ntbl, bpade, expeps = 10000, 1.0 / 0.278, 1.e-20
+    tfn = np.arange(1, ntbl) / float(ntbl)
+    tau = np.empty(ntbl + 1); ex = np.empty(ntbl + 1); tf = np.empty(ntbl + 1)
+    tau[0], tau[ntbl], ex[0], ex[ntbl], tf[0], tf[ntbl] = 0.0, 1.e10, 1.0, expeps, 0.0, 1.0
+    tau[1:ntbl] = bpade * tfn / (1. - tfn)
+    ex[1:ntbl] = np.maximum(np.exp(-tau[1:ntbl]), expeps)
+    t, e = tau[1:ntbl], ex[1:ntbl]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tf[1:ntbl] = np.where(t < 0.06, t / 6., 1. - 2. * ((1. / t) - (e / (1. - e))))
+    return tau, ex, tf, bpade
+
+
+def _lw_rt_np(s, taps, tab, dudTs=True):
+    ncol, nlay = s["ncol"], s["nlay"]
+    ngb = tab["lw.wvn.ngb"].astype(int)                                     # band of each g-point, 1-based
+    totplnk, totplnkderiv = tab["lw.wvn.totplnk"], tab["lw.wvn.totplnkderiv"]
+    wavenum1 = np.array([10., 350., 500., 630., 700., 820., 980., 1080., 1180., 1390., 1480., 1800., 2080., 2250., 2380., 2600.])
+    wavenum2 = np.array([350., 500., 630., 700., 820., 980., 1080., 1180., 1390., 1480., 1800., 2080., 2250., 2380., 2600., 3250.])
+    delwave, fluxfac, wtdiff = wavenum2 - wavenum1, np.pi * 2.e4, 0.5
+    a0 = np.array([1.66, 1.55, 1.58, 1.66, 1.54, 1.454, 1.89, 1.33, 1.668] + [1.66] * 7)
+    a1 = np.array([0.00, 0.25, 0.22, 0.00, 0.13, 0.446, -0.10, 0.40, -0.006] + [0.0] * 7)
+    a2 = np.array([0.00, -12.0, -11.7, 0.00, -0.72, -0.243, 0.19, -0.062, 0.414] + [0.0] * 7)
+    tau_tbl, exp_tbl, tfn_tbl, bpade = _lw_tables_np()
+    tblint, amd, amw, avogad, grav = 10000.0, 28.9660, 18.0160, 6.02214199e+23, 9.8066
+    ib = ngb - 1
+    out = {k: np.zeros((ncol, nlay + 1)) for k in ("uflx", "dflx", "uflxc", "dflxc", "duflx_dTs", "duflxc_dTs")}
+    out["olrb"], out["dolrb_dTs"], out["pwvcm"] = np.zeros((16, ncol)), np.zeros((16, ncol)), np.zeros(ncol)
+
+    def planck(t, tbl):                      # setcoef :278-347: table at 1 K steps from 160 K, linear in between
+        i = int(t - 159.)
+        i = min(max(i, 1), 180)
+        fr = t - 159. - float(i)
+        return tbl[i - 1] + fr * (tbl[i] - tbl[i - 1])           # all 16 bands
+
+    for c in range(ncol):
+        pz, h2o = s["plev"][c], s["h2ovmr"][c]
+        amm = (1. - h2o) * amd + h2o * amw
+        coldry = (pz[:-1] - pz[1:]) * 1.e3 * avogad / (1.e2 * grav * amm * (1. + h2o))
+        amttl = wvttl = 0.
+        for l in range(nlay):
+            btemp = h2o[l] * coldry[l]
+            amttl = amttl + coldry[l] + btemp
+            wvttl = wvttl + btemp
+        pwvcm = (amw * wvttl) / (amd * amttl) * (1.e3 * pz[0]) / (1.e2 * grav)
+        out["pwvcm"][c] = pwvcm
+        semiss = s["emis"][c]
+        plankbnd = semiss * planck(s["tsfc"][c], totplnk)
+        dplankbnd = semiss * planck(s["tsfc"][c], totplnkderiv)
+        planklev = np.array([planck(t, totplnk) for t in s["tlev"][c]])       # (nlay+1, 16)
+        planklay = np.array([planck(t, totplnk) for t in s["tlay"][c]])       # (nlay, 16)
+        secdiff = np.clip(a0 + a1 * np.exp(a2 * pwvcm), 1.50, 1.80)
+        for b in (1, 4, 10, 11, 12, 13, 14, 15, 16):
+            secdiff[b - 1] = 1.66
+        sec, sumfac = secdiff[ib], (wtdiff * delwave * fluxfac)[ib]
+        taug, pfr, tauc = taps["taug"][c], taps["pfracs"][c], taps["taucmc"][c]     # (140, nlay)
+        cloudy = taps["cldymc"][c].any(axis=0)                                       # (nlay,)
+        agas, atot = np.zeros((nlay, 140)), np.zeros((nlay, 140))
+        bbugas, bbutot = np.zeros((nlay, 140)), np.zeros((nlay, 140))
+        radld, radclrd, diverge = np.zeros(140), np.zeros(140), False
+        for l in range(nlay - 1, -1, -1):                                            # lev = nlay .. 1
+            plfrac, blay = pfr[:, l], planklay[l][ib]
+            dplankup, dplankdn = planklev[l + 1][ib] - blay, planklev[l][ib] - blay
+            odepth = np.maximum(sec * taug[:, l], 0.)
+            itgas = (tblint * (odepth / (bpade + odepth)) + 0.5).astype(int)
+            agas[l] = 1. - exp_tbl[itgas]
+            tfacgas = tfn_tbl[itgas]
+            bbdgas = plfrac * (blay + tfacgas * dplankdn)
+            bbugas[l] = plfrac * (blay + tfacgas * dplankup)
+            cld = tauc[:, l] > 0.
+            odtot = tau_tbl[itgas] + sec * tauc[:, l]
+            ittot = (tblint * (odtot / (bpade + odtot)) + 0.5).astype(int)
+            atot[l] = 1. - exp_tbl[ittot]
+            tfactot = tfn_tbl[ittot]
+            bbdtot = plfrac * (blay + tfactot * dplankdn)
+            bbutot[l] = plfrac * (blay + tfactot * dplankup)
+            radld = np.where(cld, radld + (bbdtot - radld) * atot[l], radld + (bbdgas - radld) * agas[l])
+            diverge = diverge or bool(cloudy[l])
+            radclrd = radclrd + (bbdgas - radclrd) * agas[l] if diverge else radld
+            out["dflx"][c, l] = np.sum(sumfac * radld)
+            out["dflxc"][c, l] = np.sum(sumfac * radclrd)
+        rad0, drad0 = pfr[:, 0] * plankbnd[ib], pfr[:, 0] * dplankbnd[ib]
+        reflect = 1. - semiss[ib]
+        radlu, radclru = rad0 + reflect * radld, rad0 + reflect * radclrd
+        dlu, dclru = drad0.copy(), drad0.copy()
+        out["uflx"][c, 0], out["uflxc"][c, 0] = np.sum(sumfac * radlu), np.sum(sumfac * radclru)
+        out["duflx_dTs"][c, 0], out["duflxc_dTs"][c, 0] = np.sum(sumfac * dlu), np.sum(sumfac * dclru)
+        for l in range(nlay):
+            cld = tauc[:, l] > 0.
+            a = np.where(cld, atot[l], agas[l])
+            radlu = radlu + (np.where(cld, bbutot[l], bbugas[l]) - radlu) * a
+            dlu = dlu - dlu * a
+            if diverge:
+                radclru = radclru + (bbugas[l] - radclru) * agas[l]
+                dclru = dclru - dclru * agas[l]
+            else:
+                radclru, dclru = radlu, dlu
+            out["uflx"][c, l + 1], out["uflxc"][c, l + 1] = np.sum(sumfac * radlu), np.sum(sumfac * radclru)
+            out["duflx_dTs"][c, l + 1], out["duflxc_dTs"][c, l + 1] = np.sum(sumfac * dlu), np.sum(sumfac * dclru)
+        for b in range(16):
+            if s["band_output"][b]:
+                out["olrb"][b, c] = np.sum((sumfac * radlu)[ib == b])
+                out["dolrb_dTs"][b, c] = np.sum((sumfac * dlu)[ib == b])
+    return out
+
+
+def test_lw_transfer_against_independent_numpy(oracle):
+    from geosradiation_gridcomp_b200 import synthetic, tables
+    tab = tables.load_tables()
+    s = synthetic.make_columns(40, nlay=72, seed=77)
+    s["tsfc"][:4] = [150.0, 159.5, 339.9, 345.0]                    # Planck table clamps at both ends
+    s["tlev"][4, 0] = 341.0
+    o = oracle.rrtmg_lw(s, taps=("taug", "pfracs", "taucmc", "cldymc", "pwvcm"))
+    assert o["rc"] == 0
+    tau_tbl, exp_tbl, tfn_tbl, _ = _lw_tables_np()
+    for name, mine in (("tau_tbl", tau_tbl), ("exp_tbl", exp_tbl), ("tfn_tbl", tfn_tbl)):
+        # tfn just above tau = 0.06 is a difference of nearly equal terms: one ulp of exp() shows as 4e-12
+        rtol = {"tau_tbl": 4e-16, "exp_tbl": 1e-15, "tfn_tbl": 2e-11}[name]
+        np.testing.assert_allclose(oracle.table("lw", name), mine, rtol=rtol, atol=1e-300)
+    r = _lw_rt_np(s, o, tab)
+    np.testing.assert_allclose(o["pwvcm"], r["pwvcm"], rtol=1e-13)
+    cloudy_cols = (s["cldf"] > 0).any(axis=1)
+    assert cloudy_cols.sum() >= 10 and (~cloudy_cols).sum() >= 10
+    for k in ("uflx", "dflx", "uflxc", "dflxc", "duflx_dTs", "duflxc_dTs"):
+        scale = np.abs(r[k]).max(axis=1, keepdims=True)
+        assert np.max(np.abs(o[k] - r[k]) / scale) < 2e-12, k
+    bo = np.asarray(s["band_output"], bool)
+    np.testing.assert_allclose(o["olrb"][bo], r["olrb"][bo], rtol=2e-12)
+    np.testing.assert_allclose(o["dolrb_dTs"][bo], r["dolrb_dTs"][bo], rtol=2e-12)
