@@ -512,3 +512,205 @@ def test_lw_transfer_against_independent_numpy(oracle):
     bo = np.asarray(s["band_output"], bool)
     np.testing.assert_allclose(o["olrb"][bo], r["olrb"][bo], rtol=2e-12)
     np.testing.assert_allclose(o["dolrb_dTs"][bo], r["dolrb_dTs"][bo], rtol=2e-12)
+
+
+# ---- an independent restatement of the LW gas optics for two structurally different bands ----------------------
+# setcoef (LW/src/rrtmg_lw_setcoef.F90:204-575), the g-point reduction of band 1 (LW/src/rrtmg_lw_init.F90:114-145,
+# cmbgb1 :356-437), taugb1 (one key species, N2 continuum minor; LW/src/rrtmg_lw_taumol.F90:200-296) and taugb3 (two
+# key species with the three-way specparm interpolation, N2O minor with the abundance adjustment, Planck fractions
+# interpolated in the binary parameter; :375-700), written from the Fortran in numpy on the ORIGINAL 16-g tables of
+# the data blob, without reference to oracle/lw.c or oracle/lw_init.c.
+def _lw_setcoef_np(s, c, tab):
+    import math
+    nlay = s["nlay"]
+    preflog, tref, chi = tab["lw.ref.preflog"], tab["lw.ref.tref"], tab["lw.ref.chi_mls"]
+    amd, amw, avogad, grav, stpfac = 28.9660, 18.0160, 6.02214199e+23, 9.8066, 296. / 1013.
+    pz, L = s["plev"][c], []
+    laytrop = 0
+    for l in range(nlay):
+        h2o, t, p = s["h2ovmr"][c, l], s["tlay"][c, l], s["play"][c, l]
+        amm = (1. - h2o) * amd + h2o * amw
+        coldry = (pz[l] - pz[l + 1]) * 1.e3 * avogad / (1.e2 * grav * amm * (1. + h2o))
+        summol = s["co2vmr"][c, l] + s["o3vmr"][c, l] + s["n2ovmr"][c, l] + s["ch4vmr"][c, l] + s["o2vmr"][c, l]
+        wbroad = coldry * (1. - summol)
+        wv = h2o * coldry
+        plog = math.log(p)
+        jp = min(max(int(36. - 5 * (plog + 0.04)), 1), 58)
+        fp = 5. * (preflog[jp - 1] - plog)
+        jt = min(max(int(3. + (t - tref[jp - 1]) / 15.), 1), 4)
+        ft = ((t - tref[jp - 1]) / 15.) - float(jt - 3)
+        jt1 = min(max(int(3. + (t - tref[jp]) / 15.), 1), 4)
+        ft1 = ((t - tref[jp]) / 15.) - float(jt1 - 3)
+        water = wv / coldry
+        scalefac = p * stpfac / t
+        d = dict(jp=jp, jt=jt, jt1=jt1, coldry=coldry)
+        d["forfac"] = scalefac / (1. + water)
+        if plog > 4.56:
+            laytrop += 1
+            factor = (332. - t) / 36.
+            d["indfor"] = min(2, max(1, int(factor)))
+            d["forfrac"] = factor - float(d["indfor"])
+            d["selffac"] = water * d["forfac"]
+            factor = (t - 188.) / 7.2
+            d["indself"] = min(9, max(1, int(factor) - 7))
+            d["selffrac"] = factor - float(d["indself"] + 7)
+        else:
+            factor = (t - 188.) / 36.
+            d["indfor"], d["forfrac"], d["selffac"], d["indself"], d["selffrac"] = 3, factor - 1., 0., 0, 0.
+        d["scaleminorn2"] = (p / t) * (wbroad / (coldry + wv))
+        factor = (t - 180.8) / 7.2
+        d["indminor"] = min(18, max(1, int(factor)))
+        d["minorfrac"] = factor - float(d["indminor"])
+        d["rat_h2oco2"] = chi[0, jp - 1] / chi[1, jp - 1]
+        d["rat_h2oco2_1"] = chi[0, jp] / chi[1, jp]
+        d["colh2o"] = 1.e-20 * h2o * coldry
+        d["colco2"] = 1.e-20 * s["co2vmr"][c, l] * coldry
+        d["coln2o"] = 1.e-20 * s["n2ovmr"][c, l] * coldry
+        if d["colco2"] == 0.: d["colco2"] = 1.e-32 * coldry
+        if d["coln2o"] == 0.: d["coln2o"] = 1.e-32 * coldry
+        d["colbrd"] = 1.e-20 * wbroad
+        compfp = 1. - fp
+        d["fac10"], d["fac00"], d["fac11"], d["fac01"] = compfp * ft, compfp * (1. - ft), fp * ft1, fp * (1. - ft1)
+        d["selffac"] = d["colh2o"] * d["selffac"]
+        d["forfac"] = d["colh2o"] * d["forfac"]
+        L.append(d)
+    return L, laytrop
+
+
+def _lw_reduce_band1(tab):
+    """rwgt of band 1 and the 16 -> 10 g-point combination (weighted for k, plain sums for the Planck fractions)."""
+    wt, ngn = tab["lw.wvn.wt"], tab["lw.wvn.ngn"][:10]
+    groups, i = [], 0
+    for n in ngn:
+        groups.append(list(range(i, i + n))); i += n
+    rw = np.zeros(16)
+    for g in groups:
+        wsum = 0.
+        for j in g: wsum = wsum + wt[j]
+        for j in g: rw[j] = wt[j] / wsum
+
+    def comb(a, weighted=True):                       # last axis = original g
+        out = np.zeros(a.shape[:-1] + (10,))
+        for k, g in enumerate(groups):
+            for j in g:
+                out[..., k] = out[..., k] + (a[..., j] * rw[j] if weighted else a[..., j])
+        return out
+    K = "lw.kg01."
+    return dict(ka=comb(tab[K + "kao"]), kb=comb(tab[K + "kbo"]), selfref=comb(tab[K + "selfrefo"]),
+                forref=comb(tab[K + "forrefo"]), ka_mn2=comb(tab[K + "kao_mn2"]), kb_mn2=comb(tab[K + "kbo_mn2"]),
+                fracrefa=comb(tab[K + "fracrefao"], False), fracrefb=comb(tab[K + "fracrefbo"], False))
+
+
+def _lw_taugb1_np(d, lower, p, R):
+    lin = lambda t, i, f: t[i - 1] + f * (t[i] - t[i - 1])
+    taufor = d["forfac"] * lin(R["forref"], d["indfor"], d["forfrac"])
+    scalen2 = d["colbrd"] * d["scaleminorn2"]
+    if lower:
+        corradj = 1. - 0.15 * (250. - p) / 154.4 if p < 250. else 1.
+        tauself = d["selffac"] * lin(R["selfref"], d["indself"], d["selffrac"])
+        taun2 = scalen2 * lin(R["ka_mn2"], d["indminor"], d["minorfrac"])
+        k, jp0, jp1 = R["ka"], d["jp"] - 1, d["jp"]                       # ka(jt, jp, ig), 0-based jp index
+        major = (d["fac00"] * k[d["jt"] - 1, jp0] + d["fac10"] * k[d["jt"], jp0] +
+                 d["fac01"] * k[d["jt1"] - 1, jp1] + d["fac11"] * k[d["jt1"], jp1])
+        return corradj * (d["colh2o"] * major + tauself + taufor + taun2), R["fracrefa"]
+    corradj = 1. - 0.15 * (p / 95.6)
+    taun2 = scalen2 * lin(R["kb_mn2"], d["indminor"], d["minorfrac"])
+    k, jp0, jp1 = R["kb"], d["jp"] - 13, d["jp"] - 12                      # kb(jt, 13:59, ig)
+    major = (d["fac00"] * k[d["jt"] - 1, jp0] + d["fac10"] * k[d["jt"], jp0] +
+             d["fac01"] * k[d["jt1"] - 1, jp1] + d["fac11"] * k[d["jt1"], jp1])
+    return corradj * (d["colh2o"] * major + taufor + taun2), R["fracrefb"]
+
+
+def _lw_taugb3_np(d, lower, tab):
+    import math
+    K, chi, oneminus = "lw.kg03.", tab["lw.ref.chi_mls"], 1. - 1.e-6
+    lin = lambda t, i, f: t[i - 1] + f * (t[i] - t[i - 1])
+    n = 8. if lower else 4.
+
+    def binary(rat):
+        speccomb = d["colh2o"] + rat * d["colco2"]
+        specparm = min(d["colh2o"] / speccomb, oneminus)
+        specmult = n * specparm
+        return speccomb, specparm, 1 + int(specmult), math.fmod(specmult, 1.0)
+
+    def major(k, jp0, jt, f0, f1, speccomb, specparm, js, fs):
+        """k(js, jt, jp, ig): two temperatures jt, jt+1 at one reference pressure."""
+        a = lambda dj, dt: k[js - 1 + dj, jt - 1 + dt, jp0]
+        if lower and specparm < 0.125:
+            p = fs - 1; p4 = p ** 4; fk0, fk1, fk2 = p4, 1 - p - 2.0 * p4, p + p4
+            return speccomb * (fk0 * f0 * a(0, 0) + fk1 * f0 * a(1, 0) + fk2 * f0 * a(2, 0) +
+                               fk0 * f1 * a(0, 1) + fk1 * f1 * a(1, 1) + fk2 * f1 * a(2, 1))
+        if lower and specparm > 0.875:
+            p = -fs; p4 = p ** 4; fk0, fk1, fk2 = p4, 1 - p - 2.0 * p4, p + p4
+            return speccomb * (fk2 * f0 * a(-1, 0) + fk1 * f0 * a(0, 0) + fk0 * f0 * a(1, 0) +
+                               fk2 * f1 * a(-1, 1) + fk1 * f1 * a(0, 1) + fk0 * f1 * a(1, 1))
+        return speccomb * ((1. - fs) * f0 * a(0, 0) + fs * f0 * a(1, 0) + (1. - fs) * f1 * a(0, 1) + fs * f1 * a(1, 1))
+
+    jp = d["jp"]
+    k = tab[K + ("kao" if lower else "kbo")]
+    off = 1 if lower else 13
+    tau0 = major(k, jp - off, d["jt"], d["fac00"], d["fac10"], *binary(d["rat_h2oco2"]))
+    tau1 = major(k, jp + 1 - off, d["jt1"], d["fac01"], d["fac11"], *binary(d["rat_h2oco2_1"]))
+    refrat_m = chi[0, 2] / chi[1, 2] if lower else chi[0, 12] / chi[1, 12]
+    refrat_planck = chi[0, 8] / chi[1, 8] if lower else chi[0, 12] / chi[1, 12]
+    _, _, jmn2o, fmn2o = binary(refrat_m)
+    _, _, jpl, fpl = binary(refrat_planck)
+    chi_n2o = d["coln2o"] / d["coldry"]
+    ratn2o = 1.e20 * chi_n2o / chi[3, jp]
+    if ratn2o > 1.5:
+        adjcoln2o = (0.5 + (ratn2o - 0.5) ** 0.65) * chi[3, jp] * d["coldry"] * 1.e-20
+    else:
+        adjcoln2o = d["coln2o"]
+    km = tab[K + ("kao_mn2o" if lower else "kbo_mn2o")]
+    im = d["indminor"]
+    n2om1 = km[jmn2o - 1, im - 1] + fmn2o * (km[jmn2o, im - 1] - km[jmn2o - 1, im - 1])
+    n2om2 = km[jmn2o - 1, im] + fmn2o * (km[jmn2o, im] - km[jmn2o - 1, im])
+    absn2o = n2om1 + d["minorfrac"] * (n2om2 - n2om1)
+    taufor = d["forfac"] * lin(tab[K + "forrefo"], d["indfor"], d["forfrac"])
+    tauself = d["selffac"] * lin(tab[K + "selfrefo"], d["indself"], d["selffrac"]) if lower else 0.
+    fr = tab[K + ("fracrefao" if lower else "fracrefbo")]
+    pfrac = fr[:, jpl - 1] + fpl * (fr[:, jpl] - fr[:, jpl - 1])
+    if lower:
+        return tau0 + tau1 + tauself + taufor + adjcoln2o * absn2o, pfrac
+    return tau0 + tau1 + taufor + adjcoln2o * absn2o, pfrac
+
+
+def test_lw_gas_optics_bands_1_and_3_against_independent_numpy(oracle):
+    from geosradiation_gridcomp_b200 import synthetic, tables
+    tab = tables.load_tables()
+    ncol = 24
+    s = synthetic.make_columns(ncol, nlay=72, seed=91)
+    s["n2ovmr"][:6] *= 2.5                                    # drives the N2O abundance adjustment (ratn2o > 1.5)
+    s["h2ovmr"][6:9] *= 1e-3                                  # dry columns: specparm < 0.125 in the lower atmosphere
+    s["co2vmr"][9:12] *= 1e-2                                 # CO2-poor columns: specparm > 0.875
+    o = oracle.rrtmg_lw(s, taps=("jp", "jt", "jt1", "indfor", "indself", "indminor", "laytrop", "fac00", "fac01",
+                                 "fac10", "fac11", "taug", "pfracs"))
+    assert o["rc"] == 0
+    R1 = _lw_reduce_band1(tab)
+    np.testing.assert_allclose(oracle.table("lw", "absa", 1).reshape(65, 10, order="F"),
+                               R1["ka"].reshape(65, 10, order="F"), rtol=1e-15)
+    seen = set()
+    for c in range(ncol):
+        L, laytrop = _lw_setcoef_np(s, c, tab)
+        assert laytrop == o["laytrop"][c]
+        for l, d in enumerate(L):
+            lower = l < laytrop
+            for k in ("jp", "jt", "jt1", "indfor", "indminor"):
+                assert d[k] == o[k][c, l], (k, c, l)
+            if lower:
+                assert d["indself"] == o["indself"][c, l]
+            for k in ("fac00", "fac01", "fac10", "fac11"):
+                assert abs(d[k] - o[k][c, l]) <= 1e-13, (k, c, l)
+            aer = s["tauaer_lw"][c, l]
+            t1, f1 = _lw_taugb1_np(d, lower, s["play"][c, l], R1)
+            np.testing.assert_allclose(o["taug"][c, 0:10, l], t1 + aer[0], rtol=1e-11, err_msg=f"band 1 col {c} lay {l}")
+            np.testing.assert_allclose(o["pfracs"][c, 0:10, l], f1, rtol=1e-15)
+            t3, f3 = _lw_taugb3_np(d, lower, tab)
+            np.testing.assert_allclose(o["taug"][c, 22:38, l], t3 + aer[2], rtol=1e-11, err_msg=f"band 3 col {c} lay {l}")
+            np.testing.assert_allclose(o["pfracs"][c, 22:38, l], f3, rtol=1e-11)
+            if lower:
+                sp = min(d["colh2o"] / (d["colh2o"] + d["rat_h2oco2"] * d["colco2"]), 1. - 1.e-6)
+                seen.add("lo" if sp < 0.125 else "hi" if sp > 0.875 else "mid")
+            if 1.e20 * (d["coln2o"] / d["coldry"]) / tab["lw.ref.chi_mls"][3, d["jp"]] > 1.5:
+                seen.add("adj")
+    assert seen == {"lo", "mid", "hi", "adj"}, seen
