@@ -714,3 +714,97 @@ def test_lw_gas_optics_bands_1_and_3_against_independent_numpy(oracle):
             if 1.e20 * (d["coln2o"] / d["coldry"]) / tab["lw.ref.chi_mls"][3, d["jp"]] > 1.5:
                 seen.add("adj")
     assert seen == {"lo", "mid", "hi", "adj"}, seen
+
+
+# ---- an independent restatement of the McICA subcolumn generator -----------------------------------------------
+# generate_stochastic_clouds (SH/cloud_subcol_gen.F90:93-330), the correlation lengths (:333-365), zcw_lookup
+# (SH/cloud_condensate_inhomogeneity.F90, bilinear in the beta table) and clearCounts_threeBand (:610-760) in plain
+# Python on top of kiss_python above, without reference to oracle/mcica.c.  The masks are integer work: bit-exact.
+def _mcica_python(zmid, alat, doy, play, cldfrac, ciwp, clwp, nsub, xcw, so=(1, 2, 3, 4), cwp_tiny=1e-20, inhomo=True):
+    import math
+    nlay, ncol = play.shape
+    maximo = 2147483647 - 1
+
+    def clength(am1, am2, am30, am4, lat):
+        am3 = -4. * am30 / 365. * (doy - 272) if doy > 181 else 4. * am30 / 365. * (doy - 91)
+        return (am1 + am2 * math.exp(-(lat * (180. / 3.14159265358979323846) - am3) ** 2 / am4 ** 2)) * 1.e3
+
+    def zcw_lookup(cdf, sigma):
+        r1 = cdf * (1000 - 1) + 1.
+        i1 = max(1, min(int(r1), 999)); r1 = r1 - i1
+        r2 = 40. * sigma - 3.
+        i2 = max(1, min(int(r2), 139)); r2 = r2 - i2
+        return ((1.0 - r1) * (1.0 - r2) * xcw[i1 - 1, i2 - 1] + (1.0 - r1) * r2 * xcw[i1 - 1, i2] +
+                r1 * (1.0 - r2) * xcw[i1, i2 - 1] + r1 * r2 * xcw[i1, i2])
+
+    mask = np.zeros((nlay, nsub, ncol), dtype=np.uint8)
+    ci, cw = np.zeros((nlay, nsub, ncol)), np.zeros((nlay, nsub, ncol))
+    for c in range(ncol):
+        adl = clength(1.4315, 2.1219, 7., -25.584, alat[c])
+        rdl = clength(0.72192, 0.78996, 8.5, 40.404, alat[c])
+        alpha = [0.] + [math.exp(-abs(zmid[l, c] - zmid[l - 1, c]) / adl) for l in range(1, nlay)]
+        rcorr = [0.] + [math.exp(-abs(zmid[l, c] - zmid[l - 1, c]) / rdl) for l in range(1, nlay)]
+        sigma = [0.5 if f > 0.99 else 0.71 if f > 0.9 else 1.0 for f in cldfrac[:, c]]
+        assert play[0, 0] > play[nlay - 1, 0]                         # surface at layer 1
+        pseed = [play[k, c] * 100. for k in range(4)]
+        seeds = [int((pseed[so[k] - 1] - int(pseed[so[k] - 1])) * maximo + 1) for k in range(4)]
+        ndraw = nsub * nlay * (4 if inhomo else 2)
+        u = list(kiss_python(seeds, ndraw))
+        pos = 0
+        for j in range(nsub):
+            cdf1, cdf2 = u[pos:pos + 2 * nlay:2], u[pos + 1:pos + 2 * nlay:2]; pos += 2 * nlay
+            for l in range(1, nlay):
+                if cdf2[l] < alpha[l]: cdf1[l] = cdf1[l - 1]
+            if inhomo:
+                cdf2, cdf3 = u[pos:pos + 2 * nlay:2], u[pos + 1:pos + 2 * nlay:2]; pos += 2 * nlay
+                for l in range(1, nlay):
+                    if cdf2[l] < rcorr[l]: cdf3[l] = cdf3[l - 1]
+            for l in range(nlay):
+                if cdf1[l] >= 1. - cldfrac[l, c]:
+                    z = zcw_lookup(cdf3[l], sigma[l]) if inhomo else 1.
+                    i, w = ciwp[l, c] * z if inhomo else ciwp[l, c], clwp[l, c] * z if inhomo else clwp[l, c]
+                    if i <= cwp_tiny: i = 0.
+                    if w <= cwp_tiny: w = 0.
+                    ci[l, j, c], cw[l, j, c] = i, w
+                    mask[l, j, c] = 0 if (i == 0. and w == 0.) else 1
+    return mask, ci, cw
+
+
+def _clear_counts_python(mask, cloudLM, cloudMH):
+    nlay, nsub, ncol = mask.shape
+    out = np.zeros((4, ncol), dtype=np.int32)
+    assert cloudLM < cloudMH
+    for c in range(ncol):
+        m = mask[:, :, c].astype(bool)
+        out[0, c] = (~m.any(axis=0)).sum()
+        out[3, c] = (~m[:cloudLM].any(axis=0)).sum()
+        out[2, c] = (~m[cloudLM:cloudMH].any(axis=0)).sum()
+        out[1, c] = (~m[cloudMH:].any(axis=0)).sum()
+    return out
+
+
+@pytest.mark.parametrize("inhomo", [True, False])
+def test_mcica_generator_against_independent_python(oracle, inhomo):
+    from geosradiation_gridcomp_b200 import tables
+    xcw = tables.load_tables()["mcica.xcw_beta"]
+    s = make_columns(40, 72, seed=5150)
+    cols = np.flatnonzero((s["cldf"] > 0).any(axis=1))[:5]
+    assert len(cols) == 5
+    T = lambda k: np.ascontiguousarray(s[k][cols].T)                   # (nlay, ncol) partition layout
+    zmid, play, cld, ciwp, clwp = T("zm"), T("play"), T("cldf"), T("ciwp"), T("clwp")
+    cld[10:14, 0] = [0.95, 0.995, 1.0, 0.91]                           # all three sigma_qcw classes
+    clwp[10:14, 0] = [30., 1e-21, 12., 4.]                             # a negligible water path un-clouds the cell
+    ciwp[10:14, 0] = 0.
+    alat, doy, nsub = s["alat"][cols], 200, 140
+    oracle.set_mcica(1 if inhomo else 0)
+    try:
+        m, ci, cw = oracle.generate_stochastic_clouds(zmid, alat, doy, play, cld, ciwp, clwp, nsub, seed_order=(2, 1, 4, 3))
+    finally:
+        oracle.set_mcica(1)
+    pm, pci, pcw = _mcica_python(zmid, alat, doy, play, cld, ciwp, clwp, nsub, xcw, so=(2, 1, 4, 3), inhomo=inhomo)
+    np.testing.assert_array_equal(m, pm)
+    assert 0.02 < pm.mean() < 0.5 and pm[11, :, 0].sum() == 0
+    np.testing.assert_allclose(ci, pci, rtol=1e-14, atol=0)
+    np.testing.assert_allclose(cw, pcw, rtol=1e-14, atol=0)
+    LM, MH = int(s["cloudLM"]), int(s["cloudMH"])
+    np.testing.assert_array_equal(oracle.clear_counts(m, LM, MH), _clear_counts_python(pm, LM, MH))
