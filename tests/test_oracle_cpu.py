@@ -808,3 +808,50 @@ def test_mcica_generator_against_independent_python(oracle, inhomo):
     np.testing.assert_allclose(cw, pcw, rtol=1e-14, atol=0)
     LM, MH = int(s["cloudLM"]), int(s["cloudMH"])
     np.testing.assert_array_equal(oracle.clear_counts(m, LM, MH), _clear_counts_python(pm, LM, MH))
+
+
+# ---- the clear-sky SW chain on the independent two-stream/adding restatement -------------------------------------
+# spcvmc_sw's clear-sky orchestration (SW/src/rrtmg_sw_spcvmc.F90:391-492: surface albedo per band, aerosol mixing
+# and delta scaling, direct-beam transmittances, flux accumulation with adjflux * ssi * mu0) and the driver's
+# albedo / adjflux / cossza set-up (SW/src/rrtmg_sw_rad.F90:957, :1046, :1121-1127, :1230-1248, :1365), in numpy on
+# _reftra_np / _vrtqdr_np above; fed the oracle's gas and Rayleigh optical depths and solar source (taps).
+@pytest.mark.parametrize("isolvar", [-1, 0])
+def test_sw_clear_sky_chain_against_independent_numpy(oracle, isolvar):
+    from geosradiation_gridcomp_b200 import tables
+    tab = tables.load_tables()
+    ncol, nlay = 16, 72
+    s = make_columns(ncol, nlay, seed=4242)
+    s["coszen"][0] = 1e-12                                        # clamped to zepzen = 1e-10
+    s["adjes"] = 1.0173
+    o = oracle.rrtmg_sw(s, isolvar=isolvar, normFlx=0, taps=("taug", "pfracs", "ssi"))
+    assert o["rc"] == 0
+    ibm = tab["sw.wvn.ngb"].astype(int) - 16                      # 0-based band of each g-point
+    adjflux = s["adjes"] * (s["scon"] / 1.36822e+03 if isolvar < 0 else 1.0)
+    for c in range(ncol):
+        mu = max(1.e-10, s["coszen"][c])
+        albp = np.where((ibm <= 7) | (ibm == 13), s["aldir"][c], np.where(ibm >= 9, s["asdir"][c], (s["asdir"][c] + s["aldir"][c]) / 2.))
+        albd = np.where((ibm <= 7) | (ibm == 13), s["aldif"][c], np.where(ibm >= 9, s["asdif"][c], (s["asdif"][c] + s["aldif"][c]) / 2.))
+        top_down = lambda a: a[::-1]                               # jk = nlay+1-ikl
+        taug, taur = top_down(o["taug"][c].T), top_down(o["pfracs"][c].T)          # (nlay, 112)
+        taua, omga, asya = (top_down(s[k][c])[:, ibm] for k in ("tauaer_sw", "ssaaer", "asmaer"))
+        ztauo = taur + taug + taua
+        zomco = taur + taua * omga
+        zgco = (asya * omga * taua) / zomco
+        zomco = zomco / ztauo
+        zf = zgco ** 2
+        zwf = zomco * zf
+        ztauo = (1. - zwf) * ztauo
+        zomco = (zomco - zwf) / (1. - zwf)
+        zgco = (zgco - zf) / (1. - zf)
+        ref, refd, tra, trad = (np.vstack([a, b[None, :]]) for a, b in
+                                zip(_reftra_np(ztauo, zomco, zgco, mu), (albp, albd, 0. * albp, 0. * albp)))
+        dbt = np.exp(-ztauo / mu)
+        tdbt = np.ones((nlay + 1, 112))
+        for k in range(nlay):
+            tdbt[k + 1] = dbt[k] * tdbt[k]
+        fd, fu = _vrtqdr_np(ref, refd, tra, trad, dbt, tdbt)
+        zinc = adjflux * o["ssi"][c] * mu
+        dn, up = (zinc * fd).sum(axis=1)[::-1], (zinc * fu).sum(axis=1)[::-1]       # level 1 = surface
+        scale = dn.max()
+        assert np.max(np.abs(o["swdflxc"][c] - dn)) / scale < 5e-12, c
+        assert np.max(np.abs(o["swuflxc"][c] - up)) / scale < 5e-12, c
