@@ -855,3 +855,193 @@ def test_sw_clear_sky_chain_against_independent_numpy(oracle, isolvar):
         scale = dn.max()
         assert np.max(np.abs(o["swdflxc"][c] - dn)) / scale < 5e-12, c
         assert np.max(np.abs(o["swuflxc"][c] - up)) / scale < 5e-12, c
+
+
+# ---- an independent restatement of the LW cloud optics -----------------------------------------------------------
+# cldprmc (LW/src/rrtmg_lw_cldprmc.F90:12-385): every ice parameterisation (iceflag 0-4) and the Hu & Stamnes liquid
+# table, vectorised in numpy from the McICA water paths the oracle taps, without reference to oracle/lw.c.
+def _lw_cldprmc_np(s, o, tab, iceflag):
+    ngb = tab["lw.wvn.ngb"].astype(int)                         # 1-based band of each g-point
+    ice1b = np.array([1, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5, 5, 5, 5, 5, 5])
+    cldy = o["cldymc"].astype(bool)                             # [icol][ig][ilay]
+    ciwp, clwp = o["ciwpmc"], o["clwpmc"]
+    rei, rel = s["rei"][:, None, :], s["rel"][:, None, :]       # (ncol, 1, nlay)
+
+    def table(name, factor, nmax):                              # linear interpolation with the end-interval rule
+        t = tab["lw.cld." + name]
+        idx = factor.astype(int)                                # int(): truncation, radii are positive
+        assert idx.min() >= 0 and idx.max() <= nmax
+        idx = np.where(idx == nmax, nmax - 1, np.where(idx == 0, 1, idx))
+        fint = factor - idx
+        lo, hi = t[idx - 1, ngb[None, :, None] - 1], t[idx, ngb[None, :, None] - 1]
+        return lo + fint * (hi - lo)
+
+    if iceflag == 0:
+        a = tab["lw.cld.absice0"]
+        abscoice = (a[0] + a[1] / rei) * np.ones((1, 140, 1))
+    elif iceflag == 1:
+        a = tab["lw.cld.absice1"]
+        ib = ice1b[ngb - 1][None, :, None] - 1
+        abscoice = a[0, ib] + a[1, ib] / rei
+    elif iceflag == 2:
+        abscoice = table("absice2", (rei - 2.) / 3. + 0 * ciwp, 43)
+    elif iceflag == 3:
+        abscoice = table("absice3", (rei - 2.) / 3. + 0 * ciwp, 46)
+    else:
+        abscoice = table("absice4", rei + 0 * ciwp, 200)
+    tau = np.where(cldy & (ciwp > 0.), ciwp * abscoice, 0.)
+    abscoliq = table("absliq1", rel - 1.5 + 0 * clwp, 58)
+    return np.where(cldy & (clwp > 0.), tau + clwp * abscoliq, tau)
+
+
+@pytest.mark.parametrize("iceflag", [0, 1, 2, 3, 4])
+def test_lw_cloud_optics_against_independent_numpy(oracle, iceflag):
+    from geosradiation_gridcomp_b200 import tables
+    tab = tables.load_tables()
+    s = make_columns(48, 72, seed=606)
+    if iceflag == 2:
+        s["rei"] = np.asfortranarray(np.minimum(s["rei"], 131.0))          # absice2 ends at 131 um
+    if iceflag == 4:
+        s["rei"] = np.asfortranarray(1.0 + (s["rei"] - 15.0) * 1.89)       # 1 .. 199.5: both end intervals of absice4
+    o = oracle.rrtmg_lw(s, iceflg=iceflag, taps=("cldymc", "ciwpmc", "clwpmc", "taucmc"))
+    assert o["rc"] == 0
+    mine = _lw_cldprmc_np(s, o, tab, iceflag)
+    assert (mine > 0).sum() > 5000
+    np.testing.assert_allclose(o["taucmc"], mine, rtol=1e-14, atol=0)
+
+
+# ---- the all-sky SW chain: cloud optics, cloudy-cell mixing, surface components, PAR optical thickness -------------
+# cldprmc_sw (SW/src/rrtmg_sw_cldprmc.F90:62-418, iceflag 1-4 and the liquid table with its delta scaling), the
+# cloudy pass of spcvmc_sw (SW/src/rrtmg_sw_spcvmc.F90:501-676), its PAR-weighted in-cloud optical thickness
+# (:748-1108 without the SOLAR_RADVAL blocks) and the driver's output mapping and normalisation
+# (SW/src/rrtmg_sw_rad.F90:1604-1660, :1769-1798), in numpy from the McICA cloud the oracle taps.
+def _sw_cldprmc_np(s, o, tab, iceflag):
+    ngb0 = tab["sw.wvn.ngb"].astype(int) - 16                    # 0-based band of each g-point
+    icxa = tab["sw.wvn.icxa"].astype(int)
+    cldy, ciwp, clwp = o["cldymc"].astype(bool), o["ciwpmc"], o["clwpmc"]      # [icol][ig][ilay]
+    B = ngb0[None, :, None]
+    rei, rel = s["rei"][:, None, :] + 0 * ciwp, s["rel"][:, None, :] + 0 * ciwp
+    T = lambda n: tab["sw.cld." + n]
+    lin = lambda t, idx, fint: t[idx - 1, B] + fint * (t[idx, B] - t[idx - 1, B])
+    epsg, cldmin = 1.e-06, 1.e-20
+    if iceflag == 1:
+        ib = icxa[ngb0][None, :, None] - 1
+        ext = T("abari")[ib] + T("bbari")[ib] / rei
+        ssa = 1. - T("cbari")[ib] - T("dbari")[ib] * rei
+        g = np.minimum(T("ebari")[ib] + T("fbari")[ib] * rei, 1. - epsg)
+        forw = g * g
+    else:
+        factor = rei if iceflag == 4 else (rei - 2.) / 3.
+        idx = factor.astype(int)
+        if iceflag == 2: idx = np.where(idx == 43, 42, idx)
+        if iceflag == 3: idx = np.where(idx == 46, 45, idx)
+        fint = factor - idx
+        sfx = str(iceflag)
+        ext, ssa, g = lin(T("extice" + sfx), idx, fint), lin(T("ssaice" + sfx), idx, fint), lin(T("asyice" + sfx), idx, fint)
+        forw = np.minimum(lin(T("fdlice3"), idx, fint) + 0.5 / ssa, g) if iceflag == 3 else g * g
+    noice = ciwp == 0.
+    ext, ssa, g, forw = (np.where(noice, 0., a) for a in (ext, ssa, g, forw))
+    idx = (rel - 1.5).astype(int)
+    idx = np.where(idx == 0, 1, np.where(idx == 58, 57, idx))
+    fint = rel - 1.5 - idx
+    extl, ssal, gl = lin(T("extliq1"), idx, fint), lin(T("ssaliq1"), idx, fint), lin(T("asyliq1"), idx, fint)
+    ssal = np.where((fint < 0.) & (ssal > 1.), T("ssaliq1")[idx - 1, B], ssal)
+    noliq = clwp == 0.
+    extl, ssal, gl = (np.where(noliq, 0., a) for a in (extl, ssal, gl))
+    forwl = gl * gl
+    with np.errstate(invalid="ignore", divide="ignore"):
+        tauliqorig, tauiceorig = clwp * extl, ciwp * ext
+        ssaliq = ssal * (1. - forwl) / (1. - forwl * ssal)
+        ssaice = ssa * (1. - forw) / (1. - forw * ssa)
+        tauliq, tauice = (1. - forwl * ssal) * tauliqorig, (1. - forw * ssa) * tauiceorig
+        scatliq, scatice = ssaliq * tauliq, ssaice * tauice
+        tauc = tauliq + tauice
+        tauc = np.where(tauc == 0., cldmin, tauc)
+        scatice = np.where(scatice == 0., cldmin, scatice)
+        ssac = (scatliq + scatice) / tauc
+        if iceflag == 3:
+            asmc = (1. / (scatliq + scatice)) * (scatliq * (gl - forwl) / (1. - forwl) + scatice * ((g - forw) / (1. - forw)))
+        else:
+            asmc = (scatliq * (gl - forwl) / (1. - forwl) + scatice * (g - forw) / (1. - forw)) / (scatliq + scatice)
+    z = lambda a, fill: np.where(cldy, a, fill)
+    return z(tauliqorig + tauiceorig, 0.), z(tauc, 0.), z(ssac, 1.), z(asmc, 0.)
+
+
+@pytest.mark.parametrize("iceflag", [1, 2, 3, 4])
+def test_sw_all_sky_chain_against_independent_numpy(oracle, iceflag):
+    from geosradiation_gridcomp_b200 import tables
+    tab = tables.load_tables()
+    ncol, nlay = 24, 72
+    s = make_columns(ncol, nlay, seed=977 + iceflag)
+    if iceflag == 2:
+        s["rei"] = np.asfortranarray(np.minimum(s["rei"], 131.0))
+    o = oracle.rrtmg_sw(s, iceflg=iceflag, normFlx=1, do_drfband=True,
+                        taps=("taug", "pfracs", "ssi", "cldymc", "ciwpmc", "clwpmc", "taucmc"))
+    assert o["rc"] == 0
+    taor, tauc, ssac, asmc = _sw_cldprmc_np(s, o, tab, iceflag)
+    np.testing.assert_allclose(o["taucmc"], tauc, rtol=1e-13, atol=0)
+    ibm = tab["sw.wvn.ngb"].astype(int) - 16
+    LM, MH = int(s["cloudLM"]), int(s["cloudMH"])
+    worst = 0.
+    for c in range(ncol):
+        mu = max(1.e-10, s["coszen"][c])
+        nir = (ibm <= 7) | (ibm == 13)
+        albp = np.where(nir, s["aldir"][c], np.where(ibm >= 9, s["asdir"][c], (s["asdir"][c] + s["aldir"][c]) / 2.))
+        albd = np.where(nir, s["aldif"][c], np.where(ibm >= 9, s["asdif"][c], (s["asdif"][c] + s["aldif"][c]) / 2.))
+        td = lambda a: a[::-1]
+        taug, taur = td(o["taug"][c].T), td(o["pfracs"][c].T)
+        taua, omga, asya = (td(s[k][c])[:, ibm] for k in ("tauaer_sw", "ssaaer", "asmaer"))
+        ztauo = taur + taug + taua
+        zomco = taur + taua * omga
+        zgco = (asya * omga * taua) / zomco
+        zomco = zomco / ztauo
+        zf = zgco ** 2
+        zwf = zomco * zf
+        ztauo = (1. - zwf) * ztauo
+        zomco = (zomco - zwf) / (1. - zwf)
+        zgco = (zgco - zf) / (1. - zf)
+        cld = td(o["cldymc"][c].T.astype(bool))
+        ptau, pomg, pasy = td(tauc[c].T), td(ssac[c].T), td(asmc[c].T)
+        g2 = ztauo * zomco * zgco + ptau * pomg * pasy
+        o2 = ztauo * zomco + ptau * pomg
+        t2 = ztauo + ptau
+        g2 = g2 / o2
+        o2 = o2 / t2
+        ztauo, zomco, zgco = np.where(cld, t2, ztauo), np.where(cld, o2, zomco), np.where(cld, g2, zgco)
+        ref, refd, tra, trad = (np.vstack([a, b[None, :]]) for a, b in
+                                zip(_reftra_np(ztauo, zomco, zgco, mu), (albp, albd, 0. * albp, 0. * albp)))
+        dbt = np.exp(-ztauo / mu)
+        tdbt = np.ones((nlay + 1, 112))
+        for k in range(nlay):
+            tdbt[k + 1] = dbt[k] * tdbt[k]
+        fd, fu = _vrtqdr_np(ref, refd, tra, trad, dbt, tdbt)
+        zinc = s["adjes"] * o["ssi"][c] * mu
+        dn, up = (zinc * fd).sum(axis=1)[::-1], (zinc * fu).sum(axis=1)[::-1]
+        top = max(dn[-1], 1e-7)
+        sel = lambda m, a: float((zinc * a)[m].sum())
+        dirs, tots = tdbt[nlay], fd[nlay]
+        nirr = sel((ibm <= 7) | (ibm == 13), dirs) + 0.5 * sel(ibm == 8, dirs)
+        nirt = sel((ibm <= 7) | (ibm == 13), tots) + 0.5 * sel(ibm == 8, tots)
+        parr = sel((ibm == 9) | (ibm == 10), dirs) + 0.5 * sel(ibm == 8, dirs)
+        part = sel((ibm == 9) | (ibm == 10), tots) + 0.5 * sel(ibm == 8, tots)
+        uvrr, uvrt = sel((ibm == 11) | (ibm == 12), dirs), sel((ibm == 11) | (ibm == 12), tots)
+        mine = dict(swdflx=dn / top, swuflx=up / top, nirr=nirr / top, nirf=(nirt - nirr) / top, parr=parr / top,
+                    parf=(part - parr) / top, uvrr=uvrr / top, uvrf=(uvrt - uvrr) / top,
+                    fswband=np.array([sel(ibm == b, fd[nlay] - fu[nlay]) for b in range(14)]) / top,
+                    drband=np.array([sel(ibm == b, dirs) for b in range(14)]) / top,
+                    dfband=np.array([sel(ibm == b, tots) - sel(ibm == b, dirs) for b in range(14)]) / top)
+        # PAR-weighted in-cloud optical thickness per super-layer (not normalised)
+        wgt = np.where((ibm == 9) | (ibm == 10), 1.0, np.where(ibm == 8, 0.5, 0.0)) * (s["adjes"] * o["ssi"][c])
+        t = taor[c]                                                 # (112, nlay), layer 1 = surface
+        lo, mi, hi = t[:, :LM].sum(axis=1), t[:, LM:MH].sum(axis=1), t[:, MH:].sum(axis=1)
+        tot = lo + mi + hi
+        if cld.any():
+            for key, v in (("l", lo), ("m", mi), ("h", hi), ("t", tot)):
+                mine["cotd" + key + "p"] = float(wgt[v > 0.].sum())
+                mine["cotn" + key + "p"] = float((wgt * v)[v > 0.].sum())
+        for k, v in mine.items():
+            got = o[k][c]
+            err = np.max(np.abs(got - v)) / max(np.max(np.abs(v)), 1e-30)
+            worst = max(worst, err)
+            assert err < 2e-11, (k, c, err)
+    assert (o["cotdtp"] > 0).sum() >= 8 and (o["cotdtp"] == 0).sum() >= 4     # cloudy and clear columns both seen
