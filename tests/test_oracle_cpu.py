@@ -1045,3 +1045,115 @@ def test_sw_all_sky_chain_against_independent_numpy(oracle, iceflag):
             worst = max(worst, err)
             assert err < 2e-11, (k, c, err)
     assert (o["cotdtp"] > 0).sum() >= 8 and (o["cotdtp"] == 0).sum() >= 4     # cloudy and clear columns both seen
+
+
+# ---- an independent restatement of the SW gas optics of band 17 ---------------------------------------------------
+# The driver's column amounts (SW/src/rrtmg_sw_rad.F90:1368-1383), setcoef_sw (SW/src/rrtmg_sw_setcoef.F90:44-140),
+# the 16 -> 12 g-point reduction of band 17 (SW/src/rrtmg_sw_init.F90:125-150, cmbgb17 :570-650) and taumol17
+# (two key species, self and foreign continuum, Rayleigh, solar source interpolated in the binary parameter at the
+# layer where jp crosses layreffr; SW/src/rrtmg_sw_taumol.F90:352-528), in numpy on the blob's original 16-g tables.
+def _sw_band17_np(s, c, tab, isolvar):
+    import math
+    nlay = s["nlay"]
+    K, preflog, tref = "sw.kg17.", tab["sw.ref.preflog"], tab["sw.ref.tref"]
+    wt, ngn = tab["sw.wvn.wt"], tab["sw.wvn.ngn"][6:18]
+    groups, i = [], 0
+    for n in ngn:
+        groups.append(list(range(i, i + n))); i += n
+    assert i == 16
+    rw = np.zeros(16)
+    for g in groups:
+        wsum = 0.
+        for j in g: wsum = wsum + wt[j]
+        for j in g: rw[j] = wt[j] / wsum
+
+    def comb(a, axis, weighted):
+        a = np.moveaxis(a, axis, -1)
+        out = np.zeros(a.shape[:-1] + (12,))
+        for k, g in enumerate(groups):
+            for j in g:
+                out[..., k] = out[..., k] + (a[..., j] * rw[j] if weighted else a[..., j])
+        return out
+    ka, kb = comb(tab[K + "kao"], 3, True), comb(tab[K + "kbo"], 3, True)           # (js, jt, jp, g)
+    selfref, forref = comb(tab[K + "selfrefo"], 1, True), comb(tab[K + "forrefo"], 1, True)
+    src = {n: comb(tab[K + n + "o"], 0, False) for n in ("sfluxref", "irradnce", "facbrght", "snsptdrk")}   # (js, g)
+    rayl, strrat, layreffr, oneminus = float(tab[K + "rayl"][0]), 0.364641, 30, 1. - 1.e-06
+    amd, amw, avogad, grav, stpfac = 28.9660, 18.0160, 6.02214199e+23, 9.8066, 296. / 1013.
+    lin = lambda t, i, f: t[i - 1] + f * (t[i] - t[i - 1])
+    taug, taur, jps, laytrop = np.zeros((nlay, 12)), np.zeros((nlay, 12)), [], 0
+    binpar = []
+    for l in range(nlay):
+        h2o, t, p = s["h2ovmr"][c, l], s["tlay"][c, l], s["play"][c, l]
+        coldry = (s["plev"][c, l] - s["plev"][c, l + 1]) * 1.e3 * avogad / (1.e2 * grav * ((1. - h2o) * amd + h2o * amw) * (1. + h2o))
+        colh2o, colco2 = coldry * h2o, coldry * s["co2vmr"][c, l]
+        plog = math.log(p)
+        lower = plog > 4.56
+        if plog >= 4.56: laytrop += 1
+        jp = min(max(int(36. - 5 * (plog + 0.04)), 1), 58)
+        fp = 5. * (preflog[jp - 1] - plog)
+        jt = min(max(int(3. + (t - tref[jp - 1]) / 15.), 1), 4)
+        ft = ((t - tref[jp - 1]) / 15.) - float(jt - 3)
+        jt1 = min(max(int(3. + (t - tref[jp]) / 15.), 1), 4)
+        ft1 = ((t - tref[jp]) / 15.) - float(jt1 - 3)
+        water = colh2o / coldry
+        forfac = p * stpfac / t / (1. + water)
+        if lower:
+            factor = (332. - t) / 36.
+            indfor = min(2, max(1, int(factor))); forfrac = factor - float(indfor)
+            selffac = water * forfac
+            factor = (t - 188.) / 7.2
+            indself = min(9, max(1, int(factor) - 7)); selffrac = factor - float(indself + 7)
+        else:
+            indfor, forfrac = 3, (t - 188.) / 36. - 1.
+        colh2o, colco2 = 1.e-20 * colh2o, 1.e-20 * colco2
+        colmol = 1.e-20 * coldry + colh2o
+        if colco2 == 0.: colco2 = 1.e-32 * coldry
+        compfp = 1. - fp
+        fac10, fac00, fac11, fac01 = compfp * ft, compfp * (1. - ft), fp * ft1, fp * (1. - ft1)
+        speccomb = colh2o + strrat * colco2
+        specparm = min(colh2o / speccomb, oneminus)
+        specmult = (8. if lower else 4.) * specparm
+        js, fs = 1 + int(specmult), math.fmod(specmult, 1.)
+        k, off = (ka, 1) if lower else (kb, 13)
+        a = lambda dj, jtt, jpp: k[js - 1 + dj, jtt - 1, jpp - off]
+        major = speccomb * ((1. - fs) * fac00 * a(0, jt, jp) + fs * fac00 * a(1, jt, jp) +
+                            (1. - fs) * fac10 * a(0, jt + 1, jp) + fs * fac10 * a(1, jt + 1, jp) +
+                            (1. - fs) * fac01 * a(0, jt1, jp + 1) + fs * fac01 * a(1, jt1, jp + 1) +
+                            (1. - fs) * fac11 * a(0, jt1 + 1, jp + 1) + fs * fac11 * a(1, jt1 + 1, jp + 1))
+        if lower:
+            taug[l] = major + colh2o * (selffac * lin(selfref, indself, selffrac) + forfac * lin(forref, indfor, forfrac))
+        else:
+            taug[l] = major + colh2o * forfac * lin(forref, indfor, forfrac)
+        taur[l] = colmol * rayl
+        jps.append(jp); binpar.append((js, fs))
+    laysolfr = nlay
+    ssi = None
+    for lay in range(laytrop + 1, nlay + 1):                     # 1-based layers above the tropopause
+        if jps[lay - 2] < layreffr and jps[lay - 1] >= layreffr: laysolfr = lay
+        if lay == laysolfr:
+            js, fs = binpar[lay - 1]
+            f = lambda t: t[js - 1] + fs * (t[js] - t[js - 1])
+            # isolvar = 0: the three NRLSSI2 terms share one scaling, scon over the mean-cycle integrals
+            # (SW/src/rrtmg_sw_rad.F90:1050-1055, SW/src/NRLSSI2.F90:47-49)
+            svar = s["scon"] / (0.996047 + -0.511590 + 1360.37)
+            ssi = f(src["sfluxref"]) if isolvar < 0 else svar * f(src["facbrght"]) + svar * f(src["snsptdrk"]) + svar * f(src["irradnce"])
+            break
+    return taug, taur, ssi, laytrop
+
+
+@pytest.mark.parametrize("isolvar", [-1, 0])
+def test_sw_gas_optics_band_17_against_independent_numpy(oracle, isolvar):
+    from geosradiation_gridcomp_b200 import tables
+    tab = tables.load_tables()
+    ncol = 16
+    s = make_columns(ncol, 72, seed=1717)
+    s["co2vmr"][:3] *= 30.0                                       # move the binary parameter across its range
+    s["h2ovmr"][3:6] *= 1e-2
+    o = oracle.rrtmg_sw(s, isolvar=isolvar, taps=("taug", "pfracs", "ssi", "laytrop"))
+    assert o["rc"] == 0
+    for c in range(ncol):
+        taug, taur, ssi, laytrop = _sw_band17_np(s, c, tab, isolvar)
+        assert laytrop == o["laytrop"][c]
+        np.testing.assert_allclose(o["taug"][c, 6:18, :].T, taug, rtol=1e-11, err_msg=f"taug col {c}")
+        np.testing.assert_allclose(o["pfracs"][c, 6:18, :].T, taur, rtol=1e-13, err_msg=f"taur col {c}")
+        np.testing.assert_allclose(o["ssi"][c, 6:18], ssi, rtol=1e-13, err_msg=f"ssi col {c}")
