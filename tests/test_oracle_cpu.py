@@ -1047,16 +1047,15 @@ def test_sw_all_sky_chain_against_independent_numpy(oracle, iceflag):
     assert (o["cotdtp"] > 0).sum() >= 8 and (o["cotdtp"] == 0).sum() >= 4     # cloudy and clear columns both seen
 
 
-# ---- an independent restatement of the SW gas optics of band 17 ---------------------------------------------------
+# ---- an independent restatement of the SW gas optics of bands 17 and 24 ---------------------------------------------------
 # The driver's column amounts (SW/src/rrtmg_sw_rad.F90:1368-1383), setcoef_sw (SW/src/rrtmg_sw_setcoef.F90:44-140),
 # the 16 -> 12 g-point reduction of band 17 (SW/src/rrtmg_sw_init.F90:125-150, cmbgb17 :570-650) and taumol17
 # (two key species, self and foreign continuum, Rayleigh, solar source interpolated in the binary parameter at the
 # layer where jp crosses layreffr; SW/src/rrtmg_sw_taumol.F90:352-528), in numpy on the blob's original 16-g tables.
-def _sw_band17_np(s, c, tab, isolvar):
-    import math
-    nlay = s["nlay"]
-    K, preflog, tref = "sw.kg17.", tab["sw.ref.preflog"], tab["sw.ref.tref"]
-    wt, ngn = tab["sw.wvn.wt"], tab["sw.wvn.ngn"][6:18]
+def _sw_comb(tab, band):
+    """rwgt of a band (SW/src/rrtmg_sw_init.F90:125-150) and its 16 -> ngc combination along one axis."""
+    ngs = [0] + list(tab["sw.wvn.ngs"])
+    wt, ngn = tab["sw.wvn.wt"], tab["sw.wvn.ngn"][ngs[band - 16]:ngs[band - 15]]
     groups, i = [], 0
     for n in ngn:
         groups.append(list(range(i, i + n))); i += n
@@ -1069,25 +1068,26 @@ def _sw_band17_np(s, c, tab, isolvar):
 
     def comb(a, axis, weighted):
         a = np.moveaxis(a, axis, -1)
-        out = np.zeros(a.shape[:-1] + (12,))
+        out = np.zeros(a.shape[:-1] + (len(groups),))
         for k, g in enumerate(groups):
             for j in g:
                 out[..., k] = out[..., k] + (a[..., j] * rw[j] if weighted else a[..., j])
         return out
-    ka, kb = comb(tab[K + "kao"], 3, True), comb(tab[K + "kbo"], 3, True)           # (js, jt, jp, g)
-    selfref, forref = comb(tab[K + "selfrefo"], 1, True), comb(tab[K + "forrefo"], 1, True)
-    src = {n: comb(tab[K + n + "o"], 0, False) for n in ("sfluxref", "irradnce", "facbrght", "snsptdrk")}   # (js, g)
-    rayl, strrat, layreffr, oneminus = float(tab[K + "rayl"][0]), 0.364641, 30, 1. - 1.e-06
+    return comb, slice(ngs[band - 16], ngs[band - 15])
+
+
+def _sw_setcoef_np(s, c, tab):
+    """Column amounts of the driver and setcoef_sw, layer by layer; returns (list of dicts, laytrop)."""
+    import math
+    preflog, tref = tab["sw.ref.preflog"], tab["sw.ref.tref"]
     amd, amw, avogad, grav, stpfac = 28.9660, 18.0160, 6.02214199e+23, 9.8066, 296. / 1013.
-    lin = lambda t, i, f: t[i - 1] + f * (t[i] - t[i - 1])
-    taug, taur, jps, laytrop = np.zeros((nlay, 12)), np.zeros((nlay, 12)), [], 0
-    binpar = []
-    for l in range(nlay):
+    L, laytrop = [], 0
+    for l in range(s["nlay"]):
         h2o, t, p = s["h2ovmr"][c, l], s["tlay"][c, l], s["play"][c, l]
         coldry = (s["plev"][c, l] - s["plev"][c, l + 1]) * 1.e3 * avogad / (1.e2 * grav * ((1. - h2o) * amd + h2o * amw) * (1. + h2o))
-        colh2o, colco2 = coldry * h2o, coldry * s["co2vmr"][c, l]
+        d = {k: coldry * s[k + "vmr"][c, l] for k in ("h2o", "co2", "o3", "ch4", "o2")}
         plog = math.log(p)
-        lower = plog > 4.56
+        d["lower"] = plog > 4.56
         if plog >= 4.56: laytrop += 1
         jp = min(max(int(36. - 5 * (plog + 0.04)), 1), 58)
         fp = 5. * (preflog[jp - 1] - plog)
@@ -1095,54 +1095,123 @@ def _sw_band17_np(s, c, tab, isolvar):
         ft = ((t - tref[jp - 1]) / 15.) - float(jt - 3)
         jt1 = min(max(int(3. + (t - tref[jp]) / 15.), 1), 4)
         ft1 = ((t - tref[jp]) / 15.) - float(jt1 - 3)
-        water = colh2o / coldry
-        forfac = p * stpfac / t / (1. + water)
-        if lower:
+        water = d["h2o"] / coldry
+        d["forfac"] = p * stpfac / t / (1. + water)
+        if d["lower"]:
             factor = (332. - t) / 36.
-            indfor = min(2, max(1, int(factor))); forfrac = factor - float(indfor)
-            selffac = water * forfac
+            d["indfor"] = min(2, max(1, int(factor))); d["forfrac"] = factor - float(d["indfor"])
+            d["selffac"] = water * d["forfac"]
             factor = (t - 188.) / 7.2
-            indself = min(9, max(1, int(factor) - 7)); selffrac = factor - float(indself + 7)
+            d["indself"] = min(9, max(1, int(factor) - 7)); d["selffrac"] = factor - float(d["indself"] + 7)
         else:
-            indfor, forfrac = 3, (t - 188.) / 36. - 1.
-        colh2o, colco2 = 1.e-20 * colh2o, 1.e-20 * colco2
-        colmol = 1.e-20 * coldry + colh2o
-        if colco2 == 0.: colco2 = 1.e-32 * coldry
+            d["indfor"], d["forfrac"] = 3, (t - 188.) / 36. - 1.
+        for k in ("h2o", "co2", "o3", "ch4", "o2"):
+            d[k] = 1.e-20 * d[k]
+        d["colmol"] = 1.e-20 * coldry + d["h2o"]
+        for k in ("co2", "ch4", "o2"):
+            if d[k] == 0.: d[k] = 1.e-32 * coldry
         compfp = 1. - fp
-        fac10, fac00, fac11, fac01 = compfp * ft, compfp * (1. - ft), fp * ft1, fp * (1. - ft1)
-        speccomb = colh2o + strrat * colco2
-        specparm = min(colh2o / speccomb, oneminus)
-        specmult = (8. if lower else 4.) * specparm
-        js, fs = 1 + int(specmult), math.fmod(specmult, 1.)
-        k, off = (ka, 1) if lower else (kb, 13)
-        a = lambda dj, jtt, jpp: k[js - 1 + dj, jtt - 1, jpp - off]
-        major = speccomb * ((1. - fs) * fac00 * a(0, jt, jp) + fs * fac00 * a(1, jt, jp) +
-                            (1. - fs) * fac10 * a(0, jt + 1, jp) + fs * fac10 * a(1, jt + 1, jp) +
-                            (1. - fs) * fac01 * a(0, jt1, jp + 1) + fs * fac01 * a(1, jt1, jp + 1) +
-                            (1. - fs) * fac11 * a(0, jt1 + 1, jp + 1) + fs * fac11 * a(1, jt1 + 1, jp + 1))
-        if lower:
-            taug[l] = major + colh2o * (selffac * lin(selfref, indself, selffrac) + forfac * lin(forref, indfor, forfrac))
-        else:
-            taug[l] = major + colh2o * forfac * lin(forref, indfor, forfrac)
-        taur[l] = colmol * rayl
-        jps.append(jp); binpar.append((js, fs))
-    laysolfr = nlay
-    ssi = None
+        d.update(jp=jp, jt=jt, jt1=jt1, fac10=compfp * ft, fac00=compfp * (1. - ft), fac11=fp * ft1, fac01=fp * (1. - ft1))
+        L.append(d)
+    return L, laytrop
+
+
+def _sw_binary(d, other, strrat, n):
+    import math
+    speccomb = d["h2o"] + strrat * d[other]
+    specmult = n * min(d["h2o"] / speccomb, 1. - 1.e-06)
+    return speccomb, 1 + int(specmult), math.fmod(specmult, 1.)
+
+
+def _sw_major2(k, off, d, speccomb, js, fs):
+    """speccomb * the eight-point interpolation in (binary parameter, temperature, pressure); k(js, jt, jp, ig)."""
+    a = lambda dj, jtt, jpp: k[js - 1 + dj, jtt - 1, jpp - off]
+    jp, jt, jt1 = d["jp"], d["jt"], d["jt1"]
+    return speccomb * ((1. - fs) * d["fac00"] * a(0, jt, jp) + fs * d["fac00"] * a(1, jt, jp) +
+                       (1. - fs) * d["fac10"] * a(0, jt + 1, jp) + fs * d["fac10"] * a(1, jt + 1, jp) +
+                       (1. - fs) * d["fac01"] * a(0, jt1, jp + 1) + fs * d["fac01"] * a(1, jt1, jp + 1) +
+                       (1. - fs) * d["fac11"] * a(0, jt1 + 1, jp + 1) + fs * d["fac11"] * a(1, jt1 + 1, jp + 1))
+
+
+def _sw_source(src, js, fs, isolvar, scon):
+    f = lambda t: t[js - 1] + fs * (t[js] - t[js - 1])
+    if isolvar < 0:
+        return f(src["sfluxref"])
+    # isolvar = 0: the three NRLSSI2 terms share one scaling, scon over the mean-cycle integrals
+    # (SW/src/rrtmg_sw_rad.F90:1050-1055, SW/src/NRLSSI2.F90:47-49)
+    svar = scon / (0.996047 + -0.511590 + 1360.37)
+    return svar * f(src["facbrght"]) + svar * f(src["snsptdrk"]) + svar * f(src["irradnce"])
+
+
+_lin = lambda t, i, f: t[i - 1] + f * (t[i] - t[i - 1])
+
+
+def _sw_band17_np(s, c, tab, isolvar):
+    K = "sw.kg17."
+    comb, _ = _sw_comb(tab, 17)
+    ka, kb = comb(tab[K + "kao"], 3, True), comb(tab[K + "kbo"], 3, True)           # (js, jt, jp, g)
+    selfref, forref = comb(tab[K + "selfrefo"], 1, True), comb(tab[K + "forrefo"], 1, True)
+    src = {n: comb(tab[K + n + "o"], 0, False) for n in ("sfluxref", "irradnce", "facbrght", "snsptdrk")}   # (js, g)
+    rayl, strrat, layreffr = float(tab[K + "rayl"][0]), 0.364641, 30
+    L, laytrop = _sw_setcoef_np(s, c, tab)
+    nlay = len(L)
+    taug, taur = np.zeros((nlay, 12)), np.zeros((nlay, 12))
+    for l, d in enumerate(L):
+        speccomb, js, fs = _sw_binary(d, "co2", strrat, 8. if d["lower"] else 4.)
+        major = _sw_major2(ka if d["lower"] else kb, 1 if d["lower"] else 13, d, speccomb, js, fs)
+        cont = d["forfac"] * _lin(forref, d["indfor"], d["forfrac"])
+        if d["lower"]:
+            cont = d["selffac"] * _lin(selfref, d["indself"], d["selffrac"]) + cont
+        taug[l] = major + d["h2o"] * cont
+        taur[l] = d["colmol"] * rayl
+    laysolfr, ssi = nlay, None
     for lay in range(laytrop + 1, nlay + 1):                     # 1-based layers above the tropopause
-        if jps[lay - 2] < layreffr and jps[lay - 1] >= layreffr: laysolfr = lay
+        if L[lay - 2]["jp"] < layreffr and L[lay - 1]["jp"] >= layreffr: laysolfr = lay
         if lay == laysolfr:
-            js, fs = binpar[lay - 1]
-            f = lambda t: t[js - 1] + fs * (t[js] - t[js - 1])
-            # isolvar = 0: the three NRLSSI2 terms share one scaling, scon over the mean-cycle integrals
-            # (SW/src/rrtmg_sw_rad.F90:1050-1055, SW/src/NRLSSI2.F90:47-49)
-            svar = s["scon"] / (0.996047 + -0.511590 + 1360.37)
-            ssi = f(src["sfluxref"]) if isolvar < 0 else svar * f(src["facbrght"]) + svar * f(src["snsptdrk"]) + svar * f(src["irradnce"])
+            _, js, fs = _sw_binary(L[lay - 1], "co2", strrat, 4.)
+            ssi = _sw_source(src, js, fs, isolvar, s["scon"])
+            break
+    return taug, taur, ssi, laytrop
+
+
+def _sw_band24_np(s, c, tab, isolvar):
+    """taumol24 (SW/src/rrtmg_sw_taumol.F90:1364-1504) and cmbgb24 (SW/src/rrtmg_sw_init.F90:1214-1322): H2O/O2 below
+    the tropopause with O3 and the water continuum, O2 and O3 above; the Rayleigh coefficient depends on the g-point
+    and, below, on the binary parameter; the source layer search runs over the LOWER layers."""
+    K = "sw.kg24."
+    comb, _ = _sw_comb(tab, 24)
+    ka, kb = comb(tab[K + "kao"], 3, True), comb(tab[K + "kbo"], 2, True)           # (js, jt, jp, g), (jt, jp, g)
+    selfref, forref = comb(tab[K + "selfrefo"], 1, True), comb(tab[K + "forrefo"], 1, True)
+    src = {n: comb(tab[K + n + "o"], 0, False) for n in ("sfluxref", "irradnce", "facbrght", "snsptdrk")}
+    rayla, raylb = comb(tab[K + "raylao"], 0, True), comb(tab[K + "raylbo"], 0, True)   # (js, g), (g)
+    abso3a, abso3b = comb(tab[K + "abso3ao"], 0, True), comb(tab[K + "abso3bo"], 0, True)
+    strrat, layreffr = 0.124692, 1
+    L, laytrop = _sw_setcoef_np(s, c, tab)
+    nlay = len(L)
+    taug, taur = np.zeros((nlay, 8)), np.zeros((nlay, 8))
+    for l, d in enumerate(L):
+        if d["lower"]:
+            speccomb, js, fs = _sw_binary(d, "o2", strrat, 8.)
+            cont = d["selffac"] * _lin(selfref, d["indself"], d["selffrac"]) + d["forfac"] * _lin(forref, d["indfor"], d["forfrac"])
+            taug[l] = _sw_major2(ka, 1, d, speccomb, js, fs) + d["o3"] * abso3a + d["h2o"] * cont
+            taur[l] = d["colmol"] * _lin(rayla, js, fs)
+        else:
+            jp, jt, jt1 = d["jp"], d["jt"], d["jt1"]
+            taug[l] = d["o2"] * (d["fac00"] * kb[jt - 1, jp - 13] + d["fac10"] * kb[jt, jp - 13] +
+                                 d["fac01"] * kb[jt1 - 1, jp - 12] + d["fac11"] * kb[jt1, jp - 12]) + d["o3"] * abso3b
+            taur[l] = d["colmol"] * raylb
+    laysolfr, ssi = laytrop, None
+    for lay in range(1, laytrop + 1):
+        if L[lay - 1]["jp"] < layreffr and L[lay]["jp"] >= layreffr: laysolfr = min(lay + 1, laytrop)
+        if lay == laysolfr:
+            _, js, fs = _sw_binary(L[lay - 1], "o2", strrat, 8.)
+            ssi = _sw_source(src, js, fs, isolvar, s["scon"])
             break
     return taug, taur, ssi, laytrop
 
 
 @pytest.mark.parametrize("isolvar", [-1, 0])
-def test_sw_gas_optics_band_17_against_independent_numpy(oracle, isolvar):
+def test_sw_gas_optics_bands_17_and_24_against_independent_numpy(oracle, isolvar):
     from geosradiation_gridcomp_b200 import tables
     tab = tables.load_tables()
     ncol = 16
@@ -1152,8 +1221,9 @@ def test_sw_gas_optics_band_17_against_independent_numpy(oracle, isolvar):
     o = oracle.rrtmg_sw(s, isolvar=isolvar, taps=("taug", "pfracs", "ssi", "laytrop"))
     assert o["rc"] == 0
     for c in range(ncol):
-        taug, taur, ssi, laytrop = _sw_band17_np(s, c, tab, isolvar)
-        assert laytrop == o["laytrop"][c]
-        np.testing.assert_allclose(o["taug"][c, 6:18, :].T, taug, rtol=1e-11, err_msg=f"taug col {c}")
-        np.testing.assert_allclose(o["pfracs"][c, 6:18, :].T, taur, rtol=1e-13, err_msg=f"taur col {c}")
-        np.testing.assert_allclose(o["ssi"][c, 6:18], ssi, rtol=1e-13, err_msg=f"ssi col {c}")
+        for fn, g in ((_sw_band17_np, slice(6, 18)), (_sw_band24_np, slice(66, 74))):
+            taug, taur, ssi, laytrop = fn(s, c, tab, isolvar)
+            assert laytrop == o["laytrop"][c]
+            np.testing.assert_allclose(o["taug"][c, g, :].T, taug, rtol=1e-11, err_msg=f"taug col {c}")
+            np.testing.assert_allclose(o["pfracs"][c, g, :].T, taur, rtol=1e-13, err_msg=f"taur col {c}")
+            np.testing.assert_allclose(o["ssi"][c, g], ssi, rtol=1e-13, err_msg=f"ssi col {c}")
