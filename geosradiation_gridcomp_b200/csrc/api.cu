@@ -40,14 +40,15 @@ void profile_add(const char *name, float ms) {
 namespace {
 
 constexpr int NSIDE = 4;
+constexpr int NSTAGE = 4;   // staging sets of the host-array pipeline that exist (g.stages of them are used)
 
 struct Path {   // per-path (LW or SW) execution resources
     cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
     cudaStream_t side[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev[1 + NSIDE] = {};
-    cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_free[2] = {};
+    cudaEvent_t ev_in[NSTAGE] = {}, ev_done[NSTAGE] = {}, ev_free[NSTAGE] = {};
     Slab slab;            // kernel scratch
-    Slab stage[2];        // host-pointer mode: device copies of one chunk's boundary arrays
+    Slab stage[NSTAGE];   // host-pointer mode: device copies of one chunk's boundary arrays
     Slab glue;            // fused Run-phase glue: the RRTMG argument arrays of one chunk
     Slab zeros;           // removed-gas runs: the array that stands in for the zeroed gas
     KissJump *d_jumps = nullptr;
@@ -69,6 +70,7 @@ struct Ctx {
     Path lw, sw;
     size_t chunk_cols = 0;   // 0: automatic
     size_t host_chunk_cols = 16384;
+    int stages = 2;          // staging sets in flight (RRTMGX_STAGES): deeper than double buffering measured slower, profiles/r4_d_*
     std::mutex mu;
 };
 
@@ -98,7 +100,7 @@ int path_init(Path &p) {
         if (!ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking))) return RRTMGX_ECUDA;
     for (auto &e : p.ev)
         if (!ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming))) return RRTMGX_ECUDA;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NSTAGE; ++i) {
         if (!ok(cudaEventCreateWithFlags(&p.ev_in[i], cudaEventDisableTiming))) return RRTMGX_ECUDA;
         if (!ok(cudaEventCreateWithFlags(&p.ev_done[i], cudaEventDisableTiming))) return RRTMGX_ECUDA;
         if (!ok(cudaEventCreateWithFlags(&p.ev_free[i], cudaEventDisableTiming))) return RRTMGX_ECUDA;
@@ -113,7 +115,7 @@ void path_free(Path &p) {
     if (p.d2h) cudaStreamDestroy(p.d2h);
     for (auto &s : p.side) if (s) cudaStreamDestroy(s);
     for (auto &e : p.ev) if (e) cudaEventDestroy(e);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NSTAGE; ++i) {
         if (p.ev_in[i]) cudaEventDestroy(p.ev_in[i]);
         if (p.ev_done[i]) cudaEventDestroy(p.ev_done[i]);
         if (p.ev_free[i]) cudaEventDestroy(p.ev_free[i]);
@@ -231,23 +233,24 @@ __global__ void narrow_kernel(const double *__restrict__ x, float *__restrict__ 
 }
 
 // Host-pointer mode: run `fn(chunk_args, nc)` over chunks with H2D / compute / D2H overlapped
-// on three streams and two staging sets.
+// on three streams and g.stages staging sets (a set is reused once the D2H of its previous chunk is done).
 template <class Args, class Fn>
 int run_staged(Path &p, const Args &a, Args &ca, std::vector<Arr> &arrs, int ncol, size_t chunk, Fn fn) {
     size_t stage_bytes = 0;
     for (auto &r : arrs)
         stage_bytes += (((r.rows * chunk * r.elem) + 255) & ~(size_t)255) +
                        (r.f32 ? ((r.rows * chunk * 8 + 255) & ~(size_t)255) : 0);
-    for (int s = 0; s < 2; ++s)
+    const int nstage = g.stages;
+    for (int s = 0; s < nstage; ++s)
         if (int rc = grow(p.stage[s], stage_bytes + 4096)) return rc;
     int k = 0;
     for (size_t col0 = 0; col0 < (size_t)ncol; col0 += chunk, ++k) {
-        const int s = k & 1;
+        const int s = k % nstage;
         const size_t nc = std::min(chunk, (size_t)ncol - col0);
         Slab &st = p.stage[s];
         st.used = 0;
         std::vector<void *> dev(arrs.size()), raw(arrs.size());
-        if (k >= 2) cudaStreamWaitEvent(p.h2d, p.ev_free[s], 0);
+        if (k >= nstage) cudaStreamWaitEvent(p.h2d, p.ev_free[s], 0);
         for (size_t i = 0; i < arrs.size(); ++i) {
             Arr &r = arrs[i];
             raw[i] = r.host ? (void *)st.take<char>(r.rows * nc * r.elem) : nullptr;
@@ -414,6 +417,7 @@ int rrtmgx_init(const RrtmgxConfig *cfg) {
     }
     if (const char *e = std::getenv("RRTMGX_CHUNK")) g.chunk_cols = (size_t)std::atoll(e);
     if (const char *e = std::getenv("RRTMGX_HOST_CHUNK")) g.host_chunk_cols = std::max<size_t>(1024, (size_t)std::atoll(e));
+    if (const char *e = std::getenv("RRTMGX_STAGES")) g.stages = std::min(NSTAGE, std::max(2, std::atoi(e)));
     g.ready = true;
     return 0;
 }

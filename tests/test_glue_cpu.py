@@ -2,6 +2,7 @@
 GEOS_SolarGridComp.F90:6113-6223, :6395-6447) checked by properties: the native state is the synthetic
 RRTMG state run backwards through the glue, so the glue must reproduce that state."""
 import numpy as np
+import pytest
 
 from geosradiation_gridcomp_b200.synthetic import make_columns, make_native_state
 
@@ -77,3 +78,140 @@ def test_solar_glue(oracle):
     assert (f["cottp"][~cloudy] == n["undef"]).all()
     np.testing.assert_array_equal(f["cottp"][cloudy], o["cotntp"][cloudy] / o["cotdtp"][cloudy])
     np.testing.assert_array_equal(f["cldts"], 1.0 - o["clearCounts"][:, 0] / 112.0)
+
+
+# ---- an independent restatement of the Irrad Run-phase glue ---------------------------------------------------------
+# GEOS_IrradGridComp.F90:3237-3371 in vectorised numpy, written from the Fortran without reference to oracle/glue.c:
+# the vertical flip, TLEV, water paths, radius clamps of every ice/liquid option, unit conversions, aerosol
+# absorption, ZM and the clean-up of negatives.  Same IEEE operations in the same order: bit-exact.
+def _irrad_prepare_np(n, iceflg, liqflg):
+    lm = n["lm"]
+    ple, pl, t = n["ple"], n["pl"], n["t"]                       # (ncol, LM+1) / (ncol, LM), level 1 at the model top
+    dp = ple[:, 1:] - ple[:, :-1]                                # DP(1..LM)
+    tlev = np.empty_like(ple)                                    # TLEV(1..LM+1) -> columns 0..LM
+    tlev[:, 1:lm] = (t[:, :-1] * dp[:, 1:] + t[:, 1:] * dp[:, :-1]) / (dp[:, :-1] + dp[:, 1:])
+    tlev[:, lm] = n["t2m"]
+    tlev[:, 0] = tlev[:, 1]
+    fl = lambda a: np.asfortranarray(a[:, ::-1])                 # K = 1..LM  <-  LV = LM..1
+    xx = 1.02 * 100 * dp
+    out = dict(clwp=fl(xx * n["qliq"]), ciwp=fl(xx * n["qice"]))
+    rel, rei = fl(n["rliq"]), fl(n["rice"])
+    if liqflg == 0: rel = np.minimum(np.maximum(rel, 5.0), 10.0)
+    elif liqflg == 1: rel = np.minimum(np.maximum(rel, 2.5), 60.0)
+    lim = {0: (10.0, 30.0), 1: (13.0, 130.0), 2: (5.0, 131.0), 3: (5.0, 140.0)}
+    if iceflg in lim: rei = np.minimum(np.maximum(rei, lim[iceflg][0]), lim[iceflg][1])
+    elif iceflg == 4: rei = np.minimum(np.maximum(rei * 2., 1.0), 200.0)
+    out.update(rel=rel, rei=rei)
+    plev = np.empty_like(ple); tl = np.empty_like(ple)
+    plev[:, :lm] = (ple[:, 1:] / 100.)[:, ::-1]                  # PLE_R(K-1) = PLE(LV)/100
+    tl[:, :lm] = tlev[:, 1:][:, ::-1]                            # TLEV_R(K-1) = TLEV(LV+1)
+    plev[:, lm] = ple[:, 0] / 100.
+    tl[:, lm] = tlev[:, 0]
+    out.update(plev=plev, tlev=tl, play=fl(pl / 100.), tlay=fl(t))
+    pos = lambda a: np.where(a < 0., 0., a)
+    out["h2ovmr"] = pos(fl(n["q"] / (1. - n["q"]) * (n["airmw"] / n["h2omw"])))
+    out["o3vmr"] = pos(fl(n["o3"] * (n["airmw"] / n["o3mw"])))
+    for dst, src in (("ch4vmr", "ch4"), ("n2ovmr", "n2o"), ("co2vmr", "co2"), ("cfc11vmr", "cfc11"),
+                     ("cfc12vmr", "cfc12"), ("cfc22vmr", "hcfc22"), ("cldf", "fcld")):
+        out[dst] = pos(fl(n[src]))
+    out["o2vmr"] = np.full_like(out["play"], n["o2"])
+    out["ccl4vmr"] = np.full_like(out["play"], n["ccl4"])
+    out["tauaer"] = np.maximum(n["taua_lw"] - n["ssaa_lw"], 0.)[:, ::-1, :]
+    zm = np.zeros_like(out["play"])
+    for k in range(1, lm):
+        # Fortran layer K is column k = K-1 here; PLE_R / TLEV_R are dimensioned (0:LM), so level K-1 is column k
+        zm[:, k] = zm[:, k - 1] + n["rgas"] * tl[:, k] / n["grav"] * (out["play"][:, k - 1] - out["play"][:, k]) / plev[:, k]
+    out.update(zm=zm, tsfc=n["ts"], alat=n["lats"], emis=np.repeat(n["emis"][:, None], 16, axis=1),
+               cloudLM=lm - n["lcldlm"] + 1, cloudMH=lm - n["lcldmh"] + 1)
+    return out
+
+
+@pytest.mark.parametrize("iceflg,liqflg", [(3, 1), (0, 0), (1, 1), (2, 1), (4, 1)])
+def test_irrad_prepare_against_independent_numpy(oracle, iceflg, liqflg):
+    from geosradiation_gridcomp_b200.synthetic import make_native_state
+    n = make_native_state(300, 72, seed=31)
+    got = oracle.irrad_prepare(n, iceflg=iceflg, liqflg=liqflg)
+    mine = _irrad_prepare_np(n, iceflg, liqflg)
+    assert (n["q"] < 0).any() and (n["fcld"] < 0).any()
+    for k, v in mine.items():
+        if k in ("cloudLM", "cloudMH"):
+            assert got[k] == v, k
+        else:
+            np.testing.assert_array_equal(got[k], v, err_msg=k)
+
+
+# GEOS_SolarGridComp.F90:6113-6223 (aerosol normalisation, flip, clamps, TLEV with TS at the surface, ZL) and the two
+# drivers' epilogues (GEOS_IrradGridComp.F90:3486-3533, GEOS_SolarGridComp.F90:6395-6453), same treatment.
+def _solar_prepare_np(n, iceflg, liqflg):
+    lm = n["lm"]
+    taua, ssaa, asya = n["taua_sw"], n["ssaa_sw"], n["asya_sw"]
+    good = (taua > 0.) & (ssaa > 0.)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        asy = np.where(good, asya / ssaa, 0.)
+        ssa = np.where(good, ssaa / taua, 0.)
+    tau = np.where(good, taua, 0.)
+    ple, pl, t = n["ple"], n["pl"], n["t"]
+    dpr = ple[:, 1:] - ple[:, :-1]
+    fl = lambda a: np.asfortranarray(a[:, ::-1])
+    out = dict(ciwp=(1.02 * 100 * fl(dpr)) * fl(n["qice"]), clwp=(1.02 * 100 * fl(dpr)) * fl(n["qliq"]))
+    rei, rel = fl(n["rice"]), fl(n["rliq"])
+    lim = {0: (10., 30.), 1: (13., 130.), 2: (5., 131.), 3: (5., 140.)}
+    if iceflg in lim: rei = np.minimum(np.maximum(rei, lim[iceflg][0]), lim[iceflg][1])
+    elif iceflg == 4: rei = np.minimum(np.maximum(rei * 2., 1.), 200.)
+    if liqflg == 0: rel = np.minimum(np.maximum(rel, 10.), 30.)
+    elif liqflg == 1: rel = np.minimum(np.maximum(rel, 2.5), 60.)
+    tlev = np.empty_like(ple)
+    tlev[:, 1:lm] = (t[:, :-1] * dpr[:, 1:] + t[:, 1:] * dpr[:, :-1]) / (dpr[:, :-1] + dpr[:, 1:])
+    tlev[:, lm] = n["ts"]
+    tlev[:, 0] = tlev[:, 1]
+    plev, tl = fl(ple) / 100., fl(tlev)
+    play = fl(pl) / 100.
+    pos = lambda a: np.where(a < 0., 0., a)
+    zl = np.zeros_like(play)
+    for k in range(1, lm):                       # Fortran k = 2..LM, all arrays 1-based: index k here is k+1 there
+        zl[:, k] = zl[:, k - 1] + n["rgas"] * tl[:, k] / n["grav"] * (play[:, k - 1] - play[:, k]) / plev[:, k]
+    out.update(rei=rei, rel=rel, plev=plev, play=play, tlay=fl(t), zm=zl,
+               h2ovmr=pos(fl(n["q"]) / (1. - fl(n["q"])) * (n["airmw"] / n["h2omw"])),
+               o3vmr=pos(fl(n["o3"]) * (n["airmw"] / n["o3mw"])), ch4vmr=pos(fl(n["ch4"])),
+               co2vmr=np.full_like(play, n["co2_fixed"]), o2vmr=np.full_like(play, n["o2"]), cld=pos(fl(n["fcld"])),
+               tauaer=tau[:, ::-1, :], ssaaer=ssa[:, ::-1, :], asmaer=asy[:, ::-1, :])
+    return out
+
+
+@pytest.mark.parametrize("iceflg,liqflg", [(3, 1), (0, 0), (1, 1), (2, 1), (4, 1)])
+def test_solar_prepare_against_independent_numpy(oracle, iceflg, liqflg):
+    from geosradiation_gridcomp_b200.synthetic import make_native_state
+    n = make_native_state(300, 72, seed=32)
+    n["taua_sw"][:7, 3:9, :] = 0.0                          # no aerosol: all three properties zeroed, no 0/0
+    got = oracle.solar_prepare(n, iceflg=iceflg, liqflg=liqflg)
+    for k, v in _solar_prepare_np(n, iceflg, liqflg).items():
+        np.testing.assert_array_equal(got[k], v, err_msg=k)
+    assert got["cloudLM"] == 72 - n["lcldlm"] + 1 and got["cloudMH"] == 72 - n["lcldmh"] + 1
+
+
+def test_driver_epilogues_against_independent_numpy(oracle):
+    from geosradiation_gridcomp_b200.synthetic import make_native_state
+    n = make_native_state(200, 72, seed=33)
+    lw = oracle.rrtmg_lw(oracle.irrad_prepare(n))
+    got = oracle.irrad_finish(n, lw)
+    fl = lambda a: a[:, ::-1]
+    for k, src, sign in (("flxu", "uflx", -1.), ("flxd", "dflx", 1.), ("flcu", "uflxc", -1.), ("flcd", "dflxc", 1.),
+                         ("dfdts", "duflx_dTs", -1.), ("dfdtsc", "duflxc_dTs", -1.)):
+        np.testing.assert_array_equal(got[k], sign * fl(lw[src]), err_msg=k)
+    np.testing.assert_array_equal(got["sfcem"], -(lw["uflx"][:, 0] - lw["dflx"][:, 0] * (1. - n["emis"])))
+    for j, k in enumerate(("cldtt", "cldhi", "cldmd", "cldlo")):
+        np.testing.assert_array_equal(got[k], 1.0 - lw["clearCounts"][:, j] / float(140))
+    sw = oracle.rrtmg_sw(oracle.solar_prepare(n))
+    got = oracle.solar_finish(n, sw)
+    np.testing.assert_array_equal(got["fsw"], fl(sw["swdflx"]) - fl(sw["swuflx"]))
+    np.testing.assert_array_equal(got["fsc"], fl(sw["swdflxc"]) - fl(sw["swuflxc"]))
+    np.testing.assert_array_equal(got["fswu"], fl(sw["swuflx"]))
+    np.testing.assert_array_equal(got["fscu"], fl(sw["swuflxc"]))
+    for j, k in enumerate(("cldts", "cldhs", "cldms", "cldls")):
+        np.testing.assert_array_equal(got[k], 1. - sw["clearCounts"][:, j] / float(112))
+    for k, nn, dd in (("cottp", "cotntp", "cotdtp"), ("cothp", "cotnhp", "cotdhp"), ("cotmp", "cotnmp", "cotdmp"),
+                      ("cotlp", "cotnlp", "cotdlp")):
+        ok = (sw[nn] > 0.) & (sw[dd] > 0.)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            np.testing.assert_array_equal(got[k], np.where(ok, sw[nn] / sw[dd], n["undef"]), err_msg=k)
+        assert ok.any() and (~ok).any()

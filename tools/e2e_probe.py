@@ -1,5 +1,5 @@
 """End-to-end (pinned host arrays through the C ABI) rate of one LW + one SW refresh as a function of the
-host staging chunk (RRTMGX_HOST_CHUNK, read at rrtmgx_init), beside the raw H2D rate of the box
+host staging chunk and the number of staging sets (RRTMGX_HOST_CHUNK, RRTMGX_STAGES, read at rrtmgx_init), beside the raw H2D rate of the box
 (tools/pcie_probe.py): how much of the link the chunk pipeline of api.cu keeps busy.  One JSON line per setting."""
 import json
 import os
@@ -20,8 +20,13 @@ def main():
     hp = devstate.to_device(s, pinned=True)
     ho = devstate.alloc_outputs(ncol, nlay, pinned=True)
     h2d = ((36 * nlay + 20) * 8 + (56 * nlay + 7) * 8) * ncol
-    for chunk in [int(v) for v in os.environ.get("PROBE_CHUNKS", "4096,8192,12288,16384,24576,32768").split(",")]:
+    chunks = [int(v) for v in os.environ.get("PROBE_CHUNKS", "4096,8192,12288,16384,24576,32768").split(",")]
+    stages = [int(v) for v in os.environ.get("PROBE_STAGES", "3").split(",")]
+    modes = [m == "1" for m in os.environ.get("PROBE_MODES", "1,0").split(",")]
+    nsteps = int(os.environ.get("PROBE_STEPS", 3))
+    for chunk, nst in [(c, n) for c in chunks for n in stages]:
         os.environ["RRTMGX_HOST_CHUNK"] = str(chunk)
+        os.environ["RRTMGX_STAGES"] = str(nst)
         host.finalize()
         host.init()
         h_lw = devstate.lw_runner(hp, ho, device=False)
@@ -33,10 +38,10 @@ def main():
                 t.start(); h_lw(); t.join()
             else:
                 h_lw(); h_sw()
-        out = {"host_chunk": chunk}
-        for mode in (True, False):
+        out = {"host_chunk": chunk, "stages": nst}
+        for mode in modes:
             step(mode); torch.cuda.synchronize()
-            n = 3
+            n = nsteps
             t0 = time.perf_counter()
             for _ in range(n):
                 step(mode)
