@@ -1,0 +1,359 @@
+"""Second, independent transcription of the LW gas optics of EVERY band (test infrastructure).
+
+Written from the Fortran (LW/src/rrtmg_lw_setcoef.F90:204-575, LW/src/rrtmg_lw_init.F90:114-145 and cmbgb1-16,
+LW/src/rrtmg_lw_taumol.F90 taugb1-16 and addAerosols) without reference to oracle/lw.c or oracle/lw_init.c, on the
+ORIGINAL 16-g tables of the data blob, and compared with the C oracle's optical depths and Planck fractions (taps).
+Two transcriptions that agree pin slips of sign, index, branch and table layout in either of them."""
+import math
+
+import numpy as np
+import pytest
+
+from geosradiation_gridcomp_b200 import tables
+from geosradiation_gridcomp_b200.synthetic import make_columns
+
+H2O, CO2, O3, N2O, CO, CH4, O2 = range(7)          # rows of chi_mls
+ONEMINUS = 1. - 1.e-6
+
+
+@pytest.fixture(scope="module")
+def tab():
+    return tables.load_tables()
+
+
+def lw_setcoef(s, c, tab):
+    """One column: list of per-layer dicts with everything taumol reads, and laytrop."""
+    preflog, tref = tab["lw.ref.preflog"], tab["lw.ref.tref"]
+    amd, amw, avogad, grav, stpfac = 28.9660, 18.0160, 6.02214199e+23, 9.8066, 296. / 1013.
+    pz, out, laytrop = s["plev"][c], [], 0
+    for l in range(s["nlay"]):
+        h2o, t, p = s["h2ovmr"][c, l], s["tlay"][c, l], s["play"][c, l]
+        amm = (1. - h2o) * amd + h2o * amw
+        coldry = (pz[l] - pz[l + 1]) * 1.e3 * avogad / (1.e2 * grav * amm * (1. + h2o))
+        summol = s["co2vmr"][c, l] + s["o3vmr"][c, l] + s["n2ovmr"][c, l] + s["ch4vmr"][c, l] + s["o2vmr"][c, l]
+        wbroad = coldry * (1. - summol)
+        wv = h2o * coldry
+        plog = math.log(p)
+        jp = min(max(int(36. - 5 * (plog + 0.04)), 1), 58)
+        fp = 5. * (preflog[jp - 1] - plog)
+        jt = min(max(int(3. + (t - tref[jp - 1]) / 15.), 1), 4)
+        ft = ((t - tref[jp - 1]) / 15.) - float(jt - 3)
+        jt1 = min(max(int(3. + (t - tref[jp]) / 15.), 1), 4)
+        ft1 = ((t - tref[jp]) / 15.) - float(jt1 - 3)
+        water = wv / coldry
+        scalefac = p * stpfac / t
+        d = dict(jp=jp, jt=jt, jt1=jt1, coldry=coldry, p=p, lower=plog > 4.56)
+        d["forfac"] = scalefac / (1. + water)
+        if d["lower"]:
+            laytrop += 1
+            factor = (332. - t) / 36.
+            d["indfor"] = min(2, max(1, int(factor))); d["forfrac"] = factor - float(d["indfor"])
+            d["selffac"] = water * d["forfac"]
+            factor = (t - 188.) / 7.2
+            d["indself"] = min(9, max(1, int(factor) - 7)); d["selffrac"] = factor - float(d["indself"] + 7)
+        else:
+            d["indfor"], d["forfrac"], d["selffac"] = 3, (t - 188.) / 36. - 1., 0.
+        d["scaleminor"] = p / t
+        d["scaleminorn2"] = (p / t) * (wbroad / (coldry + wv))
+        factor = (t - 180.8) / 7.2
+        d["indminor"] = min(18, max(1, int(factor))); d["minorfrac"] = factor - float(d["indminor"])
+        col = {H2O: h2o, CO2: s["co2vmr"][c, l], O3: s["o3vmr"][c, l], N2O: s["n2ovmr"][c, l], CH4: s["ch4vmr"][c, l],
+               O2: s["o2vmr"][c, l], CO: 0.}                                  # covmr = 0 (LW/src/rrtmg_lw_rad.F90:520)
+        d["col"] = {k: 1.e-20 * v * coldry for k, v in col.items()}
+        for k in (CO2, O3, N2O, CH4, CO):
+            if d["col"][k] == 0.: d["col"][k] = 1.e-32 * coldry
+        for k in ("cfc11", "cfc12", "cfc22", "ccl4"):
+            d[k] = 1.e-20 * s[k + "vmr"][c, l] * coldry
+        d["colbrd"] = 1.e-20 * wbroad
+        compfp = 1. - fp
+        d.update(fac10=compfp * ft, fac00=compfp * (1. - ft), fac11=fp * ft1, fac01=fp * (1. - ft1))
+        d["selffac"] = d["col"][H2O] * d["selffac"]
+        d["forfac"] = d["col"][H2O] * d["forfac"]
+        out.append(d)
+    return out, laytrop
+
+
+class Band:
+    """Reduced tables of one LW band: 16 original g-points -> ngc, weighted for absorption coefficients, plain
+    sums for the Planck fractions (rrtmg_lw_ini :114-145 and cmbgbN)."""
+
+    def __init__(self, tab, band):
+        ngs = [0] + list(tab["lw.wvn.ngs"])
+        self.g = slice(ngs[band - 1], ngs[band])
+        wt, ngn = tab["lw.wvn.wt"], tab["lw.wvn.ngn"][self.g]
+        self.ng = len(ngn)
+        groups, i = [], 0
+        for n in ngn:
+            groups.append(list(range(i, i + n))); i += n
+        assert i == 16
+        rw = np.zeros(16)
+        for grp in groups:
+            if self.ng < 16:
+                wsum = 0.
+                for j in grp: wsum = wsum + wt[j]
+                for j in grp: rw[j] = wt[j] / wsum
+            else:
+                rw[grp[0]] = 1.0
+        pre = "lw.kg%02d." % band
+        self.t = {}
+        for key, a in tab.items():
+            if not key.startswith(pre):
+                continue
+            name = key[len(pre):]
+            frac = name.startswith("fracref")
+            a = np.moveaxis(a, 0, -1) if frac else a                  # g last
+            out = np.zeros(a.shape[:-1] + (self.ng,))
+            for k, grp in enumerate(groups):
+                for j in grp:
+                    out[..., k] = out[..., k] + (a[..., j] if frac else a[..., j] * rw[j])
+            # the originals carry an 'o': kao -> ka, kbo_mn2 -> kb_mn2, selfrefo -> selfref, cfc11adjo -> cfc11adj
+            short = "k" + name[1] + name[3:] if name[:3] in ("kao", "kbo") else name[:-1]
+            self.t[short] = out
+
+
+def lin(t, i, f):
+    return t[i - 1] + f * (t[i] - t[i - 1])
+
+
+def continuum(B, d):
+    tauself = d["selffac"] * lin(B.t["selfref"], d["indself"], d["selffrac"]) if d["lower"] else 0.
+    return tauself, d["forfac"] * lin(B.t["forref"], d["indfor"], d["forfrac"])
+
+
+def major1(k, d):
+    """k(jt, jp, g) of one key species; lower tables start at jp = 1, upper ones at jp = 13."""
+    off = 1 if d["lower"] else 13
+    jp, jt, jt1 = d["jp"], d["jt"], d["jt1"]
+    return (d["fac00"] * k[jt - 1, jp - off] + d["fac10"] * k[jt, jp - off] +
+            d["fac01"] * k[jt1 - 1, jp + 1 - off] + d["fac11"] * k[jt1, jp + 1 - off])
+
+
+def binary(a, b, ratio, n):
+    speccomb = a + ratio * b
+    specmult = n * min(a / speccomb, ONEMINUS)
+    return speccomb, specmult / n, 1 + int(specmult), math.fmod(specmult, 1.0)
+
+
+def rat(tab, d, x, y, plus):
+    chi = tab["lw.ref.chi_mls"]
+    return chi[x, d["jp"] - 1 + plus] / chi[y, d["jp"] - 1 + plus]
+
+
+def major2(k, d, tab, x, y):
+    """Two key species: k(js, jt, jp, g); the lower atmosphere interpolates with three points near both ends of the
+    binary parameter (taugb3 :470-600 and every other two-species band), the upper one linearly."""
+    total = 0.
+    n = 8. if d["lower"] else 4.
+    off = 1 if d["lower"] else 13
+    for which, jtt, f0, f1 in ((0, d["jt"], d["fac00"], d["fac10"]), (1, d["jt1"], d["fac01"], d["fac11"])):
+        speccomb, specparm, js, fs = binary(d["col"][x], d["col"][y], rat(tab, d, x, y, which), n)
+        a = lambda dj, dt: k[js - 1 + dj, jtt - 1 + dt, d["jp"] + which - off]
+        if d["lower"] and specparm < 0.125:
+            p = fs - 1; p4 = p ** 4; fk0, fk1, fk2 = p4, 1 - p - 2.0 * p4, p + p4
+            tau = speccomb * (fk0 * f0 * a(0, 0) + fk1 * f0 * a(1, 0) + fk2 * f0 * a(2, 0) +
+                              fk0 * f1 * a(0, 1) + fk1 * f1 * a(1, 1) + fk2 * f1 * a(2, 1))
+        elif d["lower"] and specparm > 0.875:
+            p = -fs; p4 = p ** 4; fk0, fk1, fk2 = p4, 1 - p - 2.0 * p4, p + p4
+            tau = speccomb * (fk2 * f0 * a(-1, 0) + fk1 * f0 * a(0, 0) + fk0 * f0 * a(1, 0) +
+                              fk2 * f1 * a(-1, 1) + fk1 * f1 * a(0, 1) + fk0 * f1 * a(1, 1))
+        else:
+            tau = speccomb * ((1. - fs) * f0 * a(0, 0) + fs * f0 * a(1, 0) + (1. - fs) * f1 * a(0, 1) + fs * f1 * a(1, 1))
+        total = total + tau
+    return total
+
+
+def ref_binary(tab, d, x, y, jpref, n):
+    """js, fs of the binary parameter at a fixed reference ratio chi_mls(x, jpref) / chi_mls(y, jpref)."""
+    chi = tab["lw.ref.chi_mls"]
+    _, _, j, f = binary(d["col"][x], d["col"][y], chi[x, jpref - 1] / chi[y, jpref - 1], n)
+    return j, f
+
+
+def planck2(fr, tab, d, x, y, jpref):
+    j, f = ref_binary(tab, d, x, y, jpref, 8. if d["lower"] else 4.)
+    return fr[j - 1] + f * (fr[j] - fr[j - 1])                      # fracref(g, jpl) stored (jpl, g)
+
+
+def minor1(km, d):
+    return km[d["indminor"] - 1] + d["minorfrac"] * (km[d["indminor"]] - km[d["indminor"] - 1])
+
+
+def minor2(km, tab, d, x, y, jpref):
+    j, f = ref_binary(tab, d, x, y, jpref, 8. if d["lower"] else 4.)
+    im = d["indminor"]
+    m1 = km[j - 1, im - 1] + f * (km[j, im - 1] - km[j - 1, im - 1])
+    m2 = km[j - 1, im] + f * (km[j, im] - km[j - 1, im])
+    return m1 + d["minorfrac"] * (m2 - m1)
+
+
+def adjusted(tab, d, sp, threshold, base, power, ref=None):
+    """Column amount of a minor gas, damped when it exceeds its reference abundance (e.g. taugb3 :425-432)."""
+    chi = tab["lw.ref.chi_mls"][sp, d["jp"]] if ref is None else ref
+    r = 1.e20 * (d["col"][sp] / d["coldry"]) / chi
+    if r > threshold:
+        return (base + (r - base) ** power) * chi * d["coldry"] * 1.e-20
+    return d["col"][sp]
+
+
+def scale_tail(tau, first, factors):
+    tau = tau.copy()
+    for i, f in enumerate(factors):
+        tau[first - 1 + i] = tau[first - 1 + i] * f
+    return tau
+
+
+def taugb(band, B, tab, d):
+    """(taug, pfracs) of one layer for the band's reduced g-points."""
+    T, col, lo = B.t, d["col"], d["lower"]
+    tauself, taufor = continuum(B, d)
+    zero = np.zeros(B.ng)
+    if band == 1:
+        scalen2 = d["colbrd"] * d["scaleminorn2"]
+        if lo:
+            corradj = 1. - 0.15 * (250. - d["p"]) / 154.4 if d["p"] < 250. else 1.
+            return corradj * (col[H2O] * major1(T["ka"], d) + tauself + taufor + scalen2 * minor1(T["ka_mn2"], d)), T["fracrefa"]
+        corradj = 1. - 0.15 * (d["p"] / 95.6)
+        return corradj * (col[H2O] * major1(T["kb"], d) + taufor + scalen2 * minor1(T["kb_mn2"], d)), T["fracrefb"]
+    if band == 2:
+        if lo:
+            corradj = 1. - .05 * (d["p"] - 100.) / 900.
+            return corradj * (col[H2O] * major1(T["ka"], d) + tauself + taufor), T["fracrefa"]
+        return col[H2O] * major1(T["kb"], d) + taufor, T["fracrefb"]
+    if band == 3:
+        adj = adjusted(tab, d, N2O, 1.5, 0.5, 0.65)
+        if lo:
+            return (major2(T["ka"], d, tab, H2O, CO2) + tauself + taufor + adj * minor2(T["ka_mn2o"], tab, d, H2O, CO2, 3),
+                    planck2(T["fracrefa"], tab, d, H2O, CO2, 9))
+        return (major2(T["kb"], d, tab, H2O, CO2) + taufor + adj * minor2(T["kb_mn2o"], tab, d, H2O, CO2, 13),
+                planck2(T["fracrefb"], tab, d, H2O, CO2, 13))
+    if band == 4:
+        if lo:
+            return major2(T["ka"], d, tab, H2O, CO2) + tauself + taufor, planck2(T["fracrefa"], tab, d, H2O, CO2, 11)
+        tau = scale_tail(major2(T["kb"], d, tab, O3, CO2), 8, [0.92, 0.88, 1.07, 1.1, 0.99, 0.88, 0.943])
+        return tau, planck2(T["fracrefb"], tab, d, O3, CO2, 13)
+    if band == 5:
+        if lo:
+            return (major2(T["ka"], d, tab, H2O, CO2) + tauself + taufor + minor2(T["ka_mo3"], tab, d, H2O, CO2, 7) * col[O3]
+                    + d["ccl4"] * T["ccl4"], planck2(T["fracrefa"], tab, d, H2O, CO2, 5))
+        return major2(T["kb"], d, tab, O3, CO2) + d["ccl4"] * T["ccl4"], planck2(T["fracrefb"], tab, d, O3, CO2, 43)
+    if band == 6:
+        cfc = d["cfc11"] * T["cfc11adj"] + d["cfc12"] * T["cfc12"]
+        if lo:
+            adj = adjusted(tab, d, CO2, 3.0, 2.0, 0.77)
+            return col[H2O] * major1(T["ka"], d) + tauself + taufor + adj * minor1(T["ka_mco2"], d) + cfc, T["fracrefa"]
+        return 0.0 + cfc, T["fracrefa"]
+    if band == 7:
+        if lo:
+            adj = adjusted(tab, d, CO2, 3.0, 3.0, 0.79)
+            return (major2(T["ka"], d, tab, H2O, O3) + tauself + taufor + adj * minor2(T["ka_mco2"], tab, d, H2O, O3, 3),
+                    planck2(T["fracrefa"], tab, d, H2O, O3, 3))
+        adj = adjusted(tab, d, CO2, 3.0, 2.0, 0.79)
+        tau = col[O3] * major1(T["kb"], d) + adj * minor1(T["kb_mco2"], d)
+        return scale_tail(tau, 6, [0.92, 0.88, 1.07, 1.1, 0.99, 0.855]), T["fracrefb"]
+    if band == 8:
+        adj = adjusted(tab, d, CO2, 3.0, 2.0, 0.65)
+        cfc = d["cfc12"] * T["cfc12"] + d["cfc22"] * T["cfc22adj"]
+        if lo:
+            return (col[H2O] * major1(T["ka"], d) + tauself + taufor + adj * minor1(T["ka_mco2"], d)
+                    + col[O3] * minor1(T["ka_mo3"], d) + col[N2O] * minor1(T["ka_mn2o"], d) + cfc), T["fracrefa"]
+        return (col[O3] * major1(T["kb"], d) + adj * minor1(T["kb_mco2"], d) + col[N2O] * minor1(T["kb_mn2o"], d) + cfc), T["fracrefb"]
+    if band == 9:
+        adj = adjusted(tab, d, N2O, 1.5, 0.5, 0.65)
+        if lo:
+            return (major2(T["ka"], d, tab, H2O, CH4) + tauself + taufor + adj * minor2(T["ka_mn2o"], tab, d, H2O, CH4, 3),
+                    planck2(T["fracrefa"], tab, d, H2O, CH4, 9))
+        return col[CH4] * major1(T["kb"], d) + adj * minor1(T["kb_mn2o"], d), T["fracrefb"]
+    if band == 10:
+        if lo:
+            return col[H2O] * major1(T["ka"], d) + tauself + taufor, T["fracrefa"]
+        return col[H2O] * major1(T["kb"], d) + taufor, T["fracrefb"]
+    if band == 11:
+        scaleo2 = col[O2] * d["scaleminor"]
+        if lo:
+            return col[H2O] * major1(T["ka"], d) + tauself + taufor + scaleo2 * minor1(T["ka_mo2"], d), T["fracrefa"]
+        return col[H2O] * major1(T["kb"], d) + taufor + scaleo2 * minor1(T["kb_mo2"], d), T["fracrefb"]
+    if band == 12:
+        if lo:
+            return major2(T["ka"], d, tab, H2O, CO2) + tauself + taufor, planck2(T["fracrefa"], tab, d, H2O, CO2, 10)
+        return zero, zero
+    if band == 13:
+        if lo:
+            adj = adjusted(tab, d, CO2, 3.0, 2.0, 0.68, ref=3.55e-4)
+            return (major2(T["ka"], d, tab, H2O, N2O) + tauself + taufor + adj * minor2(T["ka_mco2"], tab, d, H2O, N2O, 1)
+                    + col[CO] * minor2(T["ka_mco"], tab, d, H2O, N2O, 3), planck2(T["fracrefa"], tab, d, H2O, N2O, 5))
+        return col[O3] * minor1(T["kb_mo3"], d), T["fracrefb"]
+    if band == 14:
+        if lo:
+            return col[CO2] * major1(T["ka"], d) + tauself + taufor, T["fracrefa"]
+        return col[CO2] * major1(T["kb"], d), T["fracrefb"]
+    if band == 15:
+        if lo:
+            scalen2 = d["colbrd"] * d["scaleminor"]
+            return (major2(T["ka"], d, tab, N2O, CO2) + tauself + taufor + scalen2 * minor2(T["ka_mn2"], tab, d, N2O, CO2, 1),
+                    planck2(T["fracrefa"], tab, d, N2O, CO2, 1))
+        return zero, zero
+    if band == 16:
+        if lo:
+            return major2(T["ka"], d, tab, H2O, CH4) + tauself + taufor, planck2(T["fracrefa"], tab, d, H2O, CH4, 6)
+        # nspb(16) = 0 (rrtmg_lw_init.F90:195) multiplies the upper-atmosphere row index away (taugb16 :3110-3111):
+        # ind0 = ind1 = 1 whatever jp and jt are, so all four interpolation points read rows 1 and 2 of absb
+        k = T["kb"]
+        return col[CH4] * (d["fac00"] * k[0, 0] + d["fac10"] * k[1, 0] + d["fac01"] * k[0, 0] + d["fac11"] * k[1, 0]), T["fracrefb"]
+    raise ValueError(band)
+
+
+@pytest.fixture(scope="module")
+def case(oracle):
+    ncol = 20
+    s = make_columns(ncol, nlay=72, seed=2718)
+    # move the binary parameters across all three interpolation regimes and trigger every abundance adjustment
+    s["n2ovmr"][:4] *= 2.5
+    s["co2vmr"][2:6] *= 4.0
+    s["h2ovmr"][6:9] *= 1e-3
+    s["co2vmr"][9:11] *= 1e-2
+    s["ch4vmr"][11:13] *= 1e-2
+    s["o3vmr"][13:15] *= 1e-2
+    s["h2ovmr"][15:17] *= 1e-5
+    s["n2ovmr"][17:19] *= 1e-2
+    o = oracle.rrtmg_lw(s, taps=("taug", "pfracs", "laytrop"))
+    assert o["rc"] == 0
+    return s, o
+
+
+@pytest.mark.parametrize("band", range(1, 17))
+def test_lw_band_against_independent_numpy(case, tab, band):
+    s, o = case
+    B = Band(tab, band)
+    worst_t = worst_p = 0.
+    for c in range(s["ncol"]):
+        layers, laytrop = lw_setcoef(s, c, tab)
+        assert laytrop == o["laytrop"][c]
+        for l, d in enumerate(layers):
+            tau, pfr = taugb(band, B, tab, d)
+            tau = tau + s["tauaer_lw"][c, l, band - 1]                     # addAerosols :3130-3146
+            got_t, got_p = o["taug"][c, B.g, l], o["pfracs"][c, B.g, l]
+            et = np.max(np.abs(got_t - tau) / np.maximum(np.abs(tau), 1e-300))
+            ep = np.max(np.abs(got_p - pfr) / np.maximum(np.abs(pfr), 1e-300)) if np.any(pfr) else float(np.max(np.abs(got_p)))
+            assert et < 1e-11 and ep < 1e-11, (band, c, l, d["lower"], et, ep)
+            worst_t, worst_p = max(worst_t, et), max(worst_p, ep)
+
+
+def test_lw_case_reaches_every_interpolation_regime_and_adjustment(case, tab):
+    """The comparison above means little for branches the columns never take."""
+    s, _ = case
+    pairs = {3: (H2O, CO2), 4: (H2O, CO2), 7: (H2O, O3), 9: (H2O, CH4), 13: (H2O, N2O), 15: (N2O, CO2), 16: (H2O, CH4)}
+    seen = {b: set() for b in pairs}
+    adj = set()
+    chi = tab["lw.ref.chi_mls"]
+    for c in range(s["ncol"]):
+        for d in lw_setcoef(s, c, tab)[0]:
+            if d["lower"]:
+                for b, (x, y) in pairs.items():
+                    sp = binary(d["col"][x], d["col"][y], rat(tab, d, x, y, 0), 8.)[1]
+                    seen[b].add("lo" if sp < 0.125 else "hi" if sp > 0.875 else "mid")
+            if 1.e20 * (d["col"][N2O] / d["coldry"]) / chi[N2O, d["jp"]] > 1.5: adj.add("n2o")
+            if 1.e20 * (d["col"][CO2] / d["coldry"]) / chi[CO2, d["jp"]] > 3.0: adj.add("co2")
+            if 1.e20 * (d["col"][CO2] / d["coldry"]) / 3.55e-4 > 3.0: adj.add("co2_13")
+    assert adj == {"n2o", "co2", "co2_13"}, adj
+    for b, v in seen.items():
+        assert v == {"lo", "mid", "hi"}, (b, v)
