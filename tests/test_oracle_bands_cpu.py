@@ -357,3 +357,221 @@ def test_lw_case_reaches_every_interpolation_regime_and_adjustment(case, tab):
     assert adj == {"n2o", "co2", "co2_13"}, adj
     for b, v in seen.items():
         assert v == {"lo", "mid", "hi"}, (b, v)
+
+
+# ======================================================================================================================
+# SW: the driver's column amounts (SW/src/rrtmg_sw_rad.F90:1368-1383), setcoef_sw (SW/src/rrtmg_sw_setcoef.F90:44-140),
+# the g-point reduction (SW/src/rrtmg_sw_init.F90:125-150, cmbgb16-29) and taumol16-29 (SW/src/rrtmg_sw_taumol.F90),
+# same rules as above: from the Fortran, on the original 16-g tables, without reference to oracle/sw.c / sw_init.c.
+def sw_setcoef(s, c, tab):
+    preflog, tref = tab["sw.ref.preflog"], tab["sw.ref.tref"]
+    amd, amw, avogad, grav, stpfac = 28.9660, 18.0160, 6.02214199e+23, 9.8066, 296. / 1013.
+    out, laytrop = [], 0
+    for l in range(s["nlay"]):
+        h2o, t, p = s["h2ovmr"][c, l], s["tlay"][c, l], s["play"][c, l]
+        coldry = (s["plev"][c, l] - s["plev"][c, l + 1]) * 1.e3 * avogad / (1.e2 * grav * ((1. - h2o) * amd + h2o * amw) * (1. + h2o))
+        col = {H2O: coldry * h2o, CO2: coldry * s["co2vmr"][c, l], O3: coldry * s["o3vmr"][c, l],
+               CH4: coldry * s["ch4vmr"][c, l], O2: coldry * s["o2vmr"][c, l]}
+        plog = math.log(p)
+        if plog >= 4.56: laytrop += 1
+        jp = min(max(int(36. - 5 * (plog + 0.04)), 1), 58)
+        fp = 5. * (preflog[jp - 1] - plog)
+        jt = min(max(int(3. + (t - tref[jp - 1]) / 15.), 1), 4)
+        ft = ((t - tref[jp - 1]) / 15.) - float(jt - 3)
+        jt1 = min(max(int(3. + (t - tref[jp]) / 15.), 1), 4)
+        ft1 = ((t - tref[jp]) / 15.) - float(jt1 - 3)
+        water = col[H2O] / coldry
+        d = dict(jp=jp, jt=jt, jt1=jt1, lower=plog > 4.56, forfac=p * stpfac / t / (1. + water))
+        if d["lower"]:
+            factor = (332. - t) / 36.
+            d["indfor"] = min(2, max(1, int(factor))); d["forfrac"] = factor - float(d["indfor"])
+            d["selffac"] = water * d["forfac"]
+            factor = (t - 188.) / 7.2
+            d["indself"] = min(9, max(1, int(factor) - 7)); d["selffrac"] = factor - float(d["indself"] + 7)
+        else:
+            d["indfor"], d["forfrac"], d["selffac"], d["indself"], d["selffrac"] = 3, (t - 188.) / 36. - 1., 0., 0, 0.
+        d["col"] = {k: 1.e-20 * v for k, v in col.items()}
+        d["colmol"] = 1.e-20 * coldry + d["col"][H2O]
+        for k in (CO2, CH4, O2):
+            if d["col"][k] == 0.: d["col"][k] = 1.e-32 * coldry
+        compfp = 1. - fp
+        d.update(fac10=compfp * ft, fac00=compfp * (1. - ft), fac11=fp * ft1, fac01=fp * (1. - ft1))
+        out.append(d)
+    return out, laytrop
+
+
+class SwBand:
+    SUMMED = ("sfluxref", "irradnce", "facbrght", "snsptdrk")          # solar source terms: plain sums over the group
+    G_FIRST = SUMMED + ("rayla",)                                        # (g, js) in the modules
+
+    def __init__(self, tab, band):
+        ngs = [0] + list(tab["sw.wvn.ngs"])
+        self.g = slice(ngs[band - 16], ngs[band - 15])
+        wt, ngn = tab["sw.wvn.wt"], tab["sw.wvn.ngn"][self.g]
+        self.ng = len(ngn)
+        groups, i = [], 0
+        for n in ngn:
+            groups.append(list(range(i, i + n))); i += n
+        assert i == 16
+        rw = np.zeros(16)
+        for grp in groups:
+            wsum = 0.
+            for j in grp: wsum = wsum + wt[j]
+            for j in grp: rw[j] = wt[j] / wsum
+        pre = "sw.kg%02d." % band
+        self.t = {}
+        for key, a in tab.items():
+            if not key.startswith(pre):
+                continue
+            name = key[len(pre):]
+            if name == "rayl":
+                self.t["rayl"] = float(a[0])
+                continue
+            short = "k" + name[1] + name[3:] if name[:3] in ("kao", "kbo") else name[:-1]
+            a = np.moveaxis(a, 0, -1) if (short in self.G_FIRST and a.ndim == 2) else a
+            if band == 29 and short == "irradnce":
+                # the data module itself rescales the quiet-sun term of this band for the solar function below
+                # 820 cm-1 (SW/src/rrtmg_sw_k_g_29.F90:78-81); the blob holds the constructor's numbers
+                a = (13.221 / (13.221 - 0.455)) * a
+            out = np.zeros(a.shape[:-1] + (self.ng,))
+            for k, grp in enumerate(groups):
+                for j in grp:
+                    out[..., k] = out[..., k] + (a[..., j] if short in self.SUMMED else a[..., j] * rw[j])
+            self.t[short] = out
+
+
+def sw_binary(d, x, y, strrat, n):
+    speccomb = d["col"][x] + strrat * d["col"][y]
+    specmult = n * min(d["col"][x] / speccomb, ONEMINUS)
+    return speccomb, 1 + int(specmult), math.fmod(specmult, 1.)
+
+
+def sw_major2(k, d, x, y, strrat):
+    """speccomb times the eight-point interpolation in (binary parameter, temperature, pressure); k(js, jt, jp, g)."""
+    speccomb, js, fs = sw_binary(d, x, y, strrat, 8. if d["lower"] else 4.)
+    off = 1 if d["lower"] else 13
+    a = lambda dj, jtt, jpp: k[js - 1 + dj, jtt - 1, jpp - off]
+    jp, jt, jt1 = d["jp"], d["jt"], d["jt1"]
+    return speccomb * ((1. - fs) * d["fac00"] * a(0, jt, jp) + fs * d["fac00"] * a(1, jt, jp) +
+                       (1. - fs) * d["fac10"] * a(0, jt + 1, jp) + fs * d["fac10"] * a(1, jt + 1, jp) +
+                       (1. - fs) * d["fac01"] * a(0, jt1, jp + 1) + fs * d["fac01"] * a(1, jt1, jp + 1) +
+                       (1. - fs) * d["fac11"] * a(0, jt1 + 1, jp + 1) + fs * d["fac11"] * a(1, jt1 + 1, jp + 1))
+
+
+def sw_cont(B, d):
+    """selffac * selfref + forfac * forref (lower atmosphere) or forfac * forref (upper), to be multiplied by colh2o."""
+    f = d["forfac"] * lin(B.t["forref"], d["indfor"], d["forfrac"])
+    return d["selffac"] * lin(B.t["selfref"], d["indself"], d["selffrac"]) + f if d["lower"] else f
+
+
+# band: (lower species pair or single, upper, strrat, where the solar source layer is searched, layreffr)
+SW_SPEC = {16: ((H2O, CH4), CH4, 252.131, None, 0), 17: ((H2O, CO2), (H2O, CO2), 0.364641, "upper", 30),
+           18: ((H2O, CH4), CH4, 38.9589, "lower", 6), 19: ((H2O, CO2), CO2, 5.49281, "lower", 3),
+           20: (H2O, H2O, 0., None, 0), 21: ((H2O, CO2), (H2O, CO2), 0.0045321, "lower", 8),
+           22: ((H2O, O2), O2, 1.6 * 0.022708, "lower", 2), 23: (H2O, None, 0., None, 0),
+           24: ((H2O, O2), O2, 0.124692, "lower", 1), 25: (H2O, None, 0., None, 0), 26: (None, None, 0., None, 0),
+           27: (O3, O3, 0., None, 0), 28: ((O3, O2), (O3, O2), 6.67029e-07, "upper", 42), 29: (H2O, CO2, 0., None, 0)}
+
+
+def taumol(band, B, d):
+    T, col, lo = B.t, d["col"], d["lower"]
+    spec = SW_SPEC[band][0 if lo else 1]
+    strrat = SW_SPEC[band][2]
+    zero = np.zeros(B.ng)
+    rayl = T["rayl"] if "rayl" in T else None                        # scalar (most bands) or per g-point
+    if band in (16, 18, 19, 21):
+        if lo or band == 21:
+            return sw_major2(T["ka" if lo else "kb"], d, *spec, strrat) + col[H2O] * sw_cont(B, d), d["colmol"] * rayl + zero
+        return col[spec] * major1(T["kb"], d), d["colmol"] * rayl + zero
+    if band == 17:
+        return sw_major2(T["ka" if lo else "kb"], d, *spec, strrat) + col[H2O] * sw_cont(B, d), d["colmol"] * rayl + zero
+    if band == 20:
+        return col[H2O] * (major1(T["ka" if lo else "kb"], d) + sw_cont(B, d)) + col[CH4] * T["absch4"], d["colmol"] * rayl + zero
+    if band == 22:
+        o2cont = 4.35e-4 * col[O2] / (350.0 * 2.0)
+        if lo:
+            return sw_major2(T["ka"], d, *spec, strrat) + col[H2O] * sw_cont(B, d) + o2cont, d["colmol"] * rayl + zero
+        return col[O2] * 1.6 * major1(T["kb"], d) + o2cont, d["colmol"] * rayl + zero
+    if band == 23:
+        if lo:
+            return col[H2O] * (1.029 * major1(T["ka"], d) + sw_cont(B, d)), d["colmol"] * rayl
+        return zero, d["colmol"] * rayl
+    if band == 24:
+        if lo:
+            speccomb, js, fs = sw_binary(d, H2O, O2, strrat, 8.)
+            return (sw_major2(T["ka"], d, H2O, O2, strrat) + col[O3] * T["abso3a"] + col[H2O] * sw_cont(B, d),
+                    d["colmol"] * lin(T["rayla"], js, fs))
+        return col[O2] * major1(T["kb"], d) + col[O3] * T["abso3b"], d["colmol"] * T["raylb"]
+    if band == 25:
+        if lo:
+            return col[H2O] * major1(T["ka"], d) + col[O3] * T["abso3a"], d["colmol"] * rayl
+        return col[O3] * T["abso3b"], d["colmol"] * rayl
+    if band == 26:
+        return zero, d["colmol"] * rayl
+    if band == 27:
+        return col[O3] * major1(T["ka" if lo else "kb"], d), d["colmol"] * rayl
+    if band == 28:
+        return sw_major2(T["ka" if lo else "kb"], d, *spec, strrat), d["colmol"] * rayl + zero
+    if band == 29:
+        if lo:
+            return col[H2O] * (major1(T["ka"], d) + sw_cont(B, d)) + col[CO2] * T["absco2"], d["colmol"] * rayl + zero
+        return col[CO2] * major1(T["kb"], d) + col[H2O] * T["absh2o"], d["colmol"] * rayl + zero
+    raise ValueError(band)
+
+
+def sw_source(band, B, layers, laytrop, isolvar, scon):
+    """Solar source per g-point: constant, or interpolated in the binary parameter of the layer where jp crosses the
+    band's layreffr, searched below (taumol18 :571-607) or above (taumol17 :488-527) the tropopause."""
+    lo_spec, up_spec, strrat, where, layreffr = SW_SPEC[band]
+    nlay = len(layers)
+    js = None
+    if where == "lower":
+        laysolfr = laytrop
+        for lay in range(1, laytrop + 1):
+            if layers[lay - 1]["jp"] < layreffr and layers[lay]["jp"] >= layreffr: laysolfr = min(lay + 1, laytrop)
+            if lay == laysolfr:
+                _, js, fs = sw_binary(layers[lay - 1], *lo_spec, strrat, 8.)
+                break
+    elif where == "upper":
+        laysolfr = nlay
+        for lay in range(laytrop + 1, nlay + 1):
+            if layers[lay - 2]["jp"] < layreffr and layers[lay - 1]["jp"] >= layreffr: laysolfr = lay
+            if lay == laysolfr:
+                _, js, fs = sw_binary(layers[lay - 1], *up_spec, strrat, 4.)
+                break
+    f = (lambda t: t) if where is None else (lambda t: t[js - 1] + fs * (t[js] - t[js - 1]))
+    if isolvar < 0:
+        return f(B.t["sfluxref"])
+    svar = scon / (0.996047 + -0.511590 + 1360.37)      # isolvar = 0 (SW/src/rrtmg_sw_rad.F90:1050-1055, NRLSSI2.F90:47-49)
+    return svar * f(B.t["facbrght"]) + svar * f(B.t["snsptdrk"]) + svar * f(B.t["irradnce"])
+
+
+@pytest.fixture(scope="module", params=[-1, 0])
+def sw_case(oracle, request):
+    ncol = 20
+    s = make_columns(ncol, nlay=72, seed=1618)
+    s["co2vmr"][:3] *= 30.0
+    s["h2ovmr"][3:6] *= 1e-2
+    s["ch4vmr"][6:8] *= 1e-2
+    s["o3vmr"][8:10] *= 1e-2
+    s["h2ovmr"][10:12] *= 1e-4
+    o = oracle.rrtmg_sw(s, isolvar=request.param, taps=("taug", "pfracs", "ssi", "laytrop"))
+    assert o["rc"] == 0
+    return s, o, request.param
+
+
+@pytest.mark.parametrize("band", range(16, 30))
+def test_sw_band_against_independent_numpy(sw_case, tab, band):
+    s, o, isolvar = sw_case
+    B = SwBand(tab, band)
+    for c in range(s["ncol"]):
+        layers, laytrop = sw_setcoef(s, c, tab)
+        assert laytrop == o["laytrop"][c]
+        for l, d in enumerate(layers):
+            tau, ray = taumol(band, B, d)
+            got_t, got_r = o["taug"][c, B.g, l], o["pfracs"][c, B.g, l]
+            et = np.max(np.abs(got_t - tau) / np.maximum(np.abs(tau), 1e-300)) if np.any(tau) else float(np.max(np.abs(got_t)))
+            er = np.max(np.abs(got_r - ray) / np.abs(ray))
+            assert et < 1e-11 and er < 1e-13, (band, c, l, d["lower"], et, er)
+        ssi = sw_source(band, B, layers, laytrop, isolvar, s["scon"])
+        np.testing.assert_allclose(o["ssi"][c, B.g], ssi, rtol=1e-13, err_msg=f"source band {band} col {c}")
