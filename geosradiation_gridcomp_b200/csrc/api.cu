@@ -69,7 +69,7 @@ struct Ctx {
     McicaConfig mc;
     Path lw, sw;
     size_t chunk_cols = 0;   // 0: automatic
-    size_t host_chunk_cols = 16384;
+    size_t host_chunk_cols = 8192;   // staging chunk of the host-array pipeline (RRTMGX_HOST_CHUNK; sweep: profiles/r4_c_*, r4_d_*)
     int stages = 2;          // staging sets in flight (RRTMGX_STAGES): deeper than double buffering measured slower, profiles/r4_d_*
     std::mutex mu;
 };
