@@ -519,7 +519,7 @@ def taumol(band, B, d):
     raise ValueError(band)
 
 
-def sw_source(band, B, layers, laytrop, isolvar, scon):
+def sw_source(band, B, layers, laytrop, isolvar, scon, svar=None):
     """Solar source per g-point: constant, or interpolated in the binary parameter of the layer where jp crosses the
     band's layreffr, searched below (taumol18 :571-607) or above (taumol17 :488-527) the tropopause."""
     lo_spec, up_spec, strrat, where, layreffr = SW_SPEC[band]
@@ -542,8 +542,9 @@ def sw_source(band, B, layers, laytrop, isolvar, scon):
     f = (lambda t: t) if where is None else (lambda t: t[js - 1] + fs * (t[js] - t[js - 1]))
     if isolvar < 0:
         return f(B.t["sfluxref"])
-    svar = scon / (0.996047 + -0.511590 + 1360.37)      # isolvar = 0 (SW/src/rrtmg_sw_rad.F90:1050-1055, NRLSSI2.F90:47-49)
-    return svar * f(B.t["facbrght"]) + svar * f(B.t["snsptdrk"]) + svar * f(B.t["irradnce"])
+    if svar is None:                                    # isolvar = 0 (SW/src/rrtmg_sw_rad.F90:1050-1055, NRLSSI2.F90:47-49)
+        svar = (scon / (0.996047 + -0.511590 + 1360.37),) * 3
+    return svar[0] * f(B.t["facbrght"]) + svar[1] * f(B.t["snsptdrk"]) + svar[2] * f(B.t["irradnce"])
 
 
 @pytest.fixture(scope="module", params=[-1, 0])
@@ -575,3 +576,93 @@ def test_sw_band_against_independent_numpy(sw_case, tab, band):
             assert et < 1e-11 and er < 1e-13, (band, c, l, d["lower"], et, er)
         ssi = sw_source(band, B, layers, laytrop, isolvar, s["scon"])
         np.testing.assert_allclose(o["ssi"][c, B.g], ssi, rtol=1e-13, err_msg=f"source band {band} col {c}")
+
+
+# ---- solar variability: NRLSSI2 (SW/src/NRLSSI2.F90) and the driver's isolvar 1-3 scalars (SW/src/rrtmg_sw_rad.F90:905-1127)
+FINT, SINT, IINT = 0.996047, -0.511590, 1360.37
+MG_AVG, SB_AVG, MG_0, SB_0 = 0.1567652, 909.71260, 0.14959542, 0.00066696
+NSOLFRAC = 134
+
+
+def adjust_solcyc_amplitudes(fr, ind):
+    fmin, fmax = 0.0189, 0.3750
+    d_min2max = fmax - fmin
+    d_max2min = 1. - d_min2max
+    if 0. <= fr < fmin:
+        w = (fr + 1. - fmax) / d_max2min
+        return [ind[0] + w * (1. - ind[0]), ind[1] + w * (1. - ind[1])]
+    if fmin <= fr <= fmax:
+        w = (fr - fmin) / d_min2max
+        return [1. + w * (ind[0] - 1.), 1. + w * (ind[1] - 1.)]
+    w = (fr - fmax) / d_max2min
+    return [ind[0] + w * (1. - ind[0]), ind[1] + w * (1. - ind[1])]
+
+
+def interpolate_indices(fr, tab):
+    mg, sb = tab["sw.nrlssi2.mgavgcyc"], tab["sw.nrlssi2.sbavgcyc"]
+    ilen = 1.0 / (NSOLFRAC - 2)
+    hf = 0.5 * ilen
+    if fr <= hf:
+        sfid, lo, hi = 1, 0., hf
+    elif fr < 1. - hf:
+        sfid = math.floor((fr - hf) * (NSOLFRAC - 2)) + 2
+        lo = (sfid - 2) * ilen + hf
+        hi = lo + ilen
+    else:
+        sfid, lo, hi = (NSOLFRAC - 2) + 1, 1. - hf, 1.
+    w = (fr - lo) / (hi - lo)
+    return mg[sfid - 1] + w * (mg[sfid] - mg[sfid - 1]), sb[sfid - 1] + w * (sb[sfid] - sb[sfid - 1])
+
+
+def isolvar1_means(ind, tab):
+    """initialize_NRLSSI2: cycle means of the scaled facular and sunspot terms."""
+    mg, sb = tab["sw.nrlssi2.mgavgcyc"], tab["sw.nrlssi2.sbavgcyc"]
+    mean_f = mean_s = 1.
+    s1, s2 = ind[0] != 1., ind[1] != 1.
+    if s1 or s2:
+        ilen = 1.0 / (NSOLFRAC - 2)
+        acc1 = acc2 = 0.
+        fr = 0.5 * ilen
+        for n in range(2, NSOLFRAC):
+            scl = adjust_solcyc_amplitudes(fr, ind)
+            if s1: acc1 = acc1 + scl[0] * mg[n - 1]
+            if s2: acc2 = acc2 + scl[1] * sb[n - 1]
+            fr = fr + ilen
+        if s1: mean_f = (acc1 / (NSOLFRAC - 2) - (1. + ind[0]) / 2. * MG_0) / (MG_AVG - MG_0)
+        if s2: mean_s = (acc2 / (NSOLFRAC - 2) - (1. + ind[1]) / 2. * SB_0) / (SB_AVG - SB_0)
+    return mean_f, mean_s
+
+
+@pytest.mark.parametrize("isolvar,kw", [(1, dict(solcycfrac=0.3, indsolvar=(1.2, 0.8))), (1, dict(solcycfrac=0.011)),
+                                        (1, dict(solcycfrac=0.71, indsolvar=(0.9, 1.0))),
+                                        (2, dict(indsolvar=(0.1580, 1200.))), (2, dict()),
+                                        (3, dict(bndscl=np.linspace(0.9, 1.1, 14)))])
+def test_solar_variability_modes_against_independent_python(oracle, tab, isolvar, kw):
+    s = make_columns(4, nlay=72, seed=99)
+    o = oracle.rrtmg_sw(s, isolvar=isolvar, normFlx=0, taps=("ssi",), **kw)
+    assert o["rc"] == 0
+    scon = s["scon"]
+    ind = list(kw.get("indsolvar", (1., 1.)))
+    if isolvar == 1:
+        fr = kw["solcycfrac"]
+        scl = adjust_solcyc_amplitudes(fr, ind) if (ind[0] != 1. or ind[1] != 1.) else [1., 1.]
+        mg_now, sb_now = interpolate_indices(fr, tab)
+        mean_f, mean_s = isolvar1_means(ind, tab)
+        sv = (scl[0] * (mg_now - MG_0) / (MG_AVG - MG_0), scl[1] * (sb_now - SB_0) / (SB_AVG - SB_0),
+              (scon - (mean_f * FINT + mean_s * SINT)) / IINT)
+    elif isolvar == 2:
+        ndx = ind if "indsolvar" in kw else [MG_AVG, SB_AVG]
+        f, sdk = (ndx[0] - MG_0) / (MG_AVG - MG_0), (ndx[1] - SB_0) / (SB_AVG - SB_0)
+        sv = (f, sdk, (scon - (f * FINT + sdk * SINT)) / IINT)
+    for band in range(16, 30):
+        B = SwBand(tab, band)
+        if isolvar == 3:
+            solvar = scon / (FINT + SINT + IINT) * kw["bndscl"][band - 16]
+            sv = (solvar, solvar, solvar)
+        for c in range(s["ncol"]):
+            layers, laytrop = sw_setcoef(s, c, tab)
+            ssi = sw_source(band, B, layers, laytrop, isolvar, scon, svar=sv)
+            np.testing.assert_allclose(o["ssi"][c, B.g], ssi, rtol=1e-13, err_msg=f"isolvar {isolvar} band {band}")
+    # the TOA downward flux is the band-integrated source times adjes * mu0 (no adjflux scaling for isolvar >= 0)
+    toa = np.array([s["adjes"] * o["ssi"][c].sum() * max(1e-10, s["coszen"][c]) for c in range(s["ncol"])])
+    np.testing.assert_allclose(o["swdflx"][:, -1], toa, rtol=1e-13)
