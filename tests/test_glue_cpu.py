@@ -215,3 +215,24 @@ def test_driver_epilogues_against_independent_numpy(oracle):
         with np.errstate(divide="ignore", invalid="ignore"):
             np.testing.assert_array_equal(got[k], np.where(ok, sw[nn] / sw[dd], n["undef"]), err_msg=k)
         assert ok.any() and (~ok).any()
+
+
+def test_irrad_update_against_independent_numpy(oracle):
+    """GEOS_IrradGridComp.F90:3604-3606, :3861, :3929-3990: the linear update between refreshes."""
+    n = make_native_state(150, 72, seed=34)
+    f = oracle.irrad_finish(n, oracle.rrtmg_lw(oracle.irrad_prepare(n)))
+    rng = np.random.default_rng(3)
+    ts_int = np.ascontiguousarray(n["ts"])
+    tsinst = ts_int + rng.normal(0., 2., ts_int.shape)
+    got = oracle.irrad_update(f, ts_int, tsinst)
+    delt = (tsinst - ts_int)[:, None]
+    flx_int, flc_int = f["flxd"] + f["flxu"], f["flcd"] + f["flcu"]
+    lm = 72
+    mine = dict(flx=flx_int + f["dfdts"] * delt, flc=flc_int + f["dfdtsc"] * delt,
+                flxu=f["flxu"] + f["dfdts"] * delt, flcu=f["flcu"] + f["dfdtsc"] * delt, flxd=f["flxd"], flcd=f["flcd"],
+                olr=-(flx_int[:, 0] + f["dfdts"][:, 0] * delt[:, 0]), olc=-(flc_int[:, 0] + f["dfdtsc"][:, 0] * delt[:, 0]),
+                sfcem=f["sfcem"] - f["dfdts"][:, lm] * delt[:, 0], lws=flx_int[:, lm] + f["sfcem"],
+                lcs=flc_int[:, lm] + f["sfcem"], flns=flx_int[:, lm] + f["dfdts"][:, lm] * delt[:, 0],
+                flnsc=flc_int[:, lm] + f["dfdtsc"][:, lm] * delt[:, 0])
+    for k, v in mine.items():
+        np.testing.assert_array_equal(got[k], v, err_msg=k)
