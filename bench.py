@@ -421,6 +421,9 @@ def main():
                           "device time per kernel from CUDA events; `traffic` = measured DRAM bytes per step (ncu)",
                 "algorithmic_bytes_per_column": bpc,
                 "note": "fp64-pipe-bound path: see DESIGN.md for the FP64 roof beside the HBM roof"}
+    if traffic is not None:   # the measured DRAM bytes over the measured step: how busy HBM really is (scratch included)
+        roofline["traffic_gbs"] = traffic / (dev_ms / a.steps * 1e-3) / 1e9
+        roofline["traffic_frac"] = roofline["traffic_gbs"] / peak
     cpu = None
     if not a.no_cpu and world == 1:
         r, threads, dt = cpu_oracle_rate(a.cpu_sample, nlay, a.seed, with_sw and oracle_has_sw())
