@@ -82,8 +82,10 @@ bool ok(cudaError_t e) { return e == cudaSuccess; }
 
 int grow(Slab &s, size_t bytes) {
     if (s.cap >= bytes) return 0;
-    lw_forget_clouds();   // a re-grown slab holds nothing a later RRTMGX_REUSE_CLOUDS call could keep
-    sw_forget_clouds();
+    // a re-grown kernel slab holds nothing a later RRTMGX_REUSE_CLOUDS call of that path could keep (the other
+    // path's cache is left alone: LW and SW may be called from two host threads)
+    if (&s == &g.lw.slab) lw_forget_clouds();
+    if (&s == &g.sw.slab) sw_forget_clouds();
     if (s.base) cudaFree(s.base);
     s.base = nullptr;
     s.cap = 0;
