@@ -1227,3 +1227,24 @@ def test_sw_gas_optics_bands_17_and_24_against_independent_numpy(oracle, isolvar
             np.testing.assert_allclose(o["taug"][c, g, :].T, taug, rtol=1e-11, err_msg=f"taug col {c}")
             np.testing.assert_allclose(o["pfracs"][c, g, :].T, taur, rtol=1e-13, err_msg=f"taur col {c}")
             np.testing.assert_allclose(o["ssi"][c, g], ssi, rtol=1e-13, err_msg=f"ssi col {c}")
+
+
+def test_negative_input_traps_follow_the_reference_order(oracle):
+    """LW/src/rrtmg_lw_rad.F90:209-318 (`error stop` per array, in this order) and SW/src/rrtmg_sw_rad.F90:365-383
+    (`_ASSERT` per array): the first offending array in the reference's own order decides, code -(100 + position)."""
+    lw_order = ["play", "plev", "tlay", "tlev", "tsfc", "h2ovmr", "o3vmr", "co2vmr", "ch4vmr", "n2ovmr", "o2vmr",
+                "cfc11vmr", "cfc12vmr", "cfc22vmr", "ccl4vmr", "emis", "cldf", "ciwp", "clwp", "rei", "rel", "tauaer_lw"]
+    sw_order = ["play", "plev", "tlay", "h2ovmr", "o3vmr", "co2vmr", "ch4vmr", "o2vmr", "asdir", "aldir", "asdif",
+                "aldif", "cldf", "ciwp", "clwp", "rei", "rel", "tauaer_sw", "ssaaer"]
+    s = make_columns(8, 72, seed=5)
+    for run, order in ((oracle.rrtmg_lw, lw_order), (oracle.rrtmg_sw, sw_order)):
+        for i, name in enumerate(order):
+            bad = dict(s)
+            bad[name] = s[name].copy(order="F")
+            bad[name].flat[bad[name].size // 2] = -1e-30
+            assert run(bad)["rc"] == -(101 + i), name
+            if i + 1 < len(order):                     # two offenders: the earlier array of the reference's list wins
+                later = order[-1]
+                bad[later] = s[later].copy(order="F")
+                bad[later].flat[0] = -1.0
+                assert run(bad)["rc"] == -(101 + i), (name, later)
