@@ -412,7 +412,16 @@ def main():
     except (OSError, KeyError, ValueError):
         pass
     if kernels and "dominant" in kernels:
-        kernels["dominant"]["frac"] = kernels["dominant"]["achieved_gbs"] / peak
+        dom = kernels["dominant"]
+        dom["frac"] = dom["achieved_gbs"] / peak
+        try:   # measured DRAM bytes of one launch of that kernel (ncu launch list), per launch like `achieved`
+            per_col = tj["band_kernel_dram_bytes_per_column_per_launch"][dom["name"]]
+            if tj.get("nlay") == nlay:
+                dom["traffic"] = per_col * dom["columns_per_launch"]
+                dom["traffic_gbs"] = dom["traffic"] / (dom["avg_launch_ms"] * 1e-3) / 1e9
+                dom["traffic_frac"] = dom["traffic_gbs"] / peak
+        except Exception:   # no capture of this kernel variant: leave the keys out
+            pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernels": kernels,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)",
