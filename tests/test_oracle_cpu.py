@@ -1248,3 +1248,46 @@ def test_negative_input_traps_follow_the_reference_order(oracle):
                 bad[later] = s[later].copy(order="F")
                 bad[later].flat[0] = -1.0
                 assert run(bad)["rc"] == -(101 + i), (name, later)
+
+
+# ---- the data blob against the reference's own data statements -------------------------------------------------------
+_REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(_REF), reason="the reference tree is only present in the build container")
+def test_committed_table_blob_is_a_fresh_extraction_of_the_reference(tmp_path):
+    """Every number the oracle and the CUDA library compute from is DATA of the reference (k-distributions, Planck
+    and cloud tables, reference atmospheres, NRLSSI2 cycle, McICA condensate tables): the committed blob must equal,
+    byte for byte, what tools/extract_tables.py reads out of the reference sources today."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "tables.bin"
+    env = dict(os.environ, RRTMG_TABLES_OUT=str(out))
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "extract_tables.py")], env=env,
+                          stdout=subprocess.DEVNULL)
+    committed = open(os.path.join(root, "geosradiation_gridcomp_b200", "data", "rrtmg_tables.bin"), "rb").read()
+    assert out.read_bytes() == committed
+
+
+@pytest.mark.skipif(not os.path.isdir(_REF), reason="the reference tree is only present in the build container")
+def test_blob_values_against_a_second_minimal_parser():
+    """A few constructors read straight out of the Fortran with one regular expression each (no shared code with
+    tools/extract_tables.py), from the first and the last table of a module and from both RRTMG trees."""
+    import re
+    from geosradiation_gridcomp_b200 import tables
+    tab = tables.load_tables()
+
+    def constructor(path, lhs):
+        src = open(os.path.join(_REF, path), errors="ignore").read()
+        m = re.search(re.escape(lhs) + r"\s*=\s*\(/(.*?)/\)", src, re.S)
+        assert m, lhs
+        body = re.sub(r"!.*", "", m.group(1)).replace("&", " ")
+        return np.array([float(x.lower().replace("d", "e")) for x in re.findall(r"[-+]?\d*\.?\d+(?:[eEdD][-+]?\d+)?", body)])
+
+    lw, sw = "GEOSirrad_GridComp/RRTMG/rrtmg_lw/gcm_model/src/", "GEOSsolar_GridComp/RRTMG/rrtmg_sw/gcm_model/src/"
+    np.testing.assert_array_equal(constructor(lw + "rrtmg_lw_k_g_01.F90", "kao(:, 1, 1)"), tab["lw.kg01.kao"][:, 0, 0])
+    np.testing.assert_array_equal(constructor(lw + "rrtmg_lw_k_g_01.F90", "kao(:, 2, 1)"), tab["lw.kg01.kao"][:, 1, 0])
+    np.testing.assert_array_equal(constructor(sw + "rrtmg_sw_k_g_17.F90", "kbo(:, 5,13, 1)"), tab["sw.kg17.kbo"][:, 4, 0, 0])
+    np.testing.assert_array_equal(constructor(sw + "rrtmg_sw_k_g_29.F90", "sfluxrefo(:)"), tab["sw.kg29.sfluxrefo"])
+    np.testing.assert_array_equal(constructor(sw + "rrtmg_sw_k_g_29.F90", "irradnceo(:)"), tab["sw.kg29.irradnceo"])

@@ -32,8 +32,8 @@ REF = os.environ.get("RRTMG_REFERENCE", "/root/reference")
 LW = f"{REF}/GEOSirrad_GridComp/RRTMG/rrtmg_lw/gcm_model"
 SW = f"{REF}/GEOSsolar_GridComp/RRTMG/rrtmg_sw/gcm_model"
 SH = f"{REF}/GEOS_RadiationShared"
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..",
-                   "geosradiation_gridcomp_b200", "data", "rrtmg_tables.bin")
+OUT = os.environ.get("RRTMG_TABLES_OUT") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "..",
+                                                         "geosradiation_gridcomp_b200", "data", "rrtmg_tables.bin")
 
 
 def logical_statements(path):
