@@ -1291,3 +1291,18 @@ def test_blob_values_against_a_second_minimal_parser():
     np.testing.assert_array_equal(constructor(sw + "rrtmg_sw_k_g_17.F90", "kbo(:, 5,13, 1)"), tab["sw.kg17.kbo"][:, 4, 0, 0])
     np.testing.assert_array_equal(constructor(sw + "rrtmg_sw_k_g_29.F90", "sfluxrefo(:)"), tab["sw.kg29.sfluxrefo"])
     np.testing.assert_array_equal(constructor(sw + "rrtmg_sw_k_g_29.F90", "irradnceo(:)"), tab["sw.kg29.irradnceo"])
+
+
+def test_kiss_range_matches_the_one_number_the_reference_records():
+    """SH/cloud_subcol_gen.F90:578-604 keeps the output of an `ifort` run of its own scaling at the two ends of the
+    int32 range: 8.9406967E-08 and 0.9999999 in the production real*4.  The same expression in IEEE single reproduces
+    both prints digit for digit; in the promoted real*8 of this project's contract the ends are 9.3746e-08 and
+    0.99999991, still inside (0, 1), so a draw can never reach either cloud-fraction bound exactly."""
+    f = np.float32
+    lo = f(-2147483648) * f(2.328306e-10) + f(0.5)
+    hi = f(2147483647) * f(2.328306e-10) + f(0.5)
+    assert "%.7E" % lo == "8.9406967E-08" and "%.7f" % hi == "0.9999999"
+    lo64, hi64 = -2147483648 * 2.328306e-10 + 0.5, 2147483647 * 2.328306e-10 + 0.5
+    assert 0.0 < lo64 < 1e-7 and 0.9999999 < hi64 < 1.0
+    draws = kiss_python((123456789, 362436069, 521288629, 916191069), 20000)
+    assert lo64 <= draws.min() and draws.max() <= hi64
