@@ -720,7 +720,8 @@ def test_lw_gas_optics_bands_1_and_3_against_independent_numpy(oracle):
 # generate_stochastic_clouds (SH/cloud_subcol_gen.F90:93-330), the correlation lengths (:333-365), zcw_lookup
 # (SH/cloud_condensate_inhomogeneity.F90, bilinear in the beta table) and clearCounts_threeBand (:610-760) in plain
 # Python on top of kiss_python above, without reference to oracle/mcica.c.  The masks are integer work: bit-exact.
-def _mcica_python(zmid, alat, doy, play, cldfrac, ciwp, clwp, nsub, xcw, so=(1, 2, 3, 4), cwp_tiny=1e-20, inhomo=True):
+def _mcica_python(zmid, alat, doy, play, cldfrac, ciwp, clwp, nsub, xcw, so=(1, 2, 3, 4), cwp_tiny=1e-20, inhomo=True,
+                  corr=(1.4315, 2.1219, 7., -25.584, 0.72192, 0.78996, 8.5, 40.404)):
     import math
     nlay, ncol = play.shape
     maximo = 2147483647 - 1
@@ -740,8 +741,8 @@ def _mcica_python(zmid, alat, doy, play, cldfrac, ciwp, clwp, nsub, xcw, so=(1, 
     mask = np.zeros((nlay, nsub, ncol), dtype=np.uint8)
     ci, cw = np.zeros((nlay, nsub, ncol)), np.zeros((nlay, nsub, ncol))
     for c in range(ncol):
-        adl = clength(1.4315, 2.1219, 7., -25.584, alat[c])
-        rdl = clength(0.72192, 0.78996, 8.5, 40.404, alat[c])
+        adl = clength(*corr[:4], alat[c])
+        rdl = clength(*corr[4:], alat[c])
         alpha = [0.] + [math.exp(-abs(zmid[l, c] - zmid[l - 1, c]) / adl) for l in range(1, nlay)]
         rcorr = [0.] + [math.exp(-abs(zmid[l, c] - zmid[l - 1, c]) / rdl) for l in range(1, nlay)]
         sigma = [0.5 if f > 0.99 else 0.71 if f > 0.9 else 1.0 for f in cldfrac[:, c]]
@@ -1306,3 +1307,24 @@ def test_kiss_range_matches_the_one_number_the_reference_records():
     assert 0.0 < lo64 < 1e-7 and 0.9999999 < hi64 < 1.0
     draws = kiss_python((123456789, 362436069, 521288629, 916191069), 20000)
     assert lo64 <= draws.min() and draws.max() <= hi64
+
+
+def test_mcica_generator_with_custom_correlation_lengths(oracle):
+    """initialize_cloud_subcol_gen (SH/cloud_subcol_gen.F90:108-129): non-default decorrelation lengths."""
+    from geosradiation_gridcomp_b200 import tables
+    xcw = tables.load_tables()["mcica.xcw_beta"]
+    s = make_columns(40, 72, seed=5151)
+    cols = np.flatnonzero((s["cldf"] > 0).any(axis=1))[:4]
+    T = lambda k: np.ascontiguousarray(s[k][cols].T)
+    corr = (0.6, 3.0, 5.0, -30.0, 0.3, 1.1, 10.0, 35.0)
+    args = (T("zm"), s["alat"][cols], 45, T("play"), T("cldf"), T("ciwp"), T("clwp"), 112)
+    oracle.set_mcica(1, corr)
+    try:
+        m, ci, cw = oracle.generate_stochastic_clouds(*args)
+    finally:
+        oracle.set_mcica(1)
+    pm, pci, pcw = _mcica_python(*args, xcw, corr=corr)
+    np.testing.assert_array_equal(m, pm)
+    np.testing.assert_allclose(cw, pcw, rtol=1e-14, atol=0)
+    m0, _, _ = oracle.generate_stochastic_clouds(*args)
+    assert (m0 != m).any()                      # the lengths do change the overlap
