@@ -1,4 +1,4 @@
-"""Non-default McICA decorrelation lengths (initialize_cloud_subcol_gen, SH/cloud_subcol_gen.F90:108-129) through the
+"""Options no earlier GPU test reaches (file sorts last): non-default McICA decorrelation lengths (initialize_cloud_subcol_gen, SH/cloud_subcol_gen.F90:108-129) through the
 C ABI against the oracle: masks and clear counts bit-exact, fluxes within the flux tolerance."""
 import numpy as np
 import pytest
@@ -32,3 +32,18 @@ def test_custom_correlation_lengths(rx, oracle):
     # and the lengths matter: the default ones give other clear counts somewhere
     d_lw = oracle.rrtmg_lw(s)
     assert (d_lw["clearCounts"] != o_lw["clearCounts"]).any()
+
+
+@pytest.mark.parametrize("iceflg", [0, 1, 2, 4])
+def test_lw_ice_parameterisations(rx, oracle, iceflg):
+    """The LW ice options other than the GEOS default 3 (LW/src/rrtmg_lw_cldprmc.F90:66-268)."""
+    s = make_columns(192, 72, seed=67)
+    o = oracle.rrtmg_lw(s, iceflg=iceflg, taps=("taucmc",))
+    assert o["rc"] == 0
+    g = rx.run_lw(s, iceflg=iceflg, taps=("taucmc",))
+    rel = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-30 + 1e-12 * np.max(np.abs(b)))))
+    assert (o["taucmc"] > 0).sum() > 1000
+    assert rel(g["taucmc"], o["taucmc"]) <= 1e-13
+    np.testing.assert_array_equal(g["clearCounts"], o["clearCounts"])
+    for k in ("uflx", "dflx", "uflxc", "dflxc"):
+        assert rel(g[k], o[k]) <= 1e-9, k
