@@ -47,3 +47,16 @@ def test_lw_ice_parameterisations(rx, oracle, iceflg):
     np.testing.assert_array_equal(g["clearCounts"], o["clearCounts"])
     for k in ("uflx", "dflx", "uflxc", "dflxc"):
         assert rel(g[k], o[k]) <= 1e-9, k
+
+
+@pytest.mark.parametrize("iceflg,liqflg", [(0, 0), (1, 1), (2, 1), (4, 1)])
+def test_glue_radius_limits_of_every_option(rx, oracle, iceflg, liqflg):
+    """The drivers clamp the effective radii differently for every cloud-optics option (IRR:3277-3296, SOL:6140-6170,
+    and not the same way in the two drivers for liqflag 0); the refresh tests only use the GEOS defaults (3, 1)."""
+    from geosradiation_gridcomp_b200.synthetic import make_native_state
+    n = make_native_state(300, 72, seed=71)
+    for prep_o, prep_g in ((oracle.irrad_prepare, rx.irrad_prepare), (oracle.solar_prepare, rx.solar_prepare)):
+        o = prep_o(n, iceflg=iceflg, liqflg=liqflg)
+        g = prep_g(n, iceflg=iceflg, liqflg=liqflg)
+        for k in ("rei", "rel", "ciwp", "clwp", "play", "tlay"):
+            np.testing.assert_array_equal(g[k], o[k], err_msg=f"{prep_o.__name__} {k}")
