@@ -120,3 +120,40 @@ def test_ctypes_mirrors_match_the_compiled_header(tmp_path):
     got = {l.split()[0]: (int(l.split()[1]), int(l.split()[2])) for l in out if l.strip()}
     for name, mirror, last in pairs:
         assert got[name] == (C.sizeof(mirror), getattr(mirror, last).offset), name
+
+
+# ---- the Fortran shim keeps the reference's own dummy-argument lists (the drop-in claim, checked on the text) ---------
+_REF_TREE = "/root/reference"
+
+
+def _dummy_arguments(path, name, strip_radval=True):
+    """Ordered dummy-argument names of `subroutine name(...)` in a free-form Fortran file (continuation lines joined,
+    comments and the reference's compile-time-off SOLAR_RADVAL blocks dropped)."""
+    import re
+    out, skip = [], False
+    for line in open(path, errors="ignore"):
+        s = line.strip()
+        if s.startswith("#ifdef SOLAR_RADVAL"):
+            skip = True
+        elif s.startswith("#endif") or s.startswith("#else"):
+            skip = False
+        elif not (skip and strip_radval) and not s.startswith("#"):
+            out.append(line.split("!")[0].rstrip())
+    text = "\n".join(out)
+    m = re.search(r"subroutine\s+" + name + r"\s*\((.*?)\)", text, re.S | re.I)
+    assert m, (path, name)
+    return [a.strip().lower() for a in m.group(1).replace("&", " ").replace("\n", " ").split(",") if a.strip()]
+
+
+@pytest.mark.skipif(not os.path.isdir(_REF_TREE), reason="the reference tree is only present in the build container")
+@pytest.mark.parametrize("ref_file,shim_file,name", [
+    ("GEOSirrad_GridComp/RRTMG/rrtmg_lw/gcm_model/src/rrtmg_lw_rad.F90", "rrtmg_lw_rad.F90", "rrtmg_lw"),
+    ("GEOSsolar_GridComp/RRTMG/rrtmg_sw/gcm_model/src/rrtmg_sw_rad.F90", "rrtmg_sw_rad.F90", "rrtmg_sw"),
+    ("GEOS_RadiationShared/cloud_subcol_gen.F90", "rrtmgx_init_mods.F90", "initialize_cloud_subcol_gen"),
+    ("GEOS_RadiationShared/cloud_condensate_inhomogeneity.F90", "rrtmgx_init_mods.F90", "set_inhomogeneity"),
+])
+def test_fortran_shim_has_the_reference_argument_lists(ref_file, shim_file, name):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = _dummy_arguments(os.path.join(_REF_TREE, ref_file), name)
+    mine = _dummy_arguments(os.path.join(root, "geosradiation_gridcomp_b200", "fortran", shim_file), name)
+    assert mine == ref, name
