@@ -666,3 +666,25 @@ def test_solar_variability_modes_against_independent_python(oracle, tab, isolvar
     # the TOA downward flux is the band-integrated source times adjes * mu0 (no adjflux scaling for isolvar >= 0)
     toa = np.array([s["adjes"] * o["ssi"][c].sum() * max(1e-10, s["coszen"][c]) for c in range(s["ncol"])])
     np.testing.assert_allclose(o["swdflx"][:, -1], toa, rtol=1e-13)
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference"), reason="the reference tree is only present in the build container")
+def test_sw_band_constants_against_the_reference_text():
+    """strrat / layreffr of SW_SPEC (typed in from reading the bands) parsed out of SW/src/rrtmg_sw_taumol.F90."""
+    import re
+    src = open("/root/reference/GEOSsolar_GridComp/RRTMG/rrtmg_sw/gcm_model/src/rrtmg_sw_taumol.F90", errors="ignore").read()
+    for band, (_, _, strrat, where, layreffr) in SW_SPEC.items():
+        body = re.search(r"subroutine taumol%d\(.*?end subroutine" % band, src, re.S).group(0)
+        body = "\n".join(line.split("!")[0] for line in body.splitlines())
+        num = lambda name: [float(v) for v in re.findall(r"^\s*" + name + r"\s*=\s*([-+0-9.eE]+)\s*$", body, re.M)]
+        s = num("strrat") + num("strrat1")
+        if band == 22:
+            assert s == [0.022708] and num("o2adj") == [1.6] and abs(strrat - 1.6 * 0.022708) < 1e-18
+        elif strrat:
+            assert s == [strrat], (band, s)
+        else:
+            assert s == [] or band in (20, 23, 25, 26, 27, 29), (band, s)
+        if where is not None:
+            assert num("layreffr") == [float(layreffr)], band
+            assert ("jp(lay-1,icol) < layreffr" in body) == (where == "upper"), band
+    assert "givfac = 1.029" in src
