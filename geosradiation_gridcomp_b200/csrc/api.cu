@@ -5,6 +5,7 @@
 // There is no CPU fallback: every entry point fails with RRTMGX_ENODEVICE / RRTMGX_ENOTINIT
 // when no CUDA device is usable.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -23,7 +24,7 @@
 
 namespace rrtmgx {
 
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 bool g_profile = false;
 namespace {
 struct ProfEntry { long long n = 0; double ms = 0.; };
@@ -61,6 +62,9 @@ struct Path {   // per-path (LW or SW) execution resources
     bool has_taps = false;
 };
 
+constexpr size_t kHostChunkDefault = 8192;
+constexpr int kStagesDefault = 2;
+
 struct Ctx {
     bool ready = false;
     int device = 0;
@@ -69,8 +73,8 @@ struct Ctx {
     McicaConfig mc;
     Path lw, sw;
     size_t chunk_cols = 0;   // 0: automatic
-    size_t host_chunk_cols = 8192;   // staging chunk of the host-array pipeline (RRTMGX_HOST_CHUNK; sweep: profiles/r4_c_*, r4_d_*)
-    int stages = 2;          // staging sets in flight (RRTMGX_STAGES): deeper than double buffering measured slower, profiles/r4_d_*
+    size_t host_chunk_cols = kHostChunkDefault;   // staging chunk of the host-array pipeline (RRTMGX_HOST_CHUNK; sweep: profiles/r4_c_*, r4_d_*)
+    int stages = kStagesDefault;   // staging sets in flight (RRTMGX_STAGES): deeper than double buffering measured slower, profiles/r4_d_*
     std::mutex mu;
 };
 
@@ -163,7 +167,9 @@ int ensure_jumps(Path &p, int nsub, int nlay) {
 struct NegScan {
     const double *x[24];
     unsigned long long n[24];
+    int trap_nan;   // SW: _ASSERT(all(x >= 0.)) also fires on NaN (SW :365-383); LW: any(x < 0.) does not (LW :209-318)
 };
+__device__ __forceinline__ bool neg_bad(double v, int trap_nan) { return trap_nan ? !(v >= 0.) : (v < 0.); }
 __global__ void __launch_bounds__(256) check_negative_kernel(NegScan S, int *negpos) {
     const int a = blockIdx.y;
     const double *__restrict__ x = S.x[a];
@@ -174,11 +180,11 @@ __global__ void __launch_bounds__(256) check_negative_kernel(NegScan S, int *neg
     if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
         for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
             const double2 v = x2[i];
-            bad |= (v.x < 0.) | (v.y < 0.);
+            bad |= neg_bad(v.x, S.trap_nan) | neg_bad(v.y, S.trap_nan);
         }
-        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) bad |= x[n - 1] < 0.;
+        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) bad |= neg_bad(x[n - 1], S.trap_nan);
     } else {
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) bad |= x[i] < 0.;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) bad |= neg_bad(x[i], S.trap_nan);
     }
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicMin(negpos, a);
 }
@@ -245,6 +251,11 @@ int run_staged(Path &p, const Args &a, Args &ca, std::vector<Arr> &arrs, int nco
     const int nstage = g.stages;
     for (int s = 0; s < nstage; ++s)
         if (int rc = grow(p.stage[s], stage_bytes + 4096)) return rc;
+    // the first failing copy / event call of the loop decides the status; on any failure the three streams are
+    // drained before returning, so no copy into the caller's arrays is still in flight behind the call
+    cudaError_t first_err = cudaSuccess;
+    auto note = [&](cudaError_t e) { if (e != cudaSuccess && first_err == cudaSuccess) first_err = e; };
+    auto drain = [&]() { note(cudaStreamSynchronize(p.h2d)); note(cudaStreamSynchronize(p.stream)); note(cudaStreamSynchronize(p.d2h)); };
     int k = 0;
     for (size_t col0 = 0; col0 < (size_t)ncol; col0 += chunk, ++k) {
         const int s = k % nstage;
@@ -252,21 +263,21 @@ int run_staged(Path &p, const Args &a, Args &ca, std::vector<Arr> &arrs, int nco
         Slab &st = p.stage[s];
         st.used = 0;
         std::vector<void *> dev(arrs.size()), raw(arrs.size());
-        if (k >= nstage) cudaStreamWaitEvent(p.h2d, p.ev_free[s], 0);
+        if (k >= nstage) note(cudaStreamWaitEvent(p.h2d, p.ev_free[s], 0));
         for (size_t i = 0; i < arrs.size(); ++i) {
             Arr &r = arrs[i];
             raw[i] = r.host ? (void *)st.take<char>(r.rows * nc * r.elem) : nullptr;
             dev[i] = (r.host && r.f32) ? (void *)st.take<char>(r.rows * nc * 8) : raw[i];
             if (!r.host || !r.in) continue;
             if (r.inner)
-                cudaMemcpyAsync(raw[i], (const char *)r.host + col0 * r.rows * r.elem, r.rows * nc * r.elem,
-                                cudaMemcpyHostToDevice, p.h2d);
+                note(cudaMemcpyAsync(raw[i], (const char *)r.host + col0 * r.rows * r.elem, r.rows * nc * r.elem,
+                                     cudaMemcpyHostToDevice, p.h2d));
             else
-                cudaMemcpy2DAsync(raw[i], nc * r.elem, (const char *)r.host + col0 * r.elem, (size_t)ncol * r.elem,
-                                  nc * r.elem, r.rows, cudaMemcpyHostToDevice, p.h2d);
+                note(cudaMemcpy2DAsync(raw[i], nc * r.elem, (const char *)r.host + col0 * r.elem, (size_t)ncol * r.elem,
+                                       nc * r.elem, r.rows, cudaMemcpyHostToDevice, p.h2d));
         }
-        cudaEventRecord(p.ev_in[s], p.h2d);
-        cudaStreamWaitEvent(p.stream, p.ev_in[s], 0);
+        note(cudaEventRecord(p.ev_in[s], p.h2d));
+        note(cudaStreamWaitEvent(p.stream, p.ev_in[s], 0));
         for (size_t i = 0; i < arrs.size(); ++i)
             if (arrs[i].host && arrs[i].f32 && arrs[i].in) {
                 const size_t n = arrs[i].rows * nc;
@@ -276,27 +287,29 @@ int run_staged(Path &p, const Args &a, Args &ca, std::vector<Arr> &arrs, int nco
         ca = a;
         ca.ncol = (int)nc;
         for (size_t i = 0; i < arrs.size(); ++i) *arrs[i].slot = dev[i];
-        if (int rc = fn(ca, (int)nc)) return rc;
+        if (int rc = fn(ca, (int)nc, col0)) { drain(); return rc; }
         for (size_t i = 0; i < arrs.size(); ++i)
             if (arrs[i].host && arrs[i].f32 && arrs[i].out) {
                 const size_t n = arrs[i].rows * nc;
                 RRTMGX_LAUNCH(narrow_kernel, (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, p.stream,
                               (const double *)dev[i], (float *)raw[i], n);
             }
-        cudaEventRecord(p.ev_done[s], p.stream);
-        cudaStreamWaitEvent(p.d2h, p.ev_done[s], 0);
+        note(cudaEventRecord(p.ev_done[s], p.stream));
+        note(cudaStreamWaitEvent(p.d2h, p.ev_done[s], 0));
         for (size_t i = 0; i < arrs.size(); ++i) {
             Arr &r = arrs[i];
             if (!r.host || !r.out) continue;
             if (r.inner)
-                cudaMemcpyAsync((char *)r.host + col0 * r.rows * r.elem, raw[i], r.rows * nc * r.elem,
-                                cudaMemcpyDeviceToHost, p.d2h);
+                note(cudaMemcpyAsync((char *)r.host + col0 * r.rows * r.elem, raw[i], r.rows * nc * r.elem,
+                                     cudaMemcpyDeviceToHost, p.d2h));
             else
-                cudaMemcpy2DAsync((char *)r.host + col0 * r.elem, (size_t)ncol * r.elem, raw[i], nc * r.elem,
-                                  nc * r.elem, r.rows, cudaMemcpyDeviceToHost, p.d2h);
+                note(cudaMemcpy2DAsync((char *)r.host + col0 * r.elem, (size_t)ncol * r.elem, raw[i], nc * r.elem,
+                                       nc * r.elem, r.rows, cudaMemcpyDeviceToHost, p.d2h));
         }
-        cudaEventRecord(p.ev_free[s], p.d2h);
+        note(cudaEventRecord(p.ev_free[s], p.d2h));
+        if (first_err != cudaSuccess) break;
     }
+    if (first_err != cudaSuccess) { drain(); cudaGetLastError(); return RRTMGX_ECUDA; }
     if (!ok(cudaStreamSynchronize(p.d2h))) { cudaGetLastError(); return RRTMGX_ECUDA; }
     return 0;
 }
@@ -368,8 +381,10 @@ int build_cloud_partition(int ld, int col0, int nc, int nlay, const double *cldf
 }
 
 // arrays x[i] of cnt[i] elements, position i in the reference's order of checks; null or empty arrays are skipped
-void launch_check_negative(const double *const *x, const size_t *cnt, int narr, int *d_negpos, cudaStream_t s) {
+void launch_check_negative(const double *const *x, const size_t *cnt, int narr, int *d_negpos, cudaStream_t s,
+                           bool trap_nan) {
     NegScan S{};
+    S.trap_nan = trap_nan ? 1 : 0;
     size_t most = 0;
     for (int i = 0; i < narr && i < 24; ++i) {
         S.x[i] = x[i];
@@ -389,47 +404,77 @@ extern "C" {
 
 int rrtmgx_init(const RrtmgxConfig *cfg) {
     std::lock_guard<std::mutex> lock(g.mu);
+    // the reference's *_ini routines never touch the McICA module state (set_inhomogeneity and
+    // initialize_cloud_subcol_gen own it, RAD:565,578) and GEOS calls them on every refresh (IRR:3381,
+    // SOL:6225): a call on an initialised library is a pure no-op, whatever cfg holds
+    if (g.ready) return 0;
+    // cfg->inhomogeneity: 0..2 sets ih, -1 leaves the default (1 = beta, RAD:564); validated before anything is allocated
+    if (cfg && (cfg->inhomogeneity < -1 || cfg->inhomogeneity > 2)) return RRTMGX_EINHOMO;
     int ndev = 0;
     if (!ok(cudaGetDeviceCount(&ndev)) || ndev == 0) { cudaGetLastError(); return RRTMGX_ENODEVICE; }
     if (cfg && cfg->device >= 0) {
         if (!ok(cudaSetDevice(cfg->device))) { cudaGetLastError(); return RRTMGX_ENODEVICE; }
     }
-    if (g.ready) {   // idempotent: GEOS calls the _ini routines on every refresh
-        if (cfg && cfg->inhomogeneity >= 0 && cfg->inhomogeneity <= 2) {
-            g.mc.ih = cfg->inhomogeneity;
-            if (cfg->corr) std::memcpy(g.mc.corr, cfg->corr, sizeof g.mc.corr);
-        }
-        return 0;
-    }
     if (!ok(cudaGetDevice(&g.device))) return RRTMGX_ENODEVICE;
     const std::string blob = (cfg && cfg->table_blob) ? cfg->table_blob : default_blob();
     if (int rc = g.ht.load(blob)) return rc;
+    auto fail = [&](int rc) {   // a failed init leaves nothing allocated
+        path_free(g.lw);
+        path_free(g.sw);
+        if (g.d_arena) cudaFree(g.d_arena);
+        g.d_arena = nullptr;
+        cudaGetLastError();
+        return rc;
+    };
     const size_t bytes = g.ht.arena.size() * sizeof(double);
-    if (!ok(cudaMalloc((void **)&g.d_arena, bytes))) { cudaGetLastError(); return RRTMGX_ENODEVICE; }
-    if (!ok(cudaMemcpy(g.d_arena, g.ht.arena.data(), bytes, cudaMemcpyHostToDevice))) return RRTMGX_ECUDA;
-    if (int rc = lw_upload_tables(g.ht, g.d_arena)) return rc;
-    if (int rc = sw_upload_tables(g.ht, g.d_arena)) return rc;
-    if (int rc = path_init(g.lw)) return rc;
-    if (int rc = path_init(g.sw)) return rc;
+    if (!ok(cudaMalloc((void **)&g.d_arena, bytes))) return fail(RRTMGX_ENODEVICE);
+    if (!ok(cudaMemcpy(g.d_arena, g.ht.arena.data(), bytes, cudaMemcpyHostToDevice))) return fail(RRTMGX_ECUDA);
+    if (int rc = lw_upload_tables(g.ht, g.d_arena)) return fail(rc);
+    if (int rc = sw_upload_tables(g.ht, g.d_arena)) return fail(rc);
+    if (int rc = path_init(g.lw)) return fail(rc);
+    if (int rc = path_init(g.sw)) return fail(rc);
     g.mc = McicaConfig();
     if (cfg) {
-        if (cfg->inhomogeneity < 0 || cfg->inhomogeneity > 2) return RRTMGX_EINHOMO;
-        g.mc.ih = cfg->inhomogeneity;
+        if (cfg->inhomogeneity >= 0) g.mc.ih = cfg->inhomogeneity;
         if (cfg->corr) std::memcpy(g.mc.corr, cfg->corr, sizeof g.mc.corr);
     }
+    // tuning knobs: the defaults first, so that a finalize -> init cycle never inherits the previous environment
+    g.chunk_cols = 0;
+    g.host_chunk_cols = kHostChunkDefault;
+    g.stages = kStagesDefault;
     if (const char *e = std::getenv("RRTMGX_CHUNK")) g.chunk_cols = (size_t)std::atoll(e);
     if (const char *e = std::getenv("RRTMGX_HOST_CHUNK")) g.host_chunk_cols = std::max<size_t>(1024, (size_t)std::atoll(e));
     if (const char *e = std::getenv("RRTMGX_STAGES")) g.stages = std::min(NSTAGE, std::max(2, std::atoi(e)));
+    lw_read_env();
+    sw_read_env();
     g.ready = true;
     return 0;
 }
 
+// set_inhomogeneity + initialize_cloud_subcol_gen (SH/cloud_condensate_inhomogeneity.F90:45, SH/cloud_subcol_gen.F90:108):
+// the module state both paths read.  Taken under the library lock and stream-ordered behind the work in flight.
 int rrtmgx_set_mcica(int ih, const double corr[8]) {
+    std::lock_guard<std::mutex> lock(g.mu);
     if (!g.ready) return RRTMGX_ENOTINIT;
     if (ih < 0 || ih > 2) return RRTMGX_EINHOMO;
-    g.mc = McicaConfig();
-    g.mc.ih = ih;
-    if (corr) std::memcpy(g.mc.corr, corr, sizeof g.mc.corr);
+    McicaConfig mc;
+    mc.ih = ih;
+    if (corr) std::memcpy(mc.corr, corr, sizeof mc.corr);
+    g.mc = mc;
+    // the clouds a path still holds were drawn under the previous settings
+    lw_forget_clouds();
+    sw_forget_clouds();
+    return 0;
+}
+
+int rrtmgx_get_knobs(long long knobs[4]) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return RRTMGX_ENOTINIT;
+    if (!knobs) return RRTMGX_EARG;
+    knobs[0] = (long long)g.chunk_cols;
+    knobs[1] = (long long)g.host_chunk_cols;
+    knobs[2] = g.stages;
+    knobs[3] = g.mc.ih;
     return 0;
 }
 
@@ -470,7 +515,7 @@ const char *rrtmgx_strerror(int status) {
     return "unknown status";
 }
 
-long long rrtmgx_launch_count(void) { return g_launches; }
+long long rrtmgx_launch_count(void) { return g_launches.load(); }
 
 void rrtmgx_profile(int enable) {
     std::lock_guard<std::mutex> lock(g_prof_mu);
@@ -495,6 +540,7 @@ size_t rrtmgx_profile_report(char *buf, size_t cap) {
 }
 
 void rrtmgx_set_taps(const RrtmgxTaps *lw_taps, const RrtmgxTaps *sw_taps) {
+    std::lock_guard<std::mutex> lock(g.mu);
     g.lw.has_taps = lw_taps != nullptr;
     if (lw_taps) g.lw.taps = *lw_taps;
     g.sw.has_taps = sw_taps != nullptr;
@@ -583,7 +629,9 @@ int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *var) {
         d_var[0] = var->uflx; d_var[1] = var->dflx; d_var[2] = var->duflx_dTs;
     }
 
-    auto run_chunks_device = [&](const RrtmgxLwArgs &da) -> int {
+    // `da` holds device pointers for columns [first, first + da.ncol) of the caller's call
+    const int nchunks_dev = (int)(((size_t)ncol + chunk - 1) / chunk);
+    auto run_chunks_device = [&](const RrtmgxLwArgs &da, size_t first) -> int {
         const int n = da.ncol;
         if (!(da.flags & RRTMGX_SKIP_CHECKS)) {
             const size_t n2 = (size_t)n * nlay, n2p = (size_t)n * (nlay + 1);
@@ -597,7 +645,7 @@ int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *var) {
             const double *xs[narr];
             size_t cnts[narr];
             for (int i = 0; i < narr; ++i) { xs[i] = chk[i].x; cnts[i] = chk[i].cnt; }
-            launch_check_negative(xs, cnts, narr, p.d_err + 1, stream);
+            launch_check_negative(xs, cnts, narr, p.d_err + 1, stream, false);
         }
         // chunk by chunk: the removed-gas runs of the chunk (gas array replaced by zeros, fluxes into slab v of the
         // variant arrays), then the run with every gas; all of them on the clouds the first one generated
@@ -615,7 +663,8 @@ int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *var) {
                     if (da.dudTs) dv.duflx_dTs = d_var[2] + v * vslab;
                 }
                 if (v > 0) dv.flags |= RRTMGX_REUSE_CLOUDS;
-                if (int rc = lw_run_chunk(&dv, (int)col0, nc, mp, p.d_jumps, p.slab, p.d_err, stream, p.side, NSIDE, p.ev,
+                const ChunkId id{(long long)(first + col0), (long long)ncol, nchunks_dev};
+                if (int rc = lw_run_chunk(&dv, (int)col0, nc, id, mp, p.d_jumps, p.slab, p.d_err, stream, p.side, NSIDE, p.ev,
                                           taps, p.d_err + 1))
                     return rc;
             }
@@ -623,7 +672,7 @@ int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *var) {
         return 0;
     };
     if (devptr) {
-        if (int rc = run_chunks_device(*a)) return rc;
+        if (int rc = run_chunks_device(*a, 0)) return rc;
         p.pending = true;
         if (a->flags & RRTMGX_NO_SYNC) return 0;
         p.last_status = status_from(p);
@@ -662,13 +711,10 @@ int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *var) {
     }
     for (int k = 0; k < 3 && nvar; ++k)   // (ncol, nlay+1, nvar): nvar*(nlay+1) rows of ncol
         if (d_var[k]) arrs.push_back({d_var[k], (void **)&d_var[k], (size_t)nvar * L1, esz, false, false, true, f32});
-    int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxLwArgs &c, int nc) -> int {
+    int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxLwArgs &c, int nc, size_t first) -> int {
         (void)nc;
         c.flags |= RRTMGX_DEVICE_PTRS;
-        const size_t save = chunk;
-        int r = run_chunks_device(c);
-        chunk = save;
-        return r;
+        return run_chunks_device(c, first);
     });
     if (rc) return rc;
     p.pending = true;
@@ -764,7 +810,8 @@ int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *a, const RrtmgxSwNoAerosol *na)
         !ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, stream)))
         return RRTMGX_ECUDA;
 
-    auto run_chunks_device = [&](const RrtmgxSwArgs &da) -> int {
+    const int nchunks_dev = (int)(((size_t)ncol + chunk - 1) / chunk);
+    auto run_chunks_device = [&](const RrtmgxSwArgs &da, size_t first) -> int {
         const int n = da.ncol;
         if (!(da.flags & RRTMGX_SKIP_CHECKS)) {   // _ASSERTs :365-383 in the reference's order
             const size_t n2 = (size_t)n * nlay, n2p = (size_t)n * (nlay + 1);
@@ -777,21 +824,22 @@ int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *a, const RrtmgxSwNoAerosol *na)
             const double *xs[narr];
             size_t cnts[narr];
             for (int i = 0; i < narr; ++i) { xs[i] = chk[i].x; cnts[i] = chk[i].cnt; }
-            launch_check_negative(xs, cnts, narr, p.d_err + 1, stream);
+            launch_check_negative(xs, cnts, narr, p.d_err + 1, stream, true);
         }
         for (size_t col0 = 0; col0 < (size_t)n; col0 += chunk) {
             const int nc = (int)std::min(chunk, (size_t)n - col0);
+            const ChunkId id{(long long)(first + col0), (long long)ncol, nchunks_dev};
             if (na) {   // the no-aerosol run of the chunk first (SOL:3249-3258), its fluxes into the NA arrays
                 RrtmgxSwArgs dv = da;
                 dv.iaer = 0;
                 dv.swuflx = d_na[0]; dv.swdflx = d_na[1]; dv.swuflxc = d_na[2]; dv.swdflxc = d_na[3]; dv.fswband = d_na[4];
-                if (int rc = sw_run_chunk(&dv, sol, (int)col0, nc, mp, p.d_jumps, p.slab, p.d_err, stream, p.side, NSIDE,
+                if (int rc = sw_run_chunk(&dv, sol, (int)col0, nc, id, mp, p.d_jumps, p.slab, p.d_err, stream, p.side, NSIDE,
                                           p.ev, taps, p.d_err + 1))
                     return rc;
             }
             RrtmgxSwArgs dm = da;
             if (na) dm.flags |= RRTMGX_REUSE_CLOUDS;
-            if (int rc = sw_run_chunk(&dm, sol, (int)col0, nc, mp, p.d_jumps, p.slab, p.d_err, stream, p.side, NSIDE,
+            if (int rc = sw_run_chunk(&dm, sol, (int)col0, nc, id, mp, p.d_jumps, p.slab, p.d_err, stream, p.side, NSIDE,
                                       p.ev, taps, p.d_err + 1))
                 return rc;
         }
@@ -799,7 +847,7 @@ int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *a, const RrtmgxSwNoAerosol *na)
     };
 
     if (devptr) {
-        if (int rc = run_chunks_device(*a)) return rc;
+        if (int rc = run_chunks_device(*a, 0)) return rc;
         p.pending = true;
         if (a->flags & RRTMGX_NO_SYNC) return 0;
         p.last_status = status_from(p);
@@ -837,10 +885,10 @@ int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *a, const RrtmgxSwNoAerosol *na)
         for (int k = 0; k < 4; ++k) arrs.push_back({d_na[k], (void **)&d_na[k], L1, esz, false, false, true, f32});
         arrs.push_back({d_na[4], (void **)&d_na[4], 14, esz, false, false, true, f32});
     }
-    int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxSwArgs &c, int nc) -> int {
+    int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxSwArgs &c, int nc, size_t first) -> int {
         (void)nc;
         c.flags |= RRTMGX_DEVICE_PTRS;
-        return run_chunks_device(c);
+        return run_chunks_device(c, first);
     });
     if (rc) return rc;
     p.pending = true;
@@ -922,6 +970,7 @@ int irrad_chunk(const RrtmgxIrradArgs &S, int lds, int col0, int nc, cudaStream_
     RRTMGX_LAUNCH(irrad_prepare_kernel, (nc + 127) / 128, 128, 0, st, nc, lds, col0, S, L);
     if (int rc = rrtmgx_lw_run(&L)) return rc;
     RRTMGX_LAUNCH(irrad_finish_kernel, (nc + 127) / 128, 128, 0, st, nc, lds, col0, S, L, band_mask_of(S.band_output));
+    lw_forget_clouds();   // the glue workspace is rewritten per chunk: nothing a later RRTMGX_REUSE_CLOUDS call may keep
     return ok(cudaGetLastError()) ? 0 : RRTMGX_ECUDA;
 }
 #ifdef RRTMGX_WITH_SW
@@ -937,6 +986,7 @@ int solar_chunk(const RrtmgxSolarArgs &S, int lds, int col0, int nc, cudaStream_
     RRTMGX_LAUNCH(solar_prepare_kernel, (nc + 127) / 128, 128, 0, st, nc, lds, col0, S, L);
     if (int rc = rrtmgx_sw_run(&L)) return rc;
     RRTMGX_LAUNCH(solar_finish_kernel, (nc + 127) / 128, 128, 0, st, nc, lds, col0, S, L);
+    sw_forget_clouds();
     return ok(cudaGetLastError()) ? 0 : RRTMGX_ECUDA;
 }
 #endif
@@ -997,7 +1047,7 @@ int rrtmgx_irrad_refresh(const RrtmgxIrradArgs *a) {
         ca.olrb = nullptr; ca.dolrb_dts = nullptr;
     }
     const size_t chunk = std::min<size_t>(g.host_chunk_cols, (size_t)ncol);
-    int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxIrradArgs &c, int nc) -> int {
+    int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxIrradArgs &c, int nc, size_t) -> int {
         return irrad_chunk(c, nc, 0, nc, p.stream);
     });
     if (rc) return rc;
@@ -1159,7 +1209,7 @@ int rrtmgx_solar_refresh(const RrtmgxSolarArgs *a) {
     out(a->cldts, &ca.cldts, 1); out(a->cldhs, &ca.cldhs, 1); out(a->cldms, &ca.cldms, 1); out(a->cldls, &ca.cldls, 1);
     out(a->cottp, &ca.cottp, 1); out(a->cothp, &ca.cothp, 1); out(a->cotmp, &ca.cotmp, 1); out(a->cotlp, &ca.cotlp, 1);
     const size_t chunk = std::min<size_t>(g.host_chunk_cols, (size_t)ncol);
-    int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxSolarArgs &c, int nc) -> int {
+    int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxSolarArgs &c, int nc, size_t) -> int {
         return solar_chunk(c, nc, 0, nc, p.stream);
     });
     if (rc) return rc;

@@ -1,6 +1,7 @@
 // Internal host-side interface between the C ABI (api.cu) and the LW / SW kernel translation
 // units (lw.cu, sw.cu).  Not installed; the public surface is include/rrtmgx.h.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -13,7 +14,7 @@ namespace rrtmgx {
 // every kernel launch of the library goes through this counter (rrtmgx_launch_count); with
 // profiling switched on (rrtmgx_profile) each launch is bracketed by CUDA events on its own
 // stream and waited for, which serialises the step and attributes device time per kernel
-extern long long g_launches;
+extern std::atomic<long long> g_launches;   // LW and SW may be driven from two host threads
 extern bool g_profile;
 void profile_add(const char *name, float ms);
 struct ProfScope {
@@ -70,6 +71,25 @@ void kiss_jump_table(int nsub, int nlay, bool inhomo, KissJump *out /* 2*nsub */
 McicaParams mcica_params(const McicaConfig &cfg, const double *d_xcw_beta, const double *d_xcw_gamma,
                          int doy, const int seed_order[4]);
 
+// Which columns of the CALLER's call a chunk covers.  The scratch slab of a path holds the McICA clouds of exactly
+// one chunk; RRTMGX_REUSE_CLOUDS may keep them only when the previous run of the path was this very chunk of a
+// call of the same extent.  A host-array call crosses in several staging chunks, each of which is run with
+// chunk-local arrays (col0 = 0, ld = nc): without the call-level identity all of them would look alike.
+struct ChunkId {
+    long long first = 0;   // first column of the chunk in the caller's arrays
+    long long total = 0;   // columns of the caller's call
+    int nchunks = 1;       // chunks the call is run in (1: the slab still holds all of its clouds afterwards)
+};
+struct CloudCache {
+    const char *base = nullptr;
+    long long first = -1, total = -1;
+    int nc = 0, nlay = 0;
+    bool perm = false, valid = false;
+    bool matches(const char *b, const ChunkId &id, int nc_, int nlay_) const {
+        return valid && base == b && first == id.first && total == id.total && nc == nc_ && nlay == nlay_;
+    }
+};
+
 // ---- LW ------------------------------------------------------------------------------------
 int lw_upload_tables(const HostTables &ht, const double *d_arena);   // fills __constant__ state
 size_t lw_scratch_bytes(int nc, int nlay, bool debug);
@@ -78,9 +98,11 @@ size_t lw_scratch_bytes(int nc, int nlay, bool debug);
 struct LwDebug {                  // optional device taps, chunk-local [..][nc] layouts
     double *taug = nullptr, *pfracs = nullptr;   // [nlay][140][nc]
 };
-int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
+// `id` names the chunk within the caller's whole call (RRTMGX_REUSE_CLOUDS keys on it, see ChunkId)
+int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const ChunkId &id, const McicaParams &mp,
                  const KissJump *d_jumps, Slab &slab, int *d_err, cudaStream_t stream,
                  cudaStream_t *side, int nside, cudaEvent_t *ev, const RrtmgxTaps *taps, int *d_negpos);
+void lw_read_env();   // RRTMGX_LW_GN (called once per rrtmgx_init, under the library lock)
 
 // ---- SW ------------------------------------------------------------------------------------
 int sw_upload_tables(const HostTables &ht, const double *d_arena);
@@ -93,9 +115,10 @@ struct SwSolar {                  // host-evaluated scalars of rrtmg_sw_sub :889
 };
 // rrtmg_sw_sub :889-1127 + NRLSSI2.F90 (host scalars only); 0 or RRTMGX_ESOLVAR
 int sw_solar_setup(const RrtmgxSwArgs *a, const HostTables &ht, SwSolar *out);
-int sw_run_chunk(const RrtmgxSwArgs *a, const SwSolar &sol, int col0, int nc, const McicaParams &mp,
+int sw_run_chunk(const RrtmgxSwArgs *a, const SwSolar &sol, int col0, int nc, const ChunkId &id, const McicaParams &mp,
                  const KissJump *d_jumps, Slab &slab, int *d_err, cudaStream_t stream,
                  cudaStream_t *side, int nside, cudaEvent_t *ev, const RrtmgxTaps *taps, int *d_negpos);
+void sw_read_env();   // RRTMGX_SW_GN
 
 void lw_forget_clouds();   // drop what RRTMGX_REUSE_CLOUDS would reuse (slab freed or re-grown)
 void sw_forget_clouds();
@@ -106,6 +129,7 @@ void sw_forget_clouds();
 int build_cloud_partition(int ld, int col0, int nc, int nlay, const double *cldf, int *perm, unsigned char *flags,
                           int *ktop, void *tmp, size_t tmp_bytes, cudaStream_t stream);
 size_t cloud_partition_tmp_bytes(int nc);
-void launch_check_negative(const double *const *x, const size_t *cnt, int narr, int *d_negpos, cudaStream_t s);
+void launch_check_negative(const double *const *x, const size_t *cnt, int narr, int *d_negpos, cudaStream_t s,
+                           bool trap_nan);
 
 }  // namespace rrtmgx

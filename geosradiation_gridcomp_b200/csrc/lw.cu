@@ -1296,6 +1296,16 @@ static const LwBandLauncher lw_launchers[16][4] = {
     X(9, 2, 56) X(10, 2, 64) X(11, 2, 80) X(12, 2, 80) X(13, 1, 80) X(14, 1, 64) X(15, 1, 80) X(16, 1, 80)};
 #undef X
 static int lw_variant[16] = {0, 1, 3, 3, 3, 2, 3, 2, 3, 2, 2, 2, 2, 1, 1, 1};   // columns per block, profiles/r2_cb_tuning.txt (run r2h)
+static const int lw_variant_default[16] = {0, 1, 3, 3, 3, 2, 3, 2, 3, 2, 2, 2, 2, 1, 1, 1};
+void lw_read_env() {   // once per rrtmgx_init, under the library lock
+    for (int b = 0; b < 16; ++b) lw_variant[b] = lw_variant_default[b];
+    const char *e = std::getenv("RRTMGX_LW_GN");
+    if (!e) return;
+    int b = 0;
+    for (const char *q = e; *q && b < 16; ++q)
+        if (*q >= '0' && *q <= '3') lw_variant[b++] = *q - '0';
+    for (; b > 0 && b < 16; ++b) lw_variant[b] = lw_variant[b - 1];
+}
 
 // fixed-order sum of the band partials -> caller arrays; band OLR (:382-385, rad.F90:586-605)
 __global__ void lw_reduce_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, int dudTs, const double *__restrict__ part,
@@ -1382,11 +1392,10 @@ size_t lw_scratch_bytes(int nc, int nlay, bool debug) {
 }
 
 // what RRTMGX_REUSE_CLOUDS may keep from the previous call of this path (see lw_run_chunk)
-struct CloudCache { const char *base = nullptr; int col0 = 0, nc = 0, nlay = 0, ld = 0; bool perm = false, valid = false; };
 static CloudCache g_lw_cloud_cache;
 void lw_forget_clouds() { g_lw_cloud_cache = CloudCache(); }
 
-int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp, const KissJump *d_jumps,
+int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const ChunkId &id, const McicaParams &mp, const KissJump *d_jumps,
                  Slab &slab, int *d_err, cudaStream_t stream, cudaStream_t *side, int nside, cudaEvent_t *ev,
                  const RrtmgxTaps *taps, int *d_negpos) {
     (void)d_negpos;
@@ -1407,8 +1416,7 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
     CloudCache &cache = g_lw_cloud_cache;
     // the slab holds the clouds of ONE chunk: the previous run of this path must have been this very chunk
     const bool keep = !taps;
-    const bool reuse = (a->flags & RRTMGX_REUSE_CLOUDS) && keep && cache.valid && cache.base == slab.base &&
-                       cache.col0 == col0 && cache.nc == nc && cache.nlay == nlay && cache.ld == ld;
+    const bool reuse = (a->flags & RRTMGX_REUSE_CLOUDS) && keep && cache.matches(slab.base, id, nc, nlay);
     const int *perm = nullptr;
     if (reuse) {
         perm = cache.perm ? W.perm : nullptr;
@@ -1447,7 +1455,7 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
             for (int k = 0; k < 4; ++k)
                 cudaMemcpyAsync(W.clear_save + (size_t)k * nc, a->clearCounts + (size_t)k * ld + col0,
                                 sizeof(int32_t) * (size_t)nc, cudaMemcpyDeviceToDevice, stream);
-            cache = {slab.base, col0, nc, nlay, ld, perm != nullptr, true};
+            cache = {slab.base, id.first, id.total, nc, nlay, perm != nullptr, true};
         }
     }
 
@@ -1455,16 +1463,6 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const McicaParams &mp,
     // fan the independent band units out over the side streams
     cudaEventRecord(ev[0], stream);
     for (int s = 0; s < nside; ++s) cudaStreamWaitEvent(side[s], ev[0], 0);
-    static bool variants_read = false;
-    if (!variants_read) {
-        if (const char *e = std::getenv("RRTMGX_LW_GN")) {
-            int b = 0;
-            for (const char *q = e; *q && b < 16; ++q)
-                if (*q >= '0' && *q <= '3') lw_variant[b++] = *q - '0';
-            for (; b > 0 && b < 16; ++b) lw_variant[b] = lw_variant[b - 1];
-        }
-        variants_read = true;
-    }
     for (int b = 0; b < 16; ++b) lw_launchers[b][lw_variant[b]](nc, nside ? side[b % nside] : stream, A);
     for (int s = 0; s < nside; ++s) {
         cudaEventRecord(ev[1 + s], side[s]);

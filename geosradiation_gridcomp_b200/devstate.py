@@ -47,7 +47,7 @@ def _ptr(t, device):
 
 
 def lw_runner(d, o=None, device=True, sync=True, skip_checks=False, dudTs=True, iceflg=3, liqflg=1, stream=None,
-              f32=False):
+              f32=False, reuse_clouds=False):
     ncol, nlay = d["ncol"], d["nlay"]
     o = o if o is not None else alloc_outputs(ncol, nlay, pinned=not device)
     p = (lambda t: t) if device else (lambda t: t.data_ptr())
@@ -60,14 +60,14 @@ def lw_runner(d, o=None, device=True, sync=True, skip_checks=False, dudTs=True, 
                       p(d["tauaer_lw"]), p(d["zm"]), p(d["alat"]), d["dyofyr"], d["cloudLM"], d["cloudMH"],
                       p(o["clearCounts_lw"]), p(o["uflx"]), p(o["dflx"]), p(o["uflxc"]), p(o["dflxc"]),
                       p(o["duflx_dTs"]), p(o["duflxc_dTs"]), d["band_output"], p(o["olrb"]), p(o["dolrb_dTs"]),
-                      device=device, sync=sync, skip_checks=skip_checks, stream=stream, f32=f32)
+                      device=device, sync=sync, skip_checks=skip_checks, stream=stream, f32=f32, reuse_clouds=reuse_clouds)
         return o
     run.outputs = o
     return run
 
 
 def sw_runner(d, o=None, device=True, sync=True, skip_checks=False, iceflg=3, liqflg=1, isolvar=0, iaer=10,
-              normFlx=1, stream=None, f32=False):
+              normFlx=1, stream=None, f32=False, reuse_clouds=False):
     ncol, nlay = d["ncol"], d["nlay"]
     o = o if o is not None else alloc_outputs(ncol, nlay, pinned=not device)
     p = (lambda t: t) if device else (lambda t: t.data_ptr())
@@ -82,7 +82,7 @@ def sw_runner(d, o=None, device=True, sync=True, skip_checks=False, iceflg=3, li
                       p(o["nirr"]), p(o["nirf"]), p(o["parr"]), p(o["parf"]), p(o["uvrr"]), p(o["uvrf"]),
                       p(o["fswband"]), p(o["cotdtp"]), p(o["cotdhp"]), p(o["cotdmp"]), p(o["cotdlp"]), p(o["cotntp"]),
                       p(o["cotnhp"]), p(o["cotnmp"]), p(o["cotnlp"]), False, p(o["drband"]), p(o["dfband"]),
-                      device=device, sync=sync, skip_checks=skip_checks, stream=stream, f32=f32)
+                      device=device, sync=sync, skip_checks=skip_checks, stream=stream, f32=f32, reuse_clouds=reuse_clouds)
         return o
     run.outputs = o
     return run

@@ -27,7 +27,7 @@ module rrtmgx_c
    type, bind(C) :: rrtmgx_config
       type(c_ptr)    :: table_blob = c_null_ptr
       integer(c_int) :: device = -1
-      integer(c_int) :: inhomogeneity = 1
+      integer(c_int) :: inhomogeneity = -1   ! -1: leave the McICA state alone (the *_ini shims); 0..2 sets ih at the first init
       type(c_ptr)    :: corr = c_null_ptr
    end type
 

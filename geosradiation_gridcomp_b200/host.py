@@ -171,8 +171,10 @@ def _check(status):
         raise RrtmgxError(status, lib().rrtmgx_strerror(status).decode())
 
 
-def init(device=-1, inhomogeneity=1, corr=None, table_blob=None):
-    """rrtmg_lw_ini + rrtmg_sw_ini + set_inhomogeneity + initialize_cloud_subcol_gen; idempotent."""
+def init(device=-1, inhomogeneity=-1, corr=None, table_blob=None):
+    """rrtmg_lw_ini + rrtmg_sw_ini; idempotent.  `inhomogeneity` (0..2; -1 = the default, beta) and `corr` are
+    applied by the FIRST call only: on an initialised library the call is a pure no-op, like the reference's _ini
+    routines, which never touch the McICA module state (set_inhomogeneity / initialize_cloud_subcol_gen own it)."""
     global _initialised
     c = Config()
     c.table_blob = (table_blob or BLOB_PATH).encode()
@@ -230,6 +232,13 @@ def finalize():
     if _lib is not None:
         _lib.rrtmgx_finalize()
     _initialised = False
+
+
+def knobs():
+    """{'chunk', 'host_chunk', 'stages', 'ih'} in force (rrtmgx_get_knobs)."""
+    k = (C.c_longlong * 4)()
+    _check(lib().rrtmgx_get_knobs(k))
+    return {"chunk": int(k[0]), "host_chunk": int(k[1]), "stages": int(k[2]), "ih": int(k[3])}
 
 
 def launch_count():

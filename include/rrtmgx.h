@@ -56,8 +56,10 @@ enum {
                               /* clear counts instead of regenerating them (GEOS calls rrtmg_lw */
                               /* once more per removed gas, IRR:3405-3468, and rrtmg_sw with    */
                               /* and without aerosols, SOL:3249-3287, on one cloud state).      */
-                              /* Honoured when both calls cover their columns in one chunk of   */
-                              /* the same shape; otherwise the clouds are regenerated.          */
+                              /* Honoured when the previous run of the path was this very chunk */
+                              /* of columns of a call of the same extent (a call that crosses   */
+                              /* in several device or host staging chunks leaves only its last  */
+                              /* chunk's clouds behind); otherwise the clouds are regenerated.  */
 };
 
 /* status codes (negative) */
@@ -84,14 +86,22 @@ typedef struct {
     const char *table_blob;   /* path of rrtmg_tables.bin; NULL -> $RRTMGX_TABLES or the     */
                               /* file next to the library                                     */
     int device;               /* CUDA device ordinal, -1 = current                            */
-    int inhomogeneity;        /* ih: 0 homogeneous, 1 beta (GEOS default), 2 gamma            */
+    int inhomogeneity;        /* ih: 0 homogeneous, 1 beta (GEOS default), 2 gamma; -1 = default */
     const double *corr;       /* 8 correlation-length parameters or NULL for the defaults     */
 } RrtmgxConfig;
 
-/* rrtmg_lw_ini + rrtmg_sw_ini + set_inhomogeneity + initialize_cloud_subcol_gen.
- * Idempotent (GEOS calls the _ini routines on every refresh). */
+/* rrtmg_lw_ini + rrtmg_sw_ini (+ the initial set_inhomogeneity / initialize_cloud_subcol_gen state).
+ * Idempotent: GEOS calls the _ini routines on every refresh (IRR:3381, SOL:6225) and the reference's
+ * _ini routines never touch the McICA module state, so a call on an initialised library is a pure
+ * no-op whatever cfg holds -- inhomogeneity and corr are applied by the FIRST call only; afterwards
+ * rrtmgx_set_mcica is the one way to change them.  After rrtmgx_finalize the next call starts from
+ * the built-in defaults and the environment again (nothing of the previous life is inherited). */
 int rrtmgx_init(const RrtmgxConfig *cfg);
 int rrtmgx_set_mcica(int ih, const double corr[8]);
+/* The tuning knobs in force and the McICA inhomogeneity type, for tests and diagnostics:
+ * knobs[0] = RRTMGX_CHUNK (0 = automatic), [1] = RRTMGX_HOST_CHUNK (default 8192), [2] = RRTMGX_STAGES
+ * (default 2), [3] = ih.  Returns RRTMGX_ENOTINIT before rrtmgx_init. */
+int rrtmgx_get_knobs(long long knobs[4]);
 int rrtmgx_finalize(void);
 const char *rrtmgx_strerror(int status);
 /* number of kernels launched by this library since rrtmgx_init (bench.py gpu_launches) */

@@ -1362,9 +1362,10 @@ static int sw_partition(int cc, const int *gcols /* 0-based global columns */, i
     return rc;
 }
 
+/* _ASSERT(all(x >= 0.)) (SW/src/rrtmg_sw_rad.F90:365-383): unlike the LW driver's any(x < 0.) this also fires on NaN */
 static int any_negative(const double *x, size_t n) {
     for (size_t i = 0; i < n; ++i)
-        if (x[i] < 0.) return 1;
+        if (!(x[i] >= 0.)) return 1;
     return 0;
 }
 

@@ -1,0 +1,185 @@
+"""Regressions of round 1's red GPU suite (file sorts first, so nothing earlier in the process can mask them):
+
+* RRTMGX_REUSE_CLOUDS with host arrays crossing in SEVERAL staging chunks: the scratch slab of a path holds the McICA
+  clouds of one chunk, so a reuse call must regenerate every chunk but the very last one of the previous call
+  (IRR:3405-3478, SOL:3249-3287; include/rrtmgx.h on RRTMGX_REUSE_CLOUDS) - bit for bit a fresh call, LW and SW;
+* rrtmgx_finalize -> rrtmgx_init restores the default tuning knobs instead of inheriting the previous environment;
+* the reference's *_ini routines never touch the McICA module state (GEOS calls them on every refresh, IRR:3381,
+  SOL:6225, after set_inhomogeneity in Initialize, RAD:565): an _ini call after set_inhomogeneity(0) changes nothing;
+* the SW driver's _ASSERT(all(x >= 0.)) also fires on NaN (SW/src/rrtmg_sw_rad.F90:365-383), the LW driver's
+  any(x < 0.) does not (LW/src/rrtmg_lw_rad.F90:209-318);
+* LW and SW driven from two host threads with RRTMGX_REUSE_CLOUDS on.
+"""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from geosradiation_gridcomp_b200.synthetic import make_columns
+
+pytestmark = pytest.mark.gpu
+
+LW_OUT = ("uflx", "dflx", "uflxc", "dflxc", "duflx_dTs", "duflxc_dTs", "olrb", "dolrb_dTs", "clearCounts")
+SW_OUT = ("swuflx", "swdflx", "swuflxc", "swdflxc", "nirr", "nirf", "parr", "parf", "uvrr", "uvrf", "fswband",
+          "cotdtp", "cotdhp", "cotdmp", "cotdlp", "cotntp", "cotnhp", "cotnmp", "cotnlp", "clearCounts")
+
+
+class _Env:
+    """Re-initialise the library under a changed environment, and back."""
+
+    def __init__(self, rx, **env):
+        self.rx, self.env = rx, {k: str(v) for k, v in env.items()}
+
+    def __enter__(self):
+        self.saved = {k: os.environ.get(k) for k in self.env}
+        os.environ.update(self.env)
+        self.rx.finalize()
+        self.rx.init()
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        self.rx.finalize()
+        self.rx.init()
+
+
+def test_finalize_then_init_restores_the_default_knobs(rx):
+    base = rx.knobs()
+    assert base["host_chunk"] == 8192 and base["stages"] == 2 and base["chunk"] == 0 and base["ih"] == 1
+    with _Env(rx, RRTMGX_HOST_CHUNK=1024, RRTMGX_STAGES=3, RRTMGX_CHUNK=4096):
+        k = rx.knobs()
+        assert (k["host_chunk"], k["stages"], k["chunk"]) == (1024, 3, 4096)
+    assert rx.knobs() == base          # nothing of the previous life is inherited
+
+
+def test_reuse_clouds_over_three_host_staging_chunks_lw(rx):
+    ncol = 3 * 1024 - 100               # two full staging chunks and a ragged one
+    s = make_columns(ncol, 72, seed=131)
+    s2 = dict(s)
+    s2["ch4vmr"] = np.zeros_like(s["ch4vmr"], order="F")
+    fresh_default = rx.run_lw(s2)       # one staging chunk (default 8192)
+    with _Env(rx, RRTMGX_HOST_CHUNK=1024):
+        assert rx.knobs()["host_chunk"] == 1024
+        rx.run_lw(s)                    # leaves the clouds of the LAST staging chunk only
+        fresh = rx.run_lw(s2)
+        reused = rx.run_lw(s2, reuse_clouds=True)
+        for k in LW_OUT:
+            np.testing.assert_array_equal(reused[k], fresh[k], err_msg=k)
+            np.testing.assert_array_equal(fresh[k], fresh_default[k], err_msg=k)
+        # the removed-gas loop in one call over the same three chunks
+        rat = [np.zeros((ncol, 73, 1), order="F") for _ in range(3)]
+        main = rx.run_lw(s, rats=(("CH4",), *rat))
+        np.testing.assert_array_equal(rat[0][:, :, 0], fresh["uflx"])
+        np.testing.assert_array_equal(rat[1][:, :, 0], fresh["dflx"])
+        np.testing.assert_array_equal(main["uflx"], rx.run_lw(s)["uflx"])
+    assert np.abs(fresh["uflx"] - rx.run_lw(s)["uflx"]).max() > 1e-3   # the gas did matter
+
+
+def test_reuse_clouds_over_three_host_staging_chunks_sw(rx):
+    ncol = 3 * 1024 - 100
+    s = make_columns(ncol, 72, seed=137)
+    fresh_default = rx.run_sw(s, iaer=0)
+    with _Env(rx, RRTMGX_HOST_CHUNK=1024):
+        rx.run_sw(s)
+        fresh = rx.run_sw(s, iaer=0)
+        reused = rx.run_sw(s, iaer=0, reuse_clouds=True)
+        for k in SW_OUT:
+            np.testing.assert_array_equal(reused[k], fresh[k], err_msg=k)
+            np.testing.assert_array_equal(fresh[k], fresh_default[k], err_msg=k)
+        # clean + full passes in one call (SOL:3249-3287) over the three chunks
+        clean = {k: np.zeros_like(fresh[k], order="F") for k in ("swuflx", "swdflx", "swuflxc", "swdflxc", "fswband")}
+        full = rx.run_sw(s, clean=clean)
+        for k in clean:
+            np.testing.assert_array_equal(clean[k], fresh[k], err_msg=k)
+        np.testing.assert_array_equal(full["swuflx"], rx.run_sw(s)["swuflx"])
+    assert np.abs(fresh["swdflx"] - rx.run_sw(s)["swdflx"]).max() > 1e-6   # the aerosols did matter
+
+
+def test_reuse_clouds_over_several_device_chunks(rx):
+    """Device pointers with the columns run in three kernel chunks (RRTMGX_CHUNK): same rule, same bits."""
+    import torch
+    from geosradiation_gridcomp_b200 import devstate
+    ncol, nlay = 2900, 72
+    s = make_columns(ncol, nlay, seed=139)
+    d = devstate.to_device(s)
+    o1, o2 = devstate.alloc_outputs(ncol, nlay), devstate.alloc_outputs(ncol, nlay)
+    devstate.lw_runner(d, o1)()
+    devstate.sw_runner(d, o1)()
+    torch.cuda.synchronize()
+    with _Env(rx, RRTMGX_CHUNK=1024):
+        devstate.lw_runner(d, o2)()
+        devstate.sw_runner(d, o2)()
+        devstate.lw_runner(d, o2, reuse_clouds=True)()
+        devstate.sw_runner(d, o2, reuse_clouds=True)()
+        torch.cuda.synchronize()
+        for k in o1:
+            np.testing.assert_array_equal(o2[k].cpu().numpy(), o1[k].cpu().numpy(), err_msg=k)
+
+
+def test_ini_after_set_inhomogeneity_keeps_the_mcica_state(rx, oracle):
+    s = make_columns(256, 72, seed=149)
+    try:
+        oracle.set_mcica(0)
+        o_lw, o_sw = oracle.rrtmg_lw(s), oracle.rrtmg_sw(s)
+        rx.set_inhomogeneity(0)
+        rx.rrtmg_lw_ini()              # what GEOS does on every refresh
+        rx.rrtmg_sw_ini()
+        assert rx.knobs()["ih"] == 0
+        g_lw, g_sw = rx.run_lw(s), rx.run_sw(s)
+    finally:
+        oracle.set_mcica(1)
+        rx.set_inhomogeneity(1)
+    np.testing.assert_array_equal(g_lw["clearCounts"], o_lw["clearCounts"])
+    np.testing.assert_array_equal(g_sw["clearCounts"], o_sw["clearCounts"])
+    rel = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-30 + 1e-12 * np.max(np.abs(b)))))
+    for k in ("uflx", "dflx"):
+        assert rel(g_lw[k], o_lw[k]) <= 1e-9, k
+    for k in ("swuflx", "swdflx"):
+        assert rel(g_sw[k], o_sw[k]) <= 1e-9, k
+    # and ih matters: beta-inhomogeneous condensate gives other fluxes
+    assert np.abs(rx.run_lw(s)["uflx"] - g_lw["uflx"]).max() > 1e-6
+
+
+def test_nan_inputs_trap_in_sw_only(rx, oracle):
+    s = make_columns(64, 72, seed=151)
+    bad = dict(s)
+    bad["o3vmr"] = s["o3vmr"].copy(order="F")
+    bad["o3vmr"][5, 7] = np.nan
+    with pytest.raises(rx.RrtmgxError) as e:
+        rx.run_sw(bad)
+    assert e.value.status == -(100 + 5)                   # o3vmr is the 5th array the SW driver checks
+    assert oracle.rrtmg_sw(bad)["rc"] == -(100 + 5)
+    rx.run_lw(bad)                                        # any(x < 0.) lets NaN through, as the reference does
+    assert oracle.rrtmg_lw(bad)["rc"] == 0
+
+
+def test_lw_and_sw_from_two_host_threads_with_reuse(rx):
+    """The library is driven by two host threads (LW on one, SW on the other), each repeating its call with
+    RRTMGX_REUSE_CLOUDS: shared state (launch counter, McICA settings, cloud caches) must hold up."""
+    s = make_columns(1500, 72, seed=157)
+    ref_lw, ref_sw = rx.run_lw(s), rx.run_sw(s)
+    out, err = {}, []
+
+    def work(name, fn, ref, keys):
+        try:
+            fn(s)
+            for i in range(4):
+                got = fn(s, reuse_clouds=True)
+                for k in keys:
+                    np.testing.assert_array_equal(got[k], ref[k], err_msg=f"{name} {k} pass {i}")
+            out[name] = True
+        except Exception as exc:   # noqa: BLE001 - reported by the main thread
+            err.append(exc)
+
+    n0 = rx.launch_count()
+    t1 = threading.Thread(target=work, args=("lw", rx.run_lw, ref_lw, LW_OUT))
+    t2 = threading.Thread(target=work, args=("sw", rx.run_sw, ref_sw, SW_OUT))
+    t1.start(); t2.start(); t1.join(); t2.join()
+    assert not err, err
+    assert out == {"lw": True, "sw": True}
+    assert rx.launch_count() > n0
