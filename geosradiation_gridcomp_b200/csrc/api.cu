@@ -167,7 +167,7 @@ int ensure_jumps(Path &p, int nsub, int nlay) {
 struct NegScan {
     const double *x[24];
     unsigned long long n[24];
-    int trap_nan;   // SW: _ASSERT(all(x >= 0.)) also fires on NaN (SW :365-383); LW: any(x < 0.) does not (LW :209-318)
+    int trap_nan;   // SW: _ASSERT(all(x >= 0.)) also fires on NaN (SW :365-383); LW: any(x < 0.) (LW :209-318) would not, see the call
 };
 __device__ __forceinline__ bool neg_bad(double v, int trap_nan) { return trap_nan ? !(v >= 0.) : (v < 0.); }
 __global__ void __launch_bounds__(256) check_negative_kernel(NegScan S, int *negpos) {
@@ -645,7 +645,9 @@ int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *var) {
             const double *xs[narr];
             size_t cnts[narr];
             for (int i = 0; i < narr; ++i) { xs[i] = chk[i].x; cnts[i] = chk[i].cnt; }
-            launch_check_negative(xs, cnts, narr, p.d_err + 1, stream, false);
+            // NaN trapped too: the reference's any(x < 0.) lets a NaN through to int() conversions of undefined result
+            // (out-of-range table reads); here it is refused at the same position as a negative value
+            launch_check_negative(xs, cnts, narr, p.d_err + 1, stream, true);
         }
         // chunk by chunk: the removed-gas runs of the chunk (gas array replaced by zeros, fluxes into slab v of the
         // variant arrays), then the run with every gas; all of them on the clouds the first one generated

@@ -96,6 +96,7 @@ McicaParams mcica_params(const McicaConfig &cfg, const double *d_xcw_beta, const
     P.adl_am1 = cfg.corr[0]; P.adl_am2 = cfg.corr[1]; P.adl_am3 = am3(cfg.corr[2]); P.adl_am4 = cfg.corr[3];
     P.rdl_am1 = cfg.corr[4]; P.rdl_am2 = cfg.corr[5]; P.rdl_am3 = am3(cfg.corr[6]); P.rdl_am4 = cfg.corr[7];
     for (int i = 0; i < 4; ++i) P.seed_order[i] = seed_order[i];
+    P.trap = nullptr;
     return P;
 }
 

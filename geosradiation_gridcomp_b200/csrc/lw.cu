@@ -146,6 +146,7 @@ enum LwF {
 
 struct LwWork {
     int nc, nlay;
+    const int *trap;          // position of the first refused input of the call (>= 2^30: none), see RRTMGX_TRAPPED
     int *idx;                 // [tile][nlay][32] packed jp|jt|jt1|indfor|indself|indminor
     double *fbase;            // [tile][nlay][F_COUNT][32]: the setcoef state of a 32-column tile is contiguous
     size_t n2;                // nlay*nc
@@ -209,7 +210,7 @@ lw_setcoef_kernel(int ld, int col0, const int *__restrict__ perm, LwWork W, int 
                   const double *__restrict__ cfc22vmr, const double *__restrict__ ccl4vmr, int *err) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int nc = W.nc, nlay = W.nlay;
-    if (c >= nc) return;
+    if (c >= nc || RRTMGX_TRAPPED(W.trap)) return;
     const size_t col = gcol(col0, perm, c);
     const double amd = 28.9660, amw = 18.0160;
     const double stpfac = 296. / 1013.;
@@ -1080,6 +1081,7 @@ lw_band_kernel(const LwBandArgs A) {
     static_assert(NY * GN == LwBandInfo<BAND>::ng, "GN must divide the band's g-points");
     __shared__ double red_buf[NY > 1 ? 2 * 4 * NY * CB : 1];
     const LwWork &W = A.W;
+    if (RRTMGX_TRAPPED(W.trap)) return;   // block-uniform
     const int nc = W.nc, nlay = W.nlay;
     const int ty = threadIdx.x;
     const int c0 = blockIdx.x * CB + threadIdx.y;
@@ -1349,7 +1351,7 @@ __global__ void lw_reduce_kernel(int ld, int col0, const int *__restrict__ perm,
 // ---------------------------------------------------------------------------------------------
 static LwWork lw_carve(Slab &slab, int nc, int nlay) {
     LwWork W;
-    W.nc = nc; W.nlay = nlay;
+    W.nc = nc; W.nlay = nlay; W.trap = nullptr;
     const size_t n2 = (size_t)nlay * nc, nw = (size_t)((nlay + 31) / 32);
     W.ncp = (nc + 31) & ~31;
     W.n2p = (size_t)nlay * W.ncp;
@@ -1395,13 +1397,15 @@ size_t lw_scratch_bytes(int nc, int nlay, bool debug) {
 static CloudCache g_lw_cloud_cache;
 void lw_forget_clouds() { g_lw_cloud_cache = CloudCache(); }
 
-int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const ChunkId &id, const McicaParams &mp, const KissJump *d_jumps,
+int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const ChunkId &id, const McicaParams &mp_in, const KissJump *d_jumps,
                  Slab &slab, int *d_err, cudaStream_t stream, cudaStream_t *side, int nside, cudaEvent_t *ev,
                  const RrtmgxTaps *taps, int *d_negpos) {
-    (void)d_negpos;
     const int ld = a->ncol, nlay = a->nlay;
     slab.used = 0;
     LwWork W = lw_carve(slab, nc, nlay);
+    W.trap = d_negpos;
+    McicaParams mp = mp_in;
+    mp.trap = d_negpos;
     const bool want_dbg = taps && (taps->taug || taps->pfracs);
     double *dbg_taug = nullptr, *dbg_pfracs = nullptr;
     if (want_dbg) {

@@ -132,7 +132,7 @@ static __global__ void mcica_prep_kernel(int ld, int col0, const int *__restrict
                                   double *__restrict__ alpha,     // [nlay][nc], k >= 1
                                   double *__restrict__ rcorr) {   // [nlay][nc], k >= 1
     int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nc) return;
+    if (c >= nc || RRTMGX_TRAPPED(P.trap)) return;
     if (ktop && ktop[perm[c]] < 0) return;   // a cloud-free column draws nothing
     const size_t col = gcol(col0, perm, c);
     const double r2d = 180.0 / 3.14159265358979323846;
@@ -200,7 +200,7 @@ mcica_kernel(int ld, int col0, const int *__restrict__ perm, int nc, int nlay, i
              Optics opt, int *err) {
     const int isub = blockIdx.x * MCICA_XS + threadIdx.x;
     const int c = blockIdx.y * MCICA_YC + threadIdx.y;
-    if (c >= nc || isub >= nsub) return;
+    if (c >= nc || isub >= nsub || RRTMGX_TRAPPED(P.trap)) return;
     const size_t col = gcol(col0, perm, c);
     if (ncloudy && c >= *ncloudy) {
         // cldfrac = 0 in every layer: cdf1 >= 1 - cldfrac never holds (ran_num < 1), so whatever the
