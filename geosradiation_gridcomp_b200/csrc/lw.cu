@@ -177,6 +177,7 @@ struct LwWork {
     uint32_t *cloudy_any;     // [nw][nc]
     double *taucmc;           // per-cell layout (lw_cell), valid where the mask bit is set
     uint32_t *it;             // per-cell layout (lw_cell): itgas | ittot << 16 (0xffff: clear cell)
+    double *pfs;              // per-cell layout (lw_cell): Planck fraction of the cell (down sweep -> up sweep)
     double *part;             // [16][LP_COUNT][nlay+1][nc]
 };
 
@@ -1005,6 +1006,11 @@ struct LwBandArgs {
 // of the band, threadIdx.y over the block's columns) in ascending g order and store the Q totals at
 // dst + q*qstride.  `red` holds Q*CB*NY doubles; callers alternate two buffers so one barrier per call
 // suffices.
+// the g-point groups of a column are NY adjacent lanes of one warp when NY is a power of two and the block is
+// made of whole warps: the sums are then an xor butterfly of warp shuffles (no shared memory, no block barrier)
+template <int NY, int CB> __host__ __device__ constexpr bool lw_shuffle_sums() {
+    return NY > 1 && NY <= 32 && (NY & (NY - 1)) == 0 && (NY * CB) % 32 == 0;
+}
 template <int Q, int NY, int CB>
 __device__ __forceinline__ void block_sum_store(const double (&v)[Q], double *__restrict__ red,
                                                 double *__restrict__ dst, size_t qstride, bool active) {
@@ -1014,6 +1020,22 @@ __device__ __forceinline__ void block_sum_store(const double (&v)[Q], double *__
 #pragma unroll
             for (int q = 0; q < Q; ++q) dst[q * qstride] = v[q];
         }
+        return;
+    }
+    if constexpr (lw_shuffle_sums<NY, CB>()) {
+        double s[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) s[q] = v[q];
+#pragma unroll
+        for (int m = NY / 2; m >= 1; m >>= 1) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) s[q] = s[q] + __shfl_xor_sync(0xffffffffu, s[q], m);
+        }
+        if (active && ty == 0) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) dst[q * qstride] = s[q];
+        }
+        (void)red; (void)lane;
         return;
     }
 #pragma unroll
@@ -1073,28 +1095,22 @@ enum LwPart { LP_U, LP_UC, LP_DU, LP_DUC, LP_D, LP_DC, LP_COUNT };
 // one contiguous run.  (With 32 columns per warp every gather touched 32 scattered rows: the L1 data
 // pipe was 88 % busy, profiles/r2_d_*.)  The g-point sums of every level are formed in the block
 // (block_sum_store) in ascending g order, like the reference's sequential accumulation.
-template <int BAND, int GN, int REGS, int CB>
-__global__ void __launch_bounds__(CB * (LwBandInfo<BAND>::ng / GN), min_blocks(CB * (LwBandInfo<BAND>::ng / GN), REGS))
-lw_band_kernel(const LwBandArgs A) {
+// Both sweeps of one (column, GN g-points of BAND) thread: rtrnmc :198-385 on the band's gas optics.  `ty` = the
+// thread's g-point group, `sum` forms the g-point sums of a level over the column's threads (a block-level or a
+// warp-level policy, below), `etab` = the {exp, tfn} transmittance table (global memory or the block's shared copy).
+template <int BAND, int GN, class Sum>
+__device__ __forceinline__ void lw_column_sweeps(const LwBandArgs &A, const int c, const bool active, const int ty,
+                                                 const double2 *__restrict__ etab, Sum &sum) {
     constexpr int NY = LwBandInfo<BAND>::ng / GN;
     constexpr int NG = LwBandInfo<BAND>::ng;
-    static_assert(NY * GN == LwBandInfo<BAND>::ng, "GN must divide the band's g-points");
-    __shared__ double red_buf[NY > 1 ? 2 * 4 * NY * CB : 1];
     const LwWork &W = A.W;
-    if (RRTMGX_TRAPPED(W.trap)) return;   // block-uniform
     const int nc = W.nc, nlay = W.nlay;
-    const int ty = threadIdx.x;
-    const int c0 = blockIdx.x * CB + threadIdx.y;
-    const bool active = c0 < nc;
-    const int c = active ? c0 : nc - 1;   // idle lanes shadow the last column and never store
     const size_t col = gcol(A.col0, A.perm, c);
     constexpr int ib = BAND - 1;
     const int gs = BAND == 1 ? 0 : c_lw.ngs[ib - 1];   // first g-point (0-based) of the band
     const int G0 = ty * GN;
     const int g_first = gs + G0;
     const int laytrop = W.laytrop[c];
-    int flip = 0;
-    auto red = [&]() { flip ^= 1; return red_buf + (NY > 1 ? flip * 4 * NY * CB : 0); };
 
     // diffusivity angle, :177-186
     double secdiff;
@@ -1175,7 +1191,7 @@ lw_band_kernel(const LwBandArgs A) {
             if (odepth < 0.) odepth = 0.;
             double tblind = ddiv(odepth, bpade + odepth);
             const int itgas = f_int(tblint * tblind + 0.5);
-            const double2 et = reinterpret_cast<const double2 *>(c_lw.exptfn)[itgas];
+            const double2 et = etab[itgas];
             const double agas = 1. - et.x;
             const double bbdgas = pf[ig] * (blay + et.y * dplankdn);
             uint32_t code = (uint32_t)itgas | 0xffff0000u;
@@ -1186,7 +1202,7 @@ lw_band_kernel(const LwBandArgs A) {
                 const double odtot = c_lw.tau_tbl[itgas] + odcld;
                 tblind = ddiv(odtot, bpade + odtot);
                 const int ittot = f_int(tblint * tblind + 0.5);
-                const double2 ett = reinterpret_cast<const double2 *>(c_lw.exptfn)[ittot];
+                const double2 ett = etab[ittot];
                 const double atot = 1. - ett.x;
                 const double bbdtot = pf[ig] * (blay + ett.y * dplankdn);
                 radld[ig] = radld[ig] + (bbdtot - radld[ig]) * atot;
@@ -1198,7 +1214,11 @@ lw_band_kernel(const LwBandArgs A) {
             else radclrd[ig] = radld[ig];
             sums[1] = sums[1] + sumfac * radclrd[ig];
         }
-        block_sum_store<2, NY, CB>(sums, red(), part + LP_D * fstride + jl, fstride, active);
+        if (active) {   // the upward sweep reads the fractions back instead of redoing the band's spectral interpolation
+            if constexpr (GN == 2) __stcs(reinterpret_cast<double2 *>(W.pfs + koff), make_double2(pf[0], pf[1]));
+            else FORG __stcs(W.pfs + koff + ig, pf[ig]);
+        }
+        sum.template store<2>(sums, part + LP_D * fstride + jl, fstride, active);
         koff -= lay_cell;
     }
     koff += lay_cell;   // back on layer 0
@@ -1221,46 +1241,67 @@ lw_band_kernel(const LwBandArgs A) {
             sums[2] = sums[2] + sumfac * drad[ig];
         }
         sums[3] = sums[2];
-        block_sum_store<4, NY, CB>(sums, red(), part, fstride, active);
+        sum.template store<4>(sums, part, fstride, active);
     }
 
     // ---- upward sweep, :336-379 ----
+    // The cell's table indices (it) and Planck fractions (pfs) come back from the downward sweep.  The gas look-up
+    // is software-pipelined: the indices of layer lay+2 are loaded while the table entries of layer lay+1 are
+    // fetched and layer lay is computed, so neither the index load nor the data-dependent table read is waited
+    // for (they were 16 % of the kernel's stall samples, profiles/s2_a_*).
+    auto ld_code = [&](size_t off, uint32_t (&code)[GN]) {
+        if constexpr (GN == 2) {
+            const uint2 t = __ldcs(reinterpret_cast<const uint2 *>(W.it + off));
+            code[0] = t.x; code[1] = t.y;
+        } else {
+            FORG code[ig] = __ldcs(W.it + off + ig);
+        }
+    };
+    auto ld_tab = [&](const uint32_t (&code)[GN], double2 (&eg)[GN]) {
+        FORG eg[ig] = etab[code[ig] & 0xffffu];
+    };
+    uint32_t cur[GN], code1[GN], code2[GN];   // indices of layers lay, lay+1, lay+2
+    double2 eg0[GN], eg1[GN];                 // gas entries of layers lay, lay+1 (cloudy cells read theirs on demand)
+    ld_code(koff, cur);
+    ld_tab(cur, eg0);                  // layer 0
+    FORG { code1[ig] = 0xffff0000u; code2[ig] = 0xffff0000u; }
+    if (nlay > 1) ld_code(koff + lay_cell, code1);
+    if (nlay > 2) ld_code(koff + 2 * (size_t)lay_cell, code2);
+    ld_tab(code1, eg1);                // layer 1
     for (int lay = 0; lay < nlay; ++lay) {
         const int jl = lay * nc;
+        double2 ett[GN];
+        FORG {
+            const uint32_t ittot = cur[ig] >> 16;
+            if (ittot != 0xffffu) ett[ig] = etab[ittot];
+        }
+        if (lay + 3 < nlay) prefetch_l1(W.it + koff + 3 * (size_t)lay_cell);
         if (lay + 1 < nlay) {
-            prefetch_l1(W.it + koff + lay_cell);
+            prefetch_l1(W.pfs + koff + lay_cell);
             if (ty == 0) {
-                prefetch_l1(pidx + (lay + 1) * 32);
-                constexpr unsigned fm = lw_band_fmask_up<BAND>();
-#pragma unroll
-                for (int k = 0; k < F_COUNT; ++k)
-                    if ((fm >> k) & 1u) prefetch_l1(pfac + ((lay + 1) * F_COUNT + k) * 32);
                 prefetch_l1(planklay + jl + nc);
                 prefetch_l1(planklev + jl + 2 * nc);
             }
         }
-        Lay L;
-        L.fj = pfac + lay * (F_COUNT * 32);
-        const int pk = pidx[lay * 32];
-        L.jp = pk & 63; L.jt = (pk >> 6) & 7; L.jt1 = (pk >> 9) & 7;
-        L.indfor = (pk >> 12) & 3; L.indself = (pk >> 14) & 15; L.indminor = (pk >> 18) & 31;
-        lw_band_layer<BAND, GN, false>(L, lay < laytrop, 0., G0, taug, pf);
+        if constexpr (GN == 2) {
+            const double2 t = __ldcs(reinterpret_cast<const double2 *>(W.pfs + koff));
+            pf[0] = t.x; pf[1] = t.y;
+        } else {
+            FORG pf[ig] = __ldcs(W.pfs + koff + ig);
+        }
         const double blay = planklay[jl];
         const double dplankup = planklev[jl + nc] - blay;
         double sums[4] = {0., 0., 0., 0.};
         FORG {
-            const uint32_t code = __ldcs(W.it + koff + ig);
-            const int itgas = code & 0xffffu, ittot = code >> 16;
-            const double2 et = reinterpret_cast<const double2 *>(c_lw.exptfn)[itgas];
+            const double2 et = eg0[ig];
             const double agas = 1. - et.x;
             const double bbugas = pf[ig] * (blay + et.y * dplankup);
-            if (ittot == 0xffff) {
+            if ((cur[ig] >> 16) == 0xffffu) {
                 radlu[ig] = radlu[ig] + (bbugas - radlu[ig]) * agas;
                 if (A.dudTs) drad[ig] = drad[ig] - drad[ig] * agas;
             } else {
-                const double2 ett = reinterpret_cast<const double2 *>(c_lw.exptfn)[ittot];
-                const double atot = 1. - ett.x;
-                const double bbutot = pf[ig] * (blay + ett.y * dplankup);
+                const double atot = 1. - ett[ig].x;
+                const double bbutot = pf[ig] * (blay + ett[ig].y * dplankup);
                 radlu[ig] = radlu[ig] + (bbutot - radlu[ig]) * atot;
                 if (A.dudTs) drad[ig] = drad[ig] - drad[ig] * atot;
             }
@@ -1275,8 +1316,105 @@ lw_band_kernel(const LwBandArgs A) {
                 sums[3] = sums[3] + sumfac * dradc[ig];
             }
         }
-        block_sum_store<4, NY, CB>(sums, red(), part + jl + nc, fstride, active);
+        sum.template store<4>(sums, part + jl + nc, fstride, active);
+        // rotate the pipeline: layer lay+1 becomes current, the entries of lay+2 are fetched, the indices of lay+3 loaded
+        FORG { cur[ig] = code1[ig]; eg0[ig] = eg1[ig]; code1[ig] = code2[ig]; }
+        if (lay + 2 < nlay) ld_tab(code1, eg1);
+        if (lay + 3 < nlay) ld_code(koff + 3 * (size_t)lay_cell, code2);
         koff += lay_cell;
+    }
+}
+
+// g-point sums of a level over the threads of a column, block-level: shared memory + barrier, or warp shuffles when
+// the column's threads are a power-of-two run of lanes (block_sum_store)
+template <int NY, int CB> struct LwBlockSum {
+    double *red_buf;
+    int flip = 0;
+    template <int Q>
+    __device__ __forceinline__ void store(const double (&v)[Q], double *__restrict__ dst, size_t qstride, bool active) {
+        flip ^= 1;
+        block_sum_store<Q, NY, CB>(v, red_buf + ((NY > 1 && !lw_shuffle_sums<NY, CB>()) ? flip * 4 * NY * CB : 0), dst,
+                                   qstride, active);
+    }
+};
+// warp-level: the column's NY threads are lanes [seg*NY, seg*NY + NY) of the warp, any NY <= 32.  Three (NY <= 8) or
+// four shuffle steps leave the sum in the first lane of the run: lane l adds lane l + off while l + off is inside
+// its run.  Fixed order, no shared memory, no barrier: the warps of a block never wait for one another.
+template <int NY> struct LwWarpSum {
+    int ty;
+    template <int Q>
+    __device__ __forceinline__ void store(const double (&v)[Q], double *__restrict__ dst, size_t qstride, bool active) {
+        double s[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) s[q] = v[q];
+#pragma unroll
+        for (int off = 1; off < NY; off <<= 1) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const double o = __shfl_down_sync(0xffffffffu, s[q], off);
+                if (ty + off < NY && (ty % (2 * off)) == 0) s[q] = s[q] + o;
+            }
+        }
+        if (active && ty == 0) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) dst[q * qstride] = s[q];
+        }
+    }
+};
+
+template <int BAND, int GN, int REGS, int CB>
+__global__ void __launch_bounds__(CB * (LwBandInfo<BAND>::ng / GN), min_blocks(CB * (LwBandInfo<BAND>::ng / GN), REGS))
+lw_band_kernel(const LwBandArgs A) {
+    constexpr int NY = LwBandInfo<BAND>::ng / GN;
+    static_assert(NY * GN == LwBandInfo<BAND>::ng, "GN must divide the band's g-points");
+    __shared__ double red_buf[(NY > 1 && !lw_shuffle_sums<NY, CB>()) ? 2 * 4 * NY * CB : 1];
+    const LwWork &W = A.W;
+    if (RRTMGX_TRAPPED(W.trap)) return;   // block-uniform
+    const int c0 = blockIdx.x * CB + threadIdx.y;
+    const bool active = c0 < W.nc;
+    const int c = active ? c0 : W.nc - 1;   // idle lanes shadow the last column and never store
+    LwBlockSum<NY, CB> sum{red_buf};
+    lw_column_sweeps<BAND, GN>(A, c, active, (int)threadIdx.x, reinterpret_cast<const double2 *>(c_lw.exptfn), sum);
+}
+
+// The same sweeps with the {exp, tfn} transmittance table in SHARED memory.  The table is what the longwave kernels
+// are short of: two to four data-dependent 16-byte reads per cell out of 160 KB, each lane on its own 128-byte line
+// (optical depth grows along g), i.e. up to 32 L1 wavefronts per look-up on a data pipe that is 73-81 % busy
+// (profiles/r3_h_*).  Here one persistent block per SM copies the whole table into shared memory with ONE bulk
+// asynchronous copy (cp.async.bulk, completion on an mbarrier) and keeps it for all the columns it works through;
+// a look-up is then a shared-memory read whose cost is its bank conflicts (about a third of the wavefronts).
+// A warp owns floor(32 / NY) whole columns at a time (lanes = the g-point groups of those columns, the rest idle),
+// takes its tiles round robin, and forms the g-point sums with shuffles (LwWarpSum): no block barrier after the
+// table has landed.
+constexpr int LW_TAB_ENTRIES = 10001;
+constexpr int LW_TAB_BYTES = LW_TAB_ENTRIES * 16;
+template <int BAND, int GN, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1) lw_band_persist_kernel(const LwBandArgs A) {
+    constexpr int NY = LwBandInfo<BAND>::ng / GN;
+    static_assert(NY * GN == LwBandInfo<BAND>::ng && NY <= 32, "GN must divide the band's g-points");
+    constexpr int CW = 32 / NY;   // columns per warp
+    extern __shared__ __align__(128) unsigned char lw_dyn_smem[];
+    double2 *tab = reinterpret_cast<double2 *>(lw_dyn_smem);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(lw_dyn_smem + ((LW_TAB_BYTES + 127) & ~127));
+    const LwWork &W = A.W;
+    if (RRTMGX_TRAPPED(W.trap)) return;   // block-uniform
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bar, LW_TAB_BYTES);
+        bulk_g2s(tab, c_lw.exptfn, LW_TAB_BYTES, bar);
+    }
+    __syncthreads();      // the barrier is initialised before anybody waits on it
+    mbar_wait(bar, 0);    // the table has landed
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = lane / NY, ty = lane - seg * NY;
+    const int ntiles = (W.nc + CW - 1) / CW;
+    LwWarpSum<NY> sum{ty};
+    for (int tile = blockIdx.x * WARPS + warp; tile < ntiles; tile += gridDim.x * WARPS) {
+        const int c0 = tile * CW + seg;
+        const bool active = seg < CW && c0 < W.nc;
+        const int c = active ? c0 : W.nc - 1;
+        lw_column_sweeps<BAND, GN>(A, c, active, ty, tab, sum);
     }
 }
 
@@ -1291,9 +1429,29 @@ static void lw_launch_band(int nc, cudaStream_t st, const LwBandArgs &A) {
     RRTMGX_LAUNCH_TAG(tag, (lw_band_kernel<BAND, GN, REGS, CB>), dim3((nc + CB - 1) / CB),
                       dim3(LwBandInfo<BAND>::ng / GN, CB), 0, st, A);
 }
+// persistent variant: one block per SM with the transmittance table in shared memory
+template <int BAND, int GN, int WARPS>
+static void lw_launch_persist(int nc, cudaStream_t st, const LwBandArgs &A) {
+    static char tag[48] = "";
+    static int nsm = 0;
+    constexpr int smem = ((LW_TAB_BYTES + 127) & ~127) + 16;
+    if (!tag[0]) {
+        std::snprintf(tag, sizeof tag, "lw_band_persist_kernel<%d,gn%d,w%d>", BAND, GN, WARPS);
+        cudaFuncSetAttribute(lw_band_persist_kernel<BAND, GN, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+        if (nsm <= 0) nsm = 148;
+    }
+    constexpr int CW = 32 / (LwBandInfo<BAND>::ng / GN);
+    const int ntiles = (nc + CW - 1) / CW;
+    const int blocks = std::min(nsm, (ntiles + WARPS - 1) / WARPS);
+    RRTMGX_LAUNCH_TAG(tag, (lw_band_persist_kernel<BAND, GN, WARPS>), dim3(blocks), dim3(32 * WARPS), smem, st, A);
+}
 #define X(BAND, G, R) \
-    {lw_launch_band<BAND, G, R, 32>, lw_launch_band<BAND, G, R, 16>, lw_launch_band<BAND, G, R, 8>, lw_launch_band<BAND, G, R, 4>},
-static const LwBandLauncher lw_launchers[16][4] = {
+    {lw_launch_band<BAND, G, R, 32>, lw_launch_band<BAND, G, R, 16>, lw_launch_band<BAND, G, R, 8>, lw_launch_band<BAND, G, R, 4>, \
+     lw_launch_persist<BAND, G, 24>, lw_launch_persist<BAND, G, 16>},
+static const LwBandLauncher lw_launchers[16][6] = {
     X(1, 2, 56) X(2, 2, 56) X(3, 2, 80) X(4, 2, 56) X(5, 2, 80) X(6, 2, 80) X(7, 2, 48) X(8, 2, 80)
     X(9, 2, 56) X(10, 2, 64) X(11, 2, 80) X(12, 2, 80) X(13, 1, 80) X(14, 1, 64) X(15, 1, 80) X(16, 1, 80)};
 #undef X
@@ -1305,7 +1463,7 @@ void lw_read_env() {   // once per rrtmgx_init, under the library lock
     if (!e) return;
     int b = 0;
     for (const char *q = e; *q && b < 16; ++q)
-        if (*q >= '0' && *q <= '3') lw_variant[b++] = *q - '0';
+        if (*q >= '0' && *q <= '5') lw_variant[b++] = *q - '0';
     for (; b > 0 && b < 16; ++b) lw_variant[b] = lw_variant[b - 1];
 }
 
@@ -1381,6 +1539,7 @@ static LwWork lw_carve(Slab &slab, int nc, int nlay) {
     W.cloudy_any = slab.take<uint32_t>(nw * nc);
     W.taucmc = slab.take<double>(W.n2p * 140);
     W.it = slab.take<uint32_t>(W.n2p * 140);
+    W.pfs = slab.take<double>(W.n2p * 140);
     W.part = slab.take<double>((size_t)16 * LP_COUNT * (nlay + 1) * nc);
     return W;
 }

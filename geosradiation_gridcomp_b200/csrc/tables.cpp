@@ -218,6 +218,29 @@ int HostTables::load(const std::string &blob_path) {
         }
     }
 
+    // SW: row pairs {t[row][g], t[row+1][g]} of the tables the band kernels interpolate between neighbouring rows
+    // (absa/absb along the binary-species and temperature index, selfref/forref, rayla): a thread then reads both
+    // operands of a lerp with one 16-byte load, which halves the gather instructions and the L1 tag look-ups of
+    // the SW band kernels (their lanes are 32 columns on 32 different rows).  The last row is paired with itself.
+    for (int ib = 0; ib < 14; ++ib) {
+        const int ng = sw_ngc[ib];
+        for (const char *nm : {"absa", "absb", "selfref", "forref", "rayla"}) {
+            char name[48];
+            std::snprintf(name, sizeof name, "sw.%02d.%s", ib + 16, nm);
+            const TableRef r = find(name);
+            if (!r.ok() || r.n % ng) continue;
+            const size_t rows = r.n / ng;
+            std::vector<double> pr(2 * r.n);
+            for (size_t row = 0; row < rows; ++row)
+                for (int g = 0; g < ng; ++g) {
+                    const size_t nxt = row + 1 < rows ? row + 1 : row;
+                    pr[2 * (row * ng + g)] = arena[r.off + row * ng + g];
+                    pr[2 * (row * ng + g) + 1] = arena[r.off + nxt * ng + g];
+                }
+            add(std::string(name) + "2", pr);
+        }
+    }
+
     // LW lookup tables, rrtmg_lw_init.F90:96-113
     {
         const int ntbl = 10000;
