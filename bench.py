@@ -16,6 +16,10 @@ of a larger grid (weak scaling, no data-path collective; columns are independent
             reference itself cannot be compiled here: no Fortran compiler) on a bounded sample
 
 `--impl reference` times the oracle port alone on the host cores (rank 0 only).
+`--config 4|5` runs BASELINE.json's configs[3] / [4] instead (C720 x L72, C360 x L181: the whole grid is cut into one
+contiguous column slab per rank, strong scaling); every run ends with a verification that is not timed: each rank's
+first columns are gathered on rank 0 (NCCL when N > 1) and compared bit for bit with rank 0's own recomputation of
+the same global columns through the host-array interface.
 """
 import argparse
 import json
@@ -154,8 +158,10 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(a, with_sw),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+        "config": dict(workload_config(a, with_sw), cpu_sample_columns_per_step=sample,
+                       note="each step of this arm is a bounded sample of the workload (cpu_sample_columns_per_step "
+                            "columns), the rate is per column"),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model(),
                          "sample": f"{sample} columns x L{a.nlay} per step, {'LW+SW' if with_sw else 'LW only'}, "
                                    f"OpenMP over column partitions"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -164,10 +170,31 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(a, with_sw):
-    return {"workload": f"RRTMG {'LW+SW' if with_sw else 'LW (SW not built)'} with McICA, C180 cube-sphere "
-                        f"{a.ncol} columns x L{a.nlay} per GPU, all columns sunlit, 40% clear-sky columns",
-            "ncol_per_gpu": a.ncol, "nlay": a.nlay, "ngpt_lw": 140, "ngpt_sw": 112,
+GRIDS = {3: ("C180 cube-sphere", 6 * 180 * 180, 72), 4: ("C720 cube-sphere", 6 * 720 * 720, 72),
+         5: ("C360 cube-sphere", 6 * 360 * 360, 181)}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def workload_config(a, with_sw, world=1):
+    name, total, _ = GRIDS[a.config]
+    if a.config == 3 and a.ncol == total:
+        what = f"the full {name} ({a.ncol} columns) x L{a.nlay} per GPU"
+    elif a.config in (4, 5) and a.ncol * world >= total:
+        what = f"{name} ({total} columns) x L{a.nlay} cut into {world} contiguous slabs of {a.ncol} columns, one per GPU"
+    else:
+        what = f"a slab of {a.ncol} synthetic columns x L{a.nlay} per GPU (not a whole grid)"
+    return {"workload": f"RRTMG {'LW+SW' if with_sw else 'LW (SW not built)'} with McICA, {what}, "
+                        f"all columns sunlit, 40% clear-sky columns",
+            "baseline_config": a.config, "ncol_per_gpu": a.ncol, "nlay": a.nlay, "ngpt_lw": 140, "ngpt_sw": 112,
             "l2_policy": "inputs (>10 GB per step) far exceed the 126 MB L2; no explicit flush",
             "precision": "fp64 boundary arrays and arithmetic (promoted-real contract)"}
 
@@ -205,8 +232,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ncol", type=int, default=194400, help="columns per GPU (C180 = 6*180^2)")
-    ap.add_argument("--nlay", type=int, default=72)
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5],
+                    help="BASELINE.json config: 3 = C180 L72 per GPU (weak scaling, the default), 4 = C720 L72 and "
+                         "5 = C360 L181 cut into one slab per GPU (strong scaling)")
+    ap.add_argument("--ncol", type=int, default=None, help="columns per GPU (default: from --config)")
+    ap.add_argument("--nlay", type=int, default=None)
+    ap.add_argument("--verify-cols", type=int, default=256, help="columns per rank checked after the timed region")
     ap.add_argument("--seed", type=int, default=20260121)
     ap.add_argument("--cpu-sample", type=int, default=65536, help="columns in the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
@@ -214,6 +245,12 @@ def main():
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "b200":
         a.warmup = max(a.warmup, 1)
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    _, total, lay = GRIDS[a.config]
+    if a.nlay is None:
+        a.nlay = lay
+    if a.ncol is None:
+        a.ncol = total if a.config == 3 else -(-total // max(world_env, a.gpus if a.impl == "reference" else 1))
 
     if a.impl == "reference":
         return run_reference(a)
@@ -297,6 +334,36 @@ def main():
     clocks = sampler.stop(t0, t1) if sampler else None
     value = world * ncol * a.steps / (dev_ms * 1e-3)
 
+    # ---- verification, not timed: every rank's first columns, gathered on rank 0 (NCCL when world > 1), against rank
+    # 0's own recomputation of those global columns through the HOST-array interface (other chunking, other leading
+    # dimension, other column grouping): bit for bit.  synthetic.make_columns is a pure function of (seed, global column).
+    verify = None
+    if a.verify_cols > 0:
+        from geosradiation_gridcomp_b200 import sharding
+        from geosradiation_gridcomp_b200.synthetic import make_columns
+        K = min(a.verify_cols, ncol)
+        names = ("uflx", "dflx", "swdflx", "swuflx") if with_sw else ("uflx", "dflx")
+        got = {}
+        for k in names:
+            local = np.asfortranarray(o[k][:, :K].t().contiguous().cpu().numpy())   # (K, nlay+1)
+            got[k] = sharding.gather_columns(local, K * world, dist if world > 1 else None)
+        if rank == 0:
+            worst, same = 0.0, True
+            for r in range(world):
+                sr = make_columns(K, nlay, seed=a.seed, col0=r * ncol)
+                ref = dict(host.run_lw(sr))
+                if with_sw:
+                    ref.update(host.run_sw(sr))
+                for k in names:
+                    g = got[k][r * K:(r + 1) * K]
+                    same = same and np.array_equal(g, ref[k])
+                    worst = max(worst, float(np.max(np.abs(g - ref[k]))))
+            verify = {"ranks": world, "columns_per_rank": K, "arrays": list(names), "bit_exact": bool(same),
+                      "max_abs_diff": worst, "transport": "nccl all_gather" if world > 1 else "none (one rank)",
+                      "against": "rank 0 recomputing the same global columns from host arrays"}
+            if not same:
+                print(f"bench.py: verification FAILED: {verify}", file=sys.stderr)
+
     # one extra, untimed step with the library's per-kernel CUDA-event timing (events on each
     # kernel's own stream; serialises the step) to attribute device time to kernels
     kernels = None
@@ -325,6 +392,8 @@ def main():
                                    "algorithmic_bytes_per_column": abytes,
                                    "achieved_gbs": abytes * cols / (ms / n * 1e-3) / 1e9}
 
+    if world > 1:
+        dist.barrier()   # rank 0's serialised profile step above runs on an otherwise idle node
     # ---- end-to-end arm: host (pinned) arrays through the C ABI --------------------------------
     e2e = None
     if not a.no_e2e:
@@ -389,6 +458,73 @@ def main():
                                     "note": "RRTMGX_F32_ARRAYS: arrays widened on the device, arithmetic fp64; "
                                             "informational, the headline e2e above moves fp64 arrays"}
         del hp4, ho4
+        # the interface GEOS would really call: one fused refresh per path from the drivers' NATIVE state (top-down,
+        # Pa, kg/kg, real*4), rrtmgx_irrad_refresh / rrtmgx_solar_refresh: flip, units, TLEV, ZM, aerosol
+        # normalisation, RRTMG, unflip and the cloud-fraction / COT epilogue all on the device (IRR:3237-3547,
+        # SOL:6113-6447).  Fewer and narrower arrays cross PCIe; same fp64 kernels.  On a bounded slab (the
+        # native state is generated single-threaded), rate per column.
+        try:
+            from geosradiation_gridcomp_b200.synthetic import make_native_state
+            ng = min(ncol, 65536)
+            nat = make_native_state(ng, nlay, seed=a.seed, col0=rank * ncol)
+            L = nlay
+
+            def pin(v):
+                t = torch.from_numpy(np.ascontiguousarray(v.T if v.ndim > 1 else v)).to(torch.float32).pin_memory()
+                return t
+            keep = {k: pin(v) for k, v in nat.items() if isinstance(v, np.ndarray) and v.dtype == np.float64 and v.size >= ng}
+            n4 = dict(nat)
+            n4.update({k: t.data_ptr() for k, t in keep.items()})
+            zo = lambda *sh: torch.zeros(tuple(reversed(sh)), dtype=torch.float32).pin_memory()
+            from geosradiation_gridcomp_b200.host import _IRR_OUT, _SOL_OUT
+            irr_o = {k: zo(ng, L + 1) for k in _IRR_OUT[:6]}
+            irr_o.update({k: zo(ng) for k in _IRR_OUT[6:11]})
+            irr_o["olrb"], irr_o["dolrb_dts"] = zo(16, ng), zo(16, ng)
+            sol_o = {k: zo(ng, L + 1) for k in _SOL_OUT[:4]}
+            sol_o.update({k: zo(ng) for k in _SOL_OUT[4:10] + _SOL_OUT[11:]})
+            sol_o["fswband"] = zo(ng, 14)
+            irr_p = {k: t.data_ptr() for k, t in irr_o.items()}
+            sol_p = {k: t.data_ptr() for k, t in sol_o.items()}
+
+            def glue_step():
+                err = []
+
+                def sw_call():
+                    try:
+                        host.solar_refresh(n4, out=sol_p, f32=True)
+                    except BaseException as e:
+                        err.append(e)
+                t = threading.Thread(target=sw_call) if with_sw else None
+                if t:
+                    t.start()
+                host.irrad_refresh(n4, out=irr_p, f32=True)
+                if t:
+                    t.join()
+                if err:
+                    raise err[0]
+            glue_step()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ngl = max(1, min(a.steps, 5))
+            t0 = time.perf_counter()
+            for _ in range(ngl):
+                glue_step()
+            torch.cuda.synchronize()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            in_b = ((15 * L + (L + 1) + 4 + 32 * L) + ((10 * L + (L + 1) + 7 + 42 * L) if with_sw else 0)) * 4
+            out_b = ((6 * (L + 1) + 5 + 32) + ((4 * (L + 1) + 6 + 14 + 8) if with_sw else 0)) * 4
+            e2e["native_real4_glue"] = {
+                "value": world * ng * ngl / float(tt.item()), "unit": UNIT, "columns_per_gpu": ng,
+                "h2d_bytes_per_column": in_b, "d2h_bytes_per_column": out_b,
+                "note": "rrtmgx_irrad_refresh + rrtmgx_solar_refresh from the drivers' native real*4 state (pinned host "
+                        "arrays), glue fused on the device; informational, the headline e2e above moves the fp64 "
+                        "argument lists of rrtmg_lw / rrtmg_sw"}
+            del keep, irr_o, sol_o
+        except Exception as e:   # informational arm: never takes the bench line down
+            e2e["native_real4_glue"] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
         if world > 1:
@@ -404,47 +540,77 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = (value / world) * bpc / 1e9
-    traffic = None
-    try:   # measured DRAM bytes per step of this workload from the committed ncu capture, if any
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if tj.get("nlay") == nlay:
-            traffic = tj["dram_bytes_per_column"] * ncol
-    except (OSError, KeyError, ValueError):
+    # Counters of the kernels (DRAM bytes, FP64 thread-instructions per column and launch) come from the committed
+    # ncu launch list of this bench command (profiles/kernel_counters.json, tools/ncu_counters.py; a run under the
+    # profiler cannot be a timing run): they are COUNTS, independent of the run; every TIME below is this run's own.
+    counters, fp64_peak = None, None
+    try:
+        counters = json.load(open(os.path.join(ROOT, "profiles", "kernel_counters.json")))
+    except (OSError, ValueError):
         pass
+    try:
+        fp64_peak = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))
+    except (OSError, ValueError):
+        pass
+    step_s = dev_ms / a.steps * 1e-3
+    traffic = None
+    fp64 = None
+    cnt_src = None
+    if counters and nlay == 72:
+        cnt_src = (f"profiles/kernel_counters.json (ncu launch list of commit {counters.get('commit_of_capture')}, "
+                   f"{counters.get('columns_per_launch')} columns per launch) x this run's columns; times are this run's")
+        traffic = counters["step"]["dram_bytes_per_column"] * ncol
+        if fp64_peak:
+            inst = counters["step"]["fp64_thread_instructions_per_column"] * ncol
+            pk = float(fp64_peak["mix_dmul_dadd_register_operands"])
+            fp64 = {"achieved_instr_s": inst / step_s, "peak": pk, "frac": inst / step_s / pk,
+                    "unit": "fp64 thread-instructions/s",
+                    "peak_source": "profiles/fp64_peak.json: DMUL/DADD with register operands, measured on a B200 of this "
+                                   "pool (tools/fp64_peak.py); DFMA on three distinct register pairs peaks at "
+                                   f"{float(fp64_peak['dfma_register_operands']):.3e}",
+                    "counts_from": cnt_src}
     if kernels and "dominant" in kernels:
         dom = kernels["dominant"]
         dom["frac"] = dom["achieved_gbs"] / peak
-        try:   # measured DRAM bytes of one launch of that kernel (ncu launch list), per launch like `achieved`
-            per_col = tj["band_kernel_dram_bytes_per_column_per_launch"][dom["name"]]
-            if tj.get("nlay") == nlay:
-                dom["traffic"] = per_col * dom["columns_per_launch"]
-                dom["traffic_gbs"] = dom["traffic"] / (dom["avg_launch_ms"] * 1e-3) / 1e9
-                dom["traffic_frac"] = dom["traffic_gbs"] / peak
-        except Exception:   # no capture of this kernel variant: leave the keys out
-            pass
+        kc = (counters or {}).get("kernels", {}).get(dom["name"]) if nlay == 72 else None
+        if kc:
+            launch_s = dom["avg_launch_ms"] * 1e-3
+            dom["traffic"] = kc["dram_bytes_per_column"] * dom["columns_per_launch"]
+            dom["traffic_gbs"] = dom["traffic"] / launch_s / 1e9
+            dom["traffic_frac"] = dom["traffic_gbs"] / peak
+            if fp64_peak:
+                inst = kc["fp64_thread_instructions_per_column"] * dom["columns_per_launch"]
+                pk = float(fp64_peak["mix_dmul_dadd_register_operands"])
+                dom["fp64"] = {"achieved_instr_s": inst / launch_s, "peak": pk, "frac": inst / launch_s / pk,
+                               "pipe_active_pct_under_ncu": kc.get("fp64_pipe_active_pct")}
+            dom["counts_from"] = cnt_src
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernels": kernels,
+                "traffic": traffic, "traffic_source": cnt_src, "fp64": fp64, "kernels": kernels,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)",
                 "kernel": "whole step: the fixed pipeline of LW+SW kernels of one refresh (algorithmic bytes = "
                           "boundary inputs read once + outputs written once, SURVEY.md 8d); `kernels` attributes "
-                          "device time per kernel from CUDA events; `traffic` = measured DRAM bytes per step (ncu)",
+                          "device time per kernel from CUDA events of this run; `traffic` / `fp64` put the counters of "
+                          "the committed ncu launch list over this run's times",
                 "algorithmic_bytes_per_column": bpc,
-                "note": "fp64-pipe-bound path: see DESIGN.md for the FP64 roof beside the HBM roof"}
+                "note": "neither roof binds: the band kernels are latency-bound recurrences (DESIGN.md section 4)"}
     if traffic is not None:   # the measured DRAM bytes over the measured step: how busy HBM really is (scratch included)
-        roofline["traffic_gbs"] = traffic / (dev_ms / a.steps * 1e-3) / 1e9
+        roofline["traffic_gbs"] = traffic / step_s / 1e9
         roofline["traffic_frac"] = roofline["traffic_gbs"] / peak
     cpu = None
     if not a.no_cpu and world == 1:
         r, threads, dt = cpu_oracle_rate(a.cpu_sample, nlay, a.seed, with_sw and oracle_has_sw())
-        cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
+        cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model(),
                "sample": f"{a.cpu_sample} columns x L{nlay} of the same synthetic workload, "
                          f"{'LW+SW' if with_sw else 'LW only'}, {dt:.1f} s"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(a, with_sw),
+        "dtype": "f64", "data": "synthetic", "config": workload_config(a, with_sw, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "verify": verify,
     }
+    if a.config != 3:
+        line["scaling"] = "strong"
     if e2e is not None and world > 1:
         e2e["host_numa_node_rank0"] = numa   # ranks are bound to the NUMA node of their GPU (bind_near_gpu)
     print(json.dumps(line), flush=True)

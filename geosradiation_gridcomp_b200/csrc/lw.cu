@@ -1326,7 +1326,12 @@ __device__ __forceinline__ void lw_column_sweeps(const LwBandArgs &A, const int 
 }
 
 // g-point sums of a level over the threads of a column, block-level: shared memory + barrier, or warp shuffles when
-// the column's threads are a power-of-two run of lanes (block_sum_store)
+// the column's threads are a power-of-two run of lanes (block_sum_store).
+// (A persistent variant - one 768-thread block per SM, the 160 KB {exp, tfn} table copied into shared memory by one
+// cp.async.bulk, warp-level sums - was built and measured in commit 4e691fe: it is 20-40 % SLOWER on the 14- and
+// 16-g bands, whose k-tables (75-225 KB) then fight over the 67 KB of L1 that are left, and 2-16 % faster only on
+// bands 1 and 2; with every look-up pinned to entry 0 the kernels gain 7 %: the look-ups are not what binds them.
+// profiles/s2_band_kernel_experiments.txt.)
 template <int NY, int CB> struct LwBlockSum {
     double *red_buf;
     int flip = 0;
@@ -1337,31 +1342,6 @@ template <int NY, int CB> struct LwBlockSum {
                                    qstride, active);
     }
 };
-// warp-level: the column's NY threads are lanes [seg*NY, seg*NY + NY) of the warp, any NY <= 32.  Three (NY <= 8) or
-// four shuffle steps leave the sum in the first lane of the run: lane l adds lane l + off while l + off is inside
-// its run.  Fixed order, no shared memory, no barrier: the warps of a block never wait for one another.
-template <int NY> struct LwWarpSum {
-    int ty;
-    template <int Q>
-    __device__ __forceinline__ void store(const double (&v)[Q], double *__restrict__ dst, size_t qstride, bool active) {
-        double s[Q];
-#pragma unroll
-        for (int q = 0; q < Q; ++q) s[q] = v[q];
-#pragma unroll
-        for (int off = 1; off < NY; off <<= 1) {
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const double o = __shfl_down_sync(0xffffffffu, s[q], off);
-                if (ty + off < NY && (ty % (2 * off)) == 0) s[q] = s[q] + o;
-            }
-        }
-        if (active && ty == 0) {
-#pragma unroll
-            for (int q = 0; q < Q; ++q) dst[q * qstride] = s[q];
-        }
-    }
-};
-
 template <int BAND, int GN, int REGS, int CB>
 __global__ void __launch_bounds__(CB * (LwBandInfo<BAND>::ng / GN), min_blocks(CB * (LwBandInfo<BAND>::ng / GN), REGS))
 lw_band_kernel(const LwBandArgs A) {
@@ -1377,47 +1357,6 @@ lw_band_kernel(const LwBandArgs A) {
     lw_column_sweeps<BAND, GN>(A, c, active, (int)threadIdx.x, reinterpret_cast<const double2 *>(c_lw.exptfn), sum);
 }
 
-// The same sweeps with the {exp, tfn} transmittance table in SHARED memory.  The table is what the longwave kernels
-// are short of: two to four data-dependent 16-byte reads per cell out of 160 KB, each lane on its own 128-byte line
-// (optical depth grows along g), i.e. up to 32 L1 wavefronts per look-up on a data pipe that is 73-81 % busy
-// (profiles/r3_h_*).  Here one persistent block per SM copies the whole table into shared memory with ONE bulk
-// asynchronous copy (cp.async.bulk, completion on an mbarrier) and keeps it for all the columns it works through;
-// a look-up is then a shared-memory read whose cost is its bank conflicts (about a third of the wavefronts).
-// A warp owns floor(32 / NY) whole columns at a time (lanes = the g-point groups of those columns, the rest idle),
-// takes its tiles round robin, and forms the g-point sums with shuffles (LwWarpSum): no block barrier after the
-// table has landed.
-constexpr int LW_TAB_ENTRIES = 10001;
-constexpr int LW_TAB_BYTES = LW_TAB_ENTRIES * 16;
-template <int BAND, int GN, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, 1) lw_band_persist_kernel(const LwBandArgs A) {
-    constexpr int NY = LwBandInfo<BAND>::ng / GN;
-    static_assert(NY * GN == LwBandInfo<BAND>::ng && NY <= 32, "GN must divide the band's g-points");
-    constexpr int CW = 32 / NY;   // columns per warp
-    extern __shared__ __align__(128) unsigned char lw_dyn_smem[];
-    double2 *tab = reinterpret_cast<double2 *>(lw_dyn_smem);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(lw_dyn_smem + ((LW_TAB_BYTES + 127) & ~127));
-    const LwWork &W = A.W;
-    if (RRTMGX_TRAPPED(W.trap)) return;   // block-uniform
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
-        mbar_expect_tx(bar, LW_TAB_BYTES);
-        bulk_g2s(tab, c_lw.exptfn, LW_TAB_BYTES, bar);
-    }
-    __syncthreads();      // the barrier is initialised before anybody waits on it
-    mbar_wait(bar, 0);    // the table has landed
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int seg = lane / NY, ty = lane - seg * NY;
-    const int ntiles = (W.nc + CW - 1) / CW;
-    LwWarpSum<NY> sum{ty};
-    for (int tile = blockIdx.x * WARPS + warp; tile < ntiles; tile += gridDim.x * WARPS) {
-        const int c0 = tile * CW + seg;
-        const bool active = seg < CW && c0 < W.nc;
-        const int c = active ? c0 : W.nc - 1;
-        lw_column_sweeps<BAND, GN>(A, c, active, ty, tab, sum);
-    }
-}
-
 // Compiled variants per band: the (g-points per thread, register budget) pair tuned for the band
 // (profiles/r2_cb_tuning.txt, run r3c) at CB = 32, 16, 8, 4 columns per block.  The one used is picked
 // per band from lw_variant[] (tuned on B200; RRTMGX_LW_GN="vvv..." overrides).
@@ -1429,29 +1368,9 @@ static void lw_launch_band(int nc, cudaStream_t st, const LwBandArgs &A) {
     RRTMGX_LAUNCH_TAG(tag, (lw_band_kernel<BAND, GN, REGS, CB>), dim3((nc + CB - 1) / CB),
                       dim3(LwBandInfo<BAND>::ng / GN, CB), 0, st, A);
 }
-// persistent variant: one block per SM with the transmittance table in shared memory
-template <int BAND, int GN, int WARPS>
-static void lw_launch_persist(int nc, cudaStream_t st, const LwBandArgs &A) {
-    static char tag[48] = "";
-    static int nsm = 0;
-    constexpr int smem = ((LW_TAB_BYTES + 127) & ~127) + 16;
-    if (!tag[0]) {
-        std::snprintf(tag, sizeof tag, "lw_band_persist_kernel<%d,gn%d,w%d>", BAND, GN, WARPS);
-        cudaFuncSetAttribute(lw_band_persist_kernel<BAND, GN, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-        if (nsm <= 0) nsm = 148;
-    }
-    constexpr int CW = 32 / (LwBandInfo<BAND>::ng / GN);
-    const int ntiles = (nc + CW - 1) / CW;
-    const int blocks = std::min(nsm, (ntiles + WARPS - 1) / WARPS);
-    RRTMGX_LAUNCH_TAG(tag, (lw_band_persist_kernel<BAND, GN, WARPS>), dim3(blocks), dim3(32 * WARPS), smem, st, A);
-}
 #define X(BAND, G, R) \
-    {lw_launch_band<BAND, G, R, 32>, lw_launch_band<BAND, G, R, 16>, lw_launch_band<BAND, G, R, 8>, lw_launch_band<BAND, G, R, 4>, \
-     lw_launch_persist<BAND, G, 24>, lw_launch_persist<BAND, G, 16>},
-static const LwBandLauncher lw_launchers[16][6] = {
+    {lw_launch_band<BAND, G, R, 32>, lw_launch_band<BAND, G, R, 16>, lw_launch_band<BAND, G, R, 8>, lw_launch_band<BAND, G, R, 4>},
+static const LwBandLauncher lw_launchers[16][4] = {
     X(1, 2, 56) X(2, 2, 56) X(3, 2, 80) X(4, 2, 56) X(5, 2, 80) X(6, 2, 80) X(7, 2, 48) X(8, 2, 80)
     X(9, 2, 56) X(10, 2, 64) X(11, 2, 80) X(12, 2, 80) X(13, 1, 80) X(14, 1, 64) X(15, 1, 80) X(16, 1, 80)};
 #undef X
@@ -1463,7 +1382,7 @@ void lw_read_env() {   // once per rrtmgx_init, under the library lock
     if (!e) return;
     int b = 0;
     for (const char *q = e; *q && b < 16; ++q)
-        if (*q >= '0' && *q <= '5') lw_variant[b++] = *q - '0';
+        if (*q >= '0' && *q <= '3') lw_variant[b++] = *q - '0';
     for (; b > 0 && b < 16; ++b) lw_variant[b] = lw_variant[b - 1];
 }
 

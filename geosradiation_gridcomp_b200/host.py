@@ -535,17 +535,17 @@ def irrad_update(f, ts_int, tsinst, device=False, want=None):
     return out
 
 
-def _solar_args(n, iceflg, liqflg, isolvar, device, keep):
+def _solar_args(n, iceflg, liqflg, isolvar, device, keep, f32=False):
     a = SolarArgs()
     a.ncol, a.lm, a.iceflg, a.liqflg, a.doy = int(n["ncol"]), int(n["lm"]), int(iceflg), int(liqflg), int(n["doy"])
     a.isolvar, a.lcldmh, a.lcldlm = int(isolvar), int(n["lcldmh"]), int(n["lcldlm"])
-    a.flags = DEVICE_PTRS if device else 0
+    a.flags = (DEVICE_PTRS if device else 0) | (F32_ARRAYS if f32 else 0)
     a.co2 = float(n["co2_fixed"])
     for k in ("sc", "dist", "o2", "airmw", "h2omw", "o3mw", "rgas", "grav", "undef"):
         setattr(a, k, float(n[k]))
     for k in _SOL_IN:
         v = n.get({"taua": "taua_sw", "ssaa": "ssaa_sw", "asya": "asya_sw", "cl": "fcld"}.get(k, k))
-        setattr(a, k, _addr(v, device, keep=keep))
+        setattr(a, k, _addr(v, device, dtype=np.float32 if f32 else np.float64, keep=keep))
     return a
 
 
@@ -570,7 +570,7 @@ def solar_prepare(n, iceflg=3, liqflg=1, isolvar=0):
     return o
 
 
-def solar_refresh(n, iceflg=3, liqflg=1, isolvar=0, device=False, out=None):
+def solar_refresh(n, iceflg=3, liqflg=1, isolvar=0, device=False, out=None, f32=False):
     """One SW refresh from the GEOS-native state (SORADCORE :6113-6447 around rrtmg_sw), fused on the device.
     Returns FSW, FSC, FSWU, FSCU (ncol,LM+1) top-down, the surface diagnostics, CLDTS..CLDLS and COTTP..COTLP
     (MAPL_UNDEF where no cloud)."""
@@ -578,18 +578,19 @@ def solar_refresh(n, iceflg=3, liqflg=1, isolvar=0, device=False, out=None):
         init()
     keep = []
     ncol, lm = n["ncol"], n["lm"]
-    a = _solar_args(n, iceflg, liqflg, isolvar, device, keep)
+    a = _solar_args(n, iceflg, liqflg, isolvar, device, keep, f32)
+    rk = np.float32 if f32 else np.float64
     if out is None:
         if device:
             import torch
             z = lambda *sh: torch.zeros(tuple(reversed(sh)), dtype=torch.float64, device="cuda")
         else:
-            z = lambda *sh: np.zeros(sh, order="F")
+            z = lambda *sh: np.zeros(sh, dtype=rk, order="F")
         out = {k: z(ncol, lm + 1) for k in _SOL_OUT[:4]}
         out.update({k: z(ncol) for k in _SOL_OUT[4:10] + _SOL_OUT[11:]})
         out["fswband"] = z(ncol, 14)
     for k in _SOL_OUT:
-        setattr(a, k, _addr(out[k], device, keep=keep))
+        setattr(a, k, _addr(out[k], device, dtype=rk, keep=keep))
     _check(lib().rrtmgx_solar_refresh(C.byref(a)))
     return out
 
