@@ -271,10 +271,10 @@ int run_staged(Path &p, const Args &a, Args &ca, std::vector<Arr> &arrs, int nco
             if (!r.host || !r.in) continue;
             if (r.inner)
                 note(cudaMemcpyAsync(raw[i], (const char *)r.host + col0 * r.rows * r.elem, r.rows * nc * r.elem,
-                                     cudaMemcpyHostToDevice, p.h2d));
+                                     cudaMemcpyDefault, p.h2d));
             else
                 note(cudaMemcpy2DAsync(raw[i], nc * r.elem, (const char *)r.host + col0 * r.elem, (size_t)ncol * r.elem,
-                                       nc * r.elem, r.rows, cudaMemcpyHostToDevice, p.h2d));
+                                       nc * r.elem, r.rows, cudaMemcpyDefault, p.h2d));
         }
         note(cudaEventRecord(p.ev_in[s], p.h2d));
         note(cudaStreamWaitEvent(p.stream, p.ev_in[s], 0));
@@ -301,10 +301,10 @@ int run_staged(Path &p, const Args &a, Args &ca, std::vector<Arr> &arrs, int nco
             if (!r.host || !r.out) continue;
             if (r.inner)
                 note(cudaMemcpyAsync((char *)r.host + col0 * r.rows * r.elem, raw[i], r.rows * nc * r.elem,
-                                     cudaMemcpyDeviceToHost, p.d2h));
+                                     cudaMemcpyDefault, p.d2h));
             else
                 note(cudaMemcpy2DAsync((char *)r.host + col0 * r.elem, (size_t)ncol * r.elem, raw[i], nc * r.elem,
-                                       nc * r.elem, r.rows, cudaMemcpyDeviceToHost, p.d2h));
+                                       nc * r.elem, r.rows, cudaMemcpyDefault, p.d2h));
         }
         note(cudaEventRecord(p.ev_free[s], p.d2h));
         if (first_err != cudaSuccess) break;
@@ -596,7 +596,10 @@ int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *var) {
     Path &p = g.lw;
     const bool devptr = a->flags & RRTMGX_DEVICE_PTRS;
     if ((a->flags & RRTMGX_NO_SYNC) && !devptr) return RRTMGX_EARG;
-    if ((a->flags & RRTMGX_F32_ARRAYS) && devptr) return RRTMGX_EARG;   // real*4 arrays are widened while staged
+    // real*4 arrays are widened while staged: real*4 DEVICE arrays take the staging path too (device-to-device
+    // copies instead of PCIe), so the call is synchronous for them
+    if ((a->flags & RRTMGX_F32_ARRAYS) && (a->flags & RRTMGX_NO_SYNC)) return RRTMGX_EARG;
+    const bool staged = !devptr || (a->flags & RRTMGX_F32_ARRAYS);
     const int ncol = a->ncol, nlay = a->nlay;
     if (int rc = ensure_jumps(p, 140, nlay)) return rc;
     static const int seed_order[4] = {1, 2, 3, 4};   // LW/src/rrtmg_lw_rad.F90:541-546
@@ -605,13 +608,13 @@ int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *var) {
     const RrtmgxTaps *taps = p.has_taps ? &p.taps : nullptr;
     const bool dbg = taps && (taps->taug || taps->pfracs);
     const size_t per_col = lw_scratch_bytes(1024, nlay, dbg) / 1024;
-    size_t chunk = pick_chunk(ncol, nlay, per_col + (devptr ? 0 : 2 * (size_t)(37 * nlay + 60) * 8), !devptr, p.slab.cap);
+    size_t chunk = pick_chunk(ncol, nlay, per_col + (!staged ? 0 : 2 * (size_t)(37 * nlay + 60) * 8), staged, p.slab.cap);
     if (taps) {   // taps are laid out for the whole call
         if ((size_t)ncol > chunk_cap(nlay)) return RRTMGX_EARG;
         chunk = (size_t)ncol;
     }
     if (int rc = grow(p.slab, lw_scratch_bytes((int)chunk, nlay, dbg))) return rc;
-    cudaStream_t stream = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
+    cudaStream_t stream = (!staged && a->stream) ? (cudaStream_t)a->stream : p.stream;
     p.run_stream = stream;
     if (!(devptr && (a->flags & RRTMGX_KEEP_STATUS)) &&
         !ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, stream)))
@@ -622,7 +625,7 @@ int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *var) {
     const double *d_zero = nullptr;
     double *d_var[3] = {nullptr, nullptr, nullptr};
     if (nvar) {
-        const size_t nz = (size_t)(devptr ? ncol : (int)std::min<size_t>(chunk, ncol)) * nlay;
+        const size_t nz = (size_t)(!staged ? ncol : (int)std::min<size_t>(chunk, ncol)) * nlay;
         if (int rc = grow(p.zeros, nz * sizeof(double) + 256)) return rc;
         if (!ok(cudaMemsetAsync(p.zeros.base, 0, nz * sizeof(double), stream))) return RRTMGX_ECUDA;
         d_zero = (const double *)p.zeros.base;
@@ -673,7 +676,7 @@ int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *var) {
         }
         return 0;
     };
-    if (devptr) {
+    if (!staged) {
         if (int rc = run_chunks_device(*a, 0)) return rc;
         p.pending = true;
         if (a->flags & RRTMGX_NO_SYNC) return 0;
@@ -786,7 +789,10 @@ int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *a, const RrtmgxSwNoAerosol *na)
     Path &p = g.sw;
     const bool devptr = a->flags & RRTMGX_DEVICE_PTRS;
     if ((a->flags & RRTMGX_NO_SYNC) && !devptr) return RRTMGX_EARG;
-    if ((a->flags & RRTMGX_F32_ARRAYS) && devptr) return RRTMGX_EARG;   // real*4 arrays are widened while staged
+    // real*4 arrays are widened while staged: real*4 DEVICE arrays take the staging path too (device-to-device
+    // copies instead of PCIe), so the call is synchronous for them
+    if ((a->flags & RRTMGX_F32_ARRAYS) && (a->flags & RRTMGX_NO_SYNC)) return RRTMGX_EARG;
+    const bool staged = !devptr || (a->flags & RRTMGX_F32_ARRAYS);
     if (na && (!na->swuflx || !na->swdflx || !na->swuflxc || !na->swdflxc || !na->fswband)) return RRTMGX_EARG;
     double *d_na[5] = {na ? na->swuflx : nullptr, na ? na->swdflx : nullptr, na ? na->swuflxc : nullptr,
                        na ? na->swdflxc : nullptr, na ? na->fswband : nullptr};
@@ -800,13 +806,13 @@ int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *a, const RrtmgxSwNoAerosol *na)
     const RrtmgxTaps *taps = p.has_taps ? &p.taps : nullptr;
     const bool dbg = taps && (taps->taug || taps->pfracs || taps->ssi);
     const size_t per_col = sw_scratch_bytes(1024, nlay, dbg) / 1024;
-    size_t chunk = pick_chunk(ncol, nlay, per_col + (devptr ? 0 : 2 * (size_t)(57 * nlay + 60) * 8), !devptr, p.slab.cap);
+    size_t chunk = pick_chunk(ncol, nlay, per_col + (!staged ? 0 : 2 * (size_t)(57 * nlay + 60) * 8), staged, p.slab.cap);
     if (taps) {   // taps are laid out for the whole call
         if ((size_t)ncol > chunk_cap(nlay)) return RRTMGX_EARG;
         chunk = (size_t)ncol;
     }
     if (int rc = grow(p.slab, sw_scratch_bytes((int)chunk, nlay, dbg))) return rc;
-    cudaStream_t stream = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
+    cudaStream_t stream = (!staged && a->stream) ? (cudaStream_t)a->stream : p.stream;
     p.run_stream = stream;
     if (!(devptr && (a->flags & RRTMGX_KEEP_STATUS)) &&
         !ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, stream)))
@@ -848,7 +854,7 @@ int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *a, const RrtmgxSwNoAerosol *na)
         return 0;
     };
 
-    if (devptr) {
+    if (!staged) {
         if (int rc = run_chunks_device(*a, 0)) return rc;
         p.pending = true;
         if (a->flags & RRTMGX_NO_SYNC) return 0;
@@ -1011,11 +1017,14 @@ int rrtmgx_irrad_refresh(const RrtmgxIrradArgs *a) {
     Path &p = g.lw;
     const bool devptr = a->flags & RRTMGX_DEVICE_PTRS;
     if ((a->flags & RRTMGX_NO_SYNC) && !devptr) return RRTMGX_EARG;
-    if ((a->flags & RRTMGX_F32_ARRAYS) && devptr) return RRTMGX_EARG;   // real*4 arrays are widened while staged
+    // real*4 arrays are widened while staged: real*4 DEVICE arrays take the staging path too (device-to-device
+    // copies instead of PCIe), so the call is synchronous for them
+    if ((a->flags & RRTMGX_F32_ARRAYS) && (a->flags & RRTMGX_NO_SYNC)) return RRTMGX_EARG;
+    const bool staged = !devptr || (a->flags & RRTMGX_F32_ARRAYS);
     const int ncol = a->ncol;
-    cudaStream_t st = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
+    cudaStream_t st = (!staged && a->stream) ? (cudaStream_t)a->stream : p.stream;
     if (!ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, st))) return RRTMGX_ECUDA;
-    if (devptr) {
+    if (!staged) {
         for (size_t col0 = 0; col0 < (size_t)ncol; col0 += kGlueChunk)
             if (int rc = irrad_chunk(*a, ncol, (int)col0, (int)std::min(kGlueChunk, (size_t)ncol - col0), st)) return rc;
         p.pending = true;
@@ -1178,11 +1187,14 @@ int rrtmgx_solar_refresh(const RrtmgxSolarArgs *a) {
     Path &p = g.sw;
     const bool devptr = a->flags & RRTMGX_DEVICE_PTRS;
     if ((a->flags & RRTMGX_NO_SYNC) && !devptr) return RRTMGX_EARG;
-    if ((a->flags & RRTMGX_F32_ARRAYS) && devptr) return RRTMGX_EARG;   // real*4 arrays are widened while staged
+    // real*4 arrays are widened while staged: real*4 DEVICE arrays take the staging path too (device-to-device
+    // copies instead of PCIe), so the call is synchronous for them
+    if ((a->flags & RRTMGX_F32_ARRAYS) && (a->flags & RRTMGX_NO_SYNC)) return RRTMGX_EARG;
+    const bool staged = !devptr || (a->flags & RRTMGX_F32_ARRAYS);
     const int ncol = a->ncol;
-    cudaStream_t st = (devptr && a->stream) ? (cudaStream_t)a->stream : p.stream;
+    cudaStream_t st = (!staged && a->stream) ? (cudaStream_t)a->stream : p.stream;
     if (!ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, st))) return RRTMGX_ECUDA;
-    if (devptr) {
+    if (!staged) {
         for (size_t col0 = 0; col0 < (size_t)ncol; col0 += kGlueChunk)
             if (int rc = solar_chunk(*a, ncol, (int)col0, (int)std::min(kGlueChunk, (size_t)ncol - col0), st)) return rc;
         p.pending = true;

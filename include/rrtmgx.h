@@ -45,11 +45,13 @@ enum {
     RRTMGX_SKIP_CHECKS = 4,   /* skip the negative-input scans (LW :209-318, SW :365-383)    */
     RRTMGX_KEEP_STATUS = 8,   /* device pointers only: do not clear the path's status word    */
                               /* first, so one status read covers a sequence of NO_SYNC runs  */
-    RRTMGX_F32_ARRAYS = 32,   /* host pointers only: every real array argument is real*4 (the   */
-                              /* production kind of GEOS); widened exactly on the device while  */
-                              /* staged, arithmetic stays fp64, outputs rounded once to real*4. */
-                              /* Halves the bytes that cross PCIe.  (bndscl, indsolvar and      */
-                              /* solcycfrac stay double; clearCounts stays int32.)              */
+    RRTMGX_F32_ARRAYS = 32,   /* every real array argument is real*4 (the production kind of    */
+                              /* GEOS); widened exactly on the device while staged, arithmetic  */
+                              /* stays fp64, outputs rounded once to real*4.  Halves the bytes  */
+                              /* that cross PCIe.  With RRTMGX_DEVICE_PTRS the real*4 arrays are */
+                              /* staged device to device (the call is synchronous; NO_SYNC is   */
+                              /* refused).  (bndscl, indsolvar and solcycfrac stay double;      */
+                              /* clearCounts stays int32.)                                      */
     RRTMGX_REUSE_CLOUDS = 16  /* the cloud inputs (cldf, ciwp, clwp, rei, rel, zm, play, alat,  */
                               /* dyofyr, ice/liq flags, cloudLM/MH) are those of the previous   */
                               /* call on this path: keep its McICA subcolumns, cloud optics and */

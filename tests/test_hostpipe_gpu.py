@@ -43,3 +43,37 @@ def test_host_arrays_in_many_staging_chunks_equal_the_device_run(rx, stages):
                 os.environ[k] = v
         rx.finalize()
         rx.init()
+
+
+def test_real4_device_arrays_take_the_staging_path(rx):
+    """RRTMGX_F32_ARRAYS | RRTMGX_DEVICE_PTRS: a caller that holds its real*4 state ON the device (a GPU-resident GEOS)
+    gets the same bits as the real*4 host-array call: the arrays go through the staging pipeline with device-to-device
+    copies, are widened exactly, the outputs rounded once (over three staging chunks with a ragged last one)."""
+    import torch
+    from geosradiation_gridcomp_b200 import devstate
+    ncol, nlay = 2500, 72
+    s = make_columns(ncol, nlay, seed=53)
+    saved = os.environ.get("RRTMGX_HOST_CHUNK")
+    os.environ["RRTMGX_HOST_CHUNK"] = "1024"
+    rx.finalize()
+    rx.init()
+    try:
+        hp = devstate.to_device(s, pinned=True, real4=True)
+        ho = devstate.alloc_outputs(ncol, nlay, pinned=True, real4=True)
+        devstate.lw_runner(hp, ho, device=False, f32=True)()
+        devstate.sw_runner(hp, ho, device=False, f32=True)()
+        dp = {k: (v.cuda() if hasattr(v, "is_pinned") else v) for k, v in hp.items()}
+        do = devstate.alloc_outputs(ncol, nlay, real4=True)
+        devstate.lw_runner(dp, do, device=True, f32=True)()
+        devstate.sw_runner(dp, do, device=True, f32=True)()
+        torch.cuda.synchronize()
+        assert float(ho["uflx"].abs().min()) > 0 and float(ho["swdflx"].abs().max()) > 0
+        for k, v in ho.items():
+            np.testing.assert_array_equal(do[k].cpu().numpy(), v.numpy(), err_msg=k)
+    finally:
+        if saved is None:
+            os.environ.pop("RRTMGX_HOST_CHUNK", None)
+        else:
+            os.environ["RRTMGX_HOST_CHUNK"] = saved
+        rx.finalize()
+        rx.init()
