@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Golden vectors from the REFERENCE'S OWN SOURCE TEXT, executed here without a Fortran compiler.
+
+oracle/refexec/f90py.py translates the Fortran of /root/reference (RRTMG LW, RRTMG SW, McICA, condensate
+inhomogeneity, NRLSSI2 - every file of SURVEY.md section 8a, read where it lies) into Python in memory, with the
+reference's fp64 contract (default real promoted to 8 bytes, expressions evaluated as written, 32-bit integer
+wrap-around for the KISS generator); oracle/refexec/run.py calls the reference's drivers `rrtmg_lw` / `rrtmg_sw` the
+way oracle/ref_recipe/ref_capi.F90 would.  This script runs the cases of tests/golden/refexec_cases.py and writes
+tests/golden/rrtmg_refexec_golden.npz (keys "<case>/lw/<output>", "<case>/sw/<output>").
+
+The stored numbers are the pin: tests/test_refexec_pin_cpu.py holds the C restatement (oracle/*.c) to them, and
+tests/test_refexec_pin_gpu.py the CUDA path, on the GPU box, where /root/reference does not exist.
+
+Run time: about five minutes of pure-Python arithmetic.  Usage: python tests/golden/make_golden_from_refexec.py [case ...]"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden", "rrtmg_refexec_golden.npz")
+
+
+def run_case(name, c):
+    from geosradiation_gridcomp_b200.synthetic import make_columns
+    from oracle.refexec import run
+    from refexec_cases import LW_OUT, LW_TAPS, SW_OUT, SW_TAPS
+    s = make_columns(c["ncol"], c["nlay"], seed=c["seed"])
+    out = {}
+    ns = run.namespace(c["ih"])
+    defaults = [float(ns["M_cloud_subcol_gen"].__dict__[k]) for k in run.CORR_NAMES]
+    if c["corr"] is not None:
+        run.initialize_cloud_subcol_gen(c["corr"], c["ih"])
+    try:
+        if c["lw"] is not None:
+            r = run.rrtmg_lw_taps(s, ih=c["ih"], **c["lw"]) if c["taps"] else run.rrtmg_lw(s, ih=c["ih"], **c["lw"])
+            for k in LW_OUT + (LW_TAPS if c["taps"] else ()):
+                out[f"{name}/lw/{k}"] = r[k]
+        if c["sw"] is not None:
+            r = run.rrtmg_sw_taps(s, ih=c["ih"], **c["sw"]) if c["taps"] else run.rrtmg_sw(s, ih=c["ih"], **c["sw"])
+            assert r["ret"][-1] == 0, r["ret"]
+            for k in SW_OUT + (tuple(SW_TAPS) if c["taps"] else ()):
+                out[f"{name}/sw/{k}"] = r[k]
+    finally:
+        if c["corr"] is not None:
+            run.initialize_cloud_subcol_gen(defaults, c["ih"])
+    return out
+
+
+if __name__ == "__main__":
+    from oracle.refexec import run
+    from refexec_cases import CASES, INTEGER_KEYS
+    if not run.available():
+        print("no reference tree at", run.REF, file=sys.stderr)
+        sys.exit(4)
+    only = sys.argv[1:]
+    res = dict(np.load(OUT)) if (only and os.path.exists(OUT)) else {}
+    t0 = time.time()
+    run.namespace()
+    print(f"translated and initialised in {time.time() - t0:.1f} s ({len(run.sources())} reference files)")
+    for name, c in CASES.items():
+        if only and name not in only:
+            continue
+        t = time.time()
+        for k, v in run_case(name, c).items():
+            v = np.asarray(v)
+            if k.rsplit("/", 1)[1] in INTEGER_KEYS:
+                v = v.astype(np.uint8 if k.endswith("cldymc") else np.int32)
+            res[k] = v
+        print(f"{name}: {time.time() - t:.1f} s")
+    res["real_bytes"] = np.int64(8)
+    res["reference_files"] = np.int64(len(run.sources()))
+    np.savez_compressed(OUT, **res)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes,", len(res), "arrays")
