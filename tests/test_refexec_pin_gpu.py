@@ -31,7 +31,9 @@ def test_cuda_equals_reference_source_output(rx, golden, name):
     def reset():
         rx._mcica["ih"], rx._mcica["corr"] = 1, None
         rx._apply_mcica()
-    got = rc.run_case(rx, name, set_mcica, reset)
+    # the device never materialises the sub-column condensate paths (the McICA kernel turns them into optical depths
+    # in registers); `taucmc`, which is compared, is their product with the absorption coefficients
+    got = rc.run_case(rx, name, set_mcica, reset, skip=("ciwpmc", "clwpmc"))
     n, same, worst = rc.check_case(got, golden, name, TOL_FLUX, TOL_TAPS)
     assert n >= 9
     print(f"{name}: {n} arrays, {same} bit-identical, worst relative difference {worst:.2e}")
