@@ -5,12 +5,17 @@
  * include, link or call this.  Only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs use it, as the checker and the timed CPU baseline.
  *
- * PARITY UNPINNED: the reference tree ships no golden vectors, known-answer tests or
- * fixtures for this path and no Fortran compiler exists in the build
- * container, so this restatement cannot be checked against reference output.  It is a
- * routine-by-routine restatement of the Fortran, with `real` promoted to 8 bytes (the
- * north_star fp64 contract), same loop nests, same expression order, compiled with
- * -ffp-contract=off.  Its pins are property tests (tests/test_oracle_*.py).
+ * PARITY PINNED BY THE REFERENCE'S OWN SOURCE TEXT: the reference tree ships no golden vectors,
+ * known-answer tests or fixtures for this path and no Fortran compiler
+ * exists in the build container, so the reference is executed by translation (oracle/refexec/:
+ * the 91 Fortran files of the path, read where they lie, turned into Python in memory) and its
+ * output is committed as tests/golden/rrtmg_refexec_golden.npz.  tests/test_refexec_pin_cpu.py
+ * holds this restatement to those numbers: integers bit for bit, reals <= 1e-12 (seen: 3.9e-13).
+ * Not pinned: output of a COMPILED reference (oracle/build_ref.sh is the recipe; it needs a
+ * Fortran compiler) and the drivers' Run-phase glue (glue.c), which a second numpy transcription
+ * cross-checks.  This file is a routine-by-routine restatement of the Fortran, with `real`
+ * promoted to 8 bytes (the north_star fp64 contract), same loop nests, same expression order,
+ * compiled with -ffp-contract=off.
  *
  * Array layouts are those of the reference driver interfaces (column index fastest):
  *   x(ncol,nlay) -> x[icol + ncol*ilay].
