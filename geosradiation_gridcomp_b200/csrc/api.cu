@@ -84,6 +84,8 @@ const int kErrInit[2] = {0, 1 << 30};
 
 bool ok(cudaError_t e) { return e == cudaSuccess; }
 
+Slab g_sw_lit;   // RRTMGX_LIT_ONLY: the daytime-column index list of the Solar call in flight (solar_lit_index)
+
 int grow(Slab &s, size_t bytes) {
     if (s.cap >= bytes) return 0;
     // a re-grown kernel slab holds nothing a later RRTMGX_REUSE_CLOUDS call of that path could keep (the other
@@ -488,6 +490,8 @@ int rrtmgx_finalize(void) {
     sw_forget_clouds();
     if (g.d_arena) cudaFree(g.d_arena);
     g.d_arena = nullptr;
+    if (g_sw_lit.base) cudaFree(g_sw_lit.base);
+    g_sw_lit = Slab();
     g.ready = false;
     return 0;
 }
@@ -982,7 +986,7 @@ int irrad_chunk(const RrtmgxIrradArgs &S, int lds, int col0, int nc, cudaStream_
     return ok(cudaGetLastError()) ? 0 : RRTMGX_ECUDA;
 }
 #ifdef RRTMGX_WITH_SW
-int solar_chunk(const RrtmgxSolarArgs &S, int lds, int col0, int nc, cudaStream_t st) {
+int solar_chunk(const RrtmgxSolarArgs &S, int lds, int col0, int nc, cudaStream_t st, const int *lit = nullptr) {
     Path &p = g.sw;
     if (int rc = grow(p.glue, carve_bytes<RrtmgxSwArgs>(nc, S.lm, carve_sw_args))) return rc;
     p.glue.used = 0;
@@ -991,13 +995,48 @@ int solar_chunk(const RrtmgxSolarArgs &S, int lds, int col0, int nc, cudaStream_
     carve_sw_args(p.glue, nc, S.lm, L);
     L.flags = RRTMGX_DEVICE_PTRS | RRTMGX_NO_SYNC | RRTMGX_KEEP_STATUS | (S.flags & RRTMGX_SKIP_CHECKS);
     L.stream = st;
-    RRTMGX_LAUNCH(solar_prepare_kernel, (nc + 127) / 128, 128, 0, st, nc, lds, col0, S, L);
+    RRTMGX_LAUNCH(solar_prepare_kernel, (nc + 127) / 128, 128, 0, st, nc, lds, col0, S, L, lit);
     if (int rc = rrtmgx_sw_run(&L)) return rc;
-    RRTMGX_LAUNCH(solar_finish_kernel, (nc + 127) / 128, 128, 0, st, nc, lds, col0, S, L);
+    RRTMGX_LAUNCH(solar_finish_kernel, (nc + 127) / 128, 128, 0, st, nc, lds, col0, S, L, lit);
     sw_forget_clouds();
     return ok(cudaGetLastError()) ? 0 : RRTMGX_ECUDA;
 }
 #endif
+// RRTMGX_LIT_ONLY: the daytime columns of native columns [first, first + n) of a Solar call, ascending, as offsets
+// into the arrays the kernels will see (`base` + local index), uploaded to g.sw.lit on `st`.  `zt` is the caller's
+// array (host or device, real*8 or real*4).  Returns the number of lit columns, or a negative status.
+int solar_lit_index(const void *zt, bool on_device, bool f32, size_t first, int n, int base, cudaStream_t st,
+                    const int **d_lit) {
+    std::vector<double> z8;
+    std::vector<float> z4;
+    const void *h = nullptr;
+    const size_t esz = f32 ? 4 : 8;
+    if (on_device) {
+        if (f32) z4.resize(n); else z8.resize(n);
+        void *dst = f32 ? (void *)z4.data() : (void *)z8.data();
+        if (!ok(cudaMemcpyAsync(dst, (const char *)zt + first * esz, (size_t)n * esz, cudaMemcpyDeviceToHost, st)) ||
+            !ok(cudaStreamSynchronize(st))) { cudaGetLastError(); return -RRTMGX_ECUDA; }
+        h = dst;
+    } else {
+        h = (const char *)zt + first * esz;
+    }
+    std::vector<int> lit;
+    lit.reserve(n);
+    for (int c = 0; c < n; ++c) {
+        const double z = f32 ? (double)((const float *)h)[c] : ((const double *)h)[c];
+        if (z > 0.) lit.push_back(base + c);   // daytime = ZTH > 0., SOL:3686
+    }
+    if (int rc = grow(g_sw_lit, (size_t)n * sizeof(int) + 4096)) return -rc;
+    if (!lit.empty() &&
+        !ok(cudaMemcpyAsync(g_sw_lit.base, lit.data(), lit.size() * sizeof(int), cudaMemcpyHostToDevice, st))) {
+        cudaGetLastError();
+        return -RRTMGX_ECUDA;
+    }
+    // the host vector goes out of scope: the copy from pageable memory has been staged when the call returns
+    *d_lit = (const int *)g_sw_lit.base;
+    return (int)lit.size();
+}
+
 constexpr size_t kGlueChunk = 131072;   // columns per pass of the device-pointer refresh (workspace ~25-35 KB each)
 
 template <class A> bool glue_args_ok(const A *a) {
@@ -1190,10 +1229,24 @@ int rrtmgx_solar_refresh(const RrtmgxSolarArgs *a) {
     // real*4 arrays are widened while staged: real*4 DEVICE arrays take the staging path too (device-to-device
     // copies instead of PCIe), so the call is synchronous for them
     if ((a->flags & RRTMGX_F32_ARRAYS) && (a->flags & RRTMGX_NO_SYNC)) return RRTMGX_EARG;
+    const bool lit_only = a->flags & RRTMGX_LIT_ONLY;
+    if (lit_only && (a->flags & RRTMGX_NO_SYNC)) return RRTMGX_EARG;
     const bool staged = !devptr || (a->flags & RRTMGX_F32_ARRAYS);
     const int ncol = a->ncol;
     cudaStream_t st = (!staged && a->stream) ? (cudaStream_t)a->stream : p.stream;
     if (!ok(cudaMemcpyAsync(p.d_err, kErrInit, sizeof kErrInit, cudaMemcpyHostToDevice, st))) return RRTMGX_ECUDA;
+    if (!staged && lit_only) {
+        // pack the daytime columns (SOL:3686-3687, PackIt :7753-7773): the glue kernels address the native arrays
+        // through the index list, the rrtmg_sw arguments in between hold lit columns only
+        const int *d_lit = nullptr;
+        const int nlit = solar_lit_index(a->zt, true, false, 0, ncol, 0, st, &d_lit);
+        if (nlit < 0) return -nlit;
+        RRTMGX_LAUNCH(solar_night_kernel, (ncol + 127) / 128, 128, 0, st, ncol, ncol, *a);
+        for (size_t off = 0; off < (size_t)nlit; off += kGlueChunk)
+            if (int rc = solar_chunk(*a, ncol, 0, (int)std::min(kGlueChunk, (size_t)nlit - off), st, d_lit + off)) return rc;
+        p.pending = true;
+        return p.last_status = status_from(p);
+    }
     if (!staged) {
         for (size_t col0 = 0; col0 < (size_t)ncol; col0 += kGlueChunk)
             if (int rc = solar_chunk(*a, ncol, (int)col0, (int)std::min(kGlueChunk, (size_t)ncol - col0), st)) return rc;
@@ -1223,8 +1276,14 @@ int rrtmgx_solar_refresh(const RrtmgxSolarArgs *a) {
     out(a->cldts, &ca.cldts, 1); out(a->cldhs, &ca.cldhs, 1); out(a->cldms, &ca.cldms, 1); out(a->cldls, &ca.cldls, 1);
     out(a->cottp, &ca.cottp, 1); out(a->cothp, &ca.cothp, 1); out(a->cotmp, &ca.cotmp, 1); out(a->cotlp, &ca.cotlp, 1);
     const size_t chunk = std::min<size_t>(g.host_chunk_cols, (size_t)ncol);
-    int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxSolarArgs &c, int nc, size_t) -> int {
-        return solar_chunk(c, nc, 0, nc, p.stream);
+    int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxSolarArgs &c, int nc, size_t first) -> int {
+        if (!lit_only) return solar_chunk(c, nc, 0, nc, p.stream);
+        // the staged chunk holds native columns [first, first + nc): its daytime columns, from the caller's own ZTH
+        const int *d_lit = nullptr;
+        const int nlit = solar_lit_index(a->zt, devptr, f32, first, nc, 0, p.stream, &d_lit);
+        if (nlit < 0) return -nlit;
+        RRTMGX_LAUNCH(solar_night_kernel, (nc + 127) / 128, 128, 0, p.stream, nc, nc, c);
+        return nlit ? solar_chunk(c, nc, 0, nlit, p.stream, d_lit) : 0;
     });
     if (rc) return rc;
     p.pending = true;
@@ -1240,7 +1299,7 @@ int rrtmgx_solar_prepare(const RrtmgxSolarArgs *a, RrtmgxSwArgs *sw) {
     sw_scalars(*a, nc, *sw);
     if (a->flags & RRTMGX_DEVICE_PTRS) {
         cudaStream_t st = a->stream ? (cudaStream_t)a->stream : p.stream;
-        RRTMGX_LAUNCH(solar_prepare_kernel, (nc + 127) / 128, 128, 0, st, nc, nc, 0, *a, *sw);
+        RRTMGX_LAUNCH(solar_prepare_kernel, (nc + 127) / 128, 128, 0, st, nc, nc, 0, *a, *sw, (const int *)nullptr);
         if (a->flags & RRTMGX_NO_SYNC) return ok(cudaGetLastError()) ? 0 : RRTMGX_ECUDA;
         return ok(cudaStreamSynchronize(st)) ? 0 : RRTMGX_ECUDA;
     }
@@ -1266,7 +1325,7 @@ int rrtmgx_solar_prepare(const RrtmgxSolarArgs *a, RrtmgxSwArgs *sw) {
         p.glue.used = 0;
         RrtmgxSwArgs D = *sw;
         carve_sw_args(p.glue, nc, L, D);
-        RRTMGX_LAUNCH(solar_prepare_kernel, (nc + 127) / 128, 128, 0, p.stream, nc, nc, 0, d, D);
+        RRTMGX_LAUNCH(solar_prepare_kernel, (nc + 127) / 128, 128, 0, p.stream, nc, nc, 0, d, D, (const int *)nullptr);
         struct Out { const double *src; const double *dst; size_t n; } outs[] = {
             {D.coszen, sw->coszen, (size_t)nc}, {D.play, sw->play, n2}, {D.plev, sw->plev, n2p}, {D.tlay, sw->tlay, n2},
             {D.h2ovmr, sw->h2ovmr, n2}, {D.o3vmr, sw->o3vmr, n2}, {D.co2vmr, sw->co2vmr, n2}, {D.ch4vmr, sw->ch4vmr, n2},

@@ -161,11 +161,12 @@ irrad_update_kernel(RrtmgxIrradUpdateArgs U) {
 }
 
 __global__ void __launch_bounds__(128)
-solar_prepare_kernel(int nc, int lds, int col0, RrtmgxSolarArgs S, RrtmgxSwArgs L) {
+solar_prepare_kernel(int nc, int lds, int col0, RrtmgxSolarArgs S, RrtmgxSwArgs L, const int *__restrict__ lit) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nc) return;
     const int LM = S.lm;
-    const size_t s0 = (size_t)col0 + c, ld = (size_t)lds;
+    // lit: the native column of packed column c (RRTMGX_LIT_ONLY, PackIt SOL:7753-7773); else columns col0 + c
+    const size_t s0 = lit ? (size_t)lit[c] : (size_t)col0 + c, ld = (size_t)lds;
     auto NA = [&](const double *x, int k) { return x[s0 + ld * k]; };
     auto W2 = [&](const double *x, int k) -> double & { return const_cast<double *>(x)[c + (size_t)nc * k]; };
     const double wq = S.airmw / S.h2omw, wo3 = S.airmw / S.o3mw;
@@ -213,11 +214,11 @@ solar_prepare_kernel(int nc, int lds, int col0, RrtmgxSolarArgs S, RrtmgxSwArgs 
 }
 
 __global__ void __launch_bounds__(128)
-solar_finish_kernel(int nc, int lds, int col0, RrtmgxSolarArgs S, RrtmgxSwArgs L) {
+solar_finish_kernel(int nc, int lds, int col0, RrtmgxSolarArgs S, RrtmgxSwArgs L, const int *__restrict__ lit) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nc) return;
     const int LM = S.lm;
-    const size_t s0 = (size_t)col0 + c, ld = (size_t)lds;
+    const size_t s0 = lit ? (size_t)lit[c] : (size_t)col0 + c, ld = (size_t)lds;   // UnPackIt SOL:7776-7790
     auto R2 = [&](const double *x, int k) { return x[c + (size_t)nc * k]; };
     auto OUT = [&](double *x, int k) -> double & { return x[s0 + ld * k]; };
     for (int K = 0; K <= LM; ++K) {                                               // unflip :6395-6398, fluxes :6441-6444
@@ -243,6 +244,28 @@ solar_finish_kernel(int nc, int lds, int col0, RrtmgxSolarArgs S, RrtmgxSwArgs L
         if (so[n]) so[n][s0] = si[n][c];
     if (S.fswband)
         for (int b = 0; b < 14; ++b) S.fswband[s0 + ld * b] = L.fswband[c + (size_t)nc * b];
+}
+
+
+// RRTMGX_LIT_ONLY: what UnPackIt leaves in the night columns (SOL:7791-7794, DEFAULT of the internal specs):
+// a dark sun in the fluxes and surface components, MAPL_UNDEF in the cloud fractions and optical thicknesses.
+__global__ void __launch_bounds__(128)
+solar_night_kernel(int n, int lds, RrtmgxSolarArgs S) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    if (S.zt[c] > 0.) return;   // daytime = ZTH > 0, SOL:3686
+    const size_t ld = (size_t)lds;
+    for (int K = 0; K <= S.lm; ++K) {
+        S.fsw[c + ld * K] = 0.; S.fsc[c + ld * K] = 0.; S.fswu[c + ld * K] = 0.; S.fscu[c + ld * K] = 0.;
+    }
+    double *so[6] = {S.nirr, S.nirf, S.parr, S.parf, S.uvrr, S.uvrf};
+    for (int k = 0; k < 6; ++k)
+        if (so[k]) so[k][c] = 0.;
+    if (S.fswband)
+        for (int b = 0; b < 14; ++b) S.fswband[c + ld * b] = 0.;
+    double *un[8] = {S.cldts, S.cldhs, S.cldms, S.cldls, S.cottp, S.cothp, S.cotmp, S.cotlp};
+    for (int k = 0; k < 8; ++k)
+        if (un[k]) un[k][c] = S.undef;
 }
 
 }  // namespace rrtmgx

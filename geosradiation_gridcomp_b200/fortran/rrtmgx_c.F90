@@ -20,7 +20,8 @@ module rrtmgx_c
                                                                  rrtmgx_real_kind == c_float) - 1) = 0
 
    integer(c_int), parameter :: RRTMGX_DEVICE_PTRS = 1, RRTMGX_NO_SYNC = 2, RRTMGX_SKIP_CHECKS = 4, &
-                                RRTMGX_KEEP_STATUS = 8, RRTMGX_REUSE_CLOUDS = 16, RRTMGX_F32_ARRAYS = 32
+                                RRTMGX_KEEP_STATUS = 8, RRTMGX_REUSE_CLOUDS = 16, RRTMGX_F32_ARRAYS = 32, &
+                                RRTMGX_LIT_ONLY = 64
    ! what every shim ORs into `flags`: the element kind of the caller's real arrays
    integer(c_int), parameter :: rrtmgx_real_flags = merge(0_c_int, RRTMGX_F32_ARRAYS, rrtmgx_real_kind == c_double)
 

@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(HERE, "librrtmgx.so")
 BLOB_PATH = os.path.join(HERE, "data", "rrtmg_tables.bin")
 
 NBNDLW, NGPTLW, NBNDSW, NGPTSW = 16, 140, 14, 112
-DEVICE_PTRS, NO_SYNC, SKIP_CHECKS, KEEP_STATUS, REUSE_CLOUDS, F32_ARRAYS = 1, 2, 4, 8, 16, 32
+DEVICE_PTRS, NO_SYNC, SKIP_CHECKS, KEEP_STATUS, REUSE_CLOUDS, F32_ARRAYS, LIT_ONLY = 1, 2, 4, 8, 16, 32, 64
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -570,15 +570,18 @@ def solar_prepare(n, iceflg=3, liqflg=1, isolvar=0):
     return o
 
 
-def solar_refresh(n, iceflg=3, liqflg=1, isolvar=0, device=False, out=None, f32=False):
+def solar_refresh(n, iceflg=3, liqflg=1, isolvar=0, device=False, out=None, f32=False, lit_only=False):
     """One SW refresh from the GEOS-native state (SORADCORE :6113-6447 around rrtmg_sw), fused on the device.
     Returns FSW, FSC, FSWU, FSCU (ncol,LM+1) top-down, the surface diagnostics, CLDTS..CLDLS and COTTP..COTLP
-    (MAPL_UNDEF where no cloud)."""
+    (MAPL_UNDEF where no cloud).  lit_only: only the columns with ZTH > 0 are run (the driver's PackIt / UnPackIt,
+    GEOS_SolarGridComp.F90:3686-3687, :7753-7799); night columns get 0 fluxes and MAPL_UNDEF diagnostics."""
     if not _initialised:
         init()
     keep = []
     ncol, lm = n["ncol"], n["lm"]
     a = _solar_args(n, iceflg, liqflg, isolvar, device, keep, f32)
+    if lit_only:
+        a.flags |= LIT_ONLY
     rk = np.float32 if f32 else np.float64
     if out is None:
         if device:

@@ -67,3 +67,44 @@ def max_over_ranks(value, dist=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ---- daytime columns (SW only) ---------------------------------------------------------------------------------
+# The Solar driver runs the soundings with ZTH > 0 only and balances THEM across its MPI ranks
+# (GEOS_SolarGridComp.F90:3686-3712: daytime mask, MAPL_BalanceCreate on NumLit; PackIt / UnPackIt :7753-7799).
+# With one process per GPU the same intent is a split of the LIT-column list, not of the grid: a contiguous slab of a
+# grid that is half in the dark would leave some GPUs idle.
+
+def lit_columns(zth):
+    """Indices of the daytime columns in ascending order: `daytime = ZTH > 0.` (SOL:3686) in PackIt's order."""
+    return np.nonzero(np.asarray(zth) > 0.0)[0]
+
+
+def lit_slab(zth, world_size, rank):
+    """The daytime columns `rank` runs: a contiguous run of the lit-column list, ceil(NumLit/world_size) per rank
+    (equal work per GPU wherever the terminator lies)."""
+    lit = lit_columns(zth)
+    c0, c1 = slab_bounds(len(lit), world_size, rank)
+    return lit[c0:c1]
+
+
+def pack_columns(state, index):
+    """PackIt (SOL:7753-7773) of a boundary-array / native-state dict: the columns `index` of every array whose
+    leading dimension is the column index; scalars pass through."""
+    ncol = state["ncol"]
+    out = {}
+    for k, v in state.items():
+        if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == ncol and k != "band_output":
+            out[k] = np.asfortranarray(v[index])
+        else:
+            out[k] = v
+    out["ncol"] = int(len(index))
+    return out
+
+
+def unpack_columns(packed, index, ncol, default=0.0):
+    """UnPackIt (SOL:7776-7797) of one output array: `packed` rows go to columns `index`, the rest get `default`."""
+    packed = np.asarray(packed)
+    out = np.full((ncol,) + packed.shape[1:], default, dtype=packed.dtype, order="F")
+    out[index] = packed
+    return out

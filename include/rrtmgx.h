@@ -52,7 +52,7 @@ enum {
                               /* staged device to device (the call is synchronous; NO_SYNC is   */
                               /* refused).  (bndscl, indsolvar and solcycfrac stay double;      */
                               /* clearCounts stays int32.)                                      */
-    RRTMGX_REUSE_CLOUDS = 16  /* the cloud inputs (cldf, ciwp, clwp, rei, rel, zm, play, alat,  */
+    RRTMGX_REUSE_CLOUDS = 16, /* the cloud inputs (cldf, ciwp, clwp, rei, rel, zm, play, alat,  */
                               /* dyofyr, ice/liq flags, cloudLM/MH) are those of the previous   */
                               /* call on this path: keep its McICA subcolumns, cloud optics and */
                               /* clear counts instead of regenerating them (GEOS calls rrtmg_lw */
@@ -62,6 +62,18 @@ enum {
                               /* of columns of a call of the same extent (a call that crosses   */
                               /* in several device or host staging chunks leaves only its last  */
                               /* chunk's clouds behind); otherwise the clouds are regenerated.  */
+    RRTMGX_LIT_ONLY = 64      /* rrtmgx_solar_refresh only: run the daytime columns alone.  The  */
+                              /* Solar driver packs the soundings with ZTH > 0 before SORADCORE  */
+                              /* and unpacks afterwards (GEOS_SolarGridComp.F90:3686-3687,       */
+                              /* PackIt / UnPackIt :7753-7799); here the glue kernels gather     */
+                              /* the native state of the lit columns (ascending order, as PackIt */
+                              /* does) into the rrtmg_sw arguments and scatter the results back, */
+                              /* so night columns cost nothing.  Night columns receive UnPackIt's */
+                              /* DEFAULT: 0 in the fluxes and surface components (a dark sun),   */
+                              /* `undef` in the cloud fractions and optical thicknesses (the     */
+                              /* DEFAULT = MAPL_UNDEF of their internal specs, :873-989).  The   */
+                              /* call reads the zenith cosines back first (one stream            */
+                              /* synchronisation at its start); NO_SYNC is refused.              */
 };
 
 /* status codes (negative) */

@@ -69,3 +69,27 @@ def test_two_rank_slabs_reproduce_the_single_process_result(tmp_path):
     np.testing.assert_array_equal(g["swuflx"], sw["swuflx"])
     np.testing.assert_array_equal(g["cc"], lw["clearCounts"])
     assert float(g["tmax"]) == 11.0
+
+
+def test_lit_slabs_balance_the_daytime_columns():
+    """The Solar driver balances its LIT soundings across ranks (SOL:3686-3712); lit_slab splits the lit-column list,
+    pack / unpack restate PackIt / UnPackIt (SOL:7753-7799)."""
+    from geosradiation_gridcomp_b200 import sharding
+    from geosradiation_gridcomp_b200.synthetic import make_columns
+    s = make_columns(1000, 8, seed=3, lit=False)
+    zth = s["coszen"]
+    lit = sharding.lit_columns(zth)
+    assert 300 < len(lit) < 700 and (zth[lit] > 0).all() and (np.diff(lit) > 0).all()
+    parts = [sharding.lit_slab(zth, 8, r) for r in range(8)]
+    np.testing.assert_array_equal(np.concatenate(parts), lit)
+    sizes = [len(p) for p in parts]
+    assert max(sizes) - min(sizes) <= 8 and max(sizes) == -(-len(lit) // 8)
+    # a contiguous split of the GRID would not balance: the spread of lit columns per grid slab is wider
+    grid = [int((zth[slice(*sharding.slab_bounds(1000, 8, r))] > 0).sum()) for r in range(8)]
+    assert max(grid) - min(grid) > max(sizes) - min(sizes)
+    p = sharding.pack_columns(s, lit)
+    assert p["ncol"] == len(lit) and p["play"].shape == (len(lit), 8) and (p["coszen"] > 0).all()
+    back = sharding.unpack_columns(p["play"], lit, 1000, default=-1.0)
+    np.testing.assert_array_equal(back[lit], s["play"][lit])
+    night = np.setdiff1d(np.arange(1000), lit)
+    assert (back[night] == -1.0).all()
