@@ -10,8 +10,11 @@ of a larger grid (weak scaling, no data-path collective; columns are independent
   value     whole-job columns/s with every boundary array already resident in HBM
   e2e       the same metric through the C ABI with HOST (pinned) arrays: the library stages
             chunks host->device, computes, and copies the fluxes back inside the timed region
-  roofline  algorithmic boundary bytes per column (59 560 B at L72)
-            x columns / device time against the measured HBM copy bandwidth
+  roofline  the DOMINANT KERNEL (the slowest SW band kernel: gas optics + two-stream + adding fused): algorithmic
+            boundary bytes of one launch / its average launch duration in this run (CUDA events on its own
+            stream) against the measured HBM copy bandwidth; `traffic` = its measured DRAM bytes per launch;
+            `fp64` = its FP64 thread-instructions/s against the measured DADD/DMUL and DFMA issue rates;
+            `step` = the same for the whole refresh (59 560 algorithmic B per column at L72)
   cpu_baseline  the C oracle (oracle/, the CPU restatement of the reference Fortran; the
             reference itself cannot be compiled here: no Fortran compiler) on a bounded sample
 
@@ -581,21 +584,40 @@ def main():
             if fp64_peak:
                 inst = kc["fp64_thread_instructions_per_column"] * dom["columns_per_launch"]
                 pk = float(fp64_peak["mix_dmul_dadd_register_operands"])
+                pk_fma = float(fp64_peak["dfma_register_operands"])
                 dom["fp64"] = {"achieved_instr_s": inst / launch_s, "peak": pk, "frac": inst / launch_s / pk,
-                               "pipe_active_pct_under_ncu": kc.get("fp64_pipe_active_pct")}
+                               "peak_dfma": pk_fma, "frac_of_dfma_peak": inst / launch_s / pk_fma,
+                               "unit": "fp64 thread-instructions/s",
+                               "pipe_active_pct_under_ncu": kc.get("fp64_pipe_active_pct"),
+                               "peak_source": "profiles/fp64_peak.json (tools/fp64_peak.py on a B200 of this pool): "
+                                              "DADD/DMUL with register operands; DFMA on three distinct register pairs"}
             dom["counts_from"] = cnt_src
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": cnt_src, "fp64": fp64, "kernels": kernels,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)",
-                "kernel": "whole step: the fixed pipeline of LW+SW kernels of one refresh (algorithmic bytes = "
-                          "boundary inputs read once + outputs written once, SURVEY.md 8d); `kernels` attributes "
-                          "device time per kernel from CUDA events of this run; `traffic` / `fp64` put the counters of "
-                          "the committed ncu launch list over this run's times",
-                "algorithmic_bytes_per_column": bpc,
-                "note": "neither roof binds: the band kernels are latency-bound recurrences (DESIGN.md section 4)"}
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
+    # whole step: the fixed pipeline of LW+SW kernels of one refresh; algorithmic bytes = boundary inputs read once +
+    # outputs written once
+    step_roof = {"achieved": achieved, "frac": achieved / peak, "unit": "GB/s", "algorithmic_bytes_per_column": bpc,
+                 "traffic": traffic, "traffic_source": cnt_src, "fp64": fp64}
     if traffic is not None:   # the measured DRAM bytes over the measured step: how busy HBM really is (scratch included)
-        roofline["traffic_gbs"] = traffic / step_s / 1e9
-        roofline["traffic_frac"] = roofline["traffic_gbs"] / peak
+        step_roof["traffic_gbs"] = traffic / step_s / 1e9
+        step_roof["traffic_frac"] = step_roof["traffic_gbs"] / peak
+    dom = (kernels or {}).get("dominant")
+    if dom:
+        # the contract's roofline object: the DOMINANT KERNEL, algorithmic bytes of one launch over its average launch
+        # duration of THIS run (CUDA events on the kernel's own stream); `traffic` = its measured DRAM bytes per launch
+        roofline = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                    "traffic": dom.get("traffic"), "kernel": dom["name"],
+                    "kernel_family_share_of_step": dom["family_share"], "avg_launch_ms": dom["avg_launch_ms"],
+                    "columns_per_launch": dom["columns_per_launch"],
+                    "algorithmic_bytes_per_column_and_launch": dom["algorithmic_bytes_per_column"],
+                    "traffic_gbs": dom.get("traffic_gbs"), "traffic_frac": dom.get("traffic_frac"),
+                    "traffic_source": dom.get("counts_from"), "fp64": dom.get("fp64")}
+    else:   # no per-kernel attribution (not rank 0 of the profile step): the whole step
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "kernel": "whole step", "fp64": fp64}
+    roofline.update({"peak_source": peak_src, "step": step_roof, "kernels": kernels,
+                     "note": "an FP64 code: HBM is the roof the contract names, the FP64 issue rate the one closer to "
+                             "binding (`fp64`: thread-instructions/s against the measured DADD/DMUL and DFMA rates); "
+                             "neither is reached, the band kernels are latency-bound recurrences (DESIGN.md section 4)"})
     cpu = None
     if not a.no_cpu and world == 1:
         r, threads, dt = cpu_oracle_rate(a.cpu_sample, nlay, a.seed, with_sw and oracle_has_sw())
