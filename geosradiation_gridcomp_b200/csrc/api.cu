@@ -776,6 +776,18 @@ int rrtmgx_debug_divide(size_t n, const double *a, const double *b, double *q_fa
     return ok(e) ? 0 : RRTMGX_ECUDA;
 }
 
+int rrtmgx_debug_kiss(int nstream, const int32_t *seeds, int ndraw, int32_t *kiss, double *ran8, float *ran4, int nsub,
+                      int nlay, int inhomo, uint32_t *jumped, uint32_t *replayed, int nvalue, const int32_t *values,
+                      double *val8, float *val4) {
+    if (!g.ready) return RRTMGX_ENOTINIT;
+    if (nstream <= 0 || !seeds || ndraw < 0 || nsub < 0 || nsub > 140 || nvalue < 0 || (ndraw && (!kiss || !ran8 || !ran4)) ||
+        (nsub && (nlay <= 0 || !jumped || !replayed)) || (nvalue && (!values || !val8 || !val4)))
+        return RRTMGX_EARG;
+    cudaSetDevice(g.device);
+    return debug_kiss(nstream, seeds, ndraw, kiss, ran8, ran4, nsub, nlay, inhomo, jumped, replayed, nvalue, values, val8,
+                      val4, g.lw.stream);
+}
+
 #ifndef RRTMGX_WITH_SW
 int rrtmgx_sw_run(const RrtmgxSwArgs *) { return RRTMGX_EARG; }
 int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *, const RrtmgxSwNoAerosol *) { return RRTMGX_EARG; }

@@ -68,6 +68,10 @@ struct McicaConfig {
 };
 // host: jump entries for subcolumn starts; entry 2*i: i*stride draws, 2*i+1: i*stride + 2*nlay
 void kiss_jump_table(int nsub, int nlay, bool inhomo, KissJump *out /* 2*nsub */);
+// test hook behind rrtmgx_debug_kiss (lw.cu): host arrays in and out
+int debug_kiss(int nstream, const int32_t *seeds, int ndraw, int32_t *kiss, double *ran8, float *ran4, int nsub, int nlay,
+               int inhomo, uint32_t *jumped, uint32_t *replayed, int nvalue, const int32_t *values, double *val8, float *val4,
+               cudaStream_t st);
 McicaParams mcica_params(const McicaConfig &cfg, const double *d_xcw_beta, const double *d_xcw_gamma,
                          int doy, const int seed_order[4]);
 

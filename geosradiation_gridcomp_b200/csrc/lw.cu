@@ -1622,4 +1622,89 @@ int lw_run_chunk(const RrtmgxLwArgs *a, int col0, int nc, const ChunkId &id, con
     return cudaGetLastError() == cudaSuccess ? 0 : RRTMGX_ECUDA;
 }
 
+// ---- test hook: the device KISS generator on its own (include/rrtmgx.h rrtmgx_debug_kiss) -----------------------
+// One thread per stream: the first ndraw draws of SH/cloud_subcol_gen.F90:568-575, `ran_num` in real*8 (the
+// promoted-real contract) and in real*4 (the production kind: int -> real*4 conversion, real*4 product and sum).
+static __global__ void debug_kiss_draw_kernel(int nstream, const int32_t *__restrict__ seeds, int ndraw,
+                                              int32_t *__restrict__ kiss, double *__restrict__ ran8, float *__restrict__ ran4) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nstream) return;
+    Kiss k{(uint32_t)seeds[4 * i], (uint32_t)seeds[4 * i + 1], (uint32_t)seeds[4 * i + 2], (uint32_t)seeds[4 * i + 3]};
+    for (int d = 0; d < ndraw; ++d) {
+        const int32_t v = k.draw_int();
+        const size_t o = (size_t)i * ndraw + d;
+        kiss[o] = v;
+        ran8[o] = kiss_value(v);
+        ran4[o] = (float)v * 2.328306e-10f + 0.5f;
+    }
+}
+// One thread per (jump entry, stream): the state Kiss::jump reaches beside the state after replaying J.n draws.
+static __global__ void debug_kiss_jump_kernel(int nstream, const int32_t *__restrict__ seeds, int nentry,
+                                              const KissJump *__restrict__ J, uint32_t *__restrict__ jumped,
+                                              uint32_t *__restrict__ replayed) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nstream * nentry) return;
+    const int i = t / nentry, e = t % nentry;
+    Kiss a{(uint32_t)seeds[4 * i], (uint32_t)seeds[4 * i + 1], (uint32_t)seeds[4 * i + 2], (uint32_t)seeds[4 * i + 3]};
+    Kiss b = a;
+    a.jump(J[e]);
+    for (uint32_t d = 0; d < J[e].n; ++d) (void)b.draw_int();
+    const size_t o = 4 * (size_t)t;
+    jumped[o] = a.s1; jumped[o + 1] = a.s2; jumped[o + 2] = a.s3; jumped[o + 3] = a.s4;
+    replayed[o] = b.s1; replayed[o + 1] = b.s2; replayed[o + 2] = b.s3; replayed[o + 3] = b.s4;
+}
+static __global__ void debug_kiss_value_kernel(int n, const int32_t *__restrict__ k, double *__restrict__ r8, float *__restrict__ r4) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    r8[i] = kiss_value(k[i]);
+    r4[i] = (float)k[i] * 2.328306e-10f + 0.5f;
+}
+
+int debug_kiss(int nstream, const int32_t *seeds, int ndraw, int32_t *kiss, double *ran8, float *ran4, int nsub, int nlay,
+               int inhomo, uint32_t *jumped, uint32_t *replayed, int nvalue, const int32_t *values, double *val8, float *val4,
+               cudaStream_t st) {
+    const size_t nd = (size_t)nstream * ndraw, nentry = 2 * (size_t)nsub, nj = 4 * nentry * nstream;
+    char *d = nullptr;
+    const size_t bytes = 16 * (size_t)nstream + nd * 16 + nentry * sizeof(KissJump) + nj * 8 + (size_t)nvalue * 16 + 4096;
+    if (cudaMalloc((void **)&d, bytes) != cudaSuccess) { cudaGetLastError(); return RRTMGX_ECUDA; }
+    Slab s;
+    s.base = d; s.cap = bytes;
+    int32_t *d_seed = s.take<int32_t>(4 * (size_t)nstream);
+    double *d_r8 = s.take<double>(nd + 1);
+    int32_t *d_k = s.take<int32_t>(nd + 1);
+    float *d_r4 = s.take<float>(nd + 1);
+    KissJump *d_J = s.take<KissJump>(nentry + 1);
+    uint32_t *d_a = s.take<uint32_t>(nj + 1), *d_b = s.take<uint32_t>(nj + 1);
+    double *d_v8 = s.take<double>((size_t)nvalue + 1);
+    int32_t *d_v = s.take<int32_t>((size_t)nvalue + 1);
+    float *d_v4 = s.take<float>((size_t)nvalue + 1);
+    cudaMemcpyAsync(d_seed, seeds, 16 * (size_t)nstream, cudaMemcpyHostToDevice, st);
+    if (ndraw > 0) {
+        debug_kiss_draw_kernel<<<(nstream + 63) / 64, 64, 0, st>>>(nstream, d_seed, ndraw, d_k, d_r8, d_r4);
+        cudaMemcpyAsync(kiss, d_k, nd * 4, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(ran8, d_r8, nd * 8, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(ran4, d_r4, nd * 4, cudaMemcpyDeviceToHost, st);
+    }
+    if (nsub > 0) {
+        std::vector<KissJump> h(nentry);
+        kiss_jump_table(nsub, nlay, inhomo != 0, h.data());
+        cudaMemcpyAsync(d_J, h.data(), nentry * sizeof(KissJump), cudaMemcpyHostToDevice, st);
+        const int nt = nstream * (int)nentry;
+        debug_kiss_jump_kernel<<<(nt + 63) / 64, 64, 0, st>>>(nstream, d_seed, (int)nentry, d_J, d_a, d_b);
+        cudaMemcpyAsync(jumped, d_a, nj * 4, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(replayed, d_b, nj * 4, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);   // `h` is pageable host memory
+    }
+    if (nvalue > 0) {
+        cudaMemcpyAsync(d_v, values, (size_t)nvalue * 4, cudaMemcpyHostToDevice, st);
+        debug_kiss_value_kernel<<<(nvalue + 127) / 128, 128, 0, st>>>(nvalue, d_v, d_v8, d_v4);
+        cudaMemcpyAsync(val8, d_v8, (size_t)nvalue * 8, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(val4, d_v4, (size_t)nvalue * 4, cudaMemcpyDeviceToHost, st);
+    }
+    const cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : RRTMGX_ECUDA;
+}
+
+
 }  // namespace rrtmgx

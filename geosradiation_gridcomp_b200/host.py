@@ -444,6 +444,31 @@ def debug_divide(a, b):
     return tuple(out)
 
 
+def debug_kiss(seeds, ndraw=0, jump_table=None, values=None):
+    """Test hook (include/rrtmgx.h rrtmgx_debug_kiss): the device KISS generator on its own.  seeds: (nstream, 4) int32.
+    Returns a dict: kiss / ran8 / ran4 (nstream, ndraw); jumped / replayed (nstream, 2*nsub, 4) for
+    jump_table=(nsub, nlay, inhomo); val8 / val4 for the integers `values`."""
+    if not _initialised:
+        init()
+    seeds = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1, 4)
+    ns = seeds.shape[0]
+    out = {"kiss": np.zeros((ns, ndraw), dtype=np.int32), "ran8": np.zeros((ns, ndraw)),
+           "ran4": np.zeros((ns, ndraw), dtype=np.float32)}
+    nsub, nlay, inhomo = jump_table if jump_table else (0, 0, 0)
+    out["jumped"] = np.zeros((ns, 2 * nsub, 4), dtype=np.uint32)
+    out["replayed"] = np.zeros((ns, 2 * nsub, 4), dtype=np.uint32)
+    v = np.ascontiguousarray(values if values is not None else [], dtype=np.int32)
+    out["val8"], out["val4"] = np.zeros(v.size), np.zeros(v.size, dtype=np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    L = lib()
+    L.rrtmgx_debug_kiss.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    _check(L.rrtmgx_debug_kiss(ns, p(seeds), int(ndraw), p(out["kiss"]), p(out["ran8"]), p(out["ran4"]), int(nsub),
+                               int(nlay), int(inhomo), p(out["jumped"]), p(out["replayed"]), int(v.size), p(v),
+                               p(out["val8"]), p(out["val4"])))
+    return out
+
+
 # ---- fused Run-phase glue: GEOS-native state in, GEOS-native fluxes out ---------------------------------
 def _irrad_args(n, iceflg, liqflg, device, keep, f32=False):
     a = IrradArgs()

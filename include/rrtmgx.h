@@ -329,6 +329,20 @@ int rrtmgx_solar_refresh(const RrtmgxSolarArgs *g);
 int rrtmgx_debug_divide(size_t n, const double *a, const double *b, double *q_fast, double *q_ieee,
                         double *r_fast, double *r_ieee);
 
+/* Test hook: the device KISS generator on its own (rng_kiss, GEOS_RadiationShared/cloud_subcol_gen.F90:546-607) and
+ * the O(1) jump-ahead the McICA kernel uses instead of replaying the sequence.  All arrays are host arrays.
+ *   seeds (4,nstream): seed1..seed4 of every stream.
+ *   ndraw > 0: kiss / ran8 / ran4 (ndraw,nstream) receive the first ndraw integer draws `kiss` of each stream and
+ *     `ran_num = kiss * 2.328306e-10 + 0.5` (:575) evaluated in real*8 (the promoted-real contract the library computes
+ *     in) and in real*4 (the production kind, whose range the reference records: [8.9406967E-08, 0.9999999], :597-604).
+ *   nsub > 0: for the jump table of (nsub subcolumns, nlay layers, inhomo) - entry 2i jumps i*stride draws, entry 2i+1
+ *     i*stride + 2*nlay, stride = 2*nlay or 4*nlay - jumped / replayed (4, 2*nsub, nstream) receive the generator
+ *     state after Kiss::jump and after replaying the same number of draws one by one.
+ *   nvalue > 0: val8 / val4 (nvalue) = ran_num of the given integers `values` in real*8 and real*4. */
+int rrtmgx_debug_kiss(int nstream, const int32_t *seeds, int ndraw, int32_t *kiss, double *ran8, float *ran4, int nsub,
+                      int nlay, int inhomo, uint32_t *jumped, uint32_t *replayed, int nvalue, const int32_t *values,
+                      double *val8, float *val4);
+
 /* reduced (post-cmbgb) host copies of tables for tests: kind "lw"/"sw", band as in the
  * reference (1..16 / 16..29; 0 for band-independent), g-point fastest layout [lead][ng]. */
 const double *rrtmgx_table(const char *kind, const char *name, int band, int *n);

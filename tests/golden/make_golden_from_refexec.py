@@ -50,6 +50,25 @@ def run_case(name, c):
     return out
 
 
+KISS_SEEDS = ((1, 2, 3, 4), (-2147483648, 2147483647, 65535, 65536), (123456789, 362436069, 521288629, 916191069),
+              (20260118, -77, 4095, -65536))
+KISS_DRAWS = 600
+
+
+def run_kiss():
+    """The reference's own rng_kiss (SH/cloud_subcol_gen.F90:546-576) on a few seed quadruples: the seeds after every
+    call are not kept, the real*8 ran_num is; the integer `kiss` is recovered exactly from it by the tests."""
+    from oracle.refexec import run
+    ns = run.namespace()
+    out = np.zeros((len(KISS_SEEDS), KISS_DRAWS))
+    for i, sd in enumerate(KISS_SEEDS):
+        s1, s2, s3, s4 = sd
+        for d in range(KISS_DRAWS):
+            s1, s2, s3, s4, r = ns["P_cloud_subcol_gen__rng_kiss"](s1, s2, s3, s4, 0.0)
+            out[i, d] = r
+    return {"kiss/seeds": np.array(KISS_SEEDS, dtype=np.int64), "kiss/ran_num": out}
+
+
 if __name__ == "__main__":
     from oracle.refexec import run
     from refexec_cases import CASES, INTEGER_KEYS
@@ -71,6 +90,8 @@ if __name__ == "__main__":
                 v = v.astype(np.uint8 if k.endswith("cldymc") else np.int32)
             res[k] = v
         print(f"{name}: {time.time() - t:.1f} s")
+    if not only or "kiss" in only:
+        res.update(run_kiss())
     res["real_bytes"] = np.int64(8)
     res["reference_files"] = np.int64(len(run.sources()))
     np.savez_compressed(OUT, **res)

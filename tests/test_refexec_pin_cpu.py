@@ -54,6 +54,16 @@ def test_oracle_equals_reference_source_output(oracle, golden, name):
     print(f"{name}: {n} arrays, {same} bit-identical, worst relative difference {worst:.2e}")
 
 
+def test_oracle_kiss_equals_reference_source_draws(oracle, golden):
+    """rng_kiss (SH/cloud_subcol_gen.F90:546-576) executed from the reference text, 4 seed quadruples x 600 draws
+    (with the extreme seeds of the 32-bit range): the C restatement draws the same numbers, bit for bit."""
+    seeds, ran = golden["kiss/seeds"], golden["kiss/ran_num"]
+    assert ran.shape == (4, 600) and 0.0 < ran.min() and ran.max() < 1.0
+    for i in range(seeds.shape[0]):
+        r, _ = oracle.rng_kiss(seeds[i].astype(np.int32), ran.shape[1])
+        np.testing.assert_array_equal(np.asarray(r), ran[i], err_msg=str(seeds[i]))
+
+
 @pytest.mark.skipif(not os.path.isdir(os.environ.get("REFERENCE_ROOT", "/root/reference")), reason="no reference tree on this machine")
 def test_golden_is_reproducible_from_the_reference_tree(golden):
     """One small case regenerated on the spot from /root/reference: the committed file is what the reference's text
