@@ -1011,6 +1011,38 @@ struct LwBandArgs {
 template <int NY, int CB> __host__ __device__ constexpr bool lw_shuffle_sums() {
     return NY > 1 && NY <= 32 && (NY & (NY - 1)) == 0 && (NY * CB) % 32 == 0;
 }
+// The xor butterfly over the NY lanes of a column, as a reduce-scatter: while a lane still holds several of the Q
+// values, a round halves them (the lane keeps the lower or the upper half by its bit M and sends the other half to
+// its partner) instead of exchanging all of them; the last rounds are the plain butterfly on the one value left.
+// Every total is the same tree of pairwise sums as in the full butterfly (IEEE addition commutes), so the bits do
+// not change; Q = 4 over 8 lanes takes 4 exchanges of a double instead of 12.  The totals end up spread over the
+// column's lanes: the lane whose remaining bits are zero stores its value(s).
+template <int Q, int M>
+__device__ __forceinline__ void lw_shuffle_reduce_scatter(double (&s)[Q], const int ty, const int q0, const bool store,
+                                                          double *__restrict__ dst, const size_t qstride) {
+    if constexpr (M == 0) {
+        if (store) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) dst[(size_t)(q0 + q) * qstride] = s[q];
+        }
+    } else if constexpr (Q > 1 && Q % 2 == 0) {
+        constexpr int H = Q / 2;
+        const bool upper = (ty & M) != 0;
+        double k[H];
+#pragma unroll
+        for (int q = 0; q < H; ++q) {
+            const double keep = upper ? s[H + q] : s[q];
+            const double send = upper ? s[q] : s[H + q];
+            k[q] = keep + __shfl_xor_sync(0xffffffffu, send, M);
+        }
+        lw_shuffle_reduce_scatter<H, M / 2>(k, ty, q0 + (upper ? H : 0), store, dst, qstride);
+    } else {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) s[q] = s[q] + __shfl_xor_sync(0xffffffffu, s[q], M);
+        lw_shuffle_reduce_scatter<Q, M / 2>(s, ty, q0, store && (ty & M) == 0, dst, qstride);
+    }
+}
+
 template <int Q, int NY, int CB>
 __device__ __forceinline__ void block_sum_store(const double (&v)[Q], double *__restrict__ red,
                                                 double *__restrict__ dst, size_t qstride, bool active) {
@@ -1026,15 +1058,7 @@ __device__ __forceinline__ void block_sum_store(const double (&v)[Q], double *__
         double s[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q) s[q] = v[q];
-#pragma unroll
-        for (int m = NY / 2; m >= 1; m >>= 1) {
-#pragma unroll
-            for (int q = 0; q < Q; ++q) s[q] = s[q] + __shfl_xor_sync(0xffffffffu, s[q], m);
-        }
-        if (active && ty == 0) {
-#pragma unroll
-            for (int q = 0; q < Q; ++q) dst[q * qstride] = s[q];
-        }
+        lw_shuffle_reduce_scatter<Q, NY / 2>(s, ty, 0, active, dst, qstride);
         (void)red; (void)lane;
         return;
     }
