@@ -74,3 +74,37 @@ def test_golden_is_reproducible_from_the_reference_tree(golden):
     fresh = gen.run_case(name, rc.CASES[name])
     for k, v in fresh.items():
         np.testing.assert_array_equal(np.asarray(v, dtype=golden[k].dtype), golden[k], err_msg=k)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("REFERENCE_ROOT", "/root/reference")), reason="no reference tree on this machine")
+@pytest.mark.parametrize("seed", [101, 202])
+def test_oracle_against_the_reference_source_live(oracle, seed):
+    """Not a stored vector: the reference's text is translated and EXECUTED in this test run on columns and options
+    drawn from `seed` (cloud-optics options, solar-variability mode, partition sizes, inhomogeneity), and the C
+    restatement is held to what it returns.  Build container only (needs /root/reference); 5 columns per case."""
+    from geosradiation_gridcomp_b200.synthetic import make_columns
+    from oracle.refexec import run
+    rng = np.random.default_rng(seed)
+    ih = int(rng.integers(0, 3))
+    s = make_columns(5, 72, seed=seed)
+    lw_opt = dict(psize=int(rng.integers(1, 6)), iceflg=int(rng.choice([0, 1, 2, 3, 4])), dudTs=bool(rng.integers(0, 2)))
+    isolvar = int(rng.choice([-1, 0, 2, 3]))
+    sw_opt = dict(rpart=int(rng.integers(0, 4)), iceflg=int(rng.choice([1, 2, 3, 4])), isolvar=isolvar,
+                  normFlx=int(rng.integers(0, 2)), iaer=int(rng.choice([0, 10])), do_drfband=True)
+    if isolvar == 2:
+        sw_opt["indsolvar"] = [float(rng.uniform(0.14, 0.17)), float(rng.uniform(0.0, 2000.0))]
+    if isolvar == 3:
+        sw_opt["bndscl"] = rng.uniform(0.9, 1.1, 14)
+    oracle.set_mcica(ih)
+    try:
+        ref_lw, got_lw = run.rrtmg_lw(s, ih=ih, **lw_opt), oracle.rrtmg_lw(s, **lw_opt)
+        ref_sw, got_sw = run.rrtmg_sw(s, ih=ih, **sw_opt), oracle.rrtmg_sw(s, **sw_opt)
+    finally:
+        oracle.set_mcica(1)
+    assert got_lw["rc"] == 0 and got_sw["rc"] == 0 and ref_sw["ret"][-1] == 0
+    for ref, got, keys in ((ref_lw, got_lw, rc.LW_OUT), (ref_sw, got_sw, rc.SW_OUT)):
+        for k in keys:
+            if k == "clearCounts":
+                np.testing.assert_array_equal(got[k], ref[k], err_msg=f"{seed} {k}")
+            else:
+                assert rc.rel_err(got[k], ref[k]) <= TOL, (seed, k, lw_opt, sw_opt)
