@@ -211,17 +211,21 @@ def test_sw_clean_and_full_in_one_call(rx):
     assert np.abs(clean["swdflx"] - full["swdflx"]).max() > 1e-4
 
 
-@pytest.mark.parametrize("down", ["0", "1"])
-def test_sw_split_path_streaming_downward_kernel(rx, oracle, down):
+@pytest.mark.parametrize("split,down", [("1", "0"), ("1", "1"), ("2", "0")])
+def test_sw_split_path_streaming_downward_kernel(rx, oracle, split, down):
     """RRTMGX_SW_SPLIT=1: upward kernel + the streaming downward kernel (cp.async.bulk ring, mbarrier per stage;
     RRTMGX_SW_DOWN picks the g-points per pass) instead of the fused band kernel: every SW output against the oracle
     at the contract's tolerance, and against the fused path to the rounding of the band sums' order.  Ragged column
-    count (partial last tile), cloudy and cloud-free tiles, and a deep column (six mask words)."""
+    count (partial last tile), cloudy and cloud-free tiles, and a deep column (six mask words).
+    RRTMGX_SW_SPLIT=2: the overlapped schedule (upward kernels back to back, the downward kernels as persistent grids on
+    a high-priority stream; with RRTMGX_SW_DOWN_BLOCKS=1 and 5 000 columns every block walks several tiles)."""
     import os
-    cases = [(make_columns(1000, 72, seed=61), None), (make_columns(70, 181, seed=67), None)]
+    cases = [(make_columns(5000 if split == "2" else 1000, 72, seed=61), None), (make_columns(70, 181, seed=67), None)]
     fused = [rx.run_sw(s, normFlx=0, do_drfband=True) for s, _ in cases]
-    saved = {k: os.environ.get(k) for k in ("RRTMGX_SW_SPLIT", "RRTMGX_SW_DOWN")}
-    os.environ["RRTMGX_SW_SPLIT"], os.environ["RRTMGX_SW_DOWN"] = "1", down
+    saved = {k: os.environ.get(k) for k in ("RRTMGX_SW_SPLIT", "RRTMGX_SW_DOWN", "RRTMGX_SW_DOWN_BLOCKS")}
+    os.environ["RRTMGX_SW_SPLIT"], os.environ["RRTMGX_SW_DOWN"] = split, down
+    if split == "2":
+        os.environ["RRTMGX_SW_DOWN_BLOCKS"] = "1"
     rx.finalize()
     rx.init()
     try:
