@@ -11,9 +11,9 @@
  * the 91 Fortran files of the path, read where they lie, turned into Python in memory) and its
  * output is committed as tests/golden/rrtmg_refexec_golden.npz.  tests/test_refexec_pin_cpu.py
  * holds this restatement to those numbers: integers bit for bit, reals <= 1e-12 (seen: 3.9e-13).
- * Not pinned: output of a COMPILED reference (oracle/build_ref.sh is the recipe; it needs a
- * Fortran compiler) and the drivers' Run-phase glue (glue.c), which a second numpy transcription
- * cross-checks.  This file is a routine-by-routine restatement of the Fortran, with `real`
+ * The drivers' Run-phase glue (glue.c) is held bit for bit to the reference's own line ranges,
+ * read from the driver files and executed (oracle/refexec/glue.py).  Not pinned: output of a
+ * COMPILED reference (oracle/build_ref.sh is the recipe; it needs a Fortran compiler).  This file is a routine-by-routine restatement of the Fortran, with `real`
  * promoted to 8 bytes (the north_star fp64 contract), same loop nests, same expression order,
  * compiled with -ffp-contract=off.
  *

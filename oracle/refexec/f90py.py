@@ -80,6 +80,15 @@ def _data(x):
     return x.a if isinstance(x, FA) else x
 
 
+def _section(lo, hi, step, lb):
+    """Python slice of the Fortran section lo:hi:step of a dimension with lower bound lb (hi inclusive)."""
+    step = int(step)
+    if step > 0:
+        return slice(None if lo is None else int(lo) - lb, None if hi is None else int(hi) - lb + 1, step)
+    stop = None if hi is None else int(hi) - lb - 1
+    return slice(None if lo is None else int(lo) - lb, stop if (stop is None or stop >= 0) else None, step)
+
+
 def _bind(actual, kind, dims, name):
     """Array dummy: a view of the actual argument with the dummy's bounds.  dims: list of (lo, hi) with hi None for
     assumed shape / size."""
@@ -119,7 +128,7 @@ class NamedExit(Exception):
 
 
 RUNTIME = {"np": np, "math": math, "FA": FA, "_i32": _i32, "_idiv": _idiv, "_ishft": _ishft, "_mod": _mod, "_sign": _sign,
-           "_nint": _nint, "_data": _data, "_bind": _bind, "StopError": StopError, "NamedCycle": NamedCycle,
+           "_nint": _nint, "_data": _data, "_section": _section, "_bind": _bind, "StopError": StopError, "NamedCycle": NamedCycle,
            "NamedExit": NamedExit}
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -460,8 +469,14 @@ class Apply(Node):
             if isinstance(a, Slice):
                 lo = off(a.lo.py(sc)) if a.lo is not None else ""
                 hi = f"{off(a.hi.py(sc))}+1" if a.hi is not None else ""
-                st = f":{a.step.py(sc)}" if a.step is not None else ""
-                parts.append(f"{lo}:{hi}{st}")
+                if a.step is not None:
+                    # a strided section: with a negative stride the last element is hi (inclusive) and a stop of -1
+                    # would wrap around, so the slice is built at run time (e.g. `X(:,LM:1:-1)`, SOL:6136)
+                    lo_t = a.lo.py(sc) if a.lo is not None else "None"
+                    hi_t = a.hi.py(sc) if a.hi is not None else "None"
+                    parts.append(f"_section({lo_t}, {hi_t}, {a.step.py(sc)}, {lbtxt})")
+                    continue
+                parts.append(f"{lo}:{hi}")
             elif a.rank(sc) > 0:   # vector subscript
                 parts.append(f"np.asarray({a.py(sc)})-{lbtxt}")
             else:

@@ -69,6 +69,33 @@ def run_kiss():
     return {"kiss/seeds": np.array(KISS_SEEDS, dtype=np.int64), "kiss/ran_num": out}
 
 
+REFRESH_NCOL, REFRESH_SEED = 14, 73
+IRR_EXPORTS = ("flxu", "flxd", "flcu", "flcd", "dfdts", "dfdtsc", "sfcem", "cldtt", "cldhi", "cldmd", "cldlo", "olrb", "dolrb_dts")
+SOL_EXPORTS = ("fsw", "fsc", "fswu", "fscu", "cldts", "cldhs", "cldms", "cldls", "cottp", "cothp", "cotmp", "cotlp", "nirr",
+               "nirf", "parr", "parf", "uvrr", "uvrf", "fswband")
+IRR_PREPARED = ("play", "plev", "tlay", "tlev", "tsfc", "emis", "h2ovmr", "o3vmr", "co2vmr", "ch4vmr", "n2ovmr", "o2vmr",
+                "cfc11vmr", "cfc12vmr", "cfc22vmr", "ccl4vmr", "cldf", "ciwp", "clwp", "rei", "rel", "tauaer_lw", "zm", "alat")
+SOL_PREPARED = ("play", "plev", "tlay", "h2ovmr", "o3vmr", "co2vmr", "ch4vmr", "o2vmr", "cld", "ciwp", "clwp", "rei", "rel",
+                "zm", "tauaer", "ssaaer", "asmaer")
+
+
+def run_refresh():
+    """A whole refresh of each driver from the reference's text: the Run-phase glue LINES of GEOS_IrradGridComp.F90 /
+    GEOS_SolarGridComp.F90 (oracle/refexec/glue.py) around the RRTMG sources: native state in, native exports out."""
+    from geosradiation_gridcomp_b200.synthetic import make_native_state
+    from oracle.refexec import glue
+    n = make_native_state(REFRESH_NCOL, 72, seed=REFRESH_SEED)
+    out = {}
+    s, _, f = glue.irrad_refresh(n)
+    out.update({f"refresh/irr_prepared/{k}": s[k] for k in IRR_PREPARED})
+    out.update({f"refresh/irr/{k}": f[k] for k in IRR_EXPORTS})
+    out["refresh/irr_prepared/cloudLM"], out["refresh/irr_prepared/cloudMH"] = np.int64(s["cloudLM"]), np.int64(s["cloudMH"])
+    s, _, f = glue.solar_refresh(n)
+    out.update({f"refresh/sol_prepared/{k}": s[k] for k in SOL_PREPARED})
+    out.update({f"refresh/sol/{k}": f[k] for k in SOL_EXPORTS})
+    return out
+
+
 if __name__ == "__main__":
     from oracle.refexec import run
     from refexec_cases import CASES, INTEGER_KEYS
@@ -92,6 +119,10 @@ if __name__ == "__main__":
         print(f"{name}: {time.time() - t:.1f} s")
     if not only or "kiss" in only:
         res.update(run_kiss())
+    if not only or "refresh" in only:
+        t = time.time()
+        res.update(run_refresh())
+        print(f"refresh: {time.time() - t:.1f} s")
     res["real_bytes"] = np.int64(8)
     res["reference_files"] = np.int64(len(run.sources()))
     np.savez_compressed(OUT, **res)

@@ -108,3 +108,73 @@ def test_oracle_against_the_reference_source_live(oracle, seed):
                 np.testing.assert_array_equal(got[k], ref[k], err_msg=f"{seed} {k}")
             else:
                 assert rc.rel_err(got[k], ref[k]) <= TOL, (seed, k, lw_opt, sw_opt)
+
+
+# ---- the drivers' Run-phase glue (IRR:3238-3371, 3487-3533; SOL:6116-6219, 6395-6454) ------------------------------------
+def _refresh_state():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_from_refexec as gen
+    from geosradiation_gridcomp_b200.synthetic import make_native_state
+    return gen, make_native_state(gen.REFRESH_NCOL, 72, seed=gen.REFRESH_SEED)
+
+
+def test_oracle_refresh_equals_the_reference_text_refresh(oracle, golden):
+    """A whole refresh of each driver - native GEOS state in, native exports out - as the reference's text computes it
+    (its glue LINES around its RRTMG sources, all executed through oracle/refexec; golden keys refresh/*) against the C
+    restatement's chain glue.c -> lw.c / sw.c -> glue.c: the prepared RRTMG arguments bit for bit, the exports within
+    1e-12, cloud fractions and the MAPL_UNDEF pattern of the optical thicknesses exactly."""
+    gen, n = _refresh_state()
+    s = oracle.irrad_prepare(n)
+    for k in gen.IRR_PREPARED:
+        np.testing.assert_array_equal(s["tauaer" if k == "tauaer_lw" else k], golden[f"refresh/irr_prepared/{k}"], err_msg=k)
+    assert (s["cloudLM"], s["cloudMH"]) == (int(golden["refresh/irr_prepared/cloudLM"]), int(golden["refresh/irr_prepared/cloudMH"]))
+    f = oracle.irrad_finish(n, oracle.rrtmg_lw(s))
+    for k in gen.IRR_EXPORTS:
+        ref = golden[f"refresh/irr/{k}"]
+        if k.startswith("cld"):
+            np.testing.assert_array_equal(f[k], ref, err_msg=k)
+        else:
+            assert rc.rel_err(f[k], ref) <= TOL, k
+    s = oracle.solar_prepare(n)
+    for k in gen.SOL_PREPARED:
+        np.testing.assert_array_equal(s[k], golden[f"refresh/sol_prepared/{k}"], err_msg=k)
+    f = oracle.solar_finish(n, oracle.rrtmg_sw(s))
+    for k in gen.SOL_EXPORTS:
+        ref = golden[f"refresh/sol/{k}"]
+        if k.startswith("cld"):
+            np.testing.assert_array_equal(f[k], ref, err_msg=k)
+        elif k.startswith("cot"):
+            np.testing.assert_array_equal(f[k] == n["undef"], ref == n["undef"], err_msg=k)
+            assert rc.rel_err(np.where(ref == n["undef"], 0.0, f[k]), np.where(ref == n["undef"], 0.0, ref)) <= TOL, k
+        else:
+            assert rc.rel_err(f[k], ref) <= TOL, k
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("REFERENCE_ROOT", "/root/reference")), reason="no reference tree on this machine")
+@pytest.mark.parametrize("iceflg,liqflg", [(3, 1), (0, 0), (1, 1), (2, 1), (4, 1)])
+def test_oracle_glue_equals_the_reference_lines_live(oracle, iceflg, liqflg):
+    """The glue line ranges of the two drivers, read from the reference files in this test run and executed: every radius
+    clamp of every cloud-optics option, with and without aerosols, CO2 as a field or as the fixed scalar - bit for bit."""
+    from geosradiation_gridcomp_b200.synthetic import make_native_state
+    from oracle.refexec import glue
+    n = make_native_state(20, 72, seed=71)
+    variants = [n, {k: (None if k in ("taua_lw", "ssaa_lw", "taua_sw", "ssaa_sw", "asya_sw", "co2") else v) for k, v in n.items()}]
+    for m in variants:
+        r, o = glue.irrad_prepare(m, iceflg, liqflg), oracle.irrad_prepare(m, iceflg, liqflg)
+        for k in r:
+            np.testing.assert_array_equal(np.asarray(r[k]), np.asarray(o[k]), err_msg=f"irrad {k}")
+        r, o = glue.solar_prepare(m, iceflg, liqflg), oracle.solar_prepare(m, iceflg, liqflg)
+        for k in r:
+            if k in o:
+                np.testing.assert_array_equal(np.asarray(r[k]), np.asarray(o[k]), err_msg=f"solar {k}")
+        assert r["adjes"] == m["dist"]
+    s = oracle.irrad_prepare(n)
+    lw = oracle.rrtmg_lw(s)
+    r, o = glue.irrad_finish(n, lw), oracle.irrad_finish(n, lw)
+    for k in r:
+        np.testing.assert_array_equal(r[k], o[k], err_msg=f"irrad finish {k}")
+    s = oracle.solar_prepare(n)
+    sw = oracle.rrtmg_sw(s)
+    r, o = glue.solar_finish(n, sw), oracle.solar_finish(n, sw)
+    for k in r:
+        np.testing.assert_array_equal(r[k], o[k], err_msg=f"solar finish {k}")

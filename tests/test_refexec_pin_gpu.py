@@ -37,3 +37,36 @@ def test_cuda_equals_reference_source_output(rx, golden, name):
     n, same, worst = rc.check_case(got, golden, name, TOL_FLUX, TOL_TAPS)
     assert n >= 9
     print(f"{name}: {n} arrays, {same} bit-identical, worst relative difference {worst:.2e}")
+
+
+def test_cuda_refresh_equals_the_reference_text_refresh(rx, golden):
+    """rrtmgx_irrad_refresh / rrtmgx_solar_refresh (the fused driver glue around the device RRTMG path) against a whole
+    refresh computed by the reference's text: its glue lines (GEOS_IrradGridComp.F90:3238-3371, 3487-3533,
+    GEOS_SolarGridComp.F90:6116-6219, 6395-6454) around its RRTMG sources, golden keys refresh/*.  Prepared arguments bit
+    for bit, exports within 1e-9, cloud fractions and the MAPL_UNDEF pattern exactly."""
+    import make_golden_from_refexec as gen
+    from geosradiation_gridcomp_b200.synthetic import make_native_state
+    n = make_native_state(gen.REFRESH_NCOL, 72, seed=gen.REFRESH_SEED)
+    s = rx.irrad_prepare(n)
+    for k in gen.IRR_PREPARED:
+        np.testing.assert_array_equal(s["tauaer" if k == "tauaer_lw" else k], golden[f"refresh/irr_prepared/{k}"], err_msg=k)
+    s = rx.solar_prepare(n)
+    for k in gen.SOL_PREPARED:
+        np.testing.assert_array_equal(s[k], golden[f"refresh/sol_prepared/{k}"], err_msg=k)
+    f = rx.irrad_refresh(n)
+    for k in gen.IRR_EXPORTS:
+        ref = golden[f"refresh/irr/{k}"]
+        if k.startswith("cld"):
+            np.testing.assert_array_equal(f[k], ref, err_msg=k)
+        else:
+            assert rc.rel_err(f[k], ref) <= TOL_FLUX, k
+    f = rx.solar_refresh(n)
+    for k in gen.SOL_EXPORTS:
+        ref = golden[f"refresh/sol/{k}"]
+        if k.startswith("cld"):
+            np.testing.assert_array_equal(f[k], ref, err_msg=k)
+        elif k.startswith("cot"):
+            np.testing.assert_array_equal(f[k] == n["undef"], ref == n["undef"], err_msg=k)
+            assert rc.rel_err(np.where(ref == n["undef"], 0.0, f[k]), np.where(ref == n["undef"], 0.0, ref)) <= TOL_FLUX, k
+        else:
+            assert rc.rel_err(f[k], ref) <= TOL_FLUX, k
