@@ -115,6 +115,16 @@ def _bind(actual, kind, dims, name):
     return FA(a, [int(lo) for lo, _ in dims])
 
 
+def _bind_pointer(actual, name):
+    """Pointer dummy: disassociated (None) or the actual itself, bounds included."""
+    if actual is None or isinstance(actual, FA):
+        return actual
+    a = _data(actual)
+    if not isinstance(a, np.ndarray):
+        raise TypeError(f"pointer dummy {name} got a scalar")
+    return FA(a)
+
+
 class StopError(RuntimeError):
     pass
 
@@ -128,7 +138,7 @@ class NamedExit(Exception):
 
 
 RUNTIME = {"np": np, "math": math, "FA": FA, "_i32": _i32, "_idiv": _idiv, "_ishft": _ishft, "_mod": _mod, "_sign": _sign,
-           "_nint": _nint, "_data": _data, "_section": _section, "_bind": _bind, "StopError": StopError, "NamedCycle": NamedCycle,
+           "_nint": _nint, "_data": _data, "_section": _section, "_bind": _bind, "_bind_pointer": _bind_pointer, "StopError": StopError, "NamedCycle": NamedCycle,
            "NamedExit": NamedExit}
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -1210,7 +1220,9 @@ class Scope:
         out = []
         for lo, _ in v.dims:
             if lo is None:
-                out.append(1)
+                # deferred shape: a pointer carries the bounds of its target (known at run time only);
+                # assumed-shape dummies and freshly allocated arrays without a lower bound start at 1
+                out.append(None if v.pointer else 1)
             elif re.fullmatch(r"-?\d+", lo):
                 out.append(int(lo))
             else:
@@ -1391,7 +1403,11 @@ class Translator:
             v = p.vars.get(a)
             if v is None:
                 continue   # a dummy procedure or an undeclared dummy
-            if v.dims is not None:
+            if v.dims is not None and v.pointer:
+                # a pointer dummy keeps the bounds of what it is associated with (e.g. FLX(:,:,0:LM) in IRR Update);
+                # an assumed-shape dummy starts at 1 whatever the actual's bounds
+                self.emit(i1, f"{pyname(a)} = _bind_pointer({pyname(a)}, '{a}')")
+            elif v.dims is not None:
                 self.emit(i1, f"{pyname(a)} = _bind({pyname(a)}, '{self.kind_of(v)}', {self.dims_py(sc, v)}, '{a}')")
         # parameters first (dims of locals may use them), then locals
         for v in p.vars.values():

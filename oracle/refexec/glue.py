@@ -13,6 +13,7 @@ lines compute.  Build container only (needs the reference tree).
   irrad_finish   IRR:3487-3533  clear counts -> cloud fractions, unflip, sign convention, SFCEM
   solar_prepare  SOL:6116-6219  aerosol normalisation, DPR, water paths, radius limits, TLEV, flips, conversions, ZL, aerosols
   solar_finish   SOL:6395-6454  unflip, cloud fractions, COT ratios with MAPL_UNDEF, FSW / FSC / FSWU / FSCU
+  irrad_update   IRR:3604, 3606, 3861, 3932-3992  the between-refresh linear update of the LW exports (USE_RRTMG branch)
 """
 import os
 
@@ -108,6 +109,23 @@ subroutine sol_fin(NCOL, LM, NGPTSW, include_aerosols, MAPL_UNDEF, CLEARCOUNTS, 
 """
 
 
+_IRR_UPD_HEAD = """
+module refglue_irr_upd
+contains
+subroutine irr_upd(IM, JM, LM, MAPL_UNDEF, TSINST, TS_INT, FLXU_INT, FLXD_INT, FLCU_INT, FLCD_INT, DFDTS, DFDTSC, SFCEM_INT, &
+      CLDTT, FLX, FLC, FLXU, FLCU, FLXD, FLCD, OLR, OLC, SFCEM, LWS, LCS, FLNS, FLNSC, DSFDTS, OLCC5, LCSC5, &
+      FLXA, FLA, FLXAU, FLAU, FLXAD, FLAD, OLRA, OLA, LWSA, LAS, FLNSNA, FLNSA)
+   integer, intent(in) :: IM, JM, LM
+   real, intent(in) :: MAPL_UNDEF, TSINST(IM,JM), TS_INT(IM,JM), SFCEM_INT(IM,JM), CLDTT(IM,JM)
+   real, intent(in), dimension(IM,JM,0:LM) :: FLXU_INT, FLXD_INT, FLCU_INT, FLCD_INT, DFDTS, DFDTSC
+   real, pointer, dimension(:,:,:) :: FLX, FLC, FLXU, FLCU, FLXD, FLCD, FLXA, FLA, FLXAU, FLAU, FLXAD, FLAD
+   real, pointer, dimension(:,:) :: OLR, OLC, SFCEM, LWS, LCS, FLNS, FLNSC, DSFDTS, OLCC5, LCSC5, OLRA, OLA, LWSA, LAS, &
+      FLNSNA, FLNSA
+   integer :: K
+   real :: DELT(IM,JM), FLX_INT(IM,JM,0:LM), FLC_INT(IM,JM,0:LM)
+"""
+
+
 def available():
     return os.path.isfile(IRR) and os.path.isfile(SOL)
 
@@ -122,6 +140,10 @@ def source_text():
         + "end subroutine sol_prep\nend module refglue_sol_prep\n",
         _SOL_FIN_HEAD + _lines(SOL, 6395, 6454, "SWUFLXR (:,1:LM+1) = SWUFLX (:,LM+1:1:-1)", "FSCU = SWUFLXCR")
         + "end subroutine sol_fin\nend module refglue_sol_fin\n",
+        # the between-refresh update of the LW exports: net fluxes (:3604, :3606), DELT (:3861), the USE_RRTMG branch
+        _IRR_UPD_HEAD + _lines(IRR, 3604, 3604, "FLX_INT  = FLXD_INT  + FLXU_INT", "FLX_INT") + _lines(IRR, 3606, 3606, "FLC_INT  = FLCD_INT  + FLCU_INT", "FLC_INT")
+        + _lines(IRR, 3861, 3861, "DELT = TSINST - TS_INT", "DELT") + _lines(IRR, 3932, 3992, "do K = 0, LM", "if(associated(FLNSA )) FLNSA  = MAPL_UNDEF")
+        + "end subroutine irr_upd\nend module refglue_irr_upd\n",
     ]
     return parts
 
@@ -258,6 +280,28 @@ def solar_finish(n, o):
         *[v1[k] for k in ("cldts", "cldhs", "cldms", "cldls", "cottp", "cothp", "cotmp", "cotlp")],
         *[v2[k] for k in ("fsw", "fsc", "fswu", "fscu")])
     res = {k: v.a for k, v in {**v1, **v2}.items()}
+    return res
+
+
+@_quiet
+def irrad_update(f, ts_int, tsinst, undef=1e15, cldtt=None):
+    """IRR:3604, 3606, 3861, 3932-3992 on the refresh outputs `f` (irrad_finish's dictionary): every export of the
+    USE_RRTMG branch that is not a no-aerosol diagnostic (those are MAPL_UNDEF fills and stay unassociated)."""
+    ns = namespace()
+    nc, lm1 = f["flxu"].shape
+    lm = lm1 - 1
+    g3 = lambda k: FA(np.array(f[k], dtype=np.float64, order="F").reshape(nc, 1, lm1, order="F"), (1, 1, 0))
+    o3 = {k: _z((nc, 1, lm1), (1, 1, 0)) for k in ("flx", "flc", "flxu", "flcu", "flxd", "flcd")}
+    o2 = {k: _z((nc, 1)) for k in ("olr", "olc", "sfcem", "lws", "lcs", "flns", "flnsc", "dsfdts", "olcc5", "lcsc5")}
+    ct = _f(cldtt if cldtt is not None else np.zeros(nc), (nc, 1))
+    ns["P_refglue_irr_upd__irr_upd"](
+        nc, 1, lm, float(undef), _f(tsinst, (nc, 1)), _f(ts_int, (nc, 1)), g3("flxu"), g3("flxd"), g3("flcu"), g3("flcd"),
+        g3("dfdts"), g3("dfdtsc"), _f(f["sfcem"], (nc, 1)), ct,
+        *[o3[k] for k in ("flx", "flc", "flxu", "flcu", "flxd", "flcd")],
+        *[o2[k] for k in ("olr", "olc", "sfcem", "lws", "lcs", "flns", "flnsc", "dsfdts", "olcc5", "lcsc5")],
+        *([None] * 12))
+    res = {k: v.a[:, 0, :] for k, v in o3.items()}
+    res.update({k: v.a[:, 0] for k, v in o2.items()})
     return res
 
 

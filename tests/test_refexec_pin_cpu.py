@@ -178,3 +178,27 @@ def test_oracle_glue_equals_the_reference_lines_live(oracle, iceflg, liqflg):
     r, o = glue.solar_finish(n, sw), oracle.solar_finish(n, sw)
     for k in r:
         np.testing.assert_array_equal(r[k], o[k], err_msg=f"solar finish {k}")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("REFERENCE_ROOT", "/root/reference")), reason="no reference tree on this machine")
+def test_oracle_irrad_update_equals_the_reference_lines_live(oracle):
+    """The between-refresh update of the LW exports (GEOS_IrradGridComp.F90:3604, 3606, 3861 and the USE_RRTMG branch
+    :3932-3992, read from the file and executed with its export pointers associated): all thirteen exports the library's
+    rrtmgx_irrad_update produces, bit for bit, plus the MAPL_UNDEF rule of the cloud-free composites."""
+    from geosradiation_gridcomp_b200.synthetic import make_native_state
+    from oracle.refexec import glue
+    n = make_native_state(16, 72, seed=28)
+    f = oracle.irrad_finish(n, oracle.rrtmg_lw(oracle.irrad_prepare(n)))
+    rng = np.random.default_rng(5)
+    ts_int = np.asfortranarray(n["ts"])
+    tsinst = np.asfortranarray(n["ts"] + rng.normal(0, 1.5, n["ncol"]))
+    r = glue.irrad_update(f, ts_int, tsinst, undef=n["undef"], cldtt=f["cldtt"])
+    o = oracle.irrad_update(f, ts_int, tsinst)
+    assert len(o) == 13
+    for k in o:
+        np.testing.assert_array_equal(r[k], o[k], err_msg=k)
+    np.testing.assert_array_equal(r["dsfdts"], -f["dfdts"][:, -1])
+    clear = f["cldtt"] <= 0.05
+    assert clear.any() and (~clear).any()
+    np.testing.assert_array_equal(r["olcc5"][clear], r["olc"][clear])
+    assert (r["olcc5"][~clear] == n["undef"]).all()
