@@ -821,13 +821,15 @@ int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *a, const RrtmgxSwNoAerosol *na)
                                         seed_order);
     const RrtmgxTaps *taps = p.has_taps ? &p.taps : nullptr;
     const bool dbg = taps && (taps->taug || taps->pfracs || taps->ssi);
-    const size_t per_col = sw_scratch_bytes(1024, nlay, dbg) / 1024;
-    size_t chunk = pick_chunk(ncol, nlay, per_col + (!staged ? 0 : 2 * (size_t)(57 * nlay + 60) * 8), staged, p.slab.cap);
+    const bool radval = a->radval != nullptr;   // the SOLAR_RADVAL build of rrtmg_sw (include/rrtmgx.h)
+    const size_t per_col = sw_scratch_bytes(1024, nlay, dbg, radval) / 1024;
+    size_t chunk = pick_chunk(ncol, nlay, per_col + (!staged ? 0 : 2 * (size_t)(57 * nlay + 60 + (radval ? RRTMGX_NRADVAL : 0)) * 8),
+                              staged, p.slab.cap);
     if (taps) {   // taps are laid out for the whole call
         if ((size_t)ncol > chunk_cap(nlay)) return RRTMGX_EARG;
         chunk = (size_t)ncol;
     }
-    if (int rc = grow(p.slab, sw_scratch_bytes((int)chunk, nlay, dbg))) return rc;
+    if (int rc = grow(p.slab, sw_scratch_bytes((int)chunk, nlay, dbg, radval))) return rc;
     cudaStream_t stream = (!staged && a->stream) ? (cudaStream_t)a->stream : p.stream;
     p.run_stream = stream;
     if (!(devptr && (a->flags & RRTMGX_KEEP_STATUS)) &&
@@ -905,6 +907,7 @@ int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *a, const RrtmgxSwNoAerosol *na)
     out(a->cotdlp, &ca.cotdlp, 1); out(a->cotntp, &ca.cotntp, 1); out(a->cotnhp, &ca.cotnhp, 1);
     out(a->cotnmp, &ca.cotnmp, 1); out(a->cotnlp, &ca.cotnlp, 1);
     if (a->do_drfband) { out(a->drband, &ca.drband, 14); out(a->dfband, &ca.dfband, 14); }
+    if (radval) out(a->radval, &ca.radval, RRTMGX_NRADVAL);
     if (na) {
         for (int k = 0; k < 4; ++k) arrs.push_back({d_na[k], (void **)&d_na[k], L1, esz, false, false, true, f32});
         arrs.push_back({d_na[4], (void **)&d_na[4], 14, esz, false, false, true, f32});
@@ -953,6 +956,7 @@ void carve_sw_args(Slab &s, int nc, int L, RrtmgxSwArgs &a) {
     a.cotdtp = D(nc); a.cotdhp = D(nc); a.cotdmp = D(nc); a.cotdlp = D(nc);
     a.cotntp = D(nc); a.cotnhp = D(nc); a.cotnmp = D(nc); a.cotnlp = D(nc);
     a.drband = nullptr; a.dfband = nullptr;
+    a.radval = nullptr;
 }
 template <class A, class Carve> size_t carve_bytes(int nc, int L, Carve carve) {
     Slab s;

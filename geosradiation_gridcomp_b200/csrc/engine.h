@@ -89,6 +89,7 @@ struct CloudCache {
     long long first = -1, total = -1;
     int nc = 0, nlay = 0;
     bool perm = false, valid = false;
+    bool radval = false;   // SW: the SOLAR_RADVAL layer sums of the chunk were formed with the clouds
     bool matches(const char *b, const ChunkId &id, int nc_, int nlay_) const {
         return valid && base == b && first == id.first && total == id.total && nc == nc_ && nlay == nlay_;
     }
@@ -110,7 +111,7 @@ void lw_read_env();   // RRTMGX_LW_GN (called once per rrtmgx_init, under the li
 
 // ---- SW ------------------------------------------------------------------------------------
 int sw_upload_tables(const HostTables &ht, const double *d_arena);
-size_t sw_scratch_bytes(int nc, int nlay, bool debug);
+size_t sw_scratch_bytes(int nc, int nlay, bool debug, bool radval = false);
 struct SwSolar {                  // host-evaluated scalars of rrtmg_sw_sub :889-1127
     double adjflux[14];           // adjes (* solvar) per band
     double svar_f, svar_s, svar_i;

@@ -23,6 +23,7 @@ module rrtmgx_c
                                 RRTMGX_KEEP_STATUS = 8, RRTMGX_REUSE_CLOUDS = 16, RRTMGX_F32_ARRAYS = 32, &
                                 RRTMGX_LIT_ONLY = 64
    ! what every shim ORs into `flags`: the element kind of the caller's real arrays
+   integer, parameter :: RRTMGX_NRADVAL = 120   ! the SOLAR_RADVAL dummies of rrtmg_sw (rrtmg_sw_rad.F90:85-122)
    integer(c_int), parameter :: rrtmgx_real_flags = merge(0_c_int, RRTMGX_F32_ARRAYS, rrtmgx_real_kind == c_double)
 
    type, bind(C) :: rrtmgx_config
@@ -76,6 +77,7 @@ module rrtmgx_c
       type(c_ptr) :: fswband
       type(c_ptr) :: cotdtp, cotdhp, cotdmp, cotdlp, cotntp, cotnhp, cotnmp, cotnlp
       type(c_ptr) :: drband, dfband
+      type(c_ptr) :: radval   ! c_null_ptr, or (ncol,RRTMGX_NRADVAL): the SOLAR_RADVAL build
    end type
 
    ! fused Run-phase glue; field order == RrtmgxIrradArgs in include/rrtmgx.h

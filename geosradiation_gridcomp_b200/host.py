@@ -77,7 +77,15 @@ class SwArgs(C.Structure):
                                         "cloudLM", "cloudMH", "iaer", "normFlx", "do_drfband", "flags")] +
                 [("stream", _vp), ("scon", C.c_double), ("adjes", C.c_double), ("bndscl", _vp),
                  ("indsolvar", _vp), ("solcycfrac", _vp)] +
-                [(n, _vp) for n in _SW_IN] + [("clearCounts", _vp)] + [(n, _vp) for n in _SW_OUT])
+                [(n, _vp) for n in _SW_IN] + [("clearCounts", _vp)] + [(n, _vp) for n in _SW_OUT] + [("radval", _vp)])
+
+
+# The SOLAR_RADVAL dummies of rrtmg_sw in the order of its argument list (SW/src/rrtmg_sw_rad.F90:85-122; include/rrtmgx.h
+# RRTMGX_RADVAL_FAMILIES): column q of the (ncol,120) `radval` array is RADVAL_NAMES[q].
+NRADVAL = 120
+RADVAL_FAMILIES = ("cds", "cotl", "cdsl", "coti", "cdsi", "ssal", "sdsl", "ssai", "sdsi", "asml", "adsl", "asmi", "adsi",
+                   "forl", "fori")
+RADVAL_NAMES = tuple(f + dn + lev + "p" for f in RADVAL_FAMILIES for dn in "dn" for lev in "thml")
 
 
 # ---- fused Run-phase glue (include/rrtmgx.h: RrtmgxIrradArgs, RrtmgxSolarArgs) ---------------------
@@ -366,9 +374,11 @@ def rrtmg_sw(rpart, ncol, nlay, scon, adjes, coszen, isolvar, play, plev, tlay, 
              nirr, nirf, parr, parf, uvrr, uvrf, fswband, cotdtp, cotdhp, cotdmp, cotdlp, cotntp, cotnhp, cotnmp,
              cotnlp, do_drfband=False, drband=None, dfband=None, bndscl=None, indsolvar=None, solcycfrac=None, *,
              device=False, stream=None, sync=True, skip_checks=False, reuse_clouds=False, f32=False, taps=(),
-             clean=None):
+             clean=None, radval=None):
     """Drop-in for `rrtmg_sw` (SW/src/rrtmg_sw_rad.F90:68-124) without the MAPL handle (used by
-    the reference only for timers and asserts).  Outputs are written in place."""
+    the reference only for timers and asserts).  Outputs are written in place.
+    radval: an (ncol,120) array (column fastest) selects the SOLAR_RADVAL build and receives its extra dummies
+    (:85-122) in RADVAL_NAMES order."""
     if not _initialised:
         init()
     keep = []
@@ -392,6 +402,8 @@ def rrtmg_sw(rpart, ncol, nlay, scon, adjes, coszen, isolvar, play, plev, tlay, 
     for n in _SW_IN + _SW_OUT:
         setattr(a, n, _addr(loc[n], device, dtype=rk, keep=keep))
     a.clearCounts = _addr(clearCounts, device, dtype=np.int32, keep=keep)
+    if radval is not None:
+        a.radval = _addr(radval, device, dtype=rk, keep=keep)
     t, tout = (None, {})
     if taps:
         t, tout = _new_taps(taps, ncol, nlay, NGPTSW)
@@ -658,9 +670,13 @@ def alloc_sw_outputs(ncol, nlay):
 
 
 def run_sw(s, rpart=0, isolvar=0, iceflg=3, liqflg=1, iaer=10, normFlx=1, do_drfband=False, taps=(), out=None,
-           bndscl=None, indsolvar=None, solcycfrac=None, **kw):
-    """rrtmg_sw on a synthetic.make_columns state; returns the output dict (+ taps)."""
+           bndscl=None, indsolvar=None, solcycfrac=None, radval=False, **kw):
+    """rrtmg_sw on a synthetic.make_columns state; returns the output dict (+ taps).
+    radval=True: the SOLAR_RADVAL build, the result gains "radval" (ncol,120)."""
     o = out if out is not None else alloc_sw_outputs(s["ncol"], s["nlay"])
+    if radval:
+        o.setdefault("radval", np.zeros((s["ncol"], NRADVAL), order="F"))
+        kw["radval"] = o["radval"]
     t = rrtmg_sw(rpart, s["ncol"], s["nlay"], s["scon"], s["adjes"], s["coszen"], isolvar, s["play"], s["plev"],
                  s["tlay"], s["h2ovmr"], s["o3vmr"], s["co2vmr"], s["ch4vmr"], s["o2vmr"], iceflg, liqflg,
                  s["cldf"], s["ciwp"], s["clwp"], s["rei"], s["rel"], s["dyofyr"], s["zm"], s["alat"], iaer,

@@ -184,7 +184,22 @@ typedef struct {
     double *cotdtp, *cotdhp, *cotdmp, *cotdlp;        /* (ncol)                               */
     double *cotntp, *cotnhp, *cotnmp, *cotnlp;        /* (ncol)                               */
     double *drband, *dfband;                          /* (ncol,14), touched iff do_drfband    */
+    double *radval;           /* NULL: the default build.  Otherwise the SOLAR_RADVAL build of rrtmg_sw      */
+                              /* (GEOSsolar_GridComp/CMakeLists.txt:18-20): (ncol,RRTMGX_NRADVAL) receives   */
+                              /* its 120 extra dummies, column fastest, in the order of the dummy list       */
+                              /* (rrtmg_sw_rad.F90:85-122), see RRTMGX_RADVAL_FAMILIES below                 */
 } RrtmgxSwArgs;
+
+/* The SOLAR_RADVAL diagnostics (rrtmg_sw_rad.F90:85-122, 306-345; formed in rrtmg_sw_spcvmc.F90:681-1105 from the
+ * phase-split cloud optics of rrtmg_sw_cldprmc.F90:38-47): PAR-weighted sums over the McICA subcolumns of bands
+ * 24-26 for the Tot|High|Mid|Low pressure super-layers, fifteen families of eight,
+ *   <family>{d,n}{t,h,m,l}p  ->  radval(:, 8*family + 4*(d=0,n=1) + (t=0,h=1,m=2,l=3)),
+ * families in this order: cds (delta-scaled in-cloud optical thickness); cotl, cdsl, coti, cdsi (liquid / ice,
+ * original / delta-scaled thickness); ssal, sdsl, ssai, sdsi (single-scattering albedo, tau weighted); asml, adsl,
+ * asmi, adsi (asymmetry, tau*ssa weighted); forl, fori (forward-scattering fraction, tau*ssa weighted).  A ratio
+ * n/d is the diagnosed mean; cloud-free columns hold zeros. */
+enum { RRTMGX_NRADVAL = 120 };
+#define RRTMGX_RADVAL_FAMILIES "cds cotl cdsl coti cdsi ssal sdsl ssai sdsi asml adsl asmi adsi forl fori"
 
 int rrtmgx_lw_run(const RrtmgxLwArgs *a);
 

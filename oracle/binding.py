@@ -29,7 +29,7 @@ class Taps(C.Structure):
     _fields_ = [(n, _ip) for n in ("jp", "jt", "jt1", "indfor", "indself", "indminor", "laytrop")] + \
                [(n, _dp) for n in ("fac00", "fac01", "fac10", "fac11")] + \
                [("cldymc", _up)] + \
-               [(n, _dp) for n in ("ciwpmc", "clwpmc", "taug", "pfracs", "taucmc", "pwvcm", "ssi")]
+               [(n, _dp) for n in ("ciwpmc", "clwpmc", "taug", "pfracs", "taucmc", "pwvcm", "ssi", "radval")]
 
 
 _lib = None
@@ -115,6 +115,8 @@ def _make_taps(want, ncol, nlay, ngpt):
             a = np.zeros(ncol, dtype=np.float64)
         elif name == "ssi":
             a = np.zeros((ncol, ngpt), dtype=np.float64)
+        elif name == "radval":   # the SOLAR_RADVAL dummies of rrtmg_sw, (ncol,120) column fastest
+            a = np.zeros((ncol, 120), dtype=np.float64, order="F")
         else:
             a = np.zeros((ncol, ngpt, nlay), dtype=np.float64)       # [icol][ig][ilay]
         out[name] = a
@@ -148,7 +150,10 @@ def rrtmg_lw(s, psize=4, dudTs=True, iceflg=3, liqflg=1, taps=()):
 
 
 def rrtmg_sw(s, rpart=0, isolvar=0, iceflg=3, liqflg=1, iaer=10, normFlx=1, do_drfband=False,
-             taps=(), bndscl=None, indsolvar=None, solcycfrac=None):
+             taps=(), bndscl=None, indsolvar=None, solcycfrac=None, radval=False):
+    """radval: the SOLAR_RADVAL build (SW/src/rrtmg_sw_rad.F90:85-122); the result gains "radval" (ncol,120)."""
+    if radval:
+        taps = tuple(taps) + ("radval",)
     ncol, nlay = s["ncol"], s["nlay"]
     o = {k: np.zeros((ncol, nlay + 1), order="F") for k in ("swuflx", "swdflx", "swuflxc", "swdflxc")}
     for k in ("nirr", "nirf", "parr", "parf", "uvrr", "uvrf", "cotdtp", "cotdhp", "cotdmp", "cotdlp",

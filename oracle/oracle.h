@@ -41,6 +41,9 @@ typedef struct {
     double *taucmc;                    /* [icol][ig][ilay] (LW: absorption od; SW: delta-scaled) */
     double *pwvcm;                     /* (ncol) LW only                                  */
     double *ssi;                       /* SW: [icol][ig] solar source per g-point          */
+    double *radval;                    /* SW, not a tap but a switch: non-NULL runs the SOLAR_RADVAL build of
+                                        * rrtmg_sw and receives its 120 extra dummies (SW/src/rrtmg_sw_rad.F90:85-122),
+                                        * (ncol,120) column fastest, in the order of the dummy list               */
 } OracleTaps;
 
 int oracle_init(const char *blob_path);
@@ -68,7 +71,7 @@ int oracle_rrtmg_lw(
     const int *band_output, double *olrb, double *dolrb_dTs,
     OracleTaps *taps);
 
-/* SW/src/rrtmg_sw_rad.F90:68-1801 (non-SOLAR_RADVAL build).  bndscl/indsolvar/solcycfrac may
+/* SW/src/rrtmg_sw_rad.F90:68-1801 (the default build; the SOLAR_RADVAL build when taps->radval is set).  bndscl/indsolvar/solcycfrac may
  * be NULL (absent optional arguments). drband/dfband only touched when do_drfband. */
 int oracle_rrtmg_sw(
     int rpart, int ncol, int nlay,

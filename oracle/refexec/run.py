@@ -10,7 +10,8 @@ Call sequence = oracle/ref_recipe/ref_capi.F90 (the wrappers a compiled oracle/_
   init:  rrtmg_lw_ini, rrtmg_sw_ini (LW/src/rrtmg_lw_init.F90, SW/src/rrtmg_sw_init.F90), unset_inhomogeneity,
          set_inhomogeneity(ih) (SH/cloud_condensate_inhomogeneity.F90)
   LW:    rrtmg_lw  (LW/src/rrtmg_lw_rad.F90:15)
-  SW:    rrtmg_sw  (SW/src/rrtmg_sw_rad.F90:68; SOLAR_RADVAL undefined; MAPL timers are no-ops)
+  SW:    rrtmg_sw  (SW/src/rrtmg_sw_rad.F90:68; MAPL timers are no-ops; SOLAR_RADVAL undefined, or defined in a second
+         translation of the same files: rrtmg_sw(..., radval=True))
 """
 import glob
 import os
@@ -27,6 +28,8 @@ SH = os.path.join(REF, "GEOS_RadiationShared")
 
 _ns = None
 _ih = None
+_ns_rv = None   # the same sources translated with SOLAR_RADVAL defined (GEOSsolar_GridComp/CMakeLists.txt:18-20)
+_ih_rv = None
 
 
 def available():
@@ -41,9 +44,21 @@ def sources():
     return fs
 
 
-def namespace(ih=1):
-    """Translate once, run the reference's init routines, select the condensate inhomogeneity option."""
-    global _ns, _ih
+def namespace(ih=1, radval=False):
+    """Translate once, run the reference's init routines, select the condensate inhomogeneity option.
+    radval: the translation with the SOLAR_RADVAL compile-time flag (a second, independent set of module state)."""
+    global _ns, _ih, _ns_rv, _ih_rv
+    if radval:
+        if _ns_rv is None:
+            _ns_rv = f90py.load(sources(), defines=("SOLAR_RADVAL",))
+            _ns_rv["P_rrtmg_lw_init__rrtmg_lw_ini"]()
+            _ns_rv["P_rrtmg_sw_init__rrtmg_sw_ini"]()
+        if _ih_rv != ih:
+            _ns_rv["P_cloud_condensate_inhomogeneity__unset_inhomogeneity"]()
+            if ih > 0:
+                _ns_rv["P_cloud_condensate_inhomogeneity__set_inhomogeneity"](int(ih))
+            _ih_rv = ih
+        return _ns_rv
     if _ns is None:
         _ns = f90py.load(sources())
         _ns["P_rrtmg_lw_init__rrtmg_lw_ini"]()
@@ -210,9 +225,19 @@ def rrtmg_lw(s, psize=4, dudTs=True, iceflg=3, liqflg=1, ih=1):
     return out
 
 
+# The SOLAR_RADVAL dummies of rrtmg_sw in the order of its argument list (SW/src/rrtmg_sw_rad.F90:85-122): fifteen
+# families, each <family>{d,n}{t,h,m,l}p = denominator / numerator sums of the Tot|High|Mid|Low super-layers.
+RADVAL_FAMILIES = ("cds", "cotl", "cdsl", "coti", "cdsi", "ssal", "sdsl", "ssai", "sdsi", "asml", "adsl", "asmi", "adsi",
+                   "forl", "fori")
+RADVAL_NAMES = tuple(f + dn + lev + "p" for f in RADVAL_FAMILIES for dn in "dn" for lev in "thml")
+
+
 def rrtmg_sw(s, rpart=0, isolvar=0, iceflg=3, liqflg=1, iaer=10, normFlx=1, do_drfband=False, bndscl=None,
-             indsolvar=None, solcycfrac=None, ih=1):
-    ns = namespace(ih)
+             indsolvar=None, solcycfrac=None, ih=1, radval=False):
+    """radval: call the SOLAR_RADVAL build of rrtmg_sw; the result gains "radval" (ncol, 120), columns in
+    RADVAL_NAMES order."""
+    ns = namespace(ih, radval)
+    rv = [_z(int(s["ncol"])) for _ in RADVAL_NAMES] if radval else []
     ncol, nlay = int(s["ncol"]), int(s["nlay"])
     prof = {k: _z(ncol, nlay + 1) for k in ("swuflx", "swdflx", "swuflxc", "swdflxc")}
     sfc = {k: _z(ncol) for k in ("nirr", "nirf", "parr", "parf", "uvrr", "uvrf")}
@@ -234,8 +259,10 @@ def rrtmg_sw(s, rpart=0, isolvar=0, iceflg=3, liqflg=1, iaer=10, normFlx=1, do_d
         _f(s["asdir"]), _f(s["asdif"]), _f(s["aldir"]), _f(s["aldif"]), int(s["cloudLM"]), int(s["cloudMH"]), int(normFlx),
         cc, *[prof[k] for k in ("swuflx", "swdflx", "swuflxc", "swdflxc")],
         *[sfc[k] for k in ("nirr", "nirf", "parr", "parf", "uvrr", "uvrf")], fswband,
-        *[cot[k] for k in ("cotdtp", "cotdhp", "cotdmp", "cotdlp", "cotntp", "cotnhp", "cotnmp", "cotnlp")],
+        *[cot[k] for k in ("cotdtp", "cotdhp", "cotdmp", "cotdlp", "cotntp", "cotnhp", "cotnmp", "cotnlp")], *rv,
         bool(do_drfband), drb, dfb, rc=0, **kw)
     out = {k: v.a for k, v in {**prof, **sfc, **cot}.items()}
+    if radval:
+        out["radval"] = np.stack([v.a for v in rv], axis=1)
     out.update(clearCounts=cc.a.astype(np.int32), fswband=fswband.a, drband=drb.a, dfband=dfb.a, ret=r)
     return out

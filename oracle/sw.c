@@ -212,11 +212,18 @@ static int solar_setup(Solar *S, int isolvar, double scon, double adjes, const d
 #define CT(tab, lead, i, ib) (tab)[((i)-1) + (size_t)(lead) * ((ib)-16)]
 #define LIN_CT(tab, lead, i, ib, f) (CT(tab, lead, i, ib) + (f) * (CT(tab, lead, (i) + 1, ib) - CT(tab, lead, i, ib)))
 
+/* The phase-split McICA cloud optical properties cldprmc_sw hands out in the SOLAR_RADVAL build
+ * (SW/src/rrtmg_sw_cldprmc.F90:38-47, 84-92): liquid / ice, original ("or") and delta-scaled ("c") optical depth,
+ * single-scattering albedo, asymmetry, and the forward-scattering fractions. */
+enum { RV_LTAOR, RV_LOMOR, RV_LASOR, RV_LTAUC, RV_LOMGC, RV_LASYC, RV_ITAOR, RV_IOMOR, RV_IASOR, RV_ITAUC, RV_IOMGC,
+       RV_IASYC, RV_FORWL, RV_FORWI, RV_CELL_COUNT };
+enum { RV_NOUT = 120 };   /* the SOLAR_RADVAL dummies of rrtmg_sw, SW/src/rrtmg_sw_rad.F90:85-122 */
+
 /* SW/src/rrtmg_sw_cldprmc.F90:36-418 */
 static int cldprmc_sw(int ncol, int nlay, int iceflag, int liqflag, const unsigned char *cldymc,
                       const double *ciwpmc, const double *clwpmc, const double *reicmc,
                       const double *relqmc, double *taormc, double *taucmc, double *ssacmc,
-                      double *asmcmc) {
+                      double *asmcmc, double *const *rv /* SOLAR_RADVAL (:38-47, :84-92): NULL or RV_CELL_COUNT arrays */) {
     const SwTables *T = &g_sw;
     const double epsg = 1.e-06, cldmin = 1.e-20;
     if (iceflag < 1 || iceflag > 4) return -41;
@@ -228,6 +235,12 @@ static int cldprmc_sw(int ncol, int nlay, int iceflag, int liqflag, const unsign
                 const size_t k = I3(lay, ig, icol);
                 if (!cldymc[k]) {
                     taormc[k] = 0.; taucmc[k] = 0.; ssacmc[k] = 1.; asmcmc[k] = 0.;
+                    if (rv) { /* :394-412; forwliq / forwice are left unset by the reference (0 here) */
+                        rv[RV_LTAOR][k] = 0.; rv[RV_LOMOR][k] = 1.; rv[RV_LASOR][k] = 0.;
+                        rv[RV_LTAUC][k] = 0.; rv[RV_LOMGC][k] = 1.; rv[RV_LASYC][k] = 0.;
+                        rv[RV_ITAOR][k] = 0.; rv[RV_IOMOR][k] = 1.; rv[RV_IASOR][k] = 0.;
+                        rv[RV_ITAUC][k] = 0.; rv[RV_IOMGC][k] = 1.; rv[RV_IASYC][k] = 0.;
+                    }
                     continue;
                 }
                 double extcoice, ssacoice, gice, forwice;
@@ -301,6 +314,16 @@ static int cldprmc_sw(int ncol, int nlay, int iceflag, int liqflag, const unsign
                 const double scatliq = ssaliq * tauliq;
                 double scatice = ssaice * tauice;
                 taucmc[k] = tauliq + tauice;
+                if (rv) { /* phase-split properties, original and delta-scaled, :321-328, :342-351 */
+                    rv[RV_LTAOR][k] = tauliqorig; rv[RV_ITAOR][k] = tauiceorig;
+                    rv[RV_LOMOR][k] = ssacoliq; rv[RV_IOMOR][k] = ssacoice;
+                    rv[RV_LASOR][k] = gliq; rv[RV_IASOR][k] = gice;
+                    rv[RV_LTAUC][k] = tauliq; rv[RV_ITAUC][k] = tauice;
+                    rv[RV_LOMGC][k] = ssaliq; rv[RV_IOMGC][k] = ssaice;
+                    rv[RV_LASYC][k] = (gliq - forwliq) / (1. - forwliq);
+                    rv[RV_IASYC][k] = (gice - forwice) / (1. - forwice);
+                    rv[RV_FORWL][k] = forwliq; rv[RV_FORWI][k] = forwice;
+                }
                 if (taucmc[k] == 0.) taucmc[k] = cldmin;
                 if (scatice == 0.) scatice = cldmin;
                 ssacmc[k] = (scatliq + scatice) / taucmc[k];
@@ -1012,6 +1035,64 @@ typedef struct {
     double *zsflxzen, *ssi;                                              /* (ngpt,pncol) */
 } SpcWork;
 
+/* The SOLAR_RADVAL part of the PAR super-layer diagnostics for one (column, g-point), SW/src/rrtmg_sw_spcvmc.F90:
+ * low layer :784-868, mid :872-956, high :960-1044, whole subcolumn :1048-1105.  Per super-layer fifteen layer sums:
+ *   0 stau                                   sum(ptaucmc)
+ *   1 sltao   2 sltaossa   3 sltaossag       liquid, original:      tau, tau*om, tau*om*as
+ *   4 sltau   5 sltaussa   6 sltaussag  7 sltaussaf   liquid, delta-scaled: tau, tau*om, tau*om*as, tau*om*forw
+ *   8 sitao   9 sitaossa  10 sitaossag;     11 sitau 12 sitaussa 13 sitaussag 14 sitaussaf    the same for ice
+ * (the weighted sums of a family are formed only where its optical depth sum is > 0, else 0), and fifteen output
+ * families in the order of the dummy list, each {d,n}{t,h,m,l}p: (test sum, what the "d" member accumulates beside
+ * wgt, what the "n" member accumulates).  z addresses column i of zrv; rows are pncol apart. */
+static const struct { int test, d, n; } rv_family[15] = {
+    {0, -1, 0},                                            /* cds                      */
+    {1, -1, 1}, {4, -1, 4}, {8, -1, 8}, {11, -1, 11},      /* cotl, cdsl, coti, cdsi   */
+    {1, 1, 2}, {4, 4, 5}, {8, 8, 9}, {11, 11, 12},         /* ssal, sdsl, ssai, sdsi   */
+    {1, 2, 3}, {4, 5, 6}, {8, 9, 10}, {11, 12, 13},        /* asml, adsl, asmi, adsi   */
+    {4, 5, 7}, {11, 12, 14}};                              /* forl, fori               */
+
+static void radval_sums(double *const *rv, const double *ptaucmc, int nlay, int cloudLM, int cloudMH, int iw, int icol,
+                        double wgt, double *z, int pncol) {
+    double S[4][15];   /* 0 whole subcolumn, 1 high, 2 mid, 3 low: the {t,h,m,l} order of the outputs */
+    const int first[4] = {0, cloudMH + 1, cloudLM + 1, 1}, last[4] = {0, nlay, cloudMH, cloudLM};
+    for (int L = 3; L >= 1; --L) {
+        double *s = S[L];
+        for (int q = 0; q < 15; ++q) s[q] = 0.;
+        for (int lay = first[L]; lay <= last[L]; ++lay) s[0] = s[0] + ptaucmc[I3(lay, iw, icol)];
+        for (int ph = 0; ph < 2; ++ph) {   /* liquid, ice */
+            const double *tao = rv[ph ? RV_ITAOR : RV_LTAOR], *omo = rv[ph ? RV_IOMOR : RV_LOMOR],
+                         *aso = rv[ph ? RV_IASOR : RV_LASOR], *tau = rv[ph ? RV_ITAUC : RV_LTAUC],
+                         *omg = rv[ph ? RV_IOMGC : RV_LOMGC], *asy = rv[ph ? RV_IASYC : RV_LASYC],
+                         *forw = rv[ph ? RV_FORWI : RV_FORWL];
+            double *o = s + 1 + 7 * ph;
+            for (int lay = first[L]; lay <= last[L]; ++lay) o[0] = o[0] + tao[I3(lay, iw, icol)];
+            if (o[0] > 0.)
+                for (int lay = first[L]; lay <= last[L]; ++lay) {
+                    const size_t k = I3(lay, iw, icol);
+                    o[1] = o[1] + tao[k] * omo[k];
+                    o[2] = o[2] + tao[k] * omo[k] * aso[k];
+                }
+            for (int lay = first[L]; lay <= last[L]; ++lay) o[3] = o[3] + tau[I3(lay, iw, icol)];
+            if (o[3] > 0.)
+                for (int lay = first[L]; lay <= last[L]; ++lay) {
+                    const size_t k = I3(lay, iw, icol);
+                    o[4] = o[4] + tau[k] * omg[k];
+                    o[5] = o[5] + tau[k] * omg[k] * asy[k];
+                    o[6] = o[6] + tau[k] * omg[k] * forw[k];
+                }
+        }
+    }
+    for (int q = 0; q < 15; ++q) S[0][q] = S[3][q] + S[2][q] + S[1][q];   /* lp + mp + hp, :1048-1090 */
+    for (int L = 0; L < 4; ++L)
+        for (int f = 0; f < 15; ++f) {
+            if (!(S[L][rv_family[f].test] > 0.)) continue;
+            double *zd = z + (size_t)(f * 8 + L) * pncol, *zn = z + (size_t)(f * 8 + 4 + L) * pncol;
+            *zd = *zd + (rv_family[f].d < 0 ? wgt : wgt * S[L][rv_family[f].d]);
+            *zn = *zn + wgt * S[L][rv_family[f].n];
+        }
+}
+
+
 static void spcvmc_sw(int cc, int ncol, int nlay, const SwCoef *sc, const Solar *S,
                       const double *palbd, const double *palbp, const unsigned char *pcldymc,
                       const double *ptaucmc, const double *pasycmc, const double *pomgcmc,
@@ -1020,7 +1101,9 @@ static void spcvmc_sw(int cc, int ncol, int nlay, const SwCoef *sc, const Solar 
                       SpcWork *W, double *pbbfd, double *pbbfu, double *pbbcd, double *pbbcu,
                       double *znirr, double *znirf, double *zparr, double *zparf, double *zuvrr,
                       double *zuvrf, double *fndsbnd /* (pncol,14) */, int pncol, double *zcot /* [8][pncol] */,
-                      int do_drfband, double *zdrband, double *zdfband, OracleTaps *taps, const int *gcols, int gncol) {
+                      int do_drfband, double *zdrband, double *zdfband, OracleTaps *taps, const int *gcols, int gncol,
+                      double *const *rv /* SOLAR_RADVAL: NULL or the RV_CELL_COUNT arrays of cldprmc_sw */,
+                      double *zrv /* [RV_NOUT][pncol] */) {
     const SwTables *T = &g_sw;
     const size_t np = (size_t)(nlay + 1) * pncol;
     memset(pbbcd, 0, np * 8); memset(pbbcu, 0, np * 8); memset(pbbfd, 0, np * 8); memset(pbbfu, 0, np * 8);
@@ -1164,6 +1247,7 @@ static void spcvmc_sw(int cc, int ncol, int nlay, const SwCoef *sc, const Solar 
     /* PAR-weighted in-cloud optical thickness per pressure super-layer (:748-1108); zcot rows:
      * 0 cotdtp 1 cotdhp 2 cotdmp 3 cotdlp 4 cotntp 5 cotnhp 6 cotnmp 7 cotnlp */
     for (int i = 0; i < 8 * pncol; ++i) zcot[i] = 0.;
+    if (rv) for (int i = 0; i < RV_NOUT * pncol; ++i) zrv[i] = 0.;   /* :681-745 */
     if (cc == 2)
         for (int icol = 1; icol <= ncol; ++icol)
             for (int iw = 1; iw <= NG; ++iw) {
@@ -1185,6 +1269,7 @@ static void spcvmc_sw(int cc, int ncol, int nlay, const SwCoef *sc, const Solar 
                 if (staohp > 0.) { zcot[1 * pncol + i] += wgt; zcot[5 * pncol + i] += wgt * staohp; }
                 const double staotp = staolp + staomp + staohp;
                 if (staotp > 0.) { zcot[0 * pncol + i] += wgt; zcot[4 * pncol + i] += wgt * staotp; }
+                if (rv) radval_sums(rv, ptaucmc, nlay, cloudLM, cloudMH, iw, icol, wgt, zrv + i, pncol);
             }
 #undef ZINCFLX
 }
@@ -1202,6 +1287,7 @@ typedef struct {
     int *clearCounts;
     double *swuflx, *swdflx, *swuflxc, *swdflxc, *nirr, *nirf, *parr, *parf, *uvrr, *uvrf,
         *fswband, *cot[8], *drband, *dfband;
+    double *radval;   /* SOLAR_RADVAL build: (gncol, RV_NOUT) or NULL */
 } SwOut;
 
 static int sw_partition(int cc, const int *gcols /* 0-based global columns */, int ncol, int gncol,
@@ -1242,6 +1328,9 @@ static int sw_partition(int cc, const int *gcols /* 0-based global columns */, i
 #undef TAKE
     (void)spare; (void)sp1; (void)sp2; (void)sp3;
     unsigned char *cldymcl = (unsigned char *)zalloc(n3);
+    double *rvbuf = out->radval ? (double *)zalloc(sizeof(double) * (n3 * RV_CELL_COUNT + (size_t)RV_NOUT * pncol)) : NULL;
+    double *rvcell[RV_CELL_COUNT], *zrv = rvbuf ? rvbuf + n3 * RV_CELL_COUNT : NULL;
+    for (int q = 0; q < RV_CELL_COUNT; ++q) rvcell[q] = rvbuf ? rvbuf + n3 * q : NULL;
     int *ibuf = (int *)zalloc(sizeof(int) * (n2 * 5 + (size_t)pncol * 5));
     SwCoef sc;
     sc.jp = ibuf; sc.jt = ibuf + n2; sc.jt1 = ibuf + 2 * n2; sc.indself = ibuf + 3 * n2; sc.indfor = ibuf + 4 * n2;
@@ -1305,13 +1394,14 @@ static int sw_partition(int cc, const int *gcols /* 0-based global columns */, i
         if (!rc) rc = oracle_clearCounts_threeBand(pncol, ncol, NG, nlay, cloudLM, cloudMH, cldymcl, p_clearCounts);
         if (!rc)
             rc = cldprmc_sw(ncol, nlay, iceflgsw, liqflgsw, cldymcl, ciwpmcl, clwpmcl, rei, rel, taormc, taucmc,
-                            ssacmc, asmcmc);
+                            ssacmc, asmcmc, rvbuf ? rvcell : NULL);
     }
     if (!rc) {
         setcoef_sw(&sc, ncol, nlay, play, tlay);
         spcvmc_sw(cc, ncol, nlay, &sc, S, albdif, albdir, cldymcl, taucmc, asmcmc, ssacmc, taormc, taua, asya,
                   omga, cossza, cloudLM, cloudMH, &W, zbbfd, zbbfu, zbbcd, zbbcu, znirr, znirf, zparr, zparf,
-                  zuvrr, zuvrf, fndsbnd, pncol, zcot, do_drfband, zdrband, zdfband, taps, gcols, gncol);
+                  zuvrr, zuvrf, fndsbnd, pncol, zcot, do_drfband, zdrband, zdfband, taps, gcols, gncol,
+                  rvbuf ? rvcell : NULL, zrv);
         for (int j = 0; j < ncol; ++j) {
             const size_t g = (size_t)gcols[j];
             for (int n = 0; n < 4; ++n)
@@ -1322,6 +1412,9 @@ static int sw_partition(int cc, const int *gcols /* 0-based global columns */, i
                 out->swuflx[d] = zbbfu[s]; out->swdflx[d] = zbbfd[s];
             }
             for (int q = 0; q < 8; ++q) out->cot[q][g] = cc == 1 ? 0. : zcot[(size_t)q * pncol + j];
+            if (out->radval)   /* SW/src/rrtmg_sw_rad.F90:1539-1603 (zeros), :1657-1726 */
+                for (int q = 0; q < RV_NOUT; ++q)
+                    out->radval[g + (size_t)gncol * q] = cc == 1 ? 0. : zrv[(size_t)q * pncol + j];
             out->nirr[g] = znirr[j]; out->nirf[g] = znirf[j] - znirr[j];
             out->parr[g] = zparr[j]; out->parf[g] = zparf[j] - zparr[j];
             out->uvrr[g] = zuvrr[j]; out->uvrf[g] = zuvrf[j] - zuvrr[j];
@@ -1358,7 +1451,7 @@ static int sw_partition(int cc, const int *gcols /* 0-based global columns */, i
                 }
             }
     }
-    free(buf); free(cldymcl); free(ibuf);
+    free(buf); free(cldymcl); free(ibuf); free(rvbuf);
     return rc;
 }
 
@@ -1410,7 +1503,8 @@ int oracle_rrtmg_sw(
     SwIn in = {coszen, play, plev, tlay, h2ovmr, o3vmr, co2vmr, ch4vmr, o2vmr, cld, ciwp, clwp, rei, rel,
                zm, alat, tauaer, ssaaer, asmaer, asdir, asdif, aldir, aldif};
     SwOut out = {clearCounts, swuflx, swdflx, swuflxc, swdflxc, nirr, nirf, parr, parf, uvrr, uvrf, fswband,
-                 {cotdtp, cotdhp, cotdmp, cotdlp, cotntp, cotnhp, cotnmp, cotnlp}, drband, dfband};
+                 {cotdtp, cotdhp, cotdmp, cotdlp, cotntp, cotnhp, cotnmp, cotnlp}, drband, dfband,
+                 taps ? taps->radval : NULL};
     int rc_all = 0;
     for (int cc = 1; cc <= 2; ++cc) {
         const int *list = cc == 1 ? gicol_clr : gicol_cld;

@@ -42,7 +42,7 @@ def run_case(name, c):
         if c["sw"] is not None:
             r = run.rrtmg_sw_taps(s, ih=c["ih"], **c["sw"]) if c["taps"] else run.rrtmg_sw(s, ih=c["ih"], **c["sw"])
             assert r["ret"][-1] == 0, r["ret"]
-            for k in SW_OUT + (tuple(SW_TAPS) if c["taps"] else ()):
+            for k in SW_OUT + (tuple(SW_TAPS) if c["taps"] else ()) + (("radval",) if c["sw"].get("radval") else ()):
                 out[f"{name}/sw/{k}"] = r[k]
     finally:
         if c["corr"] is not None:

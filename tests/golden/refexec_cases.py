@@ -43,6 +43,13 @@ CASES = {
     "mcica_ih0": _case(12, seed=41, ih=0, lw=dict(), sw=dict()),
     "mcica_ih2": _case(12, seed=41, ih=2, lw=dict(), sw=dict()),
     "mcica_corr": _case(12, seed=61, corr=CORR, lw=dict(), sw=dict()),
+    # the SOLAR_RADVAL build of rrtmg_sw (GEOSsolar_GridComp/CMakeLists.txt:18-20; SW/src/rrtmg_sw_rad.F90:85-122,
+    # rrtmg_sw_cldprmc.F90:38-47, rrtmg_sw_spcvmc.F90:681-1105): the 120 phase-split PAR super-layer diagnostics
+    "radval": _case(16, seed=31, sw=dict(radval=True, normFlx=0)),
+    "radval_ice1": _case(10, seed=67, sw=dict(radval=True, iceflg=1)),
+    "radval_ice2_m1": _case(10, seed=67, sw=dict(radval=True, iceflg=2, isolvar=-1)),
+    "radval_ice4_ih2": _case(10, seed=41, ih=2, sw=dict(radval=True, iceflg=4)),
+    "radval_l181": _case(6, nlay=181, seed=3, sw=dict(radval=True)),
 }
 
 LW_OUT = ("uflx", "dflx", "uflxc", "dflxc", "duflx_dTs", "duflxc_dTs", "olrb", "dolrb_dTs", "clearCounts")
@@ -96,6 +103,8 @@ def run_case(impl, name, set_mcica, reset_mcica, skip=()):
             assert r.get("rc", 0) == 0
             for k in SW_OUT:
                 out["sw/" + k] = r[k]
+            if c["sw"].get("radval"):
+                out["sw/radval"] = r["radval"]
             if c["taps"]:
                 for k, tap in SW_TAPS.items():
                     out["sw/" + k] = r[tap]

@@ -106,7 +106,7 @@ def test_ctypes_mirrors_match_the_compiled_header(tmp_path):
     against the ctypes mirrors of host.py (a drifted mirror would shift every pointer after the drift)."""
     import subprocess
     from geosradiation_gridcomp_b200 import host
-    pairs = [("RrtmgxLwArgs", host.LwArgs, "dolrb_dTs"), ("RrtmgxSwArgs", host.SwArgs, "dfband"),
+    pairs = [("RrtmgxLwArgs", host.LwArgs, "dolrb_dTs"), ("RrtmgxSwArgs", host.SwArgs, "radval"),
              ("RrtmgxIrradArgs", host.IrradArgs, "dolrb_dts"), ("RrtmgxSolarArgs", host.SolarArgs, "cotlp"),
              ("RrtmgxIrradUpdateArgs", host.IrradUpdateArgs, "flnsc"), ("RrtmgxLwVariants", host.LwVariants, "duflx_dTs"),
              ("RrtmgxSwNoAerosol", host.SwNoAerosol, "fswband"), ("RrtmgxTaps", host.Taps, "ssi"),
@@ -157,3 +157,22 @@ def test_fortran_shim_has_the_reference_argument_lists(ref_file, shim_file, name
     ref = _dummy_arguments(os.path.join(_REF_TREE, ref_file), name)
     mine = _dummy_arguments(os.path.join(root, "geosradiation_gridcomp_b200", "fortran", shim_file), name)
     assert mine == ref, name
+
+
+@pytest.mark.skipif(not os.path.isdir(_REF_TREE), reason="the reference tree is only present in the build container")
+def test_fortran_shim_has_the_reference_argument_list_of_the_radval_build():
+    """Compiled with -DSOLAR_RADVAL (GEOSsolar_GridComp/CMakeLists.txt:18-20) rrtmg_sw gains 120 dummies
+    (SW/src/rrtmg_sw_rad.F90:85-122): the shim lists them in the reference's order, which is also the column order of
+    RrtmgxSwArgs::radval (host.RADVAL_NAMES) - the shim copies column q to the q-th of them."""
+    import re
+    from geosradiation_gridcomp_b200 import host
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim_path = os.path.join(root, "geosradiation_gridcomp_b200", "fortran", "rrtmg_sw_rad.F90")
+    ref = _dummy_arguments(os.path.join(_REF_TREE, "GEOSsolar_GridComp/RRTMG/rrtmg_sw/gcm_model/src/rrtmg_sw_rad.F90"),
+                           "rrtmg_sw", strip_radval=False)
+    mine = _dummy_arguments(shim_path, "rrtmg_sw", strip_radval=False)
+    assert mine == ref and len(ref) == len(_dummy_arguments(shim_path, "rrtmg_sw")) + host.NRADVAL
+    i = ref.index("cotnlp") + 1
+    assert tuple(ref[i:i + host.NRADVAL]) == host.RADVAL_NAMES
+    copies = re.findall(r"^\s*(\w+) = radval\(:,(\d+)\)", open(shim_path).read(), flags=re.M)
+    assert [(n, int(q)) for n, q in copies] == [(n, q + 1) for q, n in enumerate(host.RADVAL_NAMES)]

@@ -5,7 +5,7 @@ Fortran of /root/reference (RRTMG LW + SW, McICA, NRLSSI2: 91 files, read where 
 oracle/refexec/f90py.py - no Fortran compiler exists in this image, so this is how the reference runs here.  The
 cases (tests/golden/refexec_cases.py) cover the GEOS defaults at L72 and L181, every LW and SW cloud-optics option,
 every solar-variability mode, the three condensate inhomogeneity options, non-default decorrelation lengths, ragged
-partitions, and every intermediate the oracle taps (jp / jt / jt1 / indices, interpolation factors, the McICA
+partitions, the SOLAR_RADVAL build of rrtmg_sw (its 120 extra diagnostics), and every intermediate the oracle taps (jp / jt / jt1 / indices, interpolation factors, the McICA
 sub-column mask, optical depths, Planck fractions, Rayleigh, solar source).
 
 Bar: integers (indices, masks, clear counts) bit for bit; reals within 1e-12 relative (what is seen is bit-identical
@@ -37,13 +37,16 @@ def test_golden_file_holds_every_case(golden):
             for k in rc.LW_OUT + (rc.LW_TAPS if c["taps"] else ()):
                 assert f"{name}/lw/{k}" in keys, (name, k)
         if c["sw"] is not None:
-            for k in rc.SW_OUT + (tuple(rc.SW_TAPS) if c["taps"] else ()):
+            for k in rc.SW_OUT + (tuple(rc.SW_TAPS) if c["taps"] else ()) + (("radval",) if c["sw"].get("radval") else ()):
                 assert f"{name}/sw/{k}" in keys, (name, k)
     # the cases are not trivially cloud-free: cloudy sub-columns exist, and the clear-sky stream differs from the total
     assert (golden["default/lw/clearCounts"][:, 0] < 140).sum() >= 10
     assert np.abs(golden["default/lw/uflx"] - golden["default/lw/uflxc"]).max() > 10.0
     assert np.abs(golden["default/sw/swdflx"] - golden["default/sw/swdflxc"]).max() > 0.1
     assert golden["taps/lw/cldymc"].sum() > 1000 and golden["taps/sw/cldymc"].sum() > 1000
+    # the SOLAR_RADVAL cases: every one of the 120 diagnostics is non-zero somewhere, liquid and ice, all super-layers
+    rv = np.concatenate([golden[f"{n}/sw/radval"] for n in rc.CASES if n.startswith("radval")])
+    assert rv.shape[1] == 120 and (np.abs(rv).max(axis=0) > 0).all()
 
 
 @pytest.mark.parametrize("name", list(rc.CASES))
