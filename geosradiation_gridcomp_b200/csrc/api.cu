@@ -74,6 +74,7 @@ struct Ctx {
     Path lw, sw;
     size_t chunk_cols = 0;   // 0: automatic
     size_t host_chunk_cols = kHostChunkDefault;   // staging chunk of the host-array pipeline (RRTMGX_HOST_CHUNK; sweep: profiles/r4_c_*, r4_d_*)
+    bool host_chunk_from_env = false;   // RRTMGX_HOST_CHUNK set: taken literally, whatever the element size
     int stages = kStagesDefault;   // staging sets in flight (RRTMGX_STAGES): deeper than double buffering measured slower, profiles/r4_d_*
     std::mutex mu;
 };
@@ -195,7 +196,14 @@ __global__ void __launch_bounds__(256) check_negative_kernel(NegScan S, int *neg
 // (at most 32 planes of nlay*nc elements)
 size_t chunk_cap(int nlay) { return (((size_t)1 << 31) - 1) / ((size_t)32 * std::max(nlay, 1)); }
 
-size_t pick_chunk(int ncol, int nlay, size_t per_col_bytes, bool host_mode, size_t own_bytes) {
+// Staging chunk of the host-array pipeline in columns.  The default is sized for fp64 arrays; real*4 arrays take
+// twice the columns (the same bytes per chunk): with half the bytes the kernels, not the link, are the longer stage
+// of the pipeline, and 8192 columns are 256 blocks per band kernel, not one wave of a B200 (measured,
+// profiles/t1_b_e2e_chunk_sweep.jsonl: +6 % end to end with real*4 arrays and through the real*4 glue at 16384,
+// nothing with fp64 arrays).  RRTMGX_HOST_CHUNK is taken literally.
+size_t host_chunk(bool f32) { return g.host_chunk_cols * ((f32 && !g.host_chunk_from_env) ? 2 : 1); }
+
+size_t pick_chunk(int ncol, int nlay, size_t per_col_bytes, bool host_mode, size_t own_bytes, bool f32 = false) {
     if (g.chunk_cols) return std::min<size_t>(std::min<size_t>(g.chunk_cols, chunk_cap(nlay)), (size_t)ncol);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
@@ -206,7 +214,7 @@ size_t pick_chunk(int ncol, int nlay, size_t per_col_bytes, bool host_mode, size
     size_t nc = std::max<size_t>(1024, budget / std::max<size_t>(per_col_bytes, 1));
     nc = std::min<size_t>(std::min<size_t>(nc, 65536), chunk_cap(nlay));
     // host arrays: smaller chunks shorten the fill/drain of the H2D -> kernels -> D2H pipeline
-    if (host_mode) nc = std::min<size_t>(nc, g.host_chunk_cols);
+    if (host_mode) nc = std::min<size_t>(nc, host_chunk(f32));
     nc &= ~(size_t)127;
     return std::min<size_t>(nc, (size_t)ncol);
 }
@@ -443,9 +451,13 @@ int rrtmgx_init(const RrtmgxConfig *cfg) {
     // tuning knobs: the defaults first, so that a finalize -> init cycle never inherits the previous environment
     g.chunk_cols = 0;
     g.host_chunk_cols = kHostChunkDefault;
+    g.host_chunk_from_env = false;
     g.stages = kStagesDefault;
     if (const char *e = std::getenv("RRTMGX_CHUNK")) g.chunk_cols = (size_t)std::atoll(e);
-    if (const char *e = std::getenv("RRTMGX_HOST_CHUNK")) g.host_chunk_cols = std::max<size_t>(1024, (size_t)std::atoll(e));
+    if (const char *e = std::getenv("RRTMGX_HOST_CHUNK")) {
+        g.host_chunk_cols = std::max<size_t>(1024, (size_t)std::atoll(e));
+        g.host_chunk_from_env = true;
+    }
     if (const char *e = std::getenv("RRTMGX_STAGES")) g.stages = std::min(NSTAGE, std::max(2, std::atoi(e)));
     lw_read_env();
     sw_read_env();
@@ -612,7 +624,8 @@ int rrtmgx_lw_run_variants(const RrtmgxLwArgs *a, const RrtmgxLwVariants *var) {
     const RrtmgxTaps *taps = p.has_taps ? &p.taps : nullptr;
     const bool dbg = taps && (taps->taug || taps->pfracs);
     const size_t per_col = lw_scratch_bytes(1024, nlay, dbg) / 1024;
-    size_t chunk = pick_chunk(ncol, nlay, per_col + (!staged ? 0 : 2 * (size_t)(37 * nlay + 60) * 8), staged, p.slab.cap);
+    size_t chunk = pick_chunk(ncol, nlay, per_col + (!staged ? 0 : 2 * (size_t)(37 * nlay + 60) * 8), staged, p.slab.cap,
+                              (a->flags & RRTMGX_F32_ARRAYS) != 0);
     if (taps) {   // taps are laid out for the whole call
         if ((size_t)ncol > chunk_cap(nlay)) return RRTMGX_EARG;
         chunk = (size_t)ncol;
@@ -824,7 +837,7 @@ int rrtmgx_sw_run_with_clean(const RrtmgxSwArgs *a, const RrtmgxSwNoAerosol *na)
     const bool radval = a->radval != nullptr;   // the SOLAR_RADVAL build of rrtmg_sw (include/rrtmgx.h)
     const size_t per_col = sw_scratch_bytes(1024, nlay, dbg, radval) / 1024;
     size_t chunk = pick_chunk(ncol, nlay, per_col + (!staged ? 0 : 2 * (size_t)(57 * nlay + 60 + (radval ? RRTMGX_NRADVAL : 0)) * 8),
-                              staged, p.slab.cap);
+                              staged, p.slab.cap, (a->flags & RRTMGX_F32_ARRAYS) != 0);
     if (taps) {   // taps are laid out for the whole call
         if ((size_t)ncol > chunk_cap(nlay)) return RRTMGX_EARG;
         chunk = (size_t)ncol;
@@ -1112,7 +1125,7 @@ int rrtmgx_irrad_refresh(const RrtmgxIrradArgs *a) {
     } else {
         ca.olrb = nullptr; ca.dolrb_dts = nullptr;
     }
-    const size_t chunk = std::min<size_t>(g.host_chunk_cols, (size_t)ncol);
+    const size_t chunk = std::min<size_t>(host_chunk(f32), (size_t)ncol);
     int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxIrradArgs &c, int nc, size_t) -> int {
         return irrad_chunk(c, nc, 0, nc, p.stream);
     });
@@ -1291,7 +1304,7 @@ int rrtmgx_solar_refresh(const RrtmgxSolarArgs *a) {
     out(a->uvrr, &ca.uvrr, 1); out(a->uvrf, &ca.uvrf, 1); out(a->fswband, &ca.fswband, 14);
     out(a->cldts, &ca.cldts, 1); out(a->cldhs, &ca.cldhs, 1); out(a->cldms, &ca.cldms, 1); out(a->cldls, &ca.cldls, 1);
     out(a->cottp, &ca.cottp, 1); out(a->cothp, &ca.cothp, 1); out(a->cotmp, &ca.cotmp, 1); out(a->cotlp, &ca.cotlp, 1);
-    const size_t chunk = std::min<size_t>(g.host_chunk_cols, (size_t)ncol);
+    const size_t chunk = std::min<size_t>(host_chunk(f32), (size_t)ncol);
     int rc = run_staged(p, *a, ca, arrs, ncol, chunk, [&](RrtmgxSolarArgs &c, int nc, size_t first) -> int {
         if (!lit_only) return solar_chunk(c, nc, 0, nc, p.stream);
         // the staged chunk holds native columns [first, first + nc): its daytime columns, from the caller's own ZTH

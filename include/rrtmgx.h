@@ -113,7 +113,8 @@ typedef struct {
 int rrtmgx_init(const RrtmgxConfig *cfg);
 int rrtmgx_set_mcica(int ih, const double corr[8]);
 /* The tuning knobs in force and the McICA inhomogeneity type, for tests and diagnostics:
- * knobs[0] = RRTMGX_CHUNK (0 = automatic), [1] = RRTMGX_HOST_CHUNK (default 8192), [2] = RRTMGX_STAGES
+ * knobs[0] = RRTMGX_CHUNK (0 = automatic), [1] = RRTMGX_HOST_CHUNK (default 8192 columns; real*4 arrays take twice
+ * the default: the same bytes per staging chunk; a value from the environment is taken literally), [2] = RRTMGX_STAGES
  * (default 2), [3] = ih.  Returns RRTMGX_ENOTINIT before rrtmgx_init. */
 int rrtmgx_get_knobs(long long knobs[4]);
 int rrtmgx_finalize(void);
