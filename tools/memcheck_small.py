@@ -15,6 +15,10 @@ for ncol, nlay in ((203, 72), (37, 181)):
     sw = rx.run_sw(s)
     rx.run_lw(s, reuse_clouds=True)
     rx.run_sw(s, iaer=0, reuse_clouds=True)
+    rv = rx.run_sw(s, radval=True)                                  # the SOLAR_RADVAL build
+    rx.run_sw(s, radval=True, iaer=0, reuse_clouds=True)
+    rx.run_sw(s, reuse_clouds=True)                                 # default build after a RADVAL call
+    assert np.isfinite(rv["radval"]).all()
     n = make_native_state(ncol, nlay, seed=78)
     f = rx.irrad_refresh(n)
     rx.solar_refresh(n)
