@@ -14,6 +14,7 @@ lines compute.  Build container only (needs the reference tree).
   solar_prepare  SOL:6116-6219  aerosol normalisation, DPR, water paths, radius limits, TLEV, flips, conversions, ZL, aerosols
   solar_finish   SOL:6395-6454  unflip, cloud fractions, COT ratios with MAPL_UNDEF, FSW / FSC / FSWU / FSCU
   irrad_update   IRR:3604, 3606, 3861, 3932-3992  the between-refresh linear update of the LW exports (USE_RRTMG branch)
+  heating_rates  RAD:801-802, 811, 813-814  DTDT, RADLW, RADSW of the parent component (GEOS_RadiationGridComp.F90)
 """
 import os
 
@@ -25,6 +26,7 @@ from .f90py import FA
 REF = os.environ.get("REFERENCE_ROOT", "/root/reference")
 IRR = os.path.join(REF, "GEOSirrad_GridComp/GEOS_IrradGridComp.F90")
 SOL = os.path.join(REF, "GEOSsolar_GridComp/GEOS_SolarGridComp.F90")
+RAD = os.path.join(REF, "GEOS_RadiationGridComp.F90")
 
 _ns = None
 
@@ -126,8 +128,20 @@ subroutine irr_upd(IM, JM, LM, MAPL_UNDEF, TSINST, TS_INT, FLXU_INT, FLXD_INT, F
 """
 
 
+_RAD_HR_HEAD = """
+module refglue_rad_hr
+contains
+subroutine rad_hr(IM, JM, LM, MAPL_GRAV, MAPL_CP, PLE, FLW, FSW, DTDT, RADLW, RADSW)
+   integer, intent(in) :: IM, JM, LM
+   real, intent(in) :: MAPL_GRAV, MAPL_CP
+   real, intent(in), dimension(IM,JM,0:LM) :: PLE, FLW, FSW
+   real, pointer, dimension(:,:,:) :: DTDT, RADLW, RADSW
+   real :: DMI(IM,JM,LM)
+"""
+
+
 def available():
-    return os.path.isfile(IRR) and os.path.isfile(SOL)
+    return os.path.isfile(IRR) and os.path.isfile(SOL) and os.path.isfile(RAD)
 
 
 def source_text():
@@ -144,6 +158,11 @@ def source_text():
         _IRR_UPD_HEAD + _lines(IRR, 3604, 3604, "FLX_INT  = FLXD_INT  + FLXU_INT", "FLX_INT") + _lines(IRR, 3606, 3606, "FLC_INT  = FLCD_INT  + FLCU_INT", "FLC_INT")
         + _lines(IRR, 3861, 3861, "DELT = TSINST - TS_INT", "DELT") + _lines(IRR, 3932, 3992, "do K = 0, LM", "if(associated(FLNSA )) FLNSA  = MAPL_UNDEF")
         + "end subroutine irr_upd\nend module refglue_irr_upd\n",
+        # the parent component's heating rates: total tendency (:801-802), DMI (:811), RADLW / RADSW (:813-814)
+        _RAD_HR_HEAD + _lines(RAD, 801, 802, "if( associated (DTDT    ) ) DTDT     = (", "(FSW(:,:,0:LM-1) - FSW(:,:,1:LM)) ) * (MAPL_GRAV/MAPL_CP)")
+        + _lines(RAD, 811, 811, "DMI = MAPL_GRAV/(MAPL_CP*(PLE(:,:,1:LM)-PLE(:,:,0:LM-1)))", "DMI")
+        + _lines(RAD, 813, 814, "if( associated (RADLW   ) ) RADLW", "if( associated (RADSW   ) ) RADSW")
+        + "end subroutine rad_hr\nend module refglue_rad_hr\n",
     ]
     return parts
 
@@ -303,6 +322,19 @@ def irrad_update(f, ts_int, tsinst, undef=1e15, cldtt=None):
     res = {k: v.a[:, 0, :] for k, v in o3.items()}
     res.update({k: v.a[:, 0] for k, v in o2.items()})
     return res
+
+
+def heating_rates(ple, flw, fsw, grav, cp):
+    """RAD:801-802, 811, 813-814 on native arrays (ncol, 0:LM), level 0 at the model top: PLE [Pa], the net LW and SW
+    fluxes FLW, FSW [W/m2, downward positive] as the parent component holds them.  Returns DTDT [K Pa / s], RADLW and
+    RADSW [K/s], each (ncol, LM)."""
+    ns = namespace()
+    nc, lm1 = np.shape(ple)
+    lm = lm1 - 1
+    g3 = lambda a: FA(np.array(a, dtype=np.float64, order="F").reshape(nc, 1, lm1, order="F"), (1, 1, 0))
+    out = [_z((nc, 1, lm)) for _ in range(3)]
+    ns["P_refglue_rad_hr__rad_hr"](nc, 1, lm, float(grav), float(cp), g3(ple), g3(flw), g3(fsw), *out)
+    return {k: v.a[:, 0, :] for k, v in zip(("dtdt", "radlw", "radsw"), out)}
 
 
 # ---- a whole refresh of a driver from the reference's text: glue lines -> RRTMG sources -> glue lines -----------------

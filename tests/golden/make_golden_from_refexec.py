@@ -70,6 +70,8 @@ def run_kiss():
 
 
 REFRESH_NCOL, REFRESH_SEED = 14, 73
+RAD_GRAV, RAD_CP = 9.80665, 1004.68506    # MAPL_GRAV, MAPL_CP
+RAD_EXPORTS = ("dtdt", "radlw", "radsw")
 IRR_EXPORTS = ("flxu", "flxd", "flcu", "flcd", "dfdts", "dfdtsc", "sfcem", "cldtt", "cldhi", "cldmd", "cldlo", "olrb", "dolrb_dts")
 SOL_EXPORTS = ("fsw", "fsc", "fswu", "fscu", "cldts", "cldhs", "cldms", "cldls", "cottp", "cothp", "cotmp", "cotlp", "nirr",
                "nirf", "parr", "parf", "uvrr", "uvrf", "fswband")
@@ -77,6 +79,12 @@ IRR_PREPARED = ("play", "plev", "tlay", "tlev", "tsfc", "emis", "h2ovmr", "o3vmr
                 "cfc11vmr", "cfc12vmr", "cfc22vmr", "ccl4vmr", "cldf", "ciwp", "clwp", "rei", "rel", "tauaer_lw", "zm", "alat")
 SOL_PREPARED = ("play", "plev", "tlay", "h2ovmr", "o3vmr", "co2vmr", "ch4vmr", "o2vmr", "cld", "ciwp", "clwp", "rei", "rel",
                 "zm", "tauaer", "ssaaer", "asmaer")
+
+
+def rad_fsw(n, fsw_normalised):
+    """The net SW flux in W/m2 the parent component sees: the refresh returns fluxes normalised by the TOA insolation
+    (normFlx = 1, SOL:6346) and the Solar Update scales them back by the instantaneous insolation."""
+    return fsw_normalised * (float(n["sc"]) * np.asarray(n["zt"], dtype=np.float64)[:, None])
 
 
 def run_refresh():
@@ -90,9 +98,13 @@ def run_refresh():
     out.update({f"refresh/irr_prepared/{k}": s[k] for k in IRR_PREPARED})
     out.update({f"refresh/irr/{k}": f[k] for k in IRR_EXPORTS})
     out["refresh/irr_prepared/cloudLM"], out["refresh/irr_prepared/cloudMH"] = np.int64(s["cloudLM"]), np.int64(s["cloudMH"])
+    flw = f["flxu"] + f["flxd"]            # the Irrad export FLX the parent component reads (IRR:3604: upward negative)
     s, _, f = glue.solar_refresh(n)
     out.update({f"refresh/sol_prepared/{k}": s[k] for k in SOL_PREPARED})
     out.update({f"refresh/sol/{k}": f[k] for k in SOL_EXPORTS})
+    # the parent component's heating rates from the two refreshes (GEOS_RadiationGridComp.F90:801-814)
+    hr = glue.heating_rates(n["ple"], flw, rad_fsw(n, f["fsw"]), RAD_GRAV, RAD_CP)
+    out.update({f"refresh/rad/{k}": hr[k] for k in RAD_EXPORTS})
     return out
 
 

@@ -135,3 +135,19 @@ def check_case(got, golden, name, tol, tol_taps=None):
         limit = tol_taps if (tol_taps is not None and key in LW_TAPS + tuple(SW_TAPS)) else tol
         assert e <= limit, f"{name}/{k}: relative difference {e:.3e} > {limit:.1e}"
     return n, same, worst
+
+
+def heating_inputs(golden, n):
+    """The arguments of rrtmgx_heating_rate (net upward flux at levels, surface first; interface pressures in hPa, surface
+    first) for the LW and the SW fluxes of the golden refresh, from the native top-down arrays the parent component
+    holds (GEOS_RadiationGridComp.F90:801-814: FLW, FSW net downward, PLE in Pa, level 0 at the model top)."""
+    import make_golden_from_refexec as gen
+    flw = golden["refresh/irr/flxu"] + golden["refresh/irr/flxd"]
+    fsw = gen.rad_fsw(n, golden["refresh/sol/fsw"])
+    plev = np.asfortranarray(np.asarray(n["ple"])[:, ::-1] / 100.0)
+    return {"radlw": np.asfortranarray(-flw[:, ::-1]), "radsw": np.asfortranarray(-fsw[:, ::-1])}, plev
+
+
+def heating_formula(fnet, plev, grav, cp):
+    """What the parity tests use as the plain restatement of the epilogue (K/day, layer 1 at the surface)."""
+    return (fnet[:, :-1] - fnet[:, 1:]) * (grav / cp) / ((plev[:, :-1] - plev[:, 1:]) * 100.0) * 86400.0

@@ -205,3 +205,35 @@ def test_oracle_irrad_update_equals_the_reference_lines_live(oracle):
     assert clear.any() and (~clear).any()
     np.testing.assert_array_equal(r["olcc5"][clear], r["olc"][clear])
     assert (r["olcc5"][~clear] == n["undef"]).all()
+
+
+def test_heating_rate_formula_equals_the_reference_lines(golden):
+    """RADLW / RADSW of the parent component (GEOS_RadiationGridComp.F90:811, 813-814, executed from the file by
+    oracle/refexec/glue.py on the golden refresh: keys refresh/rad/*, K/s, top-down) against the restatement the heating
+    rate tests compare rrtmgx_heating_rate with (K/day, surface first): the bar of north_star, 1e-6 K/day - what is
+    seen is the rounding of the unit conversions, ~1e-14 K/day."""
+    import make_golden_from_refexec as gen
+    from geosradiation_gridcomp_b200.synthetic import make_native_state
+    n = make_native_state(gen.REFRESH_NCOL, 72, seed=gen.REFRESH_SEED)
+    fnet, plev = rc.heating_inputs(golden, n)
+    for k in ("radlw", "radsw"):
+        ref = golden[f"refresh/rad/{k}"][:, ::-1] * 86400.0      # K/day, surface first
+        got = rc.heating_formula(fnet[k], plev, gen.RAD_GRAV, gen.RAD_CP)
+        assert np.abs(ref).max() > 10.0
+        assert np.abs(got - ref).max() <= 1e-6, k
+        assert np.abs(got - ref).max() <= 1e-11 * np.abs(ref).max(), k
+    # DTDT (:801-802) is the sum of the two flux divergences times g / cp
+    d = (golden["refresh/rad/radlw"] + golden["refresh/rad/radsw"]) * (np.asarray(n["ple"])[:, 1:] - np.asarray(n["ple"])[:, :-1])
+    assert rc.rel_err(d, golden["refresh/rad/dtdt"]) <= 1e-12
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("REFERENCE_ROOT", "/root/reference")), reason="no reference tree on this machine")
+def test_heating_rate_golden_is_what_the_reference_lines_give_live(golden):
+    import make_golden_from_refexec as gen
+    from geosradiation_gridcomp_b200.synthetic import make_native_state
+    from oracle.refexec import glue
+    n = make_native_state(gen.REFRESH_NCOL, 72, seed=gen.REFRESH_SEED)
+    flw = golden["refresh/irr/flxu"] + golden["refresh/irr/flxd"]
+    hr = glue.heating_rates(n["ple"], flw, gen.rad_fsw(n, golden["refresh/sol/fsw"]), gen.RAD_GRAV, gen.RAD_CP)
+    for k in gen.RAD_EXPORTS:
+        np.testing.assert_array_equal(hr[k], golden[f"refresh/rad/{k}"], err_msg=k)

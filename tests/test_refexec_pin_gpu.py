@@ -70,3 +70,23 @@ def test_cuda_refresh_equals_the_reference_text_refresh(rx, golden):
             assert rc.rel_err(np.where(ref == n["undef"], 0.0, f[k]), np.where(ref == n["undef"], 0.0, ref)) <= TOL_FLUX, k
         else:
             assert rc.rel_err(f[k], ref) <= TOL_FLUX, k
+
+
+def test_cuda_heating_rates_equal_the_reference_lines(rx, golden):
+    """rrtmgx_heating_rate against RADLW / RADSW computed by the parent component's own lines
+    (GEOS_RadiationGridComp.F90:811, 813-814, executed from the file; golden keys refresh/rad/*) on the fluxes of the
+    golden refresh: within 1e-6 K/day (north_star); host arrays and device pointers."""
+    import torch
+    import make_golden_from_refexec as gen
+    from geosradiation_gridcomp_b200.synthetic import make_native_state
+    n = make_native_state(gen.REFRESH_NCOL, 72, seed=gen.REFRESH_SEED)
+    fnet, plev = rc.heating_inputs(golden, n)
+    for k in ("radlw", "radsw"):
+        ref = golden[f"refresh/rad/{k}"][:, ::-1] * 86400.0      # K/day, surface first
+        got = rx.heating_rate(fnet[k], plev, gen.RAD_GRAV, gen.RAD_CP)
+        assert np.abs(got - ref).max() <= 1e-6, k
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).cuda()
+        out = torch.zeros((72, gen.REFRESH_NCOL), dtype=torch.float64, device="cuda")
+        rx.heating_rate(dev(fnet[k]), dev(plev), gen.RAD_GRAV, gen.RAD_CP, device=True, out=out)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(out.cpu().numpy().T, got)
