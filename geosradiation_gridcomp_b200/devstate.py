@@ -67,7 +67,8 @@ def lw_runner(d, o=None, device=True, sync=True, skip_checks=False, dudTs=True, 
 
 
 def sw_runner(d, o=None, device=True, sync=True, skip_checks=False, iceflg=3, liqflg=1, isolvar=0, iaer=10,
-              normFlx=1, stream=None, f32=False, reuse_clouds=False):
+              normFlx=1, stream=None, f32=False, reuse_clouds=False, radval=None):
+    """radval: a [120][ncol] tensor (device or pinned host like the other arrays) selects the SOLAR_RADVAL build."""
     ncol, nlay = d["ncol"], d["nlay"]
     o = o if o is not None else alloc_outputs(ncol, nlay, pinned=not device)
     p = (lambda t: t) if device else (lambda t: t.data_ptr())
@@ -82,7 +83,8 @@ def sw_runner(d, o=None, device=True, sync=True, skip_checks=False, iceflg=3, li
                       p(o["nirr"]), p(o["nirf"]), p(o["parr"]), p(o["parf"]), p(o["uvrr"]), p(o["uvrf"]),
                       p(o["fswband"]), p(o["cotdtp"]), p(o["cotdhp"]), p(o["cotdmp"]), p(o["cotdlp"]), p(o["cotntp"]),
                       p(o["cotnhp"]), p(o["cotnmp"]), p(o["cotnlp"]), False, p(o["drband"]), p(o["dfband"]),
-                      device=device, sync=sync, skip_checks=skip_checks, stream=stream, f32=f32, reuse_clouds=reuse_clouds)
+                      device=device, sync=sync, skip_checks=skip_checks, stream=stream, f32=f32, reuse_clouds=reuse_clouds,
+                      radval=None if radval is None else p(radval))
         return o
     run.outputs = o
     return run

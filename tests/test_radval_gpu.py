@@ -113,3 +113,37 @@ def test_radval_host_chunks_device_pointers_real4_and_both_passes(rx, oracle):
     got4 = rx.run_sw(s4, out=out4, radval=True, f32=True)
     np.testing.assert_array_equal(got4["radval"], want["radval"].astype(np.float32))
     np.testing.assert_array_equal(got4["swdflx"], want["swdflx"].astype(np.float32))
+
+
+def test_radval_on_the_full_c180_grid(rx):
+    """BASELINE.json's full size through size-independent properties: a slab of the 194 400-column device-resident run
+    (three chunks) equals a small run of the same columns bit for bit, and the identities hold on every column."""
+    import torch
+    import bench
+    from geosradiation_gridcomp_b200 import devstate
+    ncol, nlay, seed = 194400, 72, 20260121
+    s = bench.make_state(ncol, nlay, seed, 0, 16)
+    d = devstate.to_device(s)
+    o = devstate.alloc_outputs(ncol, nlay)
+    rv = torch.zeros((rx.NRADVAL, ncol), dtype=torch.float64, device="cuda")
+    devstate.sw_runner(d, o, radval=rv)()
+    torch.cuda.synchronize()
+    big = rv.cpu().numpy().T
+    c0, n = (ncol * 3) // 8 + 11, 96
+    sub = rx.run_sw(make_columns(n, nlay, seed=seed, col0=c0), radval=True)
+    np.testing.assert_array_equal(big[c0:c0 + n], sub["radval"])
+    np.testing.assert_array_equal(o["swdflx"].cpu().numpy().T[c0:c0 + n], sub["swdflx"])
+    q = {name: big[:, i] for i, name in enumerate(rx.RADVAL_NAMES)}
+    clear = ~(s["cldf"] > 0).any(axis=1)
+    assert clear.sum() > ncol // 4 and not big[clear].any()
+    assert np.isfinite(big).all() and (big >= 0).all()
+    cot = {k: o[k].cpu().numpy() for k in ("cotntp", "cotdtp", "cotnlp", "cotdlp")}
+    for lev in "tl":
+        tot = cot["cotn" + lev + "p"]
+        assert np.abs(q["cotln" + lev + "p"] + q["cotin" + lev + "p"] - tot).max() <= 1e-12 * tot.max()
+        # a subcolumn with liquid (or ice) cloud in the super-layer is a cloudy subcolumn of it
+        assert (q["cotld" + lev + "p"] <= cot["cotd" + lev + "p"] * (1 + 1e-14)).all()
+        assert (q["cotid" + lev + "p"] <= cot["cotd" + lev + "p"] * (1 + 1e-14)).all()
+        # delta scaling lowers the optical thickness, never the count of cloudy subcolumns
+        assert (q["cdsn" + lev + "p"] <= tot * (1 + 1e-14)).all()
+        np.testing.assert_array_equal(q["cdsd" + lev + "p"] > 0, cot["cotd" + lev + "p"] > 0)

@@ -18,18 +18,10 @@ def main():
     d = devstate.to_device(s)
     o = devstate.alloc_outputs(ncol, 72)
     rv = torch.zeros((host.NRADVAL, ncol), dtype=torch.float64, device="cuda")
-    p = lambda t: t
+    runners = {False: devstate.sw_runner(d, o), True: devstate.sw_runner(d, o, radval=rv)}
 
     def call(radval):
-        host.rrtmg_sw(0, ncol, 72, d["scon"], d["adjes"], p(d["coszen"]), 0, p(d["play"]), p(d["plev"]), p(d["tlay"]),
-                      p(d["h2ovmr"]), p(d["o3vmr"]), p(d["co2vmr"]), p(d["ch4vmr"]), p(d["o2vmr"]), 3, 1, p(d["cldf"]),
-                      p(d["ciwp"]), p(d["clwp"]), p(d["rei"]), p(d["rel"]), d["dyofyr"], p(d["zm"]), p(d["alat"]), 10,
-                      p(d["tauaer_sw"]), p(d["ssaaer"]), p(d["asmaer"]), p(d["asdir"]), p(d["asdif"]), p(d["aldir"]),
-                      p(d["aldif"]), d["cloudLM"], d["cloudMH"], 1, p(o["clearCounts_sw"]), p(o["swuflx"]), p(o["swdflx"]),
-                      p(o["swuflxc"]), p(o["swdflxc"]), p(o["nirr"]), p(o["nirf"]), p(o["parr"]), p(o["parf"]), p(o["uvrr"]),
-                      p(o["uvrf"]), p(o["fswband"]), p(o["cotdtp"]), p(o["cotdhp"]), p(o["cotdmp"]), p(o["cotdlp"]),
-                      p(o["cotntp"]), p(o["cotnhp"]), p(o["cotnmp"]), p(o["cotnlp"]), False, p(o["drband"]), p(o["dfband"]),
-                      device=True, radval=rv if radval else None)
+        runners[radval]()
 
     for radval in (False, True):
         call(radval); call(radval)
