@@ -1388,7 +1388,13 @@ typedef void (*LwBandLauncher)(int, cudaStream_t, const LwBandArgs &);
 template <int BAND, int GN, int REGS, int CB>
 static void lw_launch_band(int nc, cudaStream_t st, const LwBandArgs &A) {
     static char tag[48] = "";
-    if (!tag[0]) std::snprintf(tag, sizeof tag, "lw_band_kernel<%d,gn%d,r%d,c%d>", BAND, GN, REGS, CB);
+    if (!tag[0]) {
+        std::snprintf(tag, sizeof tag, "lw_band_kernel<%d,gn%d,r%d,c%d>", BAND, GN, REGS, CB);
+        // experiment (profiles/t1_g_*): preferred shared-memory share of the SM in percent, unset = the driver's choice
+        if (const char *e = std::getenv("RRTMGX_CARVEOUT"))
+            cudaFuncSetAttribute(lw_band_kernel<BAND, GN, REGS, CB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 std::atoi(e));
+    }
     RRTMGX_LAUNCH_TAG(tag, (lw_band_kernel<BAND, GN, REGS, CB>), dim3((nc + CB - 1) / CB),
                       dim3(LwBandInfo<BAND>::ng / GN, CB), 0, st, A);
 }
