@@ -199,7 +199,8 @@ def workload_config(a, with_sw, world=1):
                         f"all columns sunlit, 40% clear-sky columns",
             "baseline_config": a.config, "ncol_per_gpu": a.ncol, "nlay": a.nlay, "ngpt_lw": 140, "ngpt_sw": 112,
             "l2_policy": "inputs (>10 GB per step) far exceed the 126 MB L2; no explicit flush",
-            "precision": "fp64 boundary arrays and arithmetic (promoted-real contract)"}
+            "precision": "fp64 boundary arrays and arithmetic (promoted-real contract)",
+            "paths": getattr(a, "paths", "concurrent")}
 
 
 def bind_near_gpu(local):
@@ -243,6 +244,8 @@ def main():
     ap.add_argument("--verify-cols", type=int, default=256, help="columns per rank checked after the timed region")
     ap.add_argument("--seed", type=int, default=20260121)
     ap.add_argument("--cpu-sample", type=int, default=65536, help="columns in the CPU baseline sample")
+    ap.add_argument("--paths", default="concurrent", choices=["concurrent", "serial"],
+                    help="device-resident arm: LW and SW of a step on two streams at once (default) or SW after LW")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
@@ -294,7 +297,10 @@ def main():
         st_lw.wait_event(ev)
         run_lw()
         if run_sw:
-            st_sw.wait_event(ev)
+            if a.paths == "serial":
+                st_sw.wait_stream(st_lw)   # experiment (profiles/t1_j_*): one path at a time
+            else:
+                st_sw.wait_event(ev)
             run_sw()
         cur.wait_stream(st_lw)
         if run_sw:
