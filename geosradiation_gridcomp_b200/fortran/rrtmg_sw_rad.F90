@@ -128,7 +128,7 @@ contains
       integer(c_int) :: status
       real(c_double), target :: bndscl_d(14), indsolvar_d(2), solcycfrac_d   ! always double in the C ABI
 #ifdef SOLAR_RADVAL
-      real, target :: radval(ncol,RRTMGX_NRADVAL)   ! the 120 dummies in list order, one column each
+      real, allocatable, target :: radval(:,:)   ! (ncol,RRTMGX_NRADVAL): the 120 dummies in list order, one column each
 #endif
 
       a%ncol = ncol; a%nlay = nlay; a%rpart = rpart      ! rpart: cache blocking of the CPU code, ignored
@@ -168,6 +168,7 @@ contains
       end if
 
 #ifdef SOLAR_RADVAL
+      allocate(radval(ncol,RRTMGX_NRADVAL))   ! on the heap: ncol is a whole partition of the grid
       a%radval = c_loc(radval)
 #else
       a%radval = c_null_ptr
